@@ -1,0 +1,15 @@
+"""distill-bev_b200: B200-native (sm_100a) DistillBEV hot path behind the
+reference's mmdet3d operator names. See DESIGN.md and INTEGRATION.md.
+
+Import as ``distill_bev_b200`` (alias module at the repository root).
+"""
+from . import _lib  # noqa: F401
+from .plugin.ops.bev_pool import (BevPlan, QuickCumsumCuda, bev_plan_from_coords,  # noqa: F401
+                                  bev_plan_from_geom, bev_pool, bev_pool_ext, bev_pool_gather,
+                                  voxel_pooling)
+
+__version__ = "0.1.0"
+
+
+def library_path():
+    return _lib.LIB_PATH

@@ -1,0 +1,102 @@
+"""ctypes binding of libdistill_bev_b200.so (the C-ABI in include/distill_bev_b200.h).
+
+There is no CPU or PyTorch fallback anywhere in this package: if the shared
+library is missing or a tensor is not on a CUDA device the call raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdistill_bev_b200.so")
+
+_c_int = ctypes.c_int
+_c_ll = ctypes.c_longlong
+_c_size = ctypes.c_size_t
+_ptr = ctypes.c_void_p
+_fptr = ctypes.POINTER(ctypes.c_float)
+_iptr = ctypes.POINTER(ctypes.c_int)
+
+# name -> (restype, argtypes); must list every symbol include/distill_bev_b200.h declares
+SIGNATURES = {
+    "dbev_abi_version": (_c_int, []),
+    "dbev_last_error": (ctypes.c_char_p, []),
+    "dbev_build_arch": (ctypes.c_char_p, []),
+    "dbev_bev_pool_forward": (_c_int, [_c_int] * 7 + [_ptr] * 5 + [_c_int, _ptr]),
+    "dbev_bev_pool_backward": (_c_int, [_c_int] * 7 + [_ptr] * 5 + [_c_int, _ptr]),
+    "dbev_bev_plan_workspace_bytes": (_c_size, [_c_ll]),
+    "dbev_bev_plan_from_geom": (_c_int, [_ptr, _c_ll, _c_int, _fptr, _fptr, _fptr, _iptr, _c_int,
+                                         _ptr, _ptr, _ptr, _ptr, _c_size, _ptr]),
+    "dbev_bev_plan_from_coords": (_c_int, [_ptr, _c_int, _c_ll, _c_int, _c_int, _c_int, _c_int,
+                                           _c_int, _ptr, _ptr, _ptr, _ptr, _c_size, _ptr]),
+    "dbev_bev_pool_gather_forward": (_c_int, [_ptr, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int,
+                                              _c_int, _c_int, _c_ll, _c_ll, _c_ll, _ptr, _ptr]),
+    "dbev_bev_pool_gather_backward": (_c_int, [_ptr, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int,
+                                               _c_int, _c_int, _c_ll, _c_ll, _c_ll, _ptr, _ptr]),
+    "dbev_sort_workspace_bytes": (_c_size, [_c_ll]),
+    "dbev_sort_keys_iota": (_c_int, [_ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _c_size, _ptr]),
+    "dbev_scan_workspace_bytes": (_c_size, [_c_ll]),
+    "dbev_exclusive_scan_i32": (_c_int, [_ptr, _ptr, _c_int, _ptr, _ptr, _c_size, _ptr]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "distill_bev_b200: %s is missing - build it with "
+            "`python distill-bev_b200/build.py` (nvcc, sm_100a). There is no CPU fallback."
+            % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dbev_abi_version() != 1:
+        raise RuntimeError("distill_bev_b200: ABI version mismatch, rebuild the library")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().dbev_last_error().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def require_cuda(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError(
+            "%s must be a CUDA tensor: distill_bev_b200 has no CPU path (got device %s)"
+            % (name, t.device))
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("%s must have dtype %s (got %s)" % (name, dtype, t.dtype))
+    return t
+
+
+def workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+def host_f3(vals):
+    return (ctypes.c_float * 3)(*[float(v) for v in vals])
+
+
+def host_i3(vals):
+    return (ctypes.c_int * 3)(*[int(v) for v in vals])

@@ -1,0 +1,692 @@
+// LSS "splat" (frustum voxel pooling / bev_pool) for B200.
+//
+// Reference behaviour reproduced here:
+//   voxel_pooling        mmdet3d/models/necks/view_transformer_mine.py:141-181
+//   QuickCumsum          mmdet3d/models/necks/view_transformer_mine.py:30-56
+//   bev_pool (python)    mmdet3d/ops/bev_pool/bev_pool.py:83-97
+//   bev_pool_kernel      mmdet3d/ops/bev_pool/src/bev_pool_cuda.cu:20-42
+//   bev_pool_grad_kernel mmdet3d/ops/bev_pool/src/bev_pool_cuda.cu:61-84
+//
+// Design (not a port): the reference sorts the FEATURES (argsort + 3 gathers,
+// then cumsum / boolean select / diff / scatter: >= 12 passes over [n, C]).
+// Here only 4-byte point ids are sorted (a "plan": order[], cell_start[],
+// cell_end[]); the feature rows are then read exactly once, gathered by id in
+// 16-byte vectors, summed per BEV cell in a fixed order, transposed through
+// shared memory and written exactly once in the caller's final NCHW layout
+// (zeros for empty cells included: no zero-fill pass, no permute copy).
+// HBM traffic = n*C*4 (rows) + n*4 (ids) + cells*8 + out  ~ algorithmic bytes.
+#include "bev_pool.cuh"
+
+#include "sort.cuh"
+
+namespace dbev {
+
+namespace {
+
+constexpr int kPoolBlock = 256;
+constexpr int kPoolWarps = kPoolBlock / 32;
+constexpr int kTileCells = 32;
+constexpr int kTilePitch = kTileCells + 1;
+
+// ---- plan: cell keys -------------------------------------------------------
+
+// view_transformer_mine.py:150 -> ((geom - (bx - dx/2)) / dx).long(), then the
+// in-bounds test of :157-159. trunc-toward-zero semantics: a quotient in
+// (-1, 0) lands in cell 0 and is KEPT. For a float q, 0 <= trunc(q) < nx is
+// equivalent to q > -1 && q < nx (NaN fails both, as it does in the
+// reference where it converts to INT64_MIN).
+__device__ __forceinline__ bool geom_to_index(float g, float off, float dx, float nx_f, int* idx) {
+  float q = __fdiv_rn(__fsub_rn(g, off), dx);
+  if (!(q > -1.0f && q < nx_f)) return false;
+  *idx = (int)q;  // cvt.rzi
+  return true;
+}
+
+__global__ void __launch_bounds__(256)
+bev_keys_from_geom_kernel(const float* __restrict__ geom, long long n, long long pts_per_batch,
+                          float off0, float off1, float off2, float dx0, float dx1, float dx2,
+                          float nxf0, float nxf1, float nxf2, int n0, int n1, int nz,
+                          int fast_axis, uint32_t sentinel, uint32_t* __restrict__ keys) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const float g0 = geom[p * 3 + 0], g1 = geom[p * 3 + 1], g2 = geom[p * 3 + 2];
+  int i0, i1, i2;
+  bool ok = geom_to_index(g0, off0, dx0, nxf0, &i0);
+  ok = geom_to_index(g1, off1, dx1, nxf1, &i1) && ok;
+  ok = geom_to_index(g2, off2, dx2, nxf2, &i2) && ok;
+  // the float compare is against the float nx (reference); the canvas is sized
+  // by nx.to(long). Guard the integer canvas too.
+  ok = ok && i0 < n0 && i1 < n1 && i2 < nz;
+  uint32_t key = sentinel;
+  if (ok) {
+    const int b = (int)(p / pts_per_batch);
+    const int islow = fast_axis == 0 ? i1 : i0;
+    const int ifast = fast_axis == 0 ? i0 : i1;
+    const int nslow = fast_axis == 0 ? n1 : n0;
+    const int nfast = fast_axis == 0 ? n0 : n1;
+    key = (uint32_t)((((long long)b * nz + i2) * nslow + islow) * nfast + ifast);
+  }
+  keys[p] = key;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bev_keys_from_coords_kernel(const T* __restrict__ coords, long long n, int nb, int n0, int n1,
+                            int nz, int fast_axis, uint32_t sentinel,
+                            uint32_t* __restrict__ keys) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const long long c0 = (long long)coords[p * 4 + 0], c1 = (long long)coords[p * 4 + 1],
+                  c2 = (long long)coords[p * 4 + 2], c3 = (long long)coords[p * 4 + 3];
+  uint32_t key = sentinel;
+  if (c0 >= 0 && c0 < n0 && c1 >= 0 && c1 < n1 && c2 >= 0 && c2 < nz && c3 >= 0 && c3 < nb) {
+    const long long islow = fast_axis == 0 ? c1 : c0;
+    const long long ifast = fast_axis == 0 ? c0 : c1;
+    const int nslow = fast_axis == 0 ? n1 : n0;
+    const int nfast = fast_axis == 0 ? n0 : n1;
+    key = (uint32_t)(((c3 * nz + c2) * nslow + islow) * nfast + ifast);
+  }
+  keys[p] = key;
+}
+
+// sorted keys -> [start, end) of every cell; slot ncells is the dropped tail.
+__global__ void __launch_bounds__(256)
+bev_bounds_kernel(const uint32_t* __restrict__ skeys, long long n, int* __restrict__ cell_start,
+                  int* __restrict__ cell_end) {
+  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint32_t k = skeys[j];
+  if (j == 0 || skeys[j - 1] != k) cell_start[k] = (int)j;
+  if (j == n - 1 || skeys[j + 1] != k) cell_end[k] = (int)(j + 1);
+}
+
+// ---- pooling ---------------------------------------------------------------
+
+struct PoolGeom {
+  int C;
+  int nfast, nslow, nbz;  // nbz = B * nz
+  int nz;
+  int tiles_per_row;
+  long long sB, sZ, sC;  // output strides (elements) of batch, z and channel
+};
+
+__device__ __forceinline__ void f4_add(float4& a, const float4& b) {
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+}
+
+// One CTA = one tile of 32 cells that are consecutive along the output's
+// fastest axis; one warp owns 4 of them. LPR lanes cover one feature row in
+// float4s (CHUNKS float4 per lane when C > 128), 32/LPR rows per warp step.
+template <int LPR, int CHUNKS>
+__global__ void __launch_bounds__(kPoolBlock)
+bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restrict__ order,
+                           const int* __restrict__ cell_start, const int* __restrict__ cell_end,
+                           float* __restrict__ out, PoolGeom g) {
+  extern __shared__ float tile[];  // [C][kTilePitch]
+  constexpr int RPS = 32 / LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPR, rslot = lane / LPR;
+
+  const int ftile = blockIdx.x % g.tiles_per_row;
+  const long long rowid = blockIdx.x / g.tiles_per_row;  // bz * nslow + islow
+  const int f0 = ftile * kTileCells;
+  const int ncell = min(kTileCells, g.nfast - f0);
+  const long long cell0 = rowid * g.nfast + f0;
+
+  bool lane_active[CHUNKS];
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) lane_active[k] = (k * LPR + sub) * 4 < g.C;
+
+  for (int ci = warp; ci < ncell; ci += kPoolWarps) {
+    const int start = cell_start[cell0 + ci], end = cell_end[cell0 + ci];
+    float4 acc[CHUNKS];
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int base = start; base < end; base += 32) {
+      const uint32_t my = (base + lane < end) ? order[base + lane] : 0u;
+      const int cnt = min(32, end - base);
+#pragma unroll 4
+      for (int j0 = 0; j0 < cnt; j0 += RPS) {
+        const int j = j0 + rslot;
+        const uint32_t p = __shfl_sync(0xffffffffu, my, j & 31);
+        if (j < cnt) {
+          const float* row = x + (size_t)p * g.C + sub * 4;
+#pragma unroll
+          for (int k = 0; k < CHUNKS; ++k)
+            if (lane_active[k]) f4_add(acc[k], ld_stream_f4(row + k * LPR * 4));
+        }
+      }
+    }
+    // fold the RPS row slots together (fixed order -> deterministic)
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+      for (int k = 0; k < CHUNKS; ++k) {
+        acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o);
+        acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
+        acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, o);
+        acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, o);
+      }
+    }
+    if (rslot == 0) {
+#pragma unroll
+      for (int k = 0; k < CHUNKS; ++k) {
+        if (lane_active[k]) {
+          const int c = (k * LPR + sub) * 4;
+          tile[(c + 0) * kTilePitch + ci] = acc[k].x;
+          tile[(c + 1) * kTilePitch + ci] = acc[k].y;
+          tile[(c + 2) * kTilePitch + ci] = acc[k].z;
+          tile[(c + 3) * kTilePitch + ci] = acc[k].w;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  const long long bz = rowid / g.nslow;
+  const int islow = (int)(rowid % g.nslow);
+  const long long b = bz / g.nz, iz = bz % g.nz;
+  float* obase = out + b * g.sB + iz * g.sZ + (long long)islow * g.nfast + f0;
+  for (int c = warp; c < g.C; c += kPoolWarps)
+    if (lane < ncell) obase[c * g.sC + lane] = tile[c * kTilePitch + lane];
+}
+
+// scalar fallback for C % 4 != 0 (one row per warp step, lanes over channels)
+__global__ void __launch_bounds__(kPoolBlock)
+bev_pool_gather_fwd_generic_kernel(const float* __restrict__ x, const uint32_t* __restrict__ order,
+                                   const int* __restrict__ cell_start,
+                                   const int* __restrict__ cell_end, float* __restrict__ out,
+                                   PoolGeom g) {
+  extern __shared__ float tile[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ftile = blockIdx.x % g.tiles_per_row;
+  const long long rowid = blockIdx.x / g.tiles_per_row;
+  const int f0 = ftile * kTileCells;
+  const int ncell = min(kTileCells, g.nfast - f0);
+  const long long cell0 = rowid * g.nfast + f0;
+  for (int ci = warp; ci < ncell; ci += kPoolWarps) {
+    const int start = cell_start[cell0 + ci], end = cell_end[cell0 + ci];
+    for (int cb = 0; cb < g.C; cb += 32) {
+      const int c = cb + lane;
+      float acc = 0.f;
+      for (int i = start; i < end; ++i) {
+        const uint32_t p = order[i];
+        if (c < g.C) acc += x[(size_t)p * g.C + c];
+      }
+      if (c < g.C) tile[c * kTilePitch + ci] = acc;
+    }
+  }
+  __syncthreads();
+  const long long bz = rowid / g.nslow;
+  const int islow = (int)(rowid % g.nslow);
+  const long long b = bz / g.nz, iz = bz % g.nz;
+  float* obase = out + b * g.sB + iz * g.sZ + (long long)islow * g.nfast + f0;
+  for (int c = warp; c < g.C; c += kPoolWarps)
+    if (lane < ncell) obase[c * g.sC + lane] = tile[c * kTilePitch + lane];
+}
+
+// backward of the gather pool: every point of a cell receives the cell's
+// gradient row (bev_pool_cuda.cu:61-84; QuickCumsum.backward
+// view_transformer_mine.py:48-56). Rows of dropped points are written as zero
+// by bev_pool_zero_tail_kernel, so x_grad needs no prior memset.
+template <int LPR, int CHUNKS>
+__global__ void __launch_bounds__(kPoolBlock)
+bev_pool_gather_bwd_kernel(const float* __restrict__ out_grad, const uint32_t* __restrict__ order,
+                           const int* __restrict__ cell_start, const int* __restrict__ cell_end,
+                           float* __restrict__ x_grad, PoolGeom g) {
+  extern __shared__ float tile[];
+  constexpr int RPS = 32 / LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % LPR, rslot = lane / LPR;
+  const int ftile = blockIdx.x % g.tiles_per_row;
+  const long long rowid = blockIdx.x / g.tiles_per_row;
+  const int f0 = ftile * kTileCells;
+  const int ncell = min(kTileCells, g.nfast - f0);
+  const long long cell0 = rowid * g.nfast + f0;
+
+  const long long bz = rowid / g.nslow;
+  const int islow = (int)(rowid % g.nslow);
+  const long long b = bz / g.nz, iz = bz % g.nz;
+  const float* gbase = out_grad + b * g.sB + iz * g.sZ + (long long)islow * g.nfast + f0;
+  for (int c = warp; c < g.C; c += kPoolWarps)
+    if (lane < ncell) tile[c * kTilePitch + lane] = gbase[c * g.sC + lane];
+  __syncthreads();
+
+  for (int ci = warp; ci < ncell; ci += kPoolWarps) {
+    const int start = cell_start[cell0 + ci], end = cell_end[cell0 + ci];
+    if (start >= end) continue;
+    float4 val[CHUNKS];
+    bool lane_active[CHUNKS];
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+      const int c = (k * LPR + sub) * 4;
+      lane_active[k] = c < g.C;
+      if (lane_active[k])
+        val[k] = make_float4(tile[(c + 0) * kTilePitch + ci], tile[(c + 1) * kTilePitch + ci],
+                             tile[(c + 2) * kTilePitch + ci], tile[(c + 3) * kTilePitch + ci]);
+    }
+    for (int base = start; base < end; base += 32) {
+      const uint32_t my = (base + lane < end) ? order[base + lane] : 0u;
+      const int cnt = min(32, end - base);
+#pragma unroll 4
+      for (int j0 = 0; j0 < cnt; j0 += RPS) {
+        const int j = j0 + rslot;
+        const uint32_t p = __shfl_sync(0xffffffffu, my, j & 31);
+        if (j < cnt) {
+          float* row = x_grad + (size_t)p * g.C + sub * 4;
+#pragma unroll
+          for (int k = 0; k < CHUNKS; ++k)
+            if (lane_active[k]) st_stream_f4(row + k * LPR * 4, val[k]);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kPoolBlock)
+bev_pool_gather_bwd_generic_kernel(const float* __restrict__ out_grad,
+                                   const uint32_t* __restrict__ order,
+                                   const int* __restrict__ cell_start,
+                                   const int* __restrict__ cell_end, float* __restrict__ x_grad,
+                                   PoolGeom g) {
+  extern __shared__ float tile[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ftile = blockIdx.x % g.tiles_per_row;
+  const long long rowid = blockIdx.x / g.tiles_per_row;
+  const int f0 = ftile * kTileCells;
+  const int ncell = min(kTileCells, g.nfast - f0);
+  const long long cell0 = rowid * g.nfast + f0;
+  const long long bz = rowid / g.nslow;
+  const int islow = (int)(rowid % g.nslow);
+  const long long b = bz / g.nz, iz = bz % g.nz;
+  const float* gbase = out_grad + b * g.sB + iz * g.sZ + (long long)islow * g.nfast + f0;
+  for (int c = warp; c < g.C; c += kPoolWarps)
+    if (lane < ncell) tile[c * kTilePitch + lane] = gbase[c * g.sC + lane];
+  __syncthreads();
+  for (int ci = warp; ci < ncell; ci += kPoolWarps) {
+    const int start = cell_start[cell0 + ci], end = cell_end[cell0 + ci];
+    for (int i = start; i < end; ++i) {
+      const uint32_t p = order[i];
+      for (int c = lane; c < g.C; c += 32) x_grad[(size_t)p * g.C + c] = tile[c * kTilePitch + ci];
+    }
+  }
+}
+
+// rows of points that fell outside the grid get a zero gradient
+__global__ void __launch_bounds__(256)
+bev_pool_zero_tail_kernel(const uint32_t* __restrict__ order, const int* __restrict__ tail_start,
+                          const int* __restrict__ tail_end, float* __restrict__ x_grad, int C) {
+  const int start = *tail_start, end = *tail_end;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  for (int i = start + gw; i < end; i += warps_total) {
+    float* row = x_grad + (size_t)order[i] * C;
+    for (int c = lane; c < C; c += 32) row[c] = 0.f;
+  }
+}
+
+// ---- reference-ABI kernels (pre-sorted rows + interval lists) ---------------
+
+// out is [b, d, h, w, c] channels-last exactly as bev_pool_cuda.cu:32-34
+// addresses it; one warp per interval streams the interval's contiguous rows.
+template <int LPR, int CHUNKS>
+__global__ void __launch_bounds__(kPoolBlock)
+bev_pool_interval_fwd_kernel(int d, int h, int w, int c, int n_intervals,
+                             const float* __restrict__ x, const int* __restrict__ geom,
+                             const int* __restrict__ istart, const int* __restrict__ ilen,
+                             float* __restrict__ out) {
+  constexpr int RPS = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR, rslot = lane / LPR;
+  const int iv = blockIdx.x * kPoolWarps + (threadIdx.x >> 5);
+  if (iv >= n_intervals) return;
+  const int start = istart[iv], len = ilen[iv];
+  float4 acc[CHUNKS];
+  bool lane_active[CHUNKS];
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) {
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    lane_active[k] = (k * LPR + sub) * 4 < c;
+  }
+  const float* xb = x + (size_t)start * c + sub * 4;
+#pragma unroll 4
+  for (int j = rslot; j < len; j += RPS) {
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k)
+      if (lane_active[k]) f4_add(acc[k], ld_stream_f4(xb + (size_t)j * c + k * LPR * 4));
+  }
+#pragma unroll
+  for (int o = LPR; o < 32; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+      acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o);
+      acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
+      acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, o);
+      acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, o);
+    }
+  }
+  if (rslot == 0) {
+    const int* gf = geom + (size_t)start * 4;
+    float* o = out + (((size_t)gf[3] * d + gf[2]) * h + gf[0]) * (size_t)w * c + (size_t)gf[1] * c +
+               sub * 4;
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k)
+      if (lane_active[k]) *reinterpret_cast<float4*>(o + k * LPR * 4) = acc[k];
+  }
+}
+
+template <int LPR, int CHUNKS>
+__global__ void __launch_bounds__(kPoolBlock)
+bev_pool_interval_bwd_kernel(int d, int h, int w, int c, int n_intervals,
+                             const float* __restrict__ out_grad, const int* __restrict__ geom,
+                             const int* __restrict__ istart, const int* __restrict__ ilen,
+                             float* __restrict__ x_grad) {
+  constexpr int RPS = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR, rslot = lane / LPR;
+  const int iv = blockIdx.x * kPoolWarps + (threadIdx.x >> 5);
+  if (iv >= n_intervals) return;
+  const int start = istart[iv], len = ilen[iv];
+  const int* gf = geom + (size_t)start * 4;
+  const float* o = out_grad + (((size_t)gf[3] * d + gf[2]) * h + gf[0]) * (size_t)w * c +
+                   (size_t)gf[1] * c + sub * 4;
+  float4 val[CHUNKS];
+  bool lane_active[CHUNKS];
+#pragma unroll
+  for (int k = 0; k < CHUNKS; ++k) {
+    lane_active[k] = (k * LPR + sub) * 4 < c;
+    if (lane_active[k]) val[k] = *reinterpret_cast<const float4*>(o + k * LPR * 4);
+  }
+  float* xb = x_grad + (size_t)start * c + sub * 4;
+  for (int j = rslot; j < len; j += RPS) {
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k)
+      if (lane_active[k]) st_stream_f4(xb + (size_t)j * c + k * LPR * 4, val[k]);
+  }
+}
+
+// scalar version of the two interval kernels for C % 4 != 0
+template <bool FWD>
+__global__ void __launch_bounds__(kPoolBlock)
+bev_pool_interval_generic_kernel(int d, int h, int w, int c, int n_intervals,
+                                 const float* __restrict__ src, const int* __restrict__ geom,
+                                 const int* __restrict__ istart, const int* __restrict__ ilen,
+                                 float* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const int iv = blockIdx.x * kPoolWarps + (threadIdx.x >> 5);
+  if (iv >= n_intervals) return;
+  const int start = istart[iv], len = ilen[iv];
+  const int* gf = geom + (size_t)start * 4;
+  const size_t cell = ((((size_t)gf[3] * d + gf[2]) * h + gf[0]) * (size_t)w + gf[1]) * c;
+  for (int ch = lane; ch < c; ch += 32) {
+    if (FWD) {
+      float acc = 0.f;
+      for (int j = 0; j < len; ++j) acc += src[(size_t)(start + j) * c + ch];
+      dst[cell + ch] = acc;
+    } else {
+      const float v = src[cell + ch];
+      for (int j = 0; j < len; ++j) dst[(size_t)(start + j) * c + ch] = v;
+    }
+  }
+}
+
+struct VecCfg {
+  int lpr, chunks;
+};
+
+inline bool pick_vec_cfg(int C, VecCfg* cfg) {
+  if (C <= 0 || C % 4 != 0 || C > 512) return false;
+  int v = C / 4;
+  int lpr = 1;
+  while (lpr < v && lpr < 32) lpr <<= 1;
+  cfg->lpr = lpr;
+  cfg->chunks = (v + lpr - 1) / lpr;
+  return true;
+}
+
+#define DBEV_DISPATCH_VEC(cfg, LAUNCH)                  \
+  do {                                                  \
+    if (cfg.chunks == 1) {                              \
+      switch (cfg.lpr) {                                \
+        case 1: { LAUNCH(1, 1); } break;                \
+        case 2: { LAUNCH(2, 1); } break;                \
+        case 4: { LAUNCH(4, 1); } break;                \
+        case 8: { LAUNCH(8, 1); } break;                \
+        case 16: { LAUNCH(16, 1); } break;              \
+        default: { LAUNCH(32, 1); } break;              \
+      }                                                 \
+    } else if (cfg.chunks == 2) { LAUNCH(32, 2); }      \
+    else if (cfg.chunks == 3) { LAUNCH(32, 3); }        \
+    else { LAUNCH(32, 4); }                             \
+  } while (0)
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+
+size_t bev_plan_ws_bytes(long long n_points) {
+  return 3 * align_up((size_t)n_points * 4) + radix_sort_ws_bytes(n_points) + 1024;
+}
+
+static int finish_plan(uint32_t* keys0, long long n, long long ncells, uint32_t* order,
+                       int* cell_start, int* cell_end, Workspace& w, void* ws, size_t ws_bytes,
+                       cudaStream_t stream) {
+  uint32_t* keys1 = w.take<uint32_t>(n);
+  uint32_t* vals_other = w.take<uint32_t>(n);
+  if (!w.ok()) {
+    set_last_error("bev_plan: workspace too small (%zu bytes given)", ws_bytes);
+    return DBEV_ERR_WORKSPACE;
+  }
+  size_t consumed = align_up(w.used);
+  const int num_bits = bits_for((unsigned long long)ncells + 1);
+  const int passes = (num_bits + kRadixBits - 1) / kRadixBits;
+  uint32_t* keys[2] = {keys0, keys1};
+  // arrange the ping-pong so the sorted payload lands in `order`
+  uint32_t* vals[2];
+  vals[passes & 1] = order;
+  vals[(passes & 1) ^ 1] = vals_other;
+  int sel = 0;
+  int rc = radix_sort_pairs(keys, vals, /*vals_iota=*/true, (int)n, num_bits, (char*)ws + consumed,
+                            ws_bytes - consumed, stream, &sel);
+  if (rc != DBEV_OK) return rc;
+  DBEV_CUDA(cudaMemsetAsync(cell_start, 0, (size_t)(ncells + 1) * sizeof(int), stream));
+  DBEV_CUDA(cudaMemsetAsync(cell_end, 0, (size_t)(ncells + 1) * sizeof(int), stream));
+  if (n > 0) {
+    bev_bounds_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(keys[sel], n, cell_start, cell_end);
+    DBEV_CHECK_LAUNCH("bev_bounds_kernel");
+  }
+  return DBEV_OK;
+}
+
+int bev_plan_from_geom(const float* geom, long long n_points, int batch, const float off[3],
+                       const float dx[3], const float nx_f[3], const int nx_i[3], int fast_axis,
+                       uint32_t* order, int* cell_start, int* cell_end, void* ws, size_t ws_bytes,
+                       cudaStream_t stream) {
+  DBEV_CHECK_ARG(batch > 0 && n_points >= 0 && n_points % batch == 0,
+                 "bev_plan_from_geom: n_points (%lld) must be a multiple of batch (%d)", n_points,
+                 batch);
+  DBEV_CHECK_ARG(fast_axis == 0 || fast_axis == 1, "bev_plan_from_geom: fast_axis must be 0 or 1");
+  const long long ncells = (long long)batch * nx_i[0] * nx_i[1] * nx_i[2];
+  DBEV_CHECK_ARG(ncells > 0 && ncells < 0x7fffffffLL && n_points < 0x7fffffffLL,
+                 "bev_plan_from_geom: grid or point count exceeds 2^31");
+  Workspace w(ws, ws_bytes);
+  uint32_t* keys0 = w.take<uint32_t>(n_points);
+  if (!w.ok()) {
+    set_last_error("bev_plan_from_geom: workspace too small");
+    return DBEV_ERR_WORKSPACE;
+  }
+  if (n_points > 0) {
+    bev_keys_from_geom_kernel<<<ceil_div(n_points, 256), 256, 0, stream>>>(
+        geom, n_points, n_points / batch, off[0], off[1], off[2], dx[0], dx[1], dx[2], nx_f[0],
+        nx_f[1], nx_f[2], nx_i[0], nx_i[1], nx_i[2], fast_axis, (uint32_t)ncells, keys0);
+    DBEV_CHECK_LAUNCH("bev_keys_from_geom_kernel");
+  }
+  return finish_plan(keys0, n_points, ncells, order, cell_start, cell_end, w, ws, ws_bytes, stream);
+}
+
+int bev_plan_from_coords(const void* coords, int coords_i64, long long n_points, int batch, int n0,
+                         int n1, int nz, int fast_axis, uint32_t* order, int* cell_start,
+                         int* cell_end, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  DBEV_CHECK_ARG(fast_axis == 0 || fast_axis == 1, "bev_plan_from_coords: fast_axis must be 0 or 1");
+  const long long ncells = (long long)batch * n0 * n1 * nz;
+  DBEV_CHECK_ARG(ncells > 0 && ncells < 0x7fffffffLL && n_points < 0x7fffffffLL,
+                 "bev_plan_from_coords: grid or point count exceeds 2^31");
+  Workspace w(ws, ws_bytes);
+  uint32_t* keys0 = w.take<uint32_t>(n_points);
+  if (!w.ok()) {
+    set_last_error("bev_plan_from_coords: workspace too small");
+    return DBEV_ERR_WORKSPACE;
+  }
+  if (n_points > 0) {
+    if (coords_i64)
+      bev_keys_from_coords_kernel<long long><<<ceil_div(n_points, 256), 256, 0, stream>>>(
+          (const long long*)coords, n_points, batch, n0, n1, nz, fast_axis, (uint32_t)ncells, keys0);
+    else
+      bev_keys_from_coords_kernel<int><<<ceil_div(n_points, 256), 256, 0, stream>>>(
+          (const int*)coords, n_points, batch, n0, n1, nz, fast_axis, (uint32_t)ncells, keys0);
+    DBEV_CHECK_LAUNCH("bev_keys_from_coords_kernel");
+  }
+  return finish_plan(keys0, n_points, ncells, order, cell_start, cell_end, w, ws, ws_bytes, stream);
+}
+
+static int make_pool_geom(int C, int batch, int nz, int nslow, int nfast, long long sB,
+                          long long sZ, long long sC, PoolGeom* g) {
+  DBEV_CHECK_ARG(C > 0 && C <= 2048, "bev_pool: channel count %d unsupported (1..2048)", C);
+  DBEV_CHECK_ARG(batch > 0 && nz > 0 && nslow > 0 && nfast > 0, "bev_pool: empty grid");
+  g->C = C;
+  g->nfast = nfast;
+  g->nslow = nslow;
+  g->nz = nz;
+  g->nbz = batch * nz;
+  g->tiles_per_row = ceil_div(nfast, kTileCells);
+  g->sB = sB;
+  g->sZ = sZ;
+  g->sC = sC;
+  long long tiles = (long long)g->nbz * nslow * g->tiles_per_row;
+  DBEV_CHECK_ARG(tiles < 0x7fffffffLL, "bev_pool: grid too large");
+  return DBEV_OK;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    DBEV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  }
+  return DBEV_OK;
+}
+
+int bev_pool_gather_forward(const float* x, int C, const uint32_t* order, const int* cell_start,
+                            const int* cell_end, int batch, int nz, int nslow, int nfast,
+                            long long sB, long long sZ, long long sC, float* out,
+                            cudaStream_t stream) {
+  PoolGeom g;
+  int rc = make_pool_geom(C, batch, nz, nslow, nfast, sB, sZ, sC, &g);
+  if (rc != DBEV_OK) return rc;
+  const int grid = g.nbz * nslow * g.tiles_per_row;
+  const size_t smem = (size_t)C * kTilePitch * sizeof(float);
+  DBEV_CHECK_ARG(smem <= 227 * 1024, "bev_pool: C=%d needs %zu B shared memory", C, smem);
+  VecCfg cfg;
+  if (pick_vec_cfg(C, &cfg)) {
+#define LAUNCH(L, K)                                                                       \
+  rc = set_smem(bev_pool_gather_fwd_kernel<L, K>, smem);                                   \
+  if (rc != DBEV_OK) return rc;                                                            \
+  bev_pool_gather_fwd_kernel<L, K><<<grid, kPoolBlock, smem, stream>>>(x, order, cell_start, \
+                                                                     cell_end, out, g)
+    DBEV_DISPATCH_VEC(cfg, LAUNCH);
+#undef LAUNCH
+  } else {
+    rc = set_smem(bev_pool_gather_fwd_generic_kernel, smem);
+    if (rc != DBEV_OK) return rc;
+    bev_pool_gather_fwd_generic_kernel<<<grid, kPoolBlock, smem, stream>>>(x, order, cell_start,
+                                                                           cell_end, out, g);
+  }
+  DBEV_CHECK_LAUNCH("bev_pool_gather_fwd_kernel");
+  return DBEV_OK;
+}
+
+int bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* order,
+                             const int* cell_start, const int* cell_end, int batch, int nz,
+                             int nslow, int nfast, long long sB, long long sZ, long long sC,
+                             float* x_grad, cudaStream_t stream) {
+  PoolGeom g;
+  int rc = make_pool_geom(C, batch, nz, nslow, nfast, sB, sZ, sC, &g);
+  if (rc != DBEV_OK) return rc;
+  const int grid = g.nbz * nslow * g.tiles_per_row;
+  const size_t smem = (size_t)C * kTilePitch * sizeof(float);
+  DBEV_CHECK_ARG(smem <= 227 * 1024, "bev_pool: C=%d needs %zu B shared memory", C, smem);
+  VecCfg cfg;
+  if (pick_vec_cfg(C, &cfg)) {
+#define LAUNCH(L, K)                                                                        \
+  rc = set_smem(bev_pool_gather_bwd_kernel<L, K>, smem);                                    \
+  if (rc != DBEV_OK) return rc;                                                             \
+  bev_pool_gather_bwd_kernel<L, K><<<grid, kPoolBlock, smem, stream>>>(out_grad, order,     \
+                                                                     cell_start, cell_end, \
+                                                                     x_grad, g)
+    DBEV_DISPATCH_VEC(cfg, LAUNCH);
+#undef LAUNCH
+  } else {
+    rc = set_smem(bev_pool_gather_bwd_generic_kernel, smem);
+    if (rc != DBEV_OK) return rc;
+    bev_pool_gather_bwd_generic_kernel<<<grid, kPoolBlock, smem, stream>>>(
+        out_grad, order, cell_start, cell_end, x_grad, g);
+  }
+  DBEV_CHECK_LAUNCH("bev_pool_gather_bwd_kernel");
+  const long long ncells = (long long)g.nbz * nslow * nfast;
+  bev_pool_zero_tail_kernel<<<kNumSMs * 2, 256, 0, stream>>>(order, cell_start + ncells,
+                                                             cell_end + ncells, x_grad, C);
+  DBEV_CHECK_LAUNCH("bev_pool_zero_tail_kernel");
+  return DBEV_OK;
+}
+
+int bev_pool_interval_forward(int b, int d, int h, int w, int n, int c, int n_intervals,
+                              const float* x, const int* geom_feats, const int* interval_starts,
+                              const int* interval_lengths, float* out, int zero_out,
+                              cudaStream_t stream) {
+  DBEV_CHECK_ARG(b > 0 && d > 0 && h > 0 && w > 0 && c > 0 && n >= 0 && n_intervals >= 0,
+                 "bev_pool_forward: bad sizes b=%d d=%d h=%d w=%d n=%d c=%d", b, d, h, w, n, c);
+  if (zero_out)
+    DBEV_CUDA(cudaMemsetAsync(out, 0, (size_t)b * d * h * w * c * sizeof(float), stream));
+  if (n_intervals == 0) return DBEV_OK;
+  const int grid = ceil_div(n_intervals, kPoolWarps);
+  VecCfg cfg;
+  if (pick_vec_cfg(c, &cfg)) {
+#define LAUNCH(L, K)                                                      \
+  bev_pool_interval_fwd_kernel<L, K><<<grid, kPoolBlock, 0, stream>>>(    \
+      d, h, w, c, n_intervals, x, geom_feats, interval_starts, interval_lengths, out)
+    DBEV_DISPATCH_VEC(cfg, LAUNCH);
+#undef LAUNCH
+  } else {
+    bev_pool_interval_generic_kernel<true><<<grid, kPoolBlock, 0, stream>>>(
+        d, h, w, c, n_intervals, x, geom_feats, interval_starts, interval_lengths, out);
+  }
+  DBEV_CHECK_LAUNCH("bev_pool_interval_fwd_kernel");
+  return DBEV_OK;
+}
+
+int bev_pool_interval_backward(int b, int d, int h, int w, int n, int c, int n_intervals,
+                               const float* out_grad, const int* geom_feats,
+                               const int* interval_starts, const int* interval_lengths,
+                               float* x_grad, int zero_x_grad, cudaStream_t stream) {
+  DBEV_CHECK_ARG(b > 0 && d > 0 && h > 0 && w > 0 && c > 0 && n >= 0 && n_intervals >= 0,
+                 "bev_pool_backward: bad sizes b=%d d=%d h=%d w=%d n=%d c=%d", b, d, h, w, n, c);
+  if (zero_x_grad) DBEV_CUDA(cudaMemsetAsync(x_grad, 0, (size_t)n * c * sizeof(float), stream));
+  if (n_intervals == 0) return DBEV_OK;
+  const int grid = ceil_div(n_intervals, kPoolWarps);
+  VecCfg cfg;
+  if (pick_vec_cfg(c, &cfg)) {
+#define LAUNCH(L, K)                                                      \
+  bev_pool_interval_bwd_kernel<L, K><<<grid, kPoolBlock, 0, stream>>>(    \
+      d, h, w, c, n_intervals, out_grad, geom_feats, interval_starts, interval_lengths, x_grad)
+    DBEV_DISPATCH_VEC(cfg, LAUNCH);
+#undef LAUNCH
+  } else {
+    bev_pool_interval_generic_kernel<false><<<grid, kPoolBlock, 0, stream>>>(
+        d, h, w, c, n_intervals, out_grad, geom_feats, interval_starts, interval_lengths, x_grad);
+  }
+  DBEV_CHECK_LAUNCH("bev_pool_interval_bwd_kernel");
+  return DBEV_OK;
+}
+
+}  // namespace dbev

@@ -1,0 +1,126 @@
+// extern "C" boundary: forwards include/distill_bev_b200.h to the kernels.
+#include "../../include/distill_bev_b200.h"
+
+#include <stdarg.h>
+#include <string.h>
+
+#include "bev_pool.cuh"
+#include "sort.cuh"
+
+namespace dbev {
+
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace dbev
+
+using namespace dbev;
+
+extern "C" {
+
+int dbev_abi_version(void) { return DBEV_ABI_VERSION; }
+const char* dbev_last_error(void) { return g_last_error; }
+const char* dbev_build_arch(void) { return "sm_100a"; }
+
+int dbev_bev_pool_forward(int b, int d, int h, int w, int n, int c, int n_intervals,
+                          const float* x, const int* geom_feats, const int* interval_starts,
+                          const int* interval_lengths, float* out, int zero_out, void* stream) {
+  return bev_pool_interval_forward(b, d, h, w, n, c, n_intervals, x, geom_feats, interval_starts,
+                                   interval_lengths, out, zero_out, (cudaStream_t)stream);
+}
+
+int dbev_bev_pool_backward(int b, int d, int h, int w, int n, int c, int n_intervals,
+                           const float* out_grad, const int* geom_feats,
+                           const int* interval_starts, const int* interval_lengths, float* x_grad,
+                           int zero_x_grad, void* stream) {
+  return bev_pool_interval_backward(b, d, h, w, n, c, n_intervals, out_grad, geom_feats,
+                                    interval_starts, interval_lengths, x_grad, zero_x_grad,
+                                    (cudaStream_t)stream);
+}
+
+size_t dbev_bev_plan_workspace_bytes(long long n_points) { return bev_plan_ws_bytes(n_points); }
+
+int dbev_bev_plan_from_geom(const float* geom, long long n_points, int batch,
+                            const float* off_host3, const float* dx_host3,
+                            const float* nx_float_host3, const int* nx_int_host3, int fast_axis,
+                            uint32_t* order, int* cell_start, int* cell_end, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  return bev_plan_from_geom(geom, n_points, batch, off_host3, dx_host3, nx_float_host3,
+                            nx_int_host3, fast_axis, order, cell_start, cell_end, workspace,
+                            workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_bev_plan_from_coords(const void* coords, int coords_is_i64, long long n_points,
+                              int batch, int n0, int n1, int nz, int fast_axis, uint32_t* order,
+                              int* cell_start, int* cell_end, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  return bev_plan_from_coords(coords, coords_is_i64, n_points, batch, n0, n1, nz, fast_axis, order,
+                              cell_start, cell_end, workspace, workspace_bytes,
+                              (cudaStream_t)stream);
+}
+
+int dbev_bev_pool_gather_forward(const float* x, int C, const uint32_t* order,
+                                 const int* cell_start, const int* cell_end, int batch, int nz,
+                                 int nslow, int nfast, long long stride_b, long long stride_z,
+                                 long long stride_c, float* out, void* stream) {
+  return bev_pool_gather_forward(x, C, order, cell_start, cell_end, batch, nz, nslow, nfast,
+                                 stride_b, stride_z, stride_c, out, (cudaStream_t)stream);
+}
+
+int dbev_bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* order,
+                                  const int* cell_start, const int* cell_end, int batch, int nz,
+                                  int nslow, int nfast, long long stride_b, long long stride_z,
+                                  long long stride_c, float* x_grad, void* stream) {
+  return bev_pool_gather_backward(out_grad, C, order, cell_start, cell_end, batch, nz, nslow,
+                                  nfast, stride_b, stride_z, stride_c, x_grad,
+                                  (cudaStream_t)stream);
+}
+
+size_t dbev_sort_workspace_bytes(long long n) {
+  return radix_sort_ws_bytes(n) + 2 * align_up((size_t)(n > 0 ? n : 1) * 4) + 1024;
+}
+
+int dbev_sort_keys_iota(const uint32_t* keys_in, int n, int num_bits, uint32_t* keys_out,
+                        uint32_t* order_out, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  DBEV_CHECK_ARG(n >= 0 && num_bits >= 1 && num_bits <= 32, "sort: bad n=%d num_bits=%d", n,
+                 num_bits);
+  if (n == 0) return DBEV_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  Workspace w(workspace, workspace_bytes);
+  uint32_t* kt = w.take<uint32_t>(n);
+  uint32_t* vt = w.take<uint32_t>(n);
+  if (!w.ok()) {
+    set_last_error("sort: workspace too small");
+    return DBEV_ERR_WORKSPACE;
+  }
+  size_t consumed = align_up(w.used);
+  const int passes = (num_bits + kRadixBits - 1) / kRadixBits;
+  // the result must land in keys_out/order_out: seed so parity works out
+  uint32_t* keys[2];
+  uint32_t* vals[2];
+  keys[passes & 1] = keys_out;
+  keys[(passes & 1) ^ 1] = kt;
+  vals[passes & 1] = order_out;
+  vals[(passes & 1) ^ 1] = vt;
+  DBEV_CUDA(cudaMemcpyAsync(keys[0], keys_in, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+  int sel = 0;
+  return radix_sort_pairs(keys, vals, true, n, num_bits, (char*)workspace + consumed,
+                          workspace_bytes - consumed, s, &sel);
+}
+
+size_t dbev_scan_workspace_bytes(long long n) { return scan_ws_bytes(n); }
+
+int dbev_exclusive_scan_i32(const int* in, int* out, int n, int* total_out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  return exclusive_scan_i32(in, out, n, total_out, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
+}
+
+}  // extern "C"

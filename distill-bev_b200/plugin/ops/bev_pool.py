@@ -1,0 +1,261 @@
+"""`mmdet3d.ops.bev_pool` and the LSS splat on the B200 plan/gather kernels.
+
+Mirrors (same names, argument meaning and shapes):
+  * ``bev_pool(feats, coords, B, D, H, W)``      mmdet3d/ops/bev_pool/bev_pool.py:83-97
+  * ``bev_pool_ext.bev_pool_forward/backward``   mmdet3d/ops/bev_pool/src/bev_pool.cpp:22-87
+  * ``voxel_pooling(geom_feats, x)``             mmdet3d/models/necks/view_transformer_mine.py:141-181
+    (same result as ``voxel_pooling_accelerated`` :184-240)
+
+All of them run the same CUDA kernels (distill-bev_b200/csrc/bev_pool.cu)
+through the C-ABI; nothing here computes on the CPU.
+"""
+import torch
+
+from ... import _lib
+
+
+class BevPlan(object):
+    """Sorted view of the frustum points over the BEV grid (geometry only).
+
+    Reusable for every feature tensor that shares the geometry (e.g. cached
+    calibration at inference time, or fwd + bwd of one training step).
+    """
+
+    __slots__ = ("order", "cell_start", "cell_end", "n_points", "batch", "nz", "nslow", "nfast",
+                 "fast_axis", "device")
+
+    def __init__(self, order, cell_start, cell_end, n_points, batch, nz, nslow, nfast, fast_axis):
+        self.order = order
+        self.cell_start = cell_start
+        self.cell_end = cell_end
+        self.n_points = n_points
+        self.batch = batch
+        self.nz = nz
+        self.nslow = nslow
+        self.nfast = nfast
+        self.fast_axis = fast_axis
+        self.device = order.device
+
+    @property
+    def n_cells(self):
+        return self.batch * self.nz * self.nslow * self.nfast
+
+    def num_kept(self):
+        """Number of points inside the grid (device sync; for tests/diagnostics)."""
+        tail = int(self.cell_start[self.n_cells].item())
+        end = int(self.cell_end[self.n_cells].item())
+        return self.n_points - (end - tail)
+
+
+def _alloc_plan(n_points, batch, n0, n1, nz, fast_axis, device):
+    n_cells = batch * n0 * n1 * nz
+    order = torch.empty(max(n_points, 1), dtype=torch.int32, device=device)
+    cell_start = torch.empty(n_cells + 1, dtype=torch.int32, device=device)
+    cell_end = torch.empty(n_cells + 1, dtype=torch.int32, device=device)
+    nslow, nfast = (n1, n0) if fast_axis == 0 else (n0, n1)
+    return BevPlan(order, cell_start, cell_end, n_points, batch, nz, nslow, nfast, fast_axis)
+
+
+def bev_plan_from_geom(geom, batch, bx, dx, nx, fast_axis=0):
+    """Plan from ego-frame frustum coordinates.
+
+    geom: [..., 3] fp32 CUDA tensor, batch-major (e.g. [B, N, D, fH, fW, 3]);
+    bx, dx, nx: the float triples of ``gen_dx_bx`` (view_transformer_mine.py:14-18).
+    Index math, bounds test and batch index follow voxel_pooling :150-161.
+    """
+    lib = _lib.load()
+    _lib.require_cuda(geom, "geom", torch.float32)
+    geom = geom.contiguous()
+    n_points = geom.numel() // 3
+    bx32 = torch.as_tensor(bx, dtype=torch.float32).cpu()
+    dx32 = torch.as_tensor(dx, dtype=torch.float32).cpu()
+    nx32 = torch.as_tensor(nx, dtype=torch.float32).cpu()
+    off = bx32 - dx32 / 2.0            # fp32, exactly as (self.bx - self.dx / 2.)
+    nx_i = nx32.to(torch.long)          # nx.to(torch.long) truncates
+    plan = _alloc_plan(n_points, batch, int(nx_i[0]), int(nx_i[1]), int(nx_i[2]), fast_axis,
+                       geom.device)
+    with torch.cuda.device(geom.device):
+        ws_bytes = lib.dbev_bev_plan_workspace_bytes(n_points)
+        ws = _lib.workspace(ws_bytes, geom.device)
+        rc = lib.dbev_bev_plan_from_geom(
+            _lib.ptr(geom), n_points, batch, _lib.host_f3(off.tolist()), _lib.host_f3(dx32.tolist()),
+            _lib.host_f3(nx32.tolist()), _lib.host_i3(nx_i.tolist()), fast_axis,
+            _lib.ptr(plan.order), _lib.ptr(plan.cell_start), _lib.ptr(plan.cell_end),
+            _lib.ptr(ws), ws_bytes, _lib.stream_ptr(geom.device))
+    _lib.check(rc, "dbev_bev_plan_from_geom")
+    return plan
+
+
+def bev_plan_from_coords(coords, B, D, H, W, fast_axis=1):
+    """Plan from integer coords [n, 4] = (c0 < H, c1 < W, c2 < D, batch < B)."""
+    lib = _lib.load()
+    _lib.require_cuda(coords, "coords")
+    if coords.dim() != 2 or coords.shape[1] != 4:
+        raise RuntimeError("coords must be [n, 4], got %s" % (tuple(coords.shape),))
+    if coords.dtype not in (torch.int64, torch.int32):
+        coords = coords.long()
+    coords = coords.contiguous()
+    n = coords.shape[0]
+    plan = _alloc_plan(n, B, H, W, D, fast_axis, coords.device)
+    with torch.cuda.device(coords.device):
+        ws_bytes = lib.dbev_bev_plan_workspace_bytes(n)
+        ws = _lib.workspace(ws_bytes, coords.device)
+        rc = lib.dbev_bev_plan_from_coords(
+            _lib.ptr(coords), 1 if coords.dtype == torch.int64 else 0, n, B, H, W, D, fast_axis,
+            _lib.ptr(plan.order), _lib.ptr(plan.cell_start), _lib.ptr(plan.cell_end),
+            _lib.ptr(ws), ws_bytes, _lib.stream_ptr(coords.device))
+    _lib.check(rc, "dbev_bev_plan_from_coords")
+    return plan
+
+
+def _out_strides(plan, C, layout):
+    plane = plan.nslow * plan.nfast
+    if layout == "bz_c":      # [B, nz*C, slow, fast]   (voxel_pooling: cat(unbind(2), 1))
+        return (plan.batch, plan.nz * C, plan.nslow, plan.nfast), plan.nz * C * plane, C * plane, plane
+    if layout == "b_c_z":     # [B, C, nz, slow, fast]  (bev_pool: permute(0,4,1,2,3))
+        return (plan.batch, C, plan.nz, plan.nslow, plan.nfast), C * plan.nz * plane, plane, plan.nz * plane
+    raise ValueError(layout)
+
+
+class _BevPoolGather(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, plan, layout):
+        lib = _lib.load()
+        _lib.require_cuda(x, "x", torch.float32)
+        if x.dim() != 2 or x.shape[0] != plan.n_points:
+            raise RuntimeError("x must be [%d, C], got %s" % (plan.n_points, tuple(x.shape)))
+        x = x.contiguous()
+        C = x.shape[1]
+        shape, sB, sZ, sC = _out_strides(plan, C, layout)
+        out = torch.empty(shape, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.dbev_bev_pool_gather_forward(
+                _lib.ptr(x), C, _lib.ptr(plan.order), _lib.ptr(plan.cell_start),
+                _lib.ptr(plan.cell_end), plan.batch, plan.nz, plan.nslow, plan.nfast, sB, sZ, sC,
+                _lib.ptr(out), _lib.stream_ptr(x.device))
+        _lib.check(rc, "dbev_bev_pool_gather_forward")
+        ctx.plan = plan
+        ctx.layout = layout
+        ctx.C = C
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        lib = _lib.load()
+        plan, C = ctx.plan, ctx.C
+        out_grad = out_grad.contiguous().float()
+        _, sB, sZ, sC = _out_strides(plan, C, ctx.layout)
+        x_grad = torch.empty((plan.n_points, C), dtype=torch.float32, device=out_grad.device)
+        with torch.cuda.device(out_grad.device):
+            rc = lib.dbev_bev_pool_gather_backward(
+                _lib.ptr(out_grad), C, _lib.ptr(plan.order), _lib.ptr(plan.cell_start),
+                _lib.ptr(plan.cell_end), plan.batch, plan.nz, plan.nslow, plan.nfast, sB, sZ, sC,
+                _lib.ptr(x_grad), _lib.stream_ptr(out_grad.device))
+        _lib.check(rc, "dbev_bev_pool_gather_backward")
+        return x_grad, None, None
+
+
+def bev_pool_gather(x, plan, layout="bz_c"):
+    """Sum rows of x [n_points, C] into the plan's BEV cells (differentiable)."""
+    return _BevPoolGather.apply(x, plan, layout)
+
+
+def bev_pool(feats, coords, B, D, H, W):
+    """Drop-in for ``mmdet3d.ops.bev_pool`` (bev_pool.py:83-97).
+
+    feats [n, C] fp32, coords [n, 4] (x < H, y < W, z < D, b < B) -> [B, C, D, H, W].
+    """
+    assert feats.shape[0] == coords.shape[0]
+    plan = bev_plan_from_coords(coords, B, D, H, W, fast_axis=1)
+    return bev_pool_gather(feats, plan, layout="b_c_z")
+
+
+def voxel_pooling(geom_feats, x, bx, dx, nx, plan=None):
+    """Drop-in for ``ViewTransformerLiftSplatShoot.voxel_pooling`` (:141-181).
+
+    geom_feats [B, N, D, H, W, 3] fp32 ego-frame xyz, x [B, N, D, H, W, C] ->
+    [B, C * nz, ny, nx]. ``plan`` may carry a cached BevPlan for this geometry.
+    """
+    B, N, D, H, W, C = x.shape
+    Nprime = B * N * D * H * W
+    if plan is None:
+        plan = bev_plan_from_geom(geom_feats, B, bx, dx, nx, fast_axis=0)
+    x = x.reshape(Nprime, C)
+    return bev_pool_gather(x, plan, layout="bz_c")
+
+
+# --- the pybind module the reference builds (setup.py:246-252) ---------------
+
+class _BevPoolExt(object):
+    """Tensor-level twin of ``mmdet3d.ops.bev_pool.bev_pool_ext``."""
+
+    @staticmethod
+    def bev_pool_forward(x, geom_feats, interval_lengths, interval_starts, b, d, h, w):
+        lib = _lib.load()
+        _lib.require_cuda(x, "x", torch.float32)
+        _lib.require_cuda(geom_feats, "geom_feats", torch.int32)
+        _lib.require_cuda(interval_lengths, "interval_lengths", torch.int32)
+        _lib.require_cuda(interval_starts, "interval_starts", torch.int32)
+        x, geom_feats = x.contiguous(), geom_feats.contiguous()
+        interval_lengths, interval_starts = interval_lengths.contiguous(), interval_starts.contiguous()
+        n, c = x.shape
+        out = torch.empty((b, d, h, w, c), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.dbev_bev_pool_forward(
+                b, d, h, w, n, c, interval_lengths.shape[0], _lib.ptr(x), _lib.ptr(geom_feats),
+                _lib.ptr(interval_starts), _lib.ptr(interval_lengths), _lib.ptr(out), 1,
+                _lib.stream_ptr(x.device))
+        _lib.check(rc, "dbev_bev_pool_forward")
+        return out
+
+    @staticmethod
+    def bev_pool_backward(out_grad, geom_feats, interval_lengths, interval_starts, b, d, h, w):
+        lib = _lib.load()
+        _lib.require_cuda(out_grad, "out_grad", torch.float32)
+        _lib.require_cuda(geom_feats, "geom_feats", torch.int32)
+        out_grad, geom_feats = out_grad.contiguous(), geom_feats.contiguous()
+        interval_lengths, interval_starts = interval_lengths.contiguous(), interval_starts.contiguous()
+        n, c = geom_feats.shape[0], out_grad.shape[4]
+        x_grad = torch.empty((n, c), dtype=out_grad.dtype, device=out_grad.device)
+        with torch.cuda.device(out_grad.device):
+            rc = lib.dbev_bev_pool_backward(
+                b, d, h, w, n, c, interval_lengths.shape[0], _lib.ptr(out_grad),
+                _lib.ptr(geom_feats), _lib.ptr(interval_starts), _lib.ptr(interval_lengths),
+                _lib.ptr(x_grad), 1, _lib.stream_ptr(out_grad.device))
+        _lib.check(rc, "dbev_bev_pool_backward")
+        return x_grad
+
+
+bev_pool_ext = _BevPoolExt()
+
+
+def intervals_from_sorted_ranks(ranks):
+    """(interval_starts, interval_lengths) int32 of the runs of equal values in a sorted
+    rank vector - the bookkeeping of QuickCumsumCuda.forward (bev_pool.py:40-46)."""
+    n = ranks.shape[0]
+    is_head = torch.ones(n, dtype=torch.bool, device=ranks.device)
+    if n > 1:
+        torch.ne(ranks[1:], ranks[:-1], out=is_head[1:])
+    starts = is_head.nonzero(as_tuple=False).flatten().to(torch.int32)
+    ends = torch.cat([starts[1:], starts.new_tensor([n])])
+    return starts, ends - starts
+
+
+class QuickCumsumCuda(torch.autograd.Function):
+    """API twin of bev_pool.py:37-80 for callers that bring pre-sorted rows + ranks."""
+
+    @staticmethod
+    def forward(ctx, x, geom_feats, ranks, B, D, H, W):
+        starts, lengths = intervals_from_sorted_ranks(ranks)
+        geom_i32 = geom_feats.to(torch.int32)
+        ctx.save_for_backward(starts, lengths, geom_i32)
+        ctx.grid = (B, D, H, W)
+        return bev_pool_ext.bev_pool_forward(x, geom_i32, lengths, starts, B, D, H, W)
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        starts, lengths, geom_i32 = ctx.saved_tensors
+        grad = bev_pool_ext.bev_pool_backward(out_grad.contiguous(), geom_i32, lengths, starts,
+                                              *ctx.grid)
+        return (grad,) + (None,) * 6

@@ -1,0 +1,136 @@
+/*
+ * distill_bev_b200.h — C-ABI of the B200-native DistillBEV hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no
+ * torch types. Every pointer that is not marked "host" is a DEVICE pointer on
+ * the current CUDA device; `stream` is a cudaStream_t passed as void* (the
+ * caller's current stream — the library never uses another stream and never
+ * synchronises the device). Outputs and workspaces are allocated by the
+ * caller (PyTorch's caching allocator in the Python shim).
+ *
+ * Error convention (replaces the reference's TORCH_CHECK / AT_ERROR C++
+ * exceptions, mmdet3d/ops/voxel/src/voxelization.h:118,139): every function
+ * returns 0 on success or a DBEV_ERR_* code; dbev_last_error() returns the
+ * message of the last failure on the calling thread. The Python shim raises
+ * RuntimeError with that text.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative
+ * to the reference checkout, qcraftai/distill-bev @ 3e8f6a4).
+ */
+#ifndef DISTILL_BEV_B200_H_
+#define DISTILL_BEV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBEV_OK 0
+#define DBEV_ERR_INVALID 1   /* bad argument */
+#define DBEV_ERR_CUDA 2      /* CUDA runtime / launch failure */
+#define DBEV_ERR_WORKSPACE 3 /* workspace too small */
+
+#define DBEV_ABI_VERSION 1
+
+int dbev_abi_version(void);
+const char* dbev_last_error(void);
+/* "sm_100a" — the only architecture this library carries code for. */
+const char* dbev_build_arch(void);
+
+/* ------------------------------------------------------------------------ *
+ * bev_pool — reference-ABI launchers
+ * Replace:  void bev_pool(...) / void bev_pool_grad(...)
+ *           mmdet3d/ops/bev_pool/src/bev_pool.cpp:5-9 (declarations),
+ *           mmdet3d/ops/bev_pool/src/bev_pool_cuda.cu:86-98 (launchers),
+ *           bound to Python by bev_pool_forward/backward (bev_pool.cpp:22-87).
+ * Same argument meaning: x[n,c] rows PRE-SORTED by rank, geom_feats[n,4] int32
+ * (x, y, z, b), interval_starts/lengths[n_intervals]; out is [b,d,h,w,c]
+ * addressed as out[g3][g2][g0][g1][:]. The reference launcher expects `out`
+ * zero-filled by its caller (bev_pool.cpp:40); pass zero_out=1 to have the
+ * fill enqueued here instead. Unlike the reference these run on `stream`, not
+ * on the legacy default stream (bev_pool_cuda.cu:88,95).
+ * ------------------------------------------------------------------------ */
+int dbev_bev_pool_forward(int b, int d, int h, int w, int n, int c, int n_intervals,
+                          const float* x, const int* geom_feats, const int* interval_starts,
+                          const int* interval_lengths, float* out, int zero_out, void* stream);
+
+int dbev_bev_pool_backward(int b, int d, int h, int w, int n, int c, int n_intervals,
+                           const float* out_grad, const int* geom_feats,
+                           const int* interval_starts, const int* interval_lengths, float* x_grad,
+                           int zero_x_grad, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * bev_pool — B200 plan/gather path (what the Python shims actually call)
+ *
+ * A "plan" is the sorted view of the frustum points over the BEV grid:
+ *   order[n_points]        point ids, stably sorted by output cell
+ *   cell_start[n_cells+1]  first position in order[] of every cell
+ *   cell_end[n_cells+1]    one past the last; slot n_cells = dropped points
+ * with cell = ((b*nz + iz)*nslow + islow)*nfast + ifast. fast_axis selects
+ * which of the first two coordinates is the output's fastest axis:
+ *   0 -> x fastest: final[b, iz*C + c, iy, ix]  (voxel_pooling,
+ *        mmdet3d/models/necks/view_transformer_mine.py:176-179)
+ *   1 -> y fastest: out[b, c, z, x, y]          (bev_pool + permute,
+ *        mmdet3d/ops/bev_pool/bev_pool.py:96)
+ * The plan depends on geometry only (camera calibration + augmentation), so
+ * it can be cached across calls that share it.
+ * ------------------------------------------------------------------------ */
+size_t dbev_bev_plan_workspace_bytes(long long n_points);
+
+/* Replaces the index math + mask + rank + argsort of voxel_pooling
+ * (view_transformer_mine.py:150-168): geom[n_points,3] fp32 ego-frame xyz,
+ * off = bx - dx/2, dx, nx as fp32 (host float[3]) and nx.to(long) (host
+ * int[3]); points are batch-major, n_points/batch per sample. */
+int dbev_bev_plan_from_geom(const float* geom, long long n_points, int batch,
+                            const float* off_host3, const float* dx_host3,
+                            const float* nx_float_host3, const int* nx_int_host3, int fast_axis,
+                            uint32_t* order, int* cell_start, int* cell_end, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* Replaces the rank + argsort + kept/where prelude of bev_pool()
+ * (mmdet3d/ops/bev_pool/bev_pool.py:86-93,40-46). coords[n,4] = (c0,c1,c2,b),
+ * int64 (coords_is_i64=1) or int32; grid n0 x n1 x nz per sample. Rows whose
+ * coordinates fall outside the grid are dropped (the reference would write
+ * out of bounds). */
+int dbev_bev_plan_from_coords(const void* coords, int coords_is_i64, long long n_points,
+                              int batch, int n0, int n1, int nz, int fast_axis, uint32_t* order,
+                              int* cell_start, int* cell_end, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
+/* out[b*sB + iz*sZ + c*sC + islow*nfast + ifast] = sum of x[p, c] over the
+ * cell's points, 0 for empty cells (every output element is written once:
+ * no zero-fill, no permute copy). x is [n_points, C] fp32, rows 16 B aligned
+ * when C % 4 == 0. Replaces cumsum/select/diff/scatter + cat(unbind)
+ * (view_transformer_mine.py:171-179) and bev_pool_kernel + permute. */
+int dbev_bev_pool_gather_forward(const float* x, int C, const uint32_t* order,
+                                 const int* cell_start, const int* cell_end, int batch, int nz,
+                                 int nslow, int nfast, long long stride_b, long long stride_z,
+                                 long long stride_c, float* out, void* stream);
+
+/* x_grad[p, :] = out_grad[cell(p), :], zero rows for dropped points (every
+ * row written once). Replaces QuickCumsum.backward
+ * (view_transformer_mine.py:48-56) / bev_pool_grad_kernel. */
+int dbev_bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* order,
+                                  const int* cell_start, const int* cell_end, int batch, int nz,
+                                  int nslow, int nfast, long long stride_b, long long stride_z,
+                                  long long stride_c, float* x_grad, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Primitives exposed for testing (stable LSD radix sort, exclusive scan).
+ * They stand in for argsort / at::unique_dim / cumsum on the reference path.
+ * ------------------------------------------------------------------------ */
+size_t dbev_sort_workspace_bytes(long long n);
+/* Sorts (keys_in[i], i) by key bits [0,num_bits): keys_out / order_out. */
+int dbev_sort_keys_iota(const uint32_t* keys_in, int n, int num_bits, uint32_t* keys_out,
+                        uint32_t* order_out, void* workspace, size_t workspace_bytes, void* stream);
+size_t dbev_scan_workspace_bytes(long long n);
+int dbev_exclusive_scan_i32(const int* in, int* out, int n, int* total_out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DISTILL_BEV_B200_H_ */

@@ -1,0 +1,191 @@
+"""GPU parity: bev_pool / voxel_pooling CUDA path (through the C-ABI shims) vs
+the CPU oracle and the committed reference fixtures.
+
+Tolerances: indices / kept sets / empty cells are exact; pooled features are
+fp32 sums compared with the fp64-accumulated oracle at rtol 1e-5 (north_star
+bound is 1e-3 relative; the reference's own cumsum path is only good to ~1e-3).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import distill_bev_b200 as dbev
+from distill_bev_b200 import synthetic
+from oracle import lss_oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-5
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def test_voxel_pooling_golden_small(cuda, golden_dir):
+    g = np.load(os.path.join(golden_dir, "lss_small.npz"))
+    x = _t(g["x"], cuda).requires_grad_(True)
+    out = dbev.voxel_pooling(_t(g["geom"], cuda), x, g["bx"], g["dx"], g["nx"])
+    assert tuple(out.shape) == g["out_cumsum"].shape
+    o = out.detach().cpu().numpy()
+    np.testing.assert_allclose(o, g["out_accelerated"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(o, g["out_cumsum"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_array_equal(o == 0, g["out_accelerated"] == 0)
+    (out * _t(g["out_weight"], cuda)).sum().backward()
+    np.testing.assert_array_equal(x.grad.cpu().numpy(), g["x_grad"])
+
+
+def test_voxel_pooling_golden_edges(cuda, golden_dir):
+    g = np.load(os.path.join(golden_dir, "lss_edge.npz"))
+    x = _t(g["x"], cuda).requires_grad_(True)
+    geom = _t(g["geom"], cuda)
+    plan = dbev.bev_plan_from_geom(geom, 3, g["bx"], g["dx"], g["nx"])
+    assert plan.num_kept() == 10
+    out = dbev.voxel_pooling(geom, x, g["bx"], g["dx"], g["nx"], plan=plan)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out_cumsum"], rtol=RTOL, atol=1e-6)
+    (out * _t(g["out_weight"], cuda)).sum().backward()
+    np.testing.assert_array_equal(x.grad.cpu().numpy(), g["x_grad"])
+
+
+def test_bev_pool_golden_quickcumsum(cuda, golden_dir):
+    g = np.load(os.path.join(golden_dir, "quickcumsum.npz"))
+    B, D, H, W = int(g["B"]), int(g["D"]), int(g["H"]), int(g["W"])
+    feats = _t(g["feats"], cuda).requires_grad_(True)
+    out = dbev.bev_pool(feats, _t(g["coords"], cuda), B, D, H, W)
+    assert tuple(out.shape) == g["dense"].shape
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["dense"], rtol=1e-4, atol=1e-4)
+    # reference-ABI path: pre-sorted rows + ranks (QuickCumsumCuda contract)
+    order = torch.from_numpy(g["sort_index"]).to(cuda)
+    xs = _t(g["feats"], cuda)[order].requires_grad_(True)
+    cs = _t(g["coords"], cuda)[order]
+    ranks = cs[:, 0] * (W * D * B) + cs[:, 1] * (D * B) + cs[:, 2] * B + cs[:, 3]
+    dense = dbev.QuickCumsumCuda.apply(xs, cs, ranks, B, D, H, W)   # [B, D, H, W, C]
+    np.testing.assert_allclose(dense.permute(0, 4, 1, 2, 3).detach().cpu().numpy(), g["dense"],
+                               rtol=1e-4, atol=1e-4)
+    og = torch.zeros_like(dense)
+    gp = torch.from_numpy(g["geom_pooled"]).to(cuda)
+    og[gp[:, 3], gp[:, 2], gp[:, 0], gp[:, 1]] = _t(g["weight"], cuda)
+    dense.backward(og)
+    np.testing.assert_array_equal(xs.grad.cpu().numpy(), g["x_sorted_grad"])
+
+
+@pytest.mark.parametrize("C", [4, 8, 16, 32, 64, 80, 128, 256, 6, 33])
+def test_bev_pool_channel_widths(cuda, C):
+    rng = np.random.RandomState(C)
+    B, D, H, W, n = 2, 2, 40, 37, 20000
+    coords = np.stack([rng.randint(0, H, n), rng.randint(0, W, n), rng.randint(0, D, n),
+                       rng.randint(0, B, n)], 1).astype(np.int64)
+    coords[: n // 4, :2] = coords[0, :2]  # one very long interval
+    feats = rng.random_sample((n, C)).astype(np.float32)
+    ft = _t(feats, cuda).requires_grad_(True)
+    out = dbev.bev_pool(ft, _t(coords, cuda), B, D, H, W)
+    ref = lss_oracle.bev_pool(feats, coords, B, D, H, W)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref, rtol=RTOL, atol=1e-3 * RTOL * n)
+    w = rng.random_sample(ref.shape).astype(np.float32)
+    (out * _t(w, cuda)).sum().backward()
+    np.testing.assert_array_equal(ft.grad.cpu().numpy(), lss_oracle.bev_pool_backward(w, coords))
+    # int32 coords take the same path
+    out32 = dbev.bev_pool(ft.detach(), _t(coords.astype(np.int32), cuda), B, D, H, W)
+    assert torch.equal(out32, out.detach())
+
+
+def test_bev_pool_empty_and_out_of_range(cuda):
+    out = dbev.bev_pool(torch.zeros(0, 16, device=cuda), torch.zeros(0, 4, dtype=torch.long, device=cuda),
+                        2, 1, 8, 8)
+    assert tuple(out.shape) == (2, 16, 1, 8, 8) and float(out.abs().sum()) == 0.0
+    coords = torch.tensor([[0, 0, 0, 0], [8, 0, 0, 0], [-1, 3, 0, 1], [7, 7, 0, 1]], device=cuda)
+    feats = torch.ones(4, 16, device=cuda)
+    out = dbev.bev_pool(feats, coords, 2, 1, 8, 8)
+    assert float(out.sum()) == 32.0  # the two out-of-grid rows are dropped, not written out of bounds
+    assert float(out[0, :, 0, 0, 0].sum()) == 16.0 and float(out[1, :, 0, 7, 7].sum()) == 16.0
+
+
+def test_reference_abi_interval_kernels(cuda):
+    rng = np.random.RandomState(11)
+    b, d, h, w, c, n = 2, 1, 16, 16, 64, 5000
+    coords = np.stack([rng.randint(0, h, n), rng.randint(0, w, n), rng.randint(0, d, n),
+                       rng.randint(0, b, n)], 1).astype(np.int64)
+    feats = rng.random_sample((n, c)).astype(np.float32)
+    order, _, starts, lengths = lss_oracle.sorted_intervals(coords, b, d, h, w)
+    xs, cs = feats[order], coords[order].astype(np.int32)
+    ext = dbev.bev_pool_ext
+    out = ext.bev_pool_forward(_t(xs, cuda), _t(cs, cuda), _t(lengths, cuda), _t(starts, cuda), b, d, h, w)
+    ref = lss_oracle.bev_pool_interval_forward(xs, cs, starts, lengths, b, d, h, w)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+    og = rng.random_sample(ref.shape).astype(np.float32)
+    xg = ext.bev_pool_backward(_t(og, cuda), _t(cs, cuda), _t(lengths, cuda), _t(starts, cuda), b, d, h, w)
+    np.testing.assert_array_equal(xg.cpu().numpy(),
+                                  lss_oracle.bev_pool_interval_backward(og, cs, starts, lengths, n))
+
+
+def _config1_inputs(batch, seed=0, C=64, bev=128, dstep=1.0):
+    grid = synthetic.grid_config(bev, dstep)
+    dx, bx, nx = lss_oracle.gen_dx_bx(grid["xbound"], grid["ybound"], grid["zbound"])
+    frustum = lss_oracle.create_frustum(synthetic.NUSC_INPUT_SIZE, 16, grid["dbound"])
+    calib = synthetic.make_calibration(batch, 6, seed=seed)
+    geom = lss_oracle.get_geometry(frustum, *calib)
+    D, fH, fW = frustum.shape[:3]
+    x = synthetic.make_frustum_feats(batch * 6 * D * fH * fW, C, seed=seed).reshape(batch, 6, D, fH, fW, C)
+    return geom, x, bx, dx, nx
+
+
+def test_voxel_pooling_config1_full_size_vs_oracle(cuda):
+    """BASELINE.json configs[0]: 1 sample, 6 cams, D=59, 16x44, C=64 -> 128x128."""
+    geom, x, bx, dx, nx = _config1_inputs(1)
+    xt = _t(x, cuda).requires_grad_(True)
+    gt = _t(geom, cuda)
+    plan = dbev.bev_plan_from_geom(gt, 1, bx, dx, nx)
+    idx, kept = lss_oracle.voxel_indices(geom, bx, dx, nx)
+    assert plan.num_kept() == int(kept.sum())                      # exact kept set size
+    out = dbev.voxel_pooling(gt, xt, bx, dx, nx, plan=plan)
+    ref = lss_oracle.voxel_pooling(geom, x, bx, dx, nx)
+    o = out.detach().cpu().numpy()
+    assert o.shape == (1, 64, 128, 128)
+    np.testing.assert_array_equal(o == 0, ref == 0)               # same set of empty cells
+    np.testing.assert_allclose(o, ref, rtol=RTOL, atol=ATOL)
+    # plan internals are exact integers: order is the stable sort of the cell keys
+    n_i = nx.astype(np.int64)
+    key = np.where(kept, (idx[:, 2] * n_i[1] + idx[:, 1]) * n_i[0] + idx[:, 0], n_i.prod())
+    np.testing.assert_array_equal(plan.order.cpu().numpy()[: key.size], np.argsort(key, kind="stable"))
+    w = np.random.RandomState(1).random_sample(ref.shape).astype(np.float32)
+    (out * _t(w, cuda)).sum().backward()
+    xg = lss_oracle.voxel_pooling_backward(geom, w, 64, bx, dx, nx)
+    np.testing.assert_array_equal(xt.grad.cpu().numpy().reshape(-1, 64), xg)
+
+
+def test_voxel_pooling_batch8_properties(cuda):
+    """configs[1] batch (B=8): size-independent properties at full size.
+
+    linearity: pool(a*x + y) = a*pool(x) + pool(y); conservation: the sum over
+    the BEV map equals the sum over kept rows; determinism: bit-identical reruns;
+    batch independence: sample b of the batched call equals the single call.
+    """
+    B = 8
+    geom, x, bx, dx, nx = _config1_inputs(B, seed=5)
+    gt, xt = _t(geom, cuda), _t(x, cuda)
+    plan = dbev.bev_plan_from_geom(gt, B, bx, dx, nx)
+    out = dbev.voxel_pooling(gt, xt, bx, dx, nx, plan=plan)
+    out2 = dbev.voxel_pooling(gt, xt, bx, dx, nx)               # fresh plan
+    assert torch.equal(out, out2)
+    y = torch.rand_like(xt)
+    lhs = dbev.voxel_pooling(gt, 0.5 * xt + y, bx, dx, nx, plan=plan)
+    rhs = 0.5 * out + dbev.voxel_pooling(gt, y, bx, dx, nx, plan=plan)
+    torch.testing.assert_close(lhs, rhs, rtol=1e-4, atol=1e-3)
+    _, kept = lss_oracle.voxel_indices(geom, bx, dx, nx)
+    kept_t = torch.from_numpy(kept).to(cuda)
+    total = xt.reshape(-1, 64)[kept_t].double().sum()
+    assert abs(float(out.double().sum()) - float(total)) / float(total) < 1e-6
+    single = dbev.voxel_pooling(gt[3:4].contiguous(), xt[3:4].contiguous(), bx, dx, nx)
+    assert torch.equal(single[0], out[3])
+
+
+@pytest.mark.parametrize("bev,dstep,C", [(256, 1.0, 64), (128, 0.5, 64), (512, 1.0, 64), (128, 1.0, 256)])
+def test_voxel_pooling_sweep_vs_oracle(cuda, bev, dstep, C):
+    """BASELINE.json configs[4] sweep points (one sample each)."""
+    geom, x, bx, dx, nx = _config1_inputs(1, seed=2, C=C, bev=bev, dstep=dstep)
+    out = dbev.voxel_pooling(_t(geom, cuda), _t(x, cuda), bx, dx, nx)
+    ref = lss_oracle.voxel_pooling(geom, x, bx, dx, nx)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)

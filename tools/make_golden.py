@@ -1,0 +1,170 @@
+"""Generate tests/golden/*.npz by EXECUTING the reference's own Python code.
+
+Run in the build container only (needs /root/reference):
+
+    python tools/make_golden.py
+
+The reference ships no tests or golden vectors; these fixtures
+are the pin for ``oracle/``: unmodified reference files are imported through
+``tools/ref_import.py`` (import stubs only, no arithmetic changed) and run on
+the CPU on small seeded inputs. The fixtures are small (tens of KB) and are
+committed; the GPU box never sees /root/reference.
+
+Fixtures
+  lss_small.npz    ViewTransformerLiftSplatShoot: create_frustum, get_geometry,
+                   voxel_pooling (cumsum path), voxel_pooling_accelerated,
+                   autograd gradient of voxel_pooling w.r.t. x
+  lss_edge.npz     hand-placed points on cell borders / outside the grid
+                   (trunc-toward-zero leak, dropped points, empty batch item)
+  quickcumsum.npz  QuickCumsum of mmdet3d/ops/bev_pool/bev_pool.py (pure torch)
+Also prints (not stored) the full-size config-1 comparison oracle vs reference.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import ref_import  # noqa: E402
+import distill_bev_b200  # noqa: E402,F401
+from distill_bev_b200 import synthetic  # noqa: E402
+from oracle import lss_oracle  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def build_vt(vtm, grid, input_size, downsample, numC_Trans):
+    torch.manual_seed(0)
+    return vtm.ViewTransformerLiftSplatShoot(
+        grid_config=grid, data_config={"input_size": input_size}, numC_input=8,
+        numC_Trans=numC_Trans, downsample=downsample, accelerate=False)
+
+
+def lss_small(vtm):
+    grid = dict(xbound=[-8.0, 8.0, 1.0], ybound=[-8.0, 8.0, 1.0], zbound=[-10.0, 10.0, 20.0],
+                dbound=[1.0, 9.0, 1.0])
+    input_size, down, C = (64, 96), 16, 8
+    vt = build_vt(vtm, grid, input_size, down, C)
+    B, N = 2, 3
+    rots, trans, intrins, post_rots, post_trans = synthetic.make_calibration(
+        B, N, seed=3, input_size=input_size, src_size=(225, 400))
+    # shrink the scene so that many points land inside the +-8 m grid
+    intrins[:, :, 0, 0] = intrins[:, :, 1, 1] = 300.0
+    intrins[:, :, 0, 2], intrins[:, :, 1, 2] = 200.0, 112.0
+    t = [torch.from_numpy(a) for a in (rots, trans, intrins, post_rots, post_trans)]
+    geom = vt.get_geometry(*t)
+    D, fH, fW = vt.frustum.shape[:3]
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(B, N, D, fH, fW, C, generator=g)
+    x.requires_grad_(True)
+    out = vt.voxel_pooling(geom, x)
+    w = torch.rand(out.shape, generator=g)
+    (out * w).sum().backward()
+    out_acc = vt.voxel_pooling_accelerated(geom, x.detach())
+    np.savez_compressed(
+        os.path.join(GOLDEN, "lss_small.npz"),
+        grid=json.dumps(grid), input_size=np.array(input_size), downsample=down,
+        rots=rots, trans=trans, intrins=intrins, post_rots=post_rots, post_trans=post_trans,
+        frustum=vt.frustum.detach().numpy(), geom=geom.detach().numpy(),
+        dx=vt.dx.numpy(), bx=vt.bx.numpy(), nx=vt.nx.numpy(),
+        x=x.detach().numpy(), out_cumsum=out.detach().numpy(), out_accelerated=out_acc.numpy(),
+        out_weight=w.numpy(), x_grad=x.grad.numpy())
+    print("lss_small: out", tuple(out.shape), "nonzero cells",
+          int((out.detach().abs().sum(1) > 0).sum()), "max|cumsum-accel|",
+          float((out.detach() - out_acc).abs().max()))
+
+
+def lss_edge(vtm):
+    grid = dict(xbound=[-4.0, 4.0, 1.0], ybound=[-2.0, 2.0, 0.5], zbound=[-10.0, 10.0, 20.0],
+                dbound=[1.0, 3.0, 1.0])
+    vt = build_vt(vtm, grid, (32, 32), 16, 4)
+    # geometry given directly: B=3 (last sample entirely outside), N=1, D=2, H=2, W=2
+    pts = np.array([
+        [-4.0, -2.0, 0.0], [-4.5, -2.0, 0.0], [-4.999, -2.25, -29.0], [-5.0, 0.0, 0.0],   # low edge leak
+        [3.999, 1.999, 9.9], [4.0, 0.0, 0.0], [0.0, 2.0, 0.0], [0.0, 0.0, 10.0],          # high edge
+        [0.5, 0.25, 0.0], [0.5, 0.25, 1.0], [0.5, 0.25, -5.0], [0.999, 0.499, 3.0],       # many-to-one
+        [-0.5, -0.25, 0.0], [-1.0, -0.5, 0.0], [1e9, 0.0, 0.0], [0.0, -1e9, 0.0],         # far away
+        [100.0, 100.0, 0.0], [-100.0, 0.0, 0.0], [0.0, 50.0, 0.0], [9.0, 9.0, 9.0],       # sample 2: all out
+        [8.0, 0.0, 0.0], [0.0, 3.0, 0.0], [0.0, 0.0, 31.0], [-6.0, -6.0, 0.0],
+    ], dtype=np.float32)
+    geom = torch.from_numpy(pts).view(3, 1, 2, 2, 2, 3)
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(3, 1, 2, 2, 2, 4, generator=g)
+    x.requires_grad_(True)
+    out = vt.voxel_pooling(geom, x)
+    w = torch.rand(out.shape, generator=g)
+    (out * w).sum().backward()
+    np.savez_compressed(
+        os.path.join(GOLDEN, "lss_edge.npz"), grid=json.dumps(grid), geom=geom.numpy(),
+        dx=vt.dx.numpy(), bx=vt.bx.numpy(), nx=vt.nx.numpy(), x=x.detach().numpy(),
+        out_cumsum=out.detach().numpy(), out_weight=w.numpy(), x_grad=x.grad.numpy())
+    print("lss_edge: kept rows with grad", int((x.grad.abs().sum(-1) > 0).sum()), "of 24")
+
+
+def quickcumsum(bp):
+    g = torch.Generator().manual_seed(5)
+    B, D, H, W, C, n = 2, 2, 6, 5, 8, 400
+    coords = torch.stack([torch.randint(0, H, (n,), generator=g), torch.randint(0, W, (n,), generator=g),
+                          torch.randint(0, D, (n,), generator=g), torch.randint(0, B, (n,), generator=g)], 1)
+    feats = torch.rand(n, C, generator=g)
+    ranks = coords[:, 0] * (W * D * B) + coords[:, 1] * (D * B) + coords[:, 2] * B + coords[:, 3]
+    idx = ranks.argsort()
+    xs, cs, rs = feats[idx], coords[idx], ranks[idx]
+    xs.requires_grad_(True)
+    xo, go = bp.QuickCumsum.apply(xs, cs, rs)
+    wgt = torch.rand(xo.shape, generator=g)
+    (xo * wgt).sum().backward()
+    # dense [B, C, D, H, W] as bev_pool() would return after permute(0,4,1,2,3)
+    dense = torch.zeros(B, D, H, W, C)
+    dense[go[:, 3], go[:, 2], go[:, 0], go[:, 1]] = xo.detach()
+    np.savez_compressed(
+        os.path.join(GOLDEN, "quickcumsum.npz"), B=B, D=D, H=H, W=W, feats=feats.numpy(),
+        coords=coords.numpy(), sort_index=idx.numpy(), x_pooled=xo.detach().numpy(),
+        geom_pooled=go.numpy(), dense=dense.permute(0, 4, 1, 2, 3).contiguous().numpy(),
+        weight=wgt.numpy(), x_sorted_grad=xs.grad.numpy())
+    print("quickcumsum: intervals", xo.shape[0], "of", n, "rows")
+
+
+def fullsize_check(vtm):
+    """Config 1 (B=1, 6 cams, D=59, 16x44, C=64 -> 128x128): oracle vs reference, not stored."""
+    grid = synthetic.NUSC_GRID
+    vt = build_vt(vtm, grid, (256, 704), 16, 64)
+    calib = synthetic.make_calibration(1, 6, seed=0)
+    geom = vt.get_geometry(*[torch.from_numpy(a) for a in calib])
+    D, fH, fW = vt.frustum.shape[:3]
+    x = torch.from_numpy(synthetic.make_frustum_feats(6 * D * fH * fW, 64, seed=0)).view(1, 6, D, fH, fW, 64)
+    t0 = time.perf_counter()
+    ref = vt.voxel_pooling(geom, x).numpy()
+    t_ref = time.perf_counter() - t0
+    ref_acc = vt.voxel_pooling_accelerated(geom, x).numpy()
+    ours = lss_oracle.voxel_pooling(geom.numpy(), x.numpy(), vt.bx.numpy(), vt.dx.numpy(), vt.nx.numpy())
+    og = lss_oracle.get_geometry(vt.frustum.numpy(), *calib)
+    idx_ref = ((geom - (vt.bx - vt.dx / 2.)) / vt.dx).long().view(-1, 3).numpy()
+    idx_or, kept = lss_oracle.voxel_indices(geom.numpy(), vt.bx.numpy(), vt.dx.numpy(), vt.nx.numpy())
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+    rep = dict(kept=int(kept.sum()), nprime=int(kept.size),
+               nonempty_cells=int((np.abs(ref_acc).sum(1) > 0).sum()),
+               idx_equal_on_kept=bool((idx_ref[kept] == idx_or[kept]).all()),
+               rel_oracle_vs_accelerated=rel(ours, ref_acc), rel_oracle_vs_cumsum=rel(ours, ref),
+               rel_cumsum_vs_accelerated=rel(ref, ref_acc),
+               geom_max_abs_diff=float(np.abs(og - geom.numpy()).max()),
+               ref_voxel_pooling_cpu_s=t_ref, threads=torch.get_num_threads())
+    print("fullsize:", json.dumps(rep))
+    with open(os.path.join(GOLDEN, "fullsize_report.json"), "w") as f:
+        json.dump(rep, f, indent=1)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN, exist_ok=True)
+    vtm = ref_import.view_transformer_mine()
+    bp = ref_import.bev_pool_py()
+    lss_small(vtm)
+    lss_edge(vtm)
+    quickcumsum(bp)
+    fullsize_check(vtm)
