@@ -25,15 +25,20 @@ SIGNATURES = {
     "dbev_build_arch": (ctypes.c_char_p, []),
     "dbev_bev_pool_forward": (_c_int, [_c_int] * 7 + [_ptr] * 5 + [_c_int, _ptr]),
     "dbev_bev_pool_backward": (_c_int, [_c_int] * 7 + [_ptr] * 5 + [_c_int, _ptr]),
-    "dbev_bev_plan_workspace_bytes": (_c_size, [_c_ll]),
+    "dbev_bev_plan_workspace_bytes": (_c_size, [_c_ll, _c_ll]),
+    "dbev_bev_plan_max_items": (_c_ll, [_c_ll, _c_ll, _c_int, _c_int]),
     "dbev_bev_plan_from_geom": (_c_int, [_ptr, _c_ll, _c_int, _fptr, _fptr, _fptr, _iptr, _c_int,
-                                         _ptr, _ptr, _ptr, _ptr, _c_size, _ptr]),
+                                         _c_int, _ptr, _ptr, _ptr, _ptr, _c_ll, _ptr, _ptr,
+                                         _c_size, _ptr]),
     "dbev_bev_plan_from_coords": (_c_int, [_ptr, _c_int, _c_ll, _c_int, _c_int, _c_int, _c_int,
-                                           _c_int, _ptr, _ptr, _ptr, _ptr, _c_size, _ptr]),
-    "dbev_bev_pool_gather_forward": (_c_int, [_ptr, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int,
-                                              _c_int, _c_int, _c_ll, _c_ll, _c_ll, _ptr, _ptr]),
-    "dbev_bev_pool_gather_backward": (_c_int, [_ptr, _c_int, _ptr, _ptr, _ptr, _c_int, _c_int,
-                                               _c_int, _c_int, _c_ll, _c_ll, _c_ll, _ptr, _ptr]),
+                                           _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_ll, _ptr,
+                                           _ptr, _c_size, _ptr]),
+    "dbev_bev_pool_gather_forward": (_c_int, [_ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int,
+                                              _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _ptr,
+                                              _ptr]),
+    "dbev_bev_pool_gather_backward": (_c_int, [_ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int,
+                                               _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _ptr,
+                                               _ptr]),
     "dbev_sort_workspace_bytes": (_c_size, [_c_ll]),
     "dbev_sort_keys_iota": (_c_int, [_ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _c_size, _ptr]),
     "dbev_scan_workspace_bytes": (_c_size, [_c_ll]),

@@ -23,10 +23,11 @@ namespace dbev {
 
 namespace {
 
-constexpr int kPoolBlock = 256;
+constexpr int kPoolBlock = 128;
 constexpr int kPoolWarps = kPoolBlock / 32;
 constexpr int kTileCells = 32;
 constexpr int kTilePitch = kTileCells + 1;
+constexpr int kDefaultRowsPerItem = 192;
 
 // ---- plan: cell keys -------------------------------------------------------
 
@@ -114,82 +115,222 @@ __device__ __forceinline__ void f4_add(float4& a, const float4& b) {
   a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
 }
 
-// One CTA = one tile of 32 cells that are consecutive along the output's
-// fastest axis; one warp owns 4 of them. LPR lanes cover one feature row in
-// float4s (CHUNKS float4 per lane when C > 128), 32/LPR rows per warp step.
-template <int LPR, int CHUNKS>
+// ---- work items --------------------------------------------------------------
+// BEV occupancy is extremely skewed (cells next to the ego vehicle collect
+// hundreds of frustum points, far cells one or two), so a tile of 32 cells is
+// split into "items": runs of consecutive cells holding at most ~rows_per_item
+// rows (a single heavier cell is an item of its own). Items are part of the
+// plan (geometry only) and carry their row range, so a consumer needs no
+// dependent lookups: item -> {order[row_lo..row_hi), 32 cell bounds} -> rows.
+//
+// ONE WARP owns one item at a time (grid-stride over the item list) and never
+// synchronises with other warps: no block barriers, every warp is at a
+// different phase so load latency of one overlaps the epilogue of another.
+// Inside the warp the item's rows are divided evenly over "workers" (groups of
+// LPR lanes, LPR*4 = channel block <= 64), so each lane group streams the same
+// number of rows no matter how they fall into cells; U rows per worker are in
+// flight at a time (16-byte vector loads, L1 bypassed).
+
+__device__ __forceinline__ int tile_ncell(int nfast, int ftile) {
+  return min(kTileCells, nfast - ftile * kTileCells);
+}
+
+// groups of one tile: greedy split, a new group starts when the next cell
+// would push a non-empty group beyond rows_per_item. counts != null: count;
+// items != null: emit {tile, c0 | c1 << 8, row_lo, row_hi}.
+__global__ void __launch_bounds__(256)
+bev_items_kernel(const int* __restrict__ cell_start, const int* __restrict__ cell_end,
+                 long long ntiles, int nfast, int tiles_per_row, int rows_per_item,
+                 int* __restrict__ counts, const int* __restrict__ offsets,
+                 int4* __restrict__ items, int max_items) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const int ftile = (int)(t % tiles_per_row);
+  const long long rowid = t / tiles_per_row;
+  const int ncell = tile_ncell(nfast, ftile);
+  const long long cell0 = rowid * nfast + (long long)ftile * kTileCells;
+  int groups = 0, c0 = 0, rows = 0, lo = 0, hi = 0;
+  const int base = offsets ? offsets[t] : 0;
+  for (int c = 0; c < ncell; ++c) {
+    const int s = cell_start[cell0 + c], e = cell_end[cell0 + c];
+    const int len = e - s;
+    if (rows > 0 && rows + len > rows_per_item) {
+      if (items && base + groups < max_items)
+        items[base + groups] = make_int4((int)t, c0 | (c << 8), lo, hi);
+      ++groups;
+      c0 = c;
+      rows = 0;
+    }
+    if (len > 0) {
+      if (rows == 0) lo = s;
+      hi = e;
+      rows += len;
+    }
+  }
+  if (rows == 0) lo = hi = 0;
+  if (items && base + groups < max_items)
+    items[base + groups] = make_int4((int)t, c0 | (ncell << 8), lo, hi);
+  ++groups;
+  if (counts) counts[t] = groups;
+}
+
+struct ItemCtx {
+  long long cell0;   // first cell id of the tile
+  long long obase;   // output offset of (tile, channel 0, cell 0)
+  int c0, c1, row_lo, row_hi;
+};
+
+__device__ __forceinline__ ItemCtx decode_item(const int4& item, const PoolGeom& g) {
+  ItemCtx ic;
+  const long long t = item.x;
+  ic.c0 = item.y & 0xff;
+  ic.c1 = item.y >> 8;
+  ic.row_lo = item.z;
+  ic.row_hi = item.w;
+  const int ftile = (int)(t % g.tiles_per_row);
+  const long long rowid = t / g.tiles_per_row;
+  const int f0 = ftile * kTileCells;
+  ic.cell0 = rowid * g.nfast + f0;
+  const long long bz = rowid / g.nslow;
+  const int islow = (int)(rowid % g.nslow);
+  ic.obase = (bz / g.nz) * g.sB + (bz % g.nz) * g.sZ + (long long)islow * g.nfast + f0;
+  return ic;
+}
+
+template <int LPR>
 __global__ void __launch_bounds__(kPoolBlock)
 bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restrict__ order,
                            const int* __restrict__ cell_start, const int* __restrict__ cell_end,
+                           const int4* __restrict__ items, const int* __restrict__ n_items_ptr,
                            float* __restrict__ out, PoolGeom g) {
-  extern __shared__ float tile[];  // [C][kTilePitch]
-  constexpr int RPS = 32 / LPR;
+  extern __shared__ float smem[];
+  constexpr int NW = 32 / LPR;   // workers per warp
+  constexpr int CB = LPR * 4;    // channels per block
+  constexpr int U = 8;           // rows in flight per worker
+  __shared__ int cstart_s[kPoolWarps][kTileCells], cend_s[kPoolWarps][kTileCells];
+  __shared__ int side_cell_s[kPoolWarps][NW * 2];
+
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane % LPR, rslot = lane / LPR;
+  const int sub = lane % LPR, worker = lane / LPR;
+  float* tile = smem + (size_t)warp * (CB * kTilePitch + NW * 2 * CB);  // [CB][kTilePitch]
+  float* side = tile + CB * kTilePitch;                                  // [NW*2][CB]
+  int* cs = cstart_s[warp];
+  int* ce = cend_s[warp];
+  int* side_cell = side_cell_s[warp];
 
-  const int ftile = blockIdx.x % g.tiles_per_row;
-  const long long rowid = blockIdx.x / g.tiles_per_row;  // bz * nslow + islow
-  const int f0 = ftile * kTileCells;
-  const int ncell = min(kTileCells, g.nfast - f0);
-  const long long cell0 = rowid * g.nfast + f0;
+  const int nblocks = (g.C + CB - 1) / CB;
+  const long long n_virtual = (long long)(*n_items_ptr) * nblocks;
+  const long long stride = (long long)gridDim.x * kPoolWarps;
 
-  bool lane_active[CHUNKS];
+  for (long long vit = (long long)warp * gridDim.x + blockIdx.x; vit < n_virtual; vit += stride) {
+    const int4 item = items[vit / nblocks];
+    const int cb = (int)(vit % nblocks) * CB;  // first channel of this block
+    const ItemCtx ic = decode_item(item, g);
+    const bool lane_active = cb + sub * 4 < g.C;
+
+    __syncwarp();  // previous item's epilogue has finished with this warp's smem
+    {
+      const bool in = lane >= ic.c0 && lane < ic.c1;
+      cs[lane] = in ? cell_start[ic.cell0 + lane] : 0;
+      ce[lane] = in ? cell_end[ic.cell0 + lane] : 0;
+      for (int i = lane; i < NW * 2; i += 32) side_cell[i] = -1;
+    }
+    __syncwarp();
+
+    const int len = ic.row_hi - ic.row_lo;
+    const int per = (len + NW - 1) / NW;
+    const int ws = min(ic.row_lo + worker * per, ic.row_hi);
+    const int we = min(ws + per, ic.row_hi);
+
+    if (ws < we) {
+      int cur = ic.c0;
+      while (ce[cur] <= ws) ++cur;  // cell that owns row ws (empty cells have end 0)
+      int cur_end = ce[cur];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* xb = x + cb + sub * 4;
+
+      auto flush = [&](int cell) {
+        const bool complete = cs[cell] >= ws && ce[cell] <= we;
+        float* dst;
+        int pitch;
+        if (complete) {
+          dst = tile + cell;
+          pitch = kTilePitch;
+        } else {
+          const int slot = worker * 2 + ((cs[cell] < ws) ? 0 : 1);
+          dst = side + slot * CB;
+          pitch = 1;
+          if (sub == 0) side_cell[slot] = cell;
+        }
+        const int c = sub * 4;
+        dst[(c + 0) * pitch] = acc.x;
+        dst[(c + 1) * pitch] = acc.y;
+        dst[(c + 2) * pitch] = acc.z;
+        dst[(c + 3) * pitch] = acc.w;
+      };
+
+      // software pipeline: the point ids of batch i+1 are fetched while the rows of
+      // batch i are in flight, so only one global latency per batch is exposed
+      uint32_t pid[U];
 #pragma unroll
-  for (int k = 0; k < CHUNKS; ++k) lane_active[k] = (k * LPR + sub) * 4 < g.C;
-
-  for (int ci = warp; ci < ncell; ci += kPoolWarps) {
-    const int start = cell_start[cell0 + ci], end = cell_end[cell0 + ci];
-    float4 acc[CHUNKS];
+      for (int u = 0; u < U; ++u) pid[u] = (ws + u < we) ? __ldg(order + ws + u) : 0u;
+      for (int pos = ws; pos < we; pos += U) {
+        float4 v[U];
 #pragma unroll
-    for (int k = 0; k < CHUNKS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    for (int base = start; base < end; base += 32) {
-      const uint32_t my = (base + lane < end) ? order[base + lane] : 0u;
-      const int cnt = min(32, end - base);
-#pragma unroll 4
-      for (int j0 = 0; j0 < cnt; j0 += RPS) {
-        const int j = j0 + rslot;
-        const uint32_t p = __shfl_sync(0xffffffffu, my, j & 31);
-        if (j < cnt) {
-          const float* row = x + (size_t)p * g.C + sub * 4;
+        for (int u = 0; u < U; ++u)
+          if (lane_active && pos + u < we) v[u] = ld_stream_f4(xb + (size_t)pid[u] * g.C);
 #pragma unroll
-          for (int k = 0; k < CHUNKS; ++k)
-            if (lane_active[k]) f4_add(acc[k], ld_stream_f4(row + k * LPR * 4));
+        for (int u = 0; u < U; ++u) pid[u] = (pos + U + u < we) ? __ldg(order + pos + U + u) : 0u;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = pos + u;
+          if (r < we) {
+            if (r >= cur_end) {
+              flush(cur);
+              ++cur;
+              while (ce[cur] <= r) ++cur;
+              cur_end = ce[cur];
+              acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (lane_active) f4_add(acc, v[u]);
+          }
+        }
+      }
+      flush(cur);
+    }
+    __syncwarp();
+    // boundary partial sums: a cell shared by several workers has its partials in
+    // consecutive slots; first assigns, the rest add, in slot order (reproducible)
+    {
+      int prev = -1;
+      for (int w = 0; w < NW * 2; ++w) {
+        const int cell = side_cell[w];
+        if (cell >= 0) {
+          for (int c = lane; c < CB; c += 32) {
+            const float v = side[w * CB + c];
+            if (cell == prev) tile[c * kTilePitch + cell] += v;
+            else tile[c * kTilePitch + cell] = v;
+          }
+          prev = cell;
         }
       }
     }
-    // fold the RPS row slots together (fixed order -> deterministic)
-#pragma unroll
-    for (int o = LPR; o < 32; o <<= 1) {
-#pragma unroll
-      for (int k = 0; k < CHUNKS; ++k) {
-        acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o);
-        acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
-        acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, o);
-        acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, o);
-      }
-    }
-    if (rslot == 0) {
-#pragma unroll
-      for (int k = 0; k < CHUNKS; ++k) {
-        if (lane_active[k]) {
-          const int c = (k * LPR + sub) * 4;
-          tile[(c + 0) * kTilePitch + ci] = acc[k].x;
-          tile[(c + 1) * kTilePitch + ci] = acc[k].y;
-          tile[(c + 2) * kTilePitch + ci] = acc[k].z;
-          tile[(c + 3) * kTilePitch + ci] = acc[k].w;
-        }
-      }
+    __syncwarp();
+    // epilogue: lanes = (cell, channel group); empty cells are written as zero here
+    {
+      const int span = ic.c1 - ic.c0;
+      int npow = 1;
+      while (npow < span) npow <<= 1;
+      const int cpar = 32 / npow;
+      const int cell = ic.c0 + lane % npow;
+      const bool wr = cell < ic.c1;
+      const bool empty = wr ? (ce[cell] <= cs[cell]) : true;
+      float* ob = out + ic.obase + cell;
+      const int cmax = min(CB, g.C - cb);
+      for (int c = lane / npow; c < cmax; c += cpar)
+        if (wr) ob[(long long)(cb + c) * g.sC] = empty ? 0.f : tile[c * kTilePitch + cell];
     }
   }
-  __syncthreads();
-
-  const long long bz = rowid / g.nslow;
-  const int islow = (int)(rowid % g.nslow);
-  const long long b = bz / g.nz, iz = bz % g.nz;
-  float* obase = out + b * g.sB + iz * g.sZ + (long long)islow * g.nfast + f0;
-  for (int c = warp; c < g.C; c += kPoolWarps)
-    if (lane < ncell) obase[c * g.sC + lane] = tile[c * kTilePitch + lane];
 }
 
 // scalar fallback for C % 4 != 0 (one row per warp step, lanes over channels)
@@ -228,56 +369,89 @@ bev_pool_gather_fwd_generic_kernel(const float* __restrict__ x, const uint32_t* 
 
 // backward of the gather pool: every point of a cell receives the cell's
 // gradient row (bev_pool_cuda.cu:61-84; QuickCumsum.backward
-// view_transformer_mine.py:48-56). Rows of dropped points are written as zero
-// by bev_pool_zero_tail_kernel, so x_grad needs no prior memset.
-template <int LPR, int CHUNKS>
+// view_transformer_mine.py:48-56). Same items / warp-autonomous workers as
+// the forward; rows of dropped points are written as zero by
+// bev_pool_zero_tail_kernel, so x_grad needs no prior memset.
+template <int LPR>
 __global__ void __launch_bounds__(kPoolBlock)
 bev_pool_gather_bwd_kernel(const float* __restrict__ out_grad, const uint32_t* __restrict__ order,
                            const int* __restrict__ cell_start, const int* __restrict__ cell_end,
+                           const int4* __restrict__ items, const int* __restrict__ n_items_ptr,
                            float* __restrict__ x_grad, PoolGeom g) {
-  extern __shared__ float tile[];
-  constexpr int RPS = 32 / LPR;
+  extern __shared__ float smem[];
+  constexpr int NW = 32 / LPR;
+  constexpr int CB = LPR * 4;
+  __shared__ int cend_s[kPoolWarps][kTileCells];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane % LPR, rslot = lane / LPR;
-  const int ftile = blockIdx.x % g.tiles_per_row;
-  const long long rowid = blockIdx.x / g.tiles_per_row;
-  const int f0 = ftile * kTileCells;
-  const int ncell = min(kTileCells, g.nfast - f0);
-  const long long cell0 = rowid * g.nfast + f0;
+  const int sub = lane % LPR, worker = lane / LPR;
+  float* tile = smem + (size_t)warp * (CB * kTilePitch);
+  int* ce = cend_s[warp];
+  const int nblocks = (g.C + CB - 1) / CB;
+  const long long n_virtual = (long long)(*n_items_ptr) * nblocks;
+  const long long stride = (long long)gridDim.x * kPoolWarps;
 
-  const long long bz = rowid / g.nslow;
-  const int islow = (int)(rowid % g.nslow);
-  const long long b = bz / g.nz, iz = bz % g.nz;
-  const float* gbase = out_grad + b * g.sB + iz * g.sZ + (long long)islow * g.nfast + f0;
-  for (int c = warp; c < g.C; c += kPoolWarps)
-    if (lane < ncell) tile[c * kTilePitch + lane] = gbase[c * g.sC + lane];
-  __syncthreads();
+  for (long long vit = (long long)warp * gridDim.x + blockIdx.x; vit < n_virtual; vit += stride) {
+    const int4 item = items[vit / nblocks];
+    const int cb = (int)(vit % nblocks) * CB;
+    const ItemCtx ic = decode_item(item, g);
+    if (ic.row_hi <= ic.row_lo) continue;  // nothing to write for an all-empty item
+    const bool lane_active = cb + sub * 4 < g.C;
 
-  for (int ci = warp; ci < ncell; ci += kPoolWarps) {
-    const int start = cell_start[cell0 + ci], end = cell_end[cell0 + ci];
-    if (start >= end) continue;
-    float4 val[CHUNKS];
-    bool lane_active[CHUNKS];
-#pragma unroll
-    for (int k = 0; k < CHUNKS; ++k) {
-      const int c = (k * LPR + sub) * 4;
-      lane_active[k] = c < g.C;
-      if (lane_active[k])
-        val[k] = make_float4(tile[(c + 0) * kTilePitch + ci], tile[(c + 1) * kTilePitch + ci],
-                             tile[(c + 2) * kTilePitch + ci], tile[(c + 3) * kTilePitch + ci]);
+    __syncwarp();
+    {
+      const bool in = lane >= ic.c0 && lane < ic.c1;
+      ce[lane] = in ? cell_end[ic.cell0 + lane] : 0;
+      const int span = ic.c1 - ic.c0;
+      int npow = 1;
+      while (npow < span) npow <<= 1;
+      const int cpar = 32 / npow;
+      const int cell = ic.c0 + lane % npow;
+      const float* gb = out_grad + ic.obase + cell;
+      const int cmax = min(CB, g.C - cb);
+      if (cell < ic.c1)
+        for (int c = lane / npow; c < cmax; c += cpar)
+          tile[c * kTilePitch + cell] = gb[(long long)(cb + c) * g.sC];
     }
-    for (int base = start; base < end; base += 32) {
-      const uint32_t my = (base + lane < end) ? order[base + lane] : 0u;
-      const int cnt = min(32, end - base);
-#pragma unroll 4
-      for (int j0 = 0; j0 < cnt; j0 += RPS) {
-        const int j = j0 + rslot;
-        const uint32_t p = __shfl_sync(0xffffffffu, my, j & 31);
-        if (j < cnt) {
-          float* row = x_grad + (size_t)p * g.C + sub * 4;
+    __syncwarp();
+
+    const int len = ic.row_hi - ic.row_lo;
+    const int per = (len + NW - 1) / NW;
+    const int ws = min(ic.row_lo + worker * per, ic.row_hi);
+    const int we = min(ws + per, ic.row_hi);
+    if (ws < we) {
+      int cur = ic.c0;
+      while (ce[cur] <= ws) ++cur;
+      int cur_end = ce[cur];
+      float4 val;
+      auto load_cell = [&](int cell) {
+        const int c = sub * 4;
+        val = make_float4(tile[(c + 0) * kTilePitch + cell], tile[(c + 1) * kTilePitch + cell],
+                          tile[(c + 2) * kTilePitch + cell], tile[(c + 3) * kTilePitch + cell]);
+      };
+      load_cell(cur);
+      float* xb = x_grad + cb + sub * 4;
+      constexpr int U = 8;
+      uint32_t pid[U];
 #pragma unroll
-          for (int k = 0; k < CHUNKS; ++k)
-            if (lane_active[k]) st_stream_f4(row + k * LPR * 4, val[k]);
+      for (int u = 0; u < U; ++u) pid[u] = (ws + u < we) ? __ldg(order + ws + u) : 0u;
+      for (int pos = ws; pos < we; pos += U) {
+        uint32_t cur_pid[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur_pid[u] = pid[u];
+#pragma unroll
+        for (int u = 0; u < U; ++u) pid[u] = (pos + U + u < we) ? __ldg(order + pos + U + u) : 0u;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int r = pos + u;
+          if (r < we) {
+            if (r >= cur_end) {
+              ++cur;
+              while (ce[cur] <= r) ++cur;
+              cur_end = ce[cur];
+              load_cell(cur);
+            }
+            if (lane_active) st_stream_f4(xb + (size_t)cur_pid[u] * g.C, val);
+          }
         }
       }
     }
@@ -466,51 +640,105 @@ inline bool pick_vec_cfg(int C, VecCfg* cfg) {
 
 // ---------------------------------------------------------------------------
 
-size_t bev_plan_ws_bytes(long long n_points) {
-  return 3 * align_up((size_t)n_points * 4) + radix_sort_ws_bytes(n_points) + 1024;
+static long long n_tiles_of(long long ncells, int nfast) {
+  return (ncells / nfast) * ceil_div(nfast, kTileCells);
 }
 
-static int finish_plan(uint32_t* keys0, long long n, long long ncells, uint32_t* order,
-                       int* cell_start, int* cell_end, Workspace& w, void* ws, size_t ws_bytes,
-                       cudaStream_t stream) {
+long long bev_plan_max_items(long long n_points, long long ncells, int nfast, int rows_per_item) {
+  if (rows_per_item < 1) rows_per_item = kDefaultRowsPerItem;
+  return n_tiles_of(ncells, nfast) + 2 * ((n_points + rows_per_item - 1) / rows_per_item) + 1;
+}
+
+size_t bev_plan_ws_bytes(long long n_points, long long ncells) {
+  // keys x2 + payload + sort tables + per-tile counts/offsets + scan scratch
+  const long long ntiles_ub = ncells;  // nfast >= 1
+  return 3 * align_up((size_t)n_points * 4) + radix_sort_ws_bytes(n_points) +
+         2 * align_up((size_t)ntiles_ub * 4) + scan_ws_bytes(ntiles_ub) + 2048;
+}
+
+struct PlanOut {
+  uint32_t* order;
+  int* cell_start;
+  int* cell_end;
+  int4* items;
+  long long max_items;
+  int* n_items;
+  int rows_per_item;
+  int nfast;
+};
+
+static int finish_plan(uint32_t* keys0, long long n, long long ncells, const PlanOut& po,
+                       Workspace& w, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const long long ntiles = n_tiles_of(ncells, po.nfast);
   uint32_t* keys1 = w.take<uint32_t>(n);
   uint32_t* vals_other = w.take<uint32_t>(n);
+  int* counts = w.take<int>(ntiles);
+  int* offsets = w.take<int>(ntiles);
   if (!w.ok()) {
-    set_last_error("bev_plan: workspace too small (%zu bytes given)", ws_bytes);
+    set_last_error("bev_plan: workspace too small (%zu bytes given, %zu needed so far)", ws_bytes,
+                   w.used);
     return DBEV_ERR_WORKSPACE;
   }
-  size_t consumed = align_up(w.used);
+  const size_t consumed = align_up(w.used);
+  void* sub_ws = (char*)ws + consumed;
+  const size_t sub_bytes = ws_bytes > consumed ? ws_bytes - consumed : 0;
   const int num_bits = bits_for((unsigned long long)ncells + 1);
   const int passes = (num_bits + kRadixBits - 1) / kRadixBits;
   uint32_t* keys[2] = {keys0, keys1};
   // arrange the ping-pong so the sorted payload lands in `order`
   uint32_t* vals[2];
-  vals[passes & 1] = order;
+  vals[passes & 1] = po.order;
   vals[(passes & 1) ^ 1] = vals_other;
   int sel = 0;
-  int rc = radix_sort_pairs(keys, vals, /*vals_iota=*/true, (int)n, num_bits, (char*)ws + consumed,
-                            ws_bytes - consumed, stream, &sel);
+  int rc = radix_sort_pairs(keys, vals, /*vals_iota=*/true, (int)n, num_bits, sub_ws, sub_bytes,
+                            stream, &sel);
   if (rc != DBEV_OK) return rc;
-  DBEV_CUDA(cudaMemsetAsync(cell_start, 0, (size_t)(ncells + 1) * sizeof(int), stream));
-  DBEV_CUDA(cudaMemsetAsync(cell_end, 0, (size_t)(ncells + 1) * sizeof(int), stream));
+  DBEV_CUDA(cudaMemsetAsync(po.cell_start, 0, (size_t)(ncells + 1) * sizeof(int), stream));
+  DBEV_CUDA(cudaMemsetAsync(po.cell_end, 0, (size_t)(ncells + 1) * sizeof(int), stream));
   if (n > 0) {
-    bev_bounds_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(keys[sel], n, cell_start, cell_end);
+    bev_bounds_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(keys[sel], n, po.cell_start,
+                                                            po.cell_end);
     DBEV_CHECK_LAUNCH("bev_bounds_kernel");
   }
+  // work items: count per tile, scan, emit
+  const int tiles_per_row = ceil_div(po.nfast, kTileCells);
+  const int rpi = po.rows_per_item < 1 ? kDefaultRowsPerItem : po.rows_per_item;
+  bev_items_kernel<<<ceil_div(ntiles, 256), 256, 0, stream>>>(
+      po.cell_start, po.cell_end, ntiles, po.nfast, tiles_per_row, rpi, counts, nullptr, nullptr, 0);
+  DBEV_CHECK_LAUNCH("bev_items_kernel(count)");
+  rc = exclusive_scan_i32(counts, offsets, (int)ntiles, po.n_items, sub_ws, sub_bytes, stream);
+  if (rc != DBEV_OK) return rc;
+  bev_items_kernel<<<ceil_div(ntiles, 256), 256, 0, stream>>>(
+      po.cell_start, po.cell_end, ntiles, po.nfast, tiles_per_row, rpi, nullptr, offsets, po.items,
+      (int)po.max_items);
+  DBEV_CHECK_LAUNCH("bev_items_kernel(emit)");
+  return DBEV_OK;
+}
+
+static int check_plan_out(const char* who, long long n_points, long long ncells, int nfast,
+                          int rows_per_item, long long max_items) {
+  DBEV_CHECK_ARG(ncells > 0 && ncells < 0x7fffffffLL && n_points < 0x7fffffffLL,
+                 "%s: grid or point count exceeds 2^31", who);
+  const long long need = bev_plan_max_items(n_points, ncells, nfast, rows_per_item);
+  DBEV_CHECK_ARG(max_items >= need, "%s: items buffer holds %lld entries, %lld required", who,
+                 max_items, need);
   return DBEV_OK;
 }
 
 int bev_plan_from_geom(const float* geom, long long n_points, int batch, const float off[3],
                        const float dx[3], const float nx_f[3], const int nx_i[3], int fast_axis,
-                       uint32_t* order, int* cell_start, int* cell_end, void* ws, size_t ws_bytes,
+                       int rows_per_item, uint32_t* order, int* cell_start, int* cell_end,
+                       int4* items, long long max_items, int* n_items, void* ws, size_t ws_bytes,
                        cudaStream_t stream) {
   DBEV_CHECK_ARG(batch > 0 && n_points >= 0 && n_points % batch == 0,
                  "bev_plan_from_geom: n_points (%lld) must be a multiple of batch (%d)", n_points,
                  batch);
   DBEV_CHECK_ARG(fast_axis == 0 || fast_axis == 1, "bev_plan_from_geom: fast_axis must be 0 or 1");
+  DBEV_CHECK_ARG(nx_i[0] > 0 && nx_i[1] > 0 && nx_i[2] > 0, "bev_plan_from_geom: empty grid");
   const long long ncells = (long long)batch * nx_i[0] * nx_i[1] * nx_i[2];
-  DBEV_CHECK_ARG(ncells > 0 && ncells < 0x7fffffffLL && n_points < 0x7fffffffLL,
-                 "bev_plan_from_geom: grid or point count exceeds 2^31");
+  const int nfast = fast_axis == 0 ? nx_i[0] : nx_i[1];
+  int rc = check_plan_out("bev_plan_from_geom", n_points, ncells, nfast, rows_per_item, max_items);
+  if (rc != DBEV_OK) return rc;
   Workspace w(ws, ws_bytes);
   uint32_t* keys0 = w.take<uint32_t>(n_points);
   if (!w.ok()) {
@@ -523,16 +751,21 @@ int bev_plan_from_geom(const float* geom, long long n_points, int batch, const f
         nx_f[1], nx_f[2], nx_i[0], nx_i[1], nx_i[2], fast_axis, (uint32_t)ncells, keys0);
     DBEV_CHECK_LAUNCH("bev_keys_from_geom_kernel");
   }
-  return finish_plan(keys0, n_points, ncells, order, cell_start, cell_end, w, ws, ws_bytes, stream);
+  PlanOut po{order, cell_start, cell_end, items, max_items, n_items, rows_per_item, nfast};
+  return finish_plan(keys0, n_points, ncells, po, w, ws, ws_bytes, stream);
 }
 
 int bev_plan_from_coords(const void* coords, int coords_i64, long long n_points, int batch, int n0,
-                         int n1, int nz, int fast_axis, uint32_t* order, int* cell_start,
-                         int* cell_end, void* ws, size_t ws_bytes, cudaStream_t stream) {
+                         int n1, int nz, int fast_axis, int rows_per_item, uint32_t* order,
+                         int* cell_start, int* cell_end, int4* items, long long max_items,
+                         int* n_items, void* ws, size_t ws_bytes, cudaStream_t stream) {
   DBEV_CHECK_ARG(fast_axis == 0 || fast_axis == 1, "bev_plan_from_coords: fast_axis must be 0 or 1");
+  DBEV_CHECK_ARG(batch > 0 && n0 > 0 && n1 > 0 && nz > 0 && n_points >= 0,
+                 "bev_plan_from_coords: empty grid");
   const long long ncells = (long long)batch * n0 * n1 * nz;
-  DBEV_CHECK_ARG(ncells > 0 && ncells < 0x7fffffffLL && n_points < 0x7fffffffLL,
-                 "bev_plan_from_coords: grid or point count exceeds 2^31");
+  const int nfast = fast_axis == 0 ? n0 : n1;
+  int rc = check_plan_out("bev_plan_from_coords", n_points, ncells, nfast, rows_per_item, max_items);
+  if (rc != DBEV_OK) return rc;
   Workspace w(ws, ws_bytes);
   uint32_t* keys0 = w.take<uint32_t>(n_points);
   if (!w.ok()) {
@@ -548,12 +781,13 @@ int bev_plan_from_coords(const void* coords, int coords_i64, long long n_points,
           (const int*)coords, n_points, batch, n0, n1, nz, fast_axis, (uint32_t)ncells, keys0);
     DBEV_CHECK_LAUNCH("bev_keys_from_coords_kernel");
   }
-  return finish_plan(keys0, n_points, ncells, order, cell_start, cell_end, w, ws, ws_bytes, stream);
+  PlanOut po{order, cell_start, cell_end, items, max_items, n_items, rows_per_item, nfast};
+  return finish_plan(keys0, n_points, ncells, po, w, ws, ws_bytes, stream);
 }
 
 static int make_pool_geom(int C, int batch, int nz, int nslow, int nfast, long long sB,
                           long long sZ, long long sC, PoolGeom* g) {
-  DBEV_CHECK_ARG(C > 0 && C <= 2048, "bev_pool: channel count %d unsupported (1..2048)", C);
+  DBEV_CHECK_ARG(C > 0 && C <= 1024, "bev_pool: channel count %d unsupported (1..1024)", C);
   DBEV_CHECK_ARG(batch > 0 && nz > 0 && nslow > 0 && nfast > 0, "bev_pool: empty grid");
   g->C = C;
   g->nfast = nfast;
@@ -570,6 +804,19 @@ static int make_pool_geom(int C, int batch, int nz, int nslow, int nfast, long l
 }
 
 template <typename K>
+static int persistent_grid(K kernel, size_t smem, int* grid) {
+  if (smem > 48 * 1024)
+    DBEV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0, dev = 0, sms = 0;
+  DBEV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPoolBlock, smem));
+  DBEV_CUDA(cudaGetDevice(&dev));
+  DBEV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (per_sm < 1) per_sm = 1;
+  *grid = sms * per_sm;  // one resident wave; CTAs stride over the item list
+  return DBEV_OK;
+}
+
+template <typename K>
 static int set_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024) {
     DBEV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -577,26 +824,46 @@ static int set_smem(K kernel, size_t bytes) {
   return DBEV_OK;
 }
 
+static int pick_lpr(int C) {  // lanes per row of one channel block (<= 64 channels)
+  if (C % 4 != 0) return 0;
+  int lpr = 1;
+  while (lpr * 4 < C && lpr < 16) lpr <<= 1;
+  return lpr;
+}
+
+#define DBEV_DISPATCH_LPR(lpr, LAUNCH)   \
+  do {                                   \
+    switch (lpr) {                       \
+      case 1: { LAUNCH(1); } break;      \
+      case 2: { LAUNCH(2); } break;      \
+      case 4: { LAUNCH(4); } break;      \
+      case 8: { LAUNCH(8); } break;      \
+      default: { LAUNCH(16); } break;    \
+    }                                    \
+  } while (0)
+
 int bev_pool_gather_forward(const float* x, int C, const uint32_t* order, const int* cell_start,
-                            const int* cell_end, int batch, int nz, int nslow, int nfast,
-                            long long sB, long long sZ, long long sC, float* out,
-                            cudaStream_t stream) {
+                            const int* cell_end, const int4* items, const int* n_items, int batch,
+                            int nz, int nslow, int nfast, long long sB, long long sZ, long long sC,
+                            float* out, cudaStream_t stream) {
   PoolGeom g;
   int rc = make_pool_geom(C, batch, nz, nslow, nfast, sB, sZ, sC, &g);
   if (rc != DBEV_OK) return rc;
-  const int grid = g.nbz * nslow * g.tiles_per_row;
-  const size_t smem = (size_t)C * kTilePitch * sizeof(float);
-  DBEV_CHECK_ARG(smem <= 227 * 1024, "bev_pool: C=%d needs %zu B shared memory", C, smem);
-  VecCfg cfg;
-  if (pick_vec_cfg(C, &cfg)) {
-#define LAUNCH(L, K)                                                                       \
-  rc = set_smem(bev_pool_gather_fwd_kernel<L, K>, smem);                                   \
-  if (rc != DBEV_OK) return rc;                                                            \
-  bev_pool_gather_fwd_kernel<L, K><<<grid, kPoolBlock, smem, stream>>>(x, order, cell_start, \
-                                                                     cell_end, out, g)
-    DBEV_DISPATCH_VEC(cfg, LAUNCH);
+  const int lpr = pick_lpr(C);
+  if (lpr > 0) {
+    const int cb = lpr * 4, nw = 32 / lpr;
+    const size_t smem = (size_t)kPoolWarps * (cb * kTilePitch + nw * 2 * cb) * sizeof(float);
+    int grid = 0;
+#define LAUNCH(L)                                                                        \
+  rc = persistent_grid(bev_pool_gather_fwd_kernel<L>, smem, &grid);                      \
+  if (rc != DBEV_OK) return rc;                                                          \
+  bev_pool_gather_fwd_kernel<L><<<grid, kPoolBlock, smem, stream>>>(                     \
+      x, order, cell_start, cell_end, items, n_items, out, g)
+    DBEV_DISPATCH_LPR(lpr, LAUNCH);
 #undef LAUNCH
   } else {
+    const int grid = g.nbz * nslow * g.tiles_per_row;
+    const size_t smem = (size_t)C * kTilePitch * sizeof(float);
     rc = set_smem(bev_pool_gather_fwd_generic_kernel, smem);
     if (rc != DBEV_OK) return rc;
     bev_pool_gather_fwd_generic_kernel<<<grid, kPoolBlock, smem, stream>>>(x, order, cell_start,
@@ -607,26 +874,28 @@ int bev_pool_gather_forward(const float* x, int C, const uint32_t* order, const 
 }
 
 int bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* order,
-                             const int* cell_start, const int* cell_end, int batch, int nz,
-                             int nslow, int nfast, long long sB, long long sZ, long long sC,
-                             float* x_grad, cudaStream_t stream) {
+                             const int* cell_start, const int* cell_end, const int4* items,
+                             const int* n_items, int batch, int nz, int nslow, int nfast,
+                             long long sB, long long sZ, long long sC, float* x_grad,
+                             cudaStream_t stream) {
   PoolGeom g;
   int rc = make_pool_geom(C, batch, nz, nslow, nfast, sB, sZ, sC, &g);
   if (rc != DBEV_OK) return rc;
-  const int grid = g.nbz * nslow * g.tiles_per_row;
-  const size_t smem = (size_t)C * kTilePitch * sizeof(float);
-  DBEV_CHECK_ARG(smem <= 227 * 1024, "bev_pool: C=%d needs %zu B shared memory", C, smem);
-  VecCfg cfg;
-  if (pick_vec_cfg(C, &cfg)) {
-#define LAUNCH(L, K)                                                                        \
-  rc = set_smem(bev_pool_gather_bwd_kernel<L, K>, smem);                                    \
-  if (rc != DBEV_OK) return rc;                                                             \
-  bev_pool_gather_bwd_kernel<L, K><<<grid, kPoolBlock, smem, stream>>>(out_grad, order,     \
-                                                                     cell_start, cell_end, \
-                                                                     x_grad, g)
-    DBEV_DISPATCH_VEC(cfg, LAUNCH);
+  const int lpr = pick_lpr(C);
+  if (lpr > 0) {
+    const int cb = lpr * 4;
+    const size_t smem = (size_t)kPoolWarps * (cb * kTilePitch) * sizeof(float);
+    int grid = 0;
+#define LAUNCH(L)                                                                        \
+  rc = persistent_grid(bev_pool_gather_bwd_kernel<L>, smem, &grid);                      \
+  if (rc != DBEV_OK) return rc;                                                          \
+  bev_pool_gather_bwd_kernel<L><<<grid, kPoolBlock, smem, stream>>>(                     \
+      out_grad, order, cell_start, cell_end, items, n_items, x_grad, g)
+    DBEV_DISPATCH_LPR(lpr, LAUNCH);
 #undef LAUNCH
   } else {
+    const int grid = g.nbz * nslow * g.tiles_per_row;
+    const size_t smem = (size_t)C * kTilePitch * sizeof(float);
     rc = set_smem(bev_pool_gather_bwd_generic_kernel, smem);
     if (rc != DBEV_OK) return rc;
     bev_pool_gather_bwd_generic_kernel<<<grid, kPoolBlock, smem, stream>>>(

@@ -44,42 +44,55 @@ int dbev_bev_pool_backward(int b, int d, int h, int w, int n, int c, int n_inter
                                     (cudaStream_t)stream);
 }
 
-size_t dbev_bev_plan_workspace_bytes(long long n_points) { return bev_plan_ws_bytes(n_points); }
+size_t dbev_bev_plan_workspace_bytes(long long n_points, long long n_cells) {
+  return bev_plan_ws_bytes(n_points, n_cells);
+}
+
+long long dbev_bev_plan_max_items(long long n_points, long long n_cells, int nfast,
+                                  int rows_per_item) {
+  return bev_plan_max_items(n_points, n_cells, nfast < 1 ? 1 : nfast, rows_per_item);
+}
 
 int dbev_bev_plan_from_geom(const float* geom, long long n_points, int batch,
                             const float* off_host3, const float* dx_host3,
                             const float* nx_float_host3, const int* nx_int_host3, int fast_axis,
-                            uint32_t* order, int* cell_start, int* cell_end, void* workspace,
+                            int rows_per_item, uint32_t* order, int* cell_start, int* cell_end,
+                            int* items, long long max_items, int* n_items, void* workspace,
                             size_t workspace_bytes, void* stream) {
   return bev_plan_from_geom(geom, n_points, batch, off_host3, dx_host3, nx_float_host3,
-                            nx_int_host3, fast_axis, order, cell_start, cell_end, workspace,
-                            workspace_bytes, (cudaStream_t)stream);
+                            nx_int_host3, fast_axis, rows_per_item, order, cell_start, cell_end,
+                            (int4*)items, max_items, n_items, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
 }
 
 int dbev_bev_plan_from_coords(const void* coords, int coords_is_i64, long long n_points,
-                              int batch, int n0, int n1, int nz, int fast_axis, uint32_t* order,
-                              int* cell_start, int* cell_end, void* workspace,
+                              int batch, int n0, int n1, int nz, int fast_axis, int rows_per_item,
+                              uint32_t* order, int* cell_start, int* cell_end, int* items,
+                              long long max_items, int* n_items, void* workspace,
                               size_t workspace_bytes, void* stream) {
-  return bev_plan_from_coords(coords, coords_is_i64, n_points, batch, n0, n1, nz, fast_axis, order,
-                              cell_start, cell_end, workspace, workspace_bytes,
-                              (cudaStream_t)stream);
+  return bev_plan_from_coords(coords, coords_is_i64, n_points, batch, n0, n1, nz, fast_axis,
+                              rows_per_item, order, cell_start, cell_end, (int4*)items, max_items,
+                              n_items, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int dbev_bev_pool_gather_forward(const float* x, int C, const uint32_t* order,
-                                 const int* cell_start, const int* cell_end, int batch, int nz,
-                                 int nslow, int nfast, long long stride_b, long long stride_z,
-                                 long long stride_c, float* out, void* stream) {
-  return bev_pool_gather_forward(x, C, order, cell_start, cell_end, batch, nz, nslow, nfast,
-                                 stride_b, stride_z, stride_c, out, (cudaStream_t)stream);
+                                 const int* cell_start, const int* cell_end, const int* items,
+                                 const int* n_items, int batch, int nz, int nslow, int nfast,
+                                 long long stride_b, long long stride_z, long long stride_c,
+                                 float* out, void* stream) {
+  return bev_pool_gather_forward(x, C, order, cell_start, cell_end, (const int4*)items, n_items,
+                                 batch, nz, nslow, nfast, stride_b, stride_z, stride_c, out,
+                                 (cudaStream_t)stream);
 }
 
 int dbev_bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* order,
-                                  const int* cell_start, const int* cell_end, int batch, int nz,
-                                  int nslow, int nfast, long long stride_b, long long stride_z,
-                                  long long stride_c, float* x_grad, void* stream) {
-  return bev_pool_gather_backward(out_grad, C, order, cell_start, cell_end, batch, nz, nslow,
-                                  nfast, stride_b, stride_z, stride_c, x_grad,
-                                  (cudaStream_t)stream);
+                                  const int* cell_start, const int* cell_end, const int* items,
+                                  const int* n_items, int batch, int nz, int nslow, int nfast,
+                                  long long stride_b, long long stride_z, long long stride_c,
+                                  float* x_grad, void* stream) {
+  return bev_pool_gather_backward(out_grad, C, order, cell_start, cell_end, (const int4*)items,
+                                  n_items, batch, nz, nslow, nfast, stride_b, stride_z, stride_c,
+                                  x_grad, (cudaStream_t)stream);
 }
 
 size_t dbev_sort_workspace_bytes(long long n) {

@@ -21,13 +21,17 @@ class BevPlan(object):
     calibration at inference time, or fwd + bwd of one training step).
     """
 
-    __slots__ = ("order", "cell_start", "cell_end", "n_points", "batch", "nz", "nslow", "nfast",
-                 "fast_axis", "device")
+    __slots__ = ("order", "cell_start", "cell_end", "items", "n_items", "rows_per_item", "n_points",
+                 "batch", "nz", "nslow", "nfast", "fast_axis", "device")
 
-    def __init__(self, order, cell_start, cell_end, n_points, batch, nz, nslow, nfast, fast_axis):
+    def __init__(self, order, cell_start, cell_end, items, n_items, rows_per_item, n_points, batch,
+                 nz, nslow, nfast, fast_axis):
         self.order = order
         self.cell_start = cell_start
         self.cell_end = cell_end
+        self.items = items            # [max_items, 4] int32 work list (tile, c0 | c1 << 8, row_lo, row_hi)
+        self.n_items = n_items        # [1] int32, device
+        self.rows_per_item = rows_per_item
         self.n_points = n_points
         self.batch = batch
         self.nz = nz
@@ -47,16 +51,23 @@ class BevPlan(object):
         return self.n_points - (end - tail)
 
 
-def _alloc_plan(n_points, batch, n0, n1, nz, fast_axis, device):
+def _alloc_plan(n_points, batch, n0, n1, nz, fast_axis, device, rows_per_item=0):
+    lib = _lib.load()
     n_cells = batch * n0 * n1 * nz
+    if min(batch, n0, n1, nz) < 1:
+        raise RuntimeError("bev plan: empty grid (batch=%d, %dx%dx%d)" % (batch, n0, n1, nz))
     order = torch.empty(max(n_points, 1), dtype=torch.int32, device=device)
     cell_start = torch.empty(n_cells + 1, dtype=torch.int32, device=device)
     cell_end = torch.empty(n_cells + 1, dtype=torch.int32, device=device)
     nslow, nfast = (n1, n0) if fast_axis == 0 else (n0, n1)
-    return BevPlan(order, cell_start, cell_end, n_points, batch, nz, nslow, nfast, fast_axis)
+    max_items = lib.dbev_bev_plan_max_items(n_points, n_cells, nfast, rows_per_item)
+    items = torch.empty((max_items, 4), dtype=torch.int32, device=device)
+    n_items = torch.empty(1, dtype=torch.int32, device=device)
+    return BevPlan(order, cell_start, cell_end, items, n_items, rows_per_item, n_points, batch, nz,
+                   nslow, nfast, fast_axis)
 
 
-def bev_plan_from_geom(geom, batch, bx, dx, nx, fast_axis=0):
+def bev_plan_from_geom(geom, batch, bx, dx, nx, fast_axis=0, rows_per_item=0):
     """Plan from ego-frame frustum coordinates.
 
     geom: [..., 3] fp32 CUDA tensor, batch-major (e.g. [B, N, D, fH, fW, 3]);
@@ -73,20 +84,21 @@ def bev_plan_from_geom(geom, batch, bx, dx, nx, fast_axis=0):
     off = bx32 - dx32 / 2.0            # fp32, exactly as (self.bx - self.dx / 2.)
     nx_i = nx32.to(torch.long)          # nx.to(torch.long) truncates
     plan = _alloc_plan(n_points, batch, int(nx_i[0]), int(nx_i[1]), int(nx_i[2]), fast_axis,
-                       geom.device)
+                       geom.device, rows_per_item)
     with torch.cuda.device(geom.device):
-        ws_bytes = lib.dbev_bev_plan_workspace_bytes(n_points)
+        ws_bytes = lib.dbev_bev_plan_workspace_bytes(n_points, plan.n_cells)
         ws = _lib.workspace(ws_bytes, geom.device)
         rc = lib.dbev_bev_plan_from_geom(
             _lib.ptr(geom), n_points, batch, _lib.host_f3(off.tolist()), _lib.host_f3(dx32.tolist()),
-            _lib.host_f3(nx32.tolist()), _lib.host_i3(nx_i.tolist()), fast_axis,
+            _lib.host_f3(nx32.tolist()), _lib.host_i3(nx_i.tolist()), fast_axis, rows_per_item,
             _lib.ptr(plan.order), _lib.ptr(plan.cell_start), _lib.ptr(plan.cell_end),
+            _lib.ptr(plan.items), plan.items.shape[0], _lib.ptr(plan.n_items),
             _lib.ptr(ws), ws_bytes, _lib.stream_ptr(geom.device))
     _lib.check(rc, "dbev_bev_plan_from_geom")
     return plan
 
 
-def bev_plan_from_coords(coords, B, D, H, W, fast_axis=1):
+def bev_plan_from_coords(coords, B, D, H, W, fast_axis=1, rows_per_item=0):
     """Plan from integer coords [n, 4] = (c0 < H, c1 < W, c2 < D, batch < B)."""
     lib = _lib.load()
     _lib.require_cuda(coords, "coords")
@@ -96,13 +108,14 @@ def bev_plan_from_coords(coords, B, D, H, W, fast_axis=1):
         coords = coords.long()
     coords = coords.contiguous()
     n = coords.shape[0]
-    plan = _alloc_plan(n, B, H, W, D, fast_axis, coords.device)
+    plan = _alloc_plan(n, B, H, W, D, fast_axis, coords.device, rows_per_item)
     with torch.cuda.device(coords.device):
-        ws_bytes = lib.dbev_bev_plan_workspace_bytes(n)
+        ws_bytes = lib.dbev_bev_plan_workspace_bytes(n, plan.n_cells)
         ws = _lib.workspace(ws_bytes, coords.device)
         rc = lib.dbev_bev_plan_from_coords(
             _lib.ptr(coords), 1 if coords.dtype == torch.int64 else 0, n, B, H, W, D, fast_axis,
-            _lib.ptr(plan.order), _lib.ptr(plan.cell_start), _lib.ptr(plan.cell_end),
+            rows_per_item, _lib.ptr(plan.order), _lib.ptr(plan.cell_start), _lib.ptr(plan.cell_end),
+            _lib.ptr(plan.items), plan.items.shape[0], _lib.ptr(plan.n_items),
             _lib.ptr(ws), ws_bytes, _lib.stream_ptr(coords.device))
     _lib.check(rc, "dbev_bev_plan_from_coords")
     return plan
@@ -132,7 +145,8 @@ class _BevPoolGather(torch.autograd.Function):
         with torch.cuda.device(x.device):
             rc = lib.dbev_bev_pool_gather_forward(
                 _lib.ptr(x), C, _lib.ptr(plan.order), _lib.ptr(plan.cell_start),
-                _lib.ptr(plan.cell_end), plan.batch, plan.nz, plan.nslow, plan.nfast, sB, sZ, sC,
+                _lib.ptr(plan.cell_end), _lib.ptr(plan.items), _lib.ptr(plan.n_items),
+                plan.batch, plan.nz, plan.nslow, plan.nfast, sB, sZ, sC,
                 _lib.ptr(out), _lib.stream_ptr(x.device))
         _lib.check(rc, "dbev_bev_pool_gather_forward")
         ctx.plan = plan
@@ -150,7 +164,8 @@ class _BevPoolGather(torch.autograd.Function):
         with torch.cuda.device(out_grad.device):
             rc = lib.dbev_bev_pool_gather_backward(
                 _lib.ptr(out_grad), C, _lib.ptr(plan.order), _lib.ptr(plan.cell_start),
-                _lib.ptr(plan.cell_end), plan.batch, plan.nz, plan.nslow, plan.nfast, sB, sZ, sC,
+                _lib.ptr(plan.cell_end), _lib.ptr(plan.items), _lib.ptr(plan.n_items),
+                plan.batch, plan.nz, plan.nslow, plan.nfast, sB, sZ, sC,
                 _lib.ptr(x_grad), _lib.stream_ptr(out_grad.device))
         _lib.check(rc, "dbev_bev_pool_gather_backward")
         return x_grad, None, None

@@ -68,6 +68,11 @@ int dbev_bev_pool_backward(int b, int d, int h, int w, int n, int c, int n_inter
  *   order[n_points]        point ids, stably sorted by output cell
  *   cell_start[n_cells+1]  first position in order[] of every cell
  *   cell_end[n_cells+1]    one past the last; slot n_cells = dropped points
+ *   items[max_items][4]    work list: (tile, c0 | c1 << 8, row_lo, row_hi) = cells
+ *                          [c0, c1) of a 32-cell tile and their rows of order[];
+ *                          each item holds <= ~rows_per_item rows so that warps
+ *                          get equal work although BEV occupancy is extremely
+ *                          skewed (16 B aligned); *n_items = count
  * with cell = ((b*nz + iz)*nslow + islow)*nfast + ifast. fast_axis selects
  * which of the first two coordinates is the output's fastest axis:
  *   0 -> x fastest: final[b, iz*C + c, iy, ix]  (voxel_pooling,
@@ -75,9 +80,13 @@ int dbev_bev_pool_backward(int b, int d, int h, int w, int n, int c, int n_inter
  *   1 -> y fastest: out[b, c, z, x, y]          (bev_pool + permute,
  *        mmdet3d/ops/bev_pool/bev_pool.py:96)
  * The plan depends on geometry only (camera calibration + augmentation), so
- * it can be cached across calls that share it.
+ * it can be cached across calls that share it. rows_per_item <= 0 selects the
+ * default (192).
  * ------------------------------------------------------------------------ */
-size_t dbev_bev_plan_workspace_bytes(long long n_points);
+size_t dbev_bev_plan_workspace_bytes(long long n_points, long long n_cells);
+/* required capacity (entries) of items[] */
+long long dbev_bev_plan_max_items(long long n_points, long long n_cells, int nfast,
+                                  int rows_per_item);
 
 /* Replaces the index math + mask + rank + argsort of voxel_pooling
  * (view_transformer_mine.py:150-168): geom[n_points,3] fp32 ego-frame xyz,
@@ -86,7 +95,8 @@ size_t dbev_bev_plan_workspace_bytes(long long n_points);
 int dbev_bev_plan_from_geom(const float* geom, long long n_points, int batch,
                             const float* off_host3, const float* dx_host3,
                             const float* nx_float_host3, const int* nx_int_host3, int fast_axis,
-                            uint32_t* order, int* cell_start, int* cell_end, void* workspace,
+                            int rows_per_item, uint32_t* order, int* cell_start, int* cell_end,
+                            int* items, long long max_items, int* n_items, void* workspace,
                             size_t workspace_bytes, void* stream);
 
 /* Replaces the rank + argsort + kept/where prelude of bev_pool()
@@ -95,8 +105,9 @@ int dbev_bev_plan_from_geom(const float* geom, long long n_points, int batch,
  * coordinates fall outside the grid are dropped (the reference would write
  * out of bounds). */
 int dbev_bev_plan_from_coords(const void* coords, int coords_is_i64, long long n_points,
-                              int batch, int n0, int n1, int nz, int fast_axis, uint32_t* order,
-                              int* cell_start, int* cell_end, void* workspace,
+                              int batch, int n0, int n1, int nz, int fast_axis, int rows_per_item,
+                              uint32_t* order, int* cell_start, int* cell_end, int* items,
+                              long long max_items, int* n_items, void* workspace,
                               size_t workspace_bytes, void* stream);
 
 /* out[b*sB + iz*sZ + c*sC + islow*nfast + ifast] = sum of x[p, c] over the
@@ -105,17 +116,19 @@ int dbev_bev_plan_from_coords(const void* coords, int coords_is_i64, long long n
  * when C % 4 == 0. Replaces cumsum/select/diff/scatter + cat(unbind)
  * (view_transformer_mine.py:171-179) and bev_pool_kernel + permute. */
 int dbev_bev_pool_gather_forward(const float* x, int C, const uint32_t* order,
-                                 const int* cell_start, const int* cell_end, int batch, int nz,
-                                 int nslow, int nfast, long long stride_b, long long stride_z,
-                                 long long stride_c, float* out, void* stream);
+                                 const int* cell_start, const int* cell_end, const int* items,
+                                 const int* n_items, int batch, int nz, int nslow, int nfast,
+                                 long long stride_b, long long stride_z, long long stride_c,
+                                 float* out, void* stream);
 
 /* x_grad[p, :] = out_grad[cell(p), :], zero rows for dropped points (every
  * row written once). Replaces QuickCumsum.backward
  * (view_transformer_mine.py:48-56) / bev_pool_grad_kernel. */
 int dbev_bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* order,
-                                  const int* cell_start, const int* cell_end, int batch, int nz,
-                                  int nslow, int nfast, long long stride_b, long long stride_z,
-                                  long long stride_c, float* x_grad, void* stream);
+                                  const int* cell_start, const int* cell_end, const int* items,
+                                  const int* n_items, int batch, int nz, int nslow, int nfast,
+                                  long long stride_b, long long stride_z, long long stride_c,
+                                  float* x_grad, void* stream);
 
 /* ------------------------------------------------------------------------ *
  * Primitives exposed for testing (stable LSD radix sort, exclusive scan).

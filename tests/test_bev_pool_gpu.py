@@ -92,6 +92,33 @@ def test_bev_pool_channel_widths(cuda, C):
     assert torch.equal(out32, out.detach())
 
 
+@pytest.mark.parametrize("rpi", [1, 7, 64, 1000000])
+def test_work_item_split_is_invisible(cuda, rpi):
+    """The work-item split (rows_per_item) never changes what is computed."""
+    rng = np.random.RandomState(3)
+    B, D, H, W, n, C = 1, 1, 48, 70, 60000, 64
+    coords = np.stack([rng.randint(0, H, n), rng.randint(0, W, n), rng.randint(0, D, n),
+                       rng.randint(0, B, n)], 1).astype(np.int64)
+    coords[: n // 3] = coords[0]            # one cell holds a third of all rows
+    coords[n // 3: n // 2, 1] = 5           # one heavy column
+    feats = rng.random_sample((n, C)).astype(np.float32)
+    ft, ct = _t(feats, cuda), _t(coords, cuda)
+    plan = dbev.bev_plan_from_coords(ct, B, D, H, W, rows_per_item=rpi)
+    out = dbev.bev_pool_gather(ft.requires_grad_(True), plan, layout="b_c_z")
+    ref = lss_oracle.bev_pool(feats, coords, B, D, H, W)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ref, rtol=RTOL, atol=1e-2)
+    w = rng.random_sample(ref.shape).astype(np.float32)
+    (out * _t(w, cuda)).sum().backward()
+    np.testing.assert_array_equal(ft.grad.cpu().numpy(), lss_oracle.bev_pool_backward(w, coords))
+    # same plan parameters => bit-identical reruns (fixed in-cell order, fixed fix-up order);
+    # a different split only regroups fp32 partial sums
+    again = dbev.bev_pool_gather(ft.detach(), dbev.bev_plan_from_coords(ct, B, D, H, W, rows_per_item=rpi),
+                                 layout="b_c_z")
+    assert torch.equal(out.detach(), again)
+    base = dbev.bev_pool(ft.detach(), ct, B, D, H, W)
+    torch.testing.assert_close(out.detach(), base, rtol=1e-5, atol=1e-2)
+
+
 def test_bev_pool_empty_and_out_of_range(cuda):
     out = dbev.bev_pool(torch.zeros(0, 16, device=cuda), torch.zeros(0, 4, dtype=torch.long, device=cuda),
                         2, 1, 8, 8)

@@ -39,6 +39,7 @@ def main():
     ap.add_argument("--C", type=int, default=64)
     ap.add_argument("--dstep", type=float, default=1.0)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--rpi", type=int, default=0)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     grid = synthetic.grid_config(a.bev, a.dstep)
@@ -49,7 +50,7 @@ def main():
     n = geom.numel() // 3
     x = torch.rand(n, a.C, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    plan = dbev.bev_plan_from_geom(geom, a.frames, bx, dx, nx)
+    plan = dbev.bev_plan_from_geom(geom, a.frames, bx, dx, nx, rows_per_item=a.rpi)
     kept = plan.num_kept()
     out = dbev.bev_pool_gather(x, plan)
     og = torch.rand_like(out)
@@ -67,7 +68,7 @@ def main():
     t_fb = time_ms(bwd, a.iters, flush)
     fwd_bytes = kept * a.C * 4 + kept * 4 + out.numel() * 4
     bwd_bytes = out.numel() * 4 + n * 4 + n * a.C * 4
-    rep = dict(frames=a.frames, bev=a.bev, C=a.C, dstep=a.dstep, n_points=n, kept=kept,
+    rep = dict(rpi=a.rpi, n_items=int(plan.n_items.item()), frames=a.frames, bev=a.bev, C=a.C, dstep=a.dstep, n_points=n, kept=kept,
                plan_ms_med=t_plan[0], plan_ms_min=t_plan[1], fwd_ms_med=t_fwd[0], fwd_ms_min=t_fwd[1],
                fwd_GBps_med=fwd_bytes / t_fwd[0] / 1e6, fwd_GBps_best=fwd_bytes / t_fwd[1] / 1e6,
                fwdbwd_ms_med=t_fb[0], bwd_ms_est=t_fb[0] - t_fwd[0],
