@@ -8,6 +8,9 @@ from .plugin.ops.bev_pool import (BevPlan, QuickCumsumCuda, bev_plan_from_coords
                                   bev_plan_from_geom, bev_pool, bev_pool_ext, bev_pool_gather,
                                   voxel_pooling)
 
+from .plugin.ops.voxel import (DynamicScatter, Voxelization, dynamic_scatter, voxel_layer,  # noqa: F401
+                               voxelization)
+
 __version__ = "0.1.0"
 
 

@@ -39,6 +39,16 @@ SIGNATURES = {
     "dbev_bev_pool_gather_backward": (_c_int, [_ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int,
                                                _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll, _ptr,
                                                _ptr]),
+    "dbev_voxel_grid_size": (_c_int, [_fptr, _fptr, _iptr]),
+    "dbev_dynamic_voxelize": (_c_int, [_ptr, _c_int, _c_int, _fptr, _fptr, _ptr, _ptr]),
+    "dbev_hard_voxelize_workspace_bytes": (_c_size, [_c_ll]),
+    "dbev_hard_voxelize": (_c_int, [_ptr, _c_int, _c_int, _fptr, _fptr, _c_int, _c_int, _ptr, _ptr,
+                                    _ptr, _ptr, _ptr, _c_size, _ptr]),
+    "dbev_dynamic_scatter_workspace_bytes": (_c_size, [_c_ll]),
+    "dbev_dynamic_scatter_forward": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _iptr, _c_int,
+                                              _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_size, _ptr]),
+    "dbev_dynamic_scatter_backward": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_ll, _c_ll, _c_int,
+                                               _c_int, _ptr, _ptr, _ptr]),
     "dbev_sort_workspace_bytes": (_c_size, [_c_ll]),
     "dbev_sort_keys_iota": (_c_int, [_ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _c_size, _ptr]),
     "dbev_scan_workspace_bytes": (_c_size, [_c_ll]),
@@ -105,3 +115,13 @@ def host_f3(vals):
 
 def host_i3(vals):
     return (ctypes.c_int * 3)(*[int(v) for v in vals])
+
+
+def host_floats(vals):
+    vals = [float(v) for v in vals]
+    return (ctypes.c_float * len(vals))(*vals)
+
+
+def host_ints(vals):
+    vals = [int(v) for v in vals]
+    return (ctypes.c_int * len(vals))(*vals)

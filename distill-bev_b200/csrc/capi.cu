@@ -6,6 +6,7 @@
 
 #include "bev_pool.cuh"
 #include "sort.cuh"
+#include "voxelize.cuh"
 
 namespace dbev {
 
@@ -93,6 +94,49 @@ int dbev_bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* 
   return bev_pool_gather_backward(out_grad, C, order, cell_start, cell_end, (const int4*)items,
                                   n_items, batch, nz, nslow, nfast, stride_b, stride_z, stride_c,
                                   x_grad, (cudaStream_t)stream);
+}
+
+int dbev_voxel_grid_size(const float* voxel_size_host3, const float* coors_range_host6,
+                         int* grid_xyz_host3) {
+  return voxel_grid_size(voxel_size_host3, coors_range_host6, grid_xyz_host3);
+}
+
+int dbev_dynamic_voxelize(const float* points, int n, int nfeat, const float* voxel_size_host3,
+                          const float* coors_range_host6, int* coors, void* stream) {
+  return dynamic_voxelize(points, n, nfeat, voxel_size_host3, coors_range_host6, coors,
+                          (cudaStream_t)stream);
+}
+
+size_t dbev_hard_voxelize_workspace_bytes(long long n) { return hard_voxelize_ws_bytes(n); }
+
+int dbev_hard_voxelize(const float* points, int n, int nfeat, const float* voxel_size_host3,
+                       const float* coors_range_host6, int max_points, int max_voxels,
+                       float* voxels, int* coors, int* num_points_per_voxel, int* voxel_num,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  return hard_voxelize(points, n, nfeat, voxel_size_host3, coors_range_host6, max_points,
+                       max_voxels, voxels, coors, num_points_per_voxel, voxel_num, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t dbev_dynamic_scatter_workspace_bytes(long long n) { return dynamic_scatter_ws_bytes(n); }
+
+int dbev_dynamic_scatter_forward(const float* feats, const int* coors, int n, int nfeat, int ncol,
+                                 const int* dims_host, int reduce_type, float* reduced_feats,
+                                 int* out_coors, int* coors_map, int* reduce_count, int* num_out,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  return dynamic_scatter_forward(feats, coors, n, nfeat, ncol, dims_host, reduce_type,
+                                 reduced_feats, out_coors, coors_map, reduce_count, num_out,
+                                 workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_dynamic_scatter_backward(const float* grad_reduced, const float* feats,
+                                  const float* reduced, const int* coors_map,
+                                  const int* reduce_count, long long n, long long m, int nfeat,
+                                  int reduce_type, float* grad_feats, int* reduce_from_ws,
+                                  void* stream) {
+  return dynamic_scatter_backward(grad_reduced, feats, reduced, coors_map, reduce_count, n, m,
+                                  nfeat, reduce_type, grad_feats, reduce_from_ws,
+                                  (cudaStream_t)stream);
 }
 
 size_t dbev_sort_workspace_bytes(long long n) {

@@ -131,6 +131,72 @@ int dbev_bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* 
                                   float* x_grad, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * LiDAR voxelization — replaces the pybind module mmdet3d.ops.voxel.voxel_layer
+ * (mmdet3d/ops/voxel/src/voxelization.cpp:6-11, dispatch voxelization.h:58-140).
+ * voxel_size_host3 = (vx, vy, vz), coors_range_host6 = (xmin, ymin, zmin, xmax,
+ * ymax, zmax) are HOST float arrays; NDim is fixed to 3 like every caller in
+ * the reference. Coordinates are stored (z, y, x) (voxelization_cpu.cpp:30).
+ * ------------------------------------------------------------------------ */
+
+/* grid = round((max - min) / voxel) in fp32 -> host int[3] (x, y, z)
+ * (voxelization_cpu.cpp:120-123, voxelize.py:121-126). */
+int dbev_voxel_grid_size(const float* voxel_size_host3, const float* coors_range_host6,
+                         int* grid_xyz_host3);
+
+/* dynamic_voxelize(points, coors, voxel_size, coors_range, NDim=3)
+ * (voxelization.h:82-93; CPU :146-171, CUDA voxelization_cuda.cu:485-528).
+ * points[n, nfeat] fp32 -> coors[n, 3] int32, (-1, -1, -1) for points outside
+ * the range (the CPU build's convention). No device synchronisation (the
+ * reference calls cudaDeviceSynchronize, voxelization_cuda.cu:524). */
+int dbev_dynamic_voxelize(const float* points, int n, int nfeat, const float* voxel_size_host3,
+                          const float* coors_range_host6, int* coors, void* stream);
+
+/* hard_voxelize(points, voxels, coors, num_points_per_voxel, voxel_size,
+ * coors_range, max_points, max_voxels, NDim=3, deterministic=true) -> voxel_num
+ * (voxelization.h:58-80; CPU :45-144; CUDA voxelization_cuda.cu:231-402).
+ * Caller pre-allocates voxels[max_voxels, max_points, nfeat], coors[max_voxels,3],
+ * num_points_per_voxel[max_voxels] (voxelize.py:57-62). Voxel order = first
+ * appearance in point order, in-voxel order = point order, both capped
+ * exactly like the reference. Every slot of the first *voxel_num voxels is
+ * written (points or zeros), so the buffers need not be zero-filled; entries
+ * past *voxel_num are left untouched. *voxel_num is a DEVICE int (the Python
+ * shim reads it back, the one sync the reference API implies). The
+ * deterministic result is also a valid outcome of deterministic=false
+ * (voxelization_cuda.cu:404-483), so both flags map here. */
+size_t dbev_hard_voxelize_workspace_bytes(long long n);
+int dbev_hard_voxelize(const float* points, int n, int nfeat, const float* voxel_size_host3,
+                       const float* coors_range_host6, int max_points, int max_voxels,
+                       float* voxels, int* coors, int* num_points_per_voxel, int* voxel_num,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* dynamic_point_to_voxel_forward(feats, coors, reduce_type) ->
+ * [reduced_feats, out_coors, coors_map, reduce_count]
+ * (voxelization.h:107-120, scatter_points_cuda.cu:183-239).
+ * feats[n, nfeat] fp32; coors[n, ncol] int32 with ncol = 3 (z, y, x) or 4
+ * (batch, z, y, x — one call for the whole batch instead of the reference's
+ * per-sample Python loop, scatter_points.py:86-97); rows with any negative
+ * component are dropped (coors_map = -1). dims_host[ncol] = exclusive upper
+ * bound of every column. Output voxels come in lexicographic coordinate order
+ * (what at::unique_dim returns). reduce_type: 0 sum, 1 mean, 2 max
+ * (reduce_t, voxelization.h:4). Outputs are caller-allocated for the worst
+ * case (n rows); *num_out is a DEVICE int. */
+size_t dbev_dynamic_scatter_workspace_bytes(long long n);
+int dbev_dynamic_scatter_forward(const float* feats, const int* coors, int n, int nfeat, int ncol,
+                                 const int* dims_host, int reduce_type, float* reduced_feats,
+                                 int* out_coors, int* coors_map, int* reduce_count, int* num_out,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* dynamic_point_to_voxel_backward(grad_feats, grad_reduced_feats, feats,
+ * reduced_feats, coors_idx, reduce_count, reduce_type)
+ * (voxelization.h:122-138, scatter_points_cuda.cu:241-308). grad_feats[n, nfeat]
+ * is fully written. reduce_from_ws: m * nfeat ints, needed for max only. */
+int dbev_dynamic_scatter_backward(const float* grad_reduced, const float* feats,
+                                  const float* reduced, const int* coors_map,
+                                  const int* reduce_count, long long n, long long m, int nfeat,
+                                  int reduce_type, float* grad_feats, int* reduce_from_ws,
+                                  void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Primitives exposed for testing (stable LSD radix sort, exclusive scan).
  * They stand in for argsort / at::unique_dim / cumsum on the reference path.
  * ------------------------------------------------------------------------ */

@@ -1,0 +1,65 @@
+"""Build the oracle's native parts (checker only, never shipped in the product).
+
+    python oracle/build_oracle.py
+
+1. gcc: oracle/c/*.c -> oracle/_build/liboracle.so (plain C restatement).
+2. When /root/reference exists (build container), compile the reference's OWN
+   CPU voxelization sources, unmodified and where they lie, into
+   oracle/_ref/ref_voxel_layer*.so (a torch C++ extension without WITH_CUDA):
+       mmdet3d/ops/voxel/src/voxelization.cpp
+       mmdet3d/ops/voxel/src/voxelization_cpu.cpp
+       mmdet3d/ops/voxel/src/scatter_points_cpu.cpp
+   oracle/_ref/ is git-ignored but travels to the GPU box with the snapshot.
+   No reference source is copied into this repository.
+"""
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "_build")
+REF_OUT = os.path.join(HERE, "_ref")
+REF_SRC = "/root/reference/mmdet3d/ops/voxel/src"
+
+
+def build_c():
+    os.makedirs(BUILD, exist_ok=True)
+    srcs = sorted(glob.glob(os.path.join(HERE, "c", "*.c")))
+    out = os.path.join(BUILD, "liboracle.so")
+    if os.path.exists(out) and all(os.path.getmtime(s) <= os.path.getmtime(out) for s in srcs):
+        return out
+    cmd = ["gcc", "-O2", "-fPIC", "-shared", "-std=c99", "-ffp-contract=off", "-o", out] + srcs + ["-lm"]
+    subprocess.run(cmd, check=True)
+    return out
+
+
+def build_ref():
+    if not os.path.isdir(REF_SRC):
+        return None
+    os.makedirs(REF_OUT, exist_ok=True)
+    existing = glob.glob(os.path.join(REF_OUT, "ref_voxel_layer*.so"))
+    if existing:
+        return existing[0]
+    from torch.utils.cpp_extension import load
+    tmp = os.path.join(REF_OUT, "_jit")
+    os.makedirs(tmp, exist_ok=True)
+    srcs = [os.path.join(REF_SRC, f) for f in
+            ("voxelization.cpp", "voxelization_cpu.cpp", "scatter_points_cpu.cpp")]
+    load(name="ref_voxel_layer", sources=srcs, build_directory=tmp, extra_cflags=["-O2", "-w"],
+         verbose=False)
+    so = glob.glob(os.path.join(tmp, "ref_voxel_layer*.so"))[0]
+    dst = os.path.join(REF_OUT, os.path.basename(so))
+    shutil.copy(so, dst)
+    shutil.rmtree(tmp, ignore_errors=True)
+    return dst
+
+
+if __name__ == "__main__":
+    print(build_c())
+    try:
+        print(build_ref())
+    except Exception as e:  # the reference build is optional evidence, not a dependency
+        print("reference CPU build unavailable: %s" % e)
+        sys.exit(0)

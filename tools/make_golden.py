@@ -17,6 +17,8 @@ Fixtures
   lss_edge.npz     hand-placed points on cell borders / outside the grid
                    (trunc-toward-zero leak, dropped points, empty batch item)
   quickcumsum.npz  QuickCumsum of mmdet3d/ops/bev_pool/bev_pool.py (pure torch)
+  voxel_small.npz  reference voxel_layer CPU extension (oracle/_ref): dynamic_voxelize,
+                   hard_voxelize x3 configs; dynamic scatter via torch.unique(dim=0)
 Also prints (not stored) the full-size config-1 comparison oracle vs reference.
 """
 import json
@@ -160,6 +162,54 @@ def fullsize_check(vtm):
         json.dump(rep, f, indent=1)
 
 
+def voxel_small():
+    """Reference CPU extension (oracle/_ref, compiled unmodified) on a small cloud with
+    out-of-range points; dynamic scatter through torch.unique(dim=0) = at::unique_dim."""
+    from oracle import voxel_oracle
+    ref = voxel_oracle.load_reference_voxel_layer()
+    assert ref is not None, "run python oracle/build_oracle.py first"
+    rng = np.random.RandomState(7)
+    n = 3000
+    pts = np.zeros((n, 5), dtype=np.float32)
+    pts[:, 0] = rng.uniform(-12.0, 12.0, n)
+    pts[:, 1] = rng.uniform(-9.0, 9.0, n)
+    pts[:, 2] = rng.uniform(-4.0, 2.0, n)
+    pts[:, 3:] = rng.random_sample((n, 2))
+    pts[:40, 0] = 10.0   # exactly on the upper x border -> out
+    pts[40:80, 1] = -8.0  # exactly on the lower y border -> in
+    pts[80:200, :3] = pts[200:320, :3]  # duplicates -> multi-point voxels
+    vs, pcr = [0.5, 0.5, 1.0], [-10.0, -8.0, -3.0, 10.0, 8.0, 1.0]
+    tp = torch.from_numpy(pts)
+    coors = torch.zeros(n, 3, dtype=torch.int32)
+    ref.dynamic_voxelize(tp, coors, vs, pcr, 3)
+    out = dict(points=pts, voxel_size=np.array(vs, np.float32), coors_range=np.array(pcr, np.float32),
+               dyn_coors=coors.numpy())
+    for tag, (mp, mv) in dict(a=(5, 4000), b=(2, 300), c=(1, 100000 // 50)).items():
+        v = torch.zeros(mv, mp, 5)
+        c = torch.zeros(mv, 3, dtype=torch.int32)
+        k = torch.zeros(mv, dtype=torch.int32)
+        m = ref.hard_voxelize(tp, v, c, k, vs, pcr, mp, mv, 3, True)
+        out["hard_%s_cfg" % tag] = np.array([mp, mv, m])
+        out["hard_%s_voxels" % tag] = v[:m].numpy()
+        out["hard_%s_coors" % tag] = c[:m].numpy()
+        out["hard_%s_num" % tag] = k[:m].numpy()
+    # dynamic scatter: scatter_points_cuda.cu:202-214 host sequence, executed with torch CPU
+    clean = coors.masked_fill(coors.lt(0).any(-1, True), -1)
+    oc, inv, cnt = torch.unique(clean, dim=0, sorted=True, return_inverse=True, return_counts=True)
+    if oc[0, 0] < 0:
+        oc, cnt, inv = oc[1:], cnt[1:], inv - 1
+    feats = torch.from_numpy(rng.randn(n, 7).astype(np.float32))
+    valid = inv >= 0
+    m = oc.shape[0]
+    ix = inv[valid][:, None].expand(-1, 7)
+    mx = torch.full((m, 7), -float("inf")).scatter_reduce(0, ix, feats[valid], "amax")
+    sm = torch.zeros(m, 7, dtype=torch.float64).index_add_(0, inv[valid], feats[valid].double())
+    out.update(sc_feats=feats.numpy(), sc_out_coors=oc.numpy(), sc_map=inv.to(torch.int32).numpy(),
+               sc_count=cnt.to(torch.int32).numpy(), sc_max=mx.numpy(), sc_sum64=sm.numpy())
+    np.savez_compressed(os.path.join(GOLDEN, "voxel_small.npz"), **out)
+    print("voxel_small: invalid points", int((coors[:, 0] < 0).sum()), "unique voxels", m)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     vtm = ref_import.view_transformer_mine()
@@ -168,3 +218,4 @@ if __name__ == "__main__":
     lss_edge(vtm)
     quickcumsum(bp)
     fullsize_check(vtm)
+    voxel_small()
