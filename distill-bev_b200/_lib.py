@@ -18,6 +18,21 @@ _ptr = ctypes.c_void_p
 _fptr = ctypes.POINTER(ctypes.c_float)
 _iptr = ctypes.POINTER(ctypes.c_int)
 
+class FgdConfig(ctypes.Structure):
+    """Mirror of struct dbev_fgd_config (include/distill_bev_b200.h)."""
+    _fields_ = [("B", ctypes.c_int), ("C", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int),
+                ("spatial_t", ctypes.c_float), ("channel_t", ctypes.c_float),
+                ("spatial_student_ratio", ctypes.c_float),
+                ("w_fg", ctypes.c_float), ("w_bg", ctypes.c_float), ("w_fp", ctypes.c_float),
+                ("w_channel", ctypes.c_float), ("w_spatial", ctypes.c_float),
+                ("spatial_att", ctypes.c_int), ("spatial_mask", ctypes.c_int),
+                ("channel_mask", ctypes.c_int), ("scale_mask", ctypes.c_int),
+                ("use_fp", ctypes.c_int)]
+
+
+_cfgp = ctypes.POINTER(FgdConfig)
+_c_float = ctypes.c_float
+
 # name -> (restype, argtypes); must list every symbol include/distill_bev_b200.h declares
 SIGNATURES = {
     "dbev_abi_version": (_c_int, []),
@@ -49,6 +64,17 @@ SIGNATURES = {
                                               _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_size, _ptr]),
     "dbev_dynamic_scatter_backward": (_c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _c_ll, _c_ll, _c_int,
                                                _c_int, _ptr, _ptr, _ptr]),
+    "dbev_fgd_foreground_mask": (_c_int, [_ptr, _c_int, _ptr, _c_int, _c_int, _c_int, _c_int, _c_float,
+                                          _c_float, _c_float, _c_float, _c_float, _c_int, _c_int,
+                                          _ptr, _ptr, _ptr, _ptr]),
+    "dbev_heatmap_class_max": (_c_int, [_ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr]),
+    "dbev_fgd_fp_mask": (_c_int, [_ptr, _c_int, _ptr, _c_int, _ptr, _c_int, _ptr, _c_int, _c_int,
+                                  _c_int, _c_float, _c_float, _ptr, _ptr, _ptr]),
+    "dbev_fgd_state_bytes": (_c_size, [_cfgp]),
+    "dbev_fgd_loss_forward": (_c_int, [_cfgp, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                       _ptr, _c_size, _ptr, _ptr]),
+    "dbev_fgd_loss_backward": (_c_int, [_cfgp, _ptr, _ptr, _ptr, _ptr, _ptr, _c_size, _ptr, _ptr,
+                                        _ptr, _ptr, _ptr]),
     "dbev_sort_workspace_bytes": (_c_size, [_c_ll]),
     "dbev_sort_keys_iota": (_c_int, [_ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _c_size, _ptr]),
     "dbev_scan_workspace_bytes": (_c_size, [_c_ll]),

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "bev_pool.cuh"
+#include "distill_loss.cuh"
 #include "sort.cuh"
 #include "voxelize.cuh"
 
@@ -137,6 +138,53 @@ int dbev_dynamic_scatter_backward(const float* grad_reduced, const float* feats,
   return dynamic_scatter_backward(grad_reduced, feats, reduced, coors_map, reduce_count, n, m,
                                   nfeat, reduce_type, grad_feats, reduce_from_ws,
                                   (cudaStream_t)stream);
+}
+
+int dbev_fgd_foreground_mask(const float* boxes, int box_dim, const int* box_offsets,
+                             int max_boxes_per_sample, int batch, int H, int W, float voxel_x,
+                             float voxel_y, float out_size_factor, float pc_min_x, float pc_min_y,
+                             int cell_center, int transpose_mask, float* fg, float* fg_scale,
+                             int* fg_count, void* stream) {
+  return fgd_foreground_mask(boxes, box_dim, box_offsets, max_boxes_per_sample, batch, H, W,
+                             voxel_x, voxel_y, out_size_factor, pc_min_x, pc_min_y, cell_center,
+                             transpose_mask, fg, fg_scale, fg_count, (cudaStream_t)stream);
+}
+
+int dbev_heatmap_class_max(const float* heatmaps, int batch, int K, int H, int W,
+                           int apply_clip_sigmoid, float* out, void* stream) {
+  return heatmap_class_max(heatmaps, batch, K, H, W, apply_clip_sigmoid, out, (cudaStream_t)stream);
+}
+
+int dbev_fgd_fp_mask(const float* gt_max, int Sg, const float* teacher_max, int St,
+                     const float* student_max, int Ss, const float* fg, int R, int batch,
+                     int mode, float thres, float gt_thres, float* fp, int* fp_count,
+                     void* stream) {
+  return fgd_fp_mask(gt_max, Sg, teacher_max, St, student_max, Ss, fg, R, batch, mode, thres,
+                     gt_thres, fp, fp_count, (cudaStream_t)stream);
+}
+
+size_t dbev_fgd_state_bytes(const dbev_fgd_config* cfg) {
+  if (!cfg) return 0;
+  return fgd_state_bytes(*cfg);
+}
+
+int dbev_fgd_loss_forward(const dbev_fgd_config* cfg, const float* student, const float* teacher,
+                          const float* fg, const float* fg_scale, const int* fg_count,
+                          const float* fp, const int* fp_count, const float* conv_w,
+                          const float* conv_b, void* state, size_t state_bytes, float* losses,
+                          void* stream) {
+  DBEV_CHECK_ARG(cfg != nullptr, "fgd: null config");
+  return fgd_loss_forward(*cfg, student, teacher, fg, fg_scale, fg_count, fp, fp_count, conv_w,
+                          conv_b, state, state_bytes, losses, (cudaStream_t)stream);
+}
+
+int dbev_fgd_loss_backward(const dbev_fgd_config* cfg, const float* student, const float* teacher,
+                           const float* conv_w, const float* conv_b, void* state,
+                           size_t state_bytes, const float* grad_losses, float* grad_student,
+                           float* grad_conv_w, float* grad_conv_b, void* stream) {
+  DBEV_CHECK_ARG(cfg != nullptr, "fgd: null config");
+  return fgd_loss_backward(*cfg, student, teacher, conv_w, conv_b, state, state_bytes, grad_losses,
+                           grad_student, grad_conv_w, grad_conv_b, (cudaStream_t)stream);
 }
 
 size_t dbev_sort_workspace_bytes(long long n) {

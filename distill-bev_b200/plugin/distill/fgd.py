@@ -1,0 +1,247 @@
+"""DistillBEV feature-distillation loss on the B200 kernels (csrc/distill_loss.cu).
+
+Mirrors the loss part of ``BEVDetDistill`` (mmdet3d/models/detectors/bevdet_distill.py):
+  * ``foreground_scale_mask``  :755-843  (BEVFormer variant bevformer_distill.py:391-482)
+  * ``add_fp_as_fg``           :846-970
+  * ``fgd_distill_loss``       :973-1324 — everything after the adaptation layers
+with the same ``distill_params`` keys and the same loss-dict keys
+(kd_fg_feat_loss, kd_bg_feat_loss, kd_channel_loss, kd_spatial_loss,
+kd_fp_bg_feat_loss). Masks are rasterised on the device (the reference builds
+them with numpy/numba on the host for every sample and distill position).
+"""
+import ctypes
+
+import torch
+
+from ... import _lib
+
+_SCALE = {None: 0, False: 0, "": 0, "combine_gt": 1, "separate_gt": 2, "bg_only": 3}
+_FP_MODE = {"teacher": 0, "student": 1, "teacher_selected_student": 2,
+            "teacher+teacher_selected_student": 3}
+LOSS_KEYS = ("kd_fg_feat_loss", "kd_bg_feat_loss", "kd_fp_bg_feat_loss", "kd_channel_loss",
+             "kd_spatial_loss")
+
+
+def _box_tensor(b):
+    t = getattr(b, "tensor", b)          # LiDARInstance3DBoxes or a plain tensor
+    return torch.as_tensor(t, dtype=torch.float32)
+
+
+def pack_boxes(gt_bboxes_3d, device):
+    """list of per-sample boxes [M_b, >=7] -> (boxes [sum M, D] cuda, offsets [B+1] cuda int32, max M)."""
+    ts = [_box_tensor(b).reshape(-1, _box_tensor(b).shape[-1] if _box_tensor(b).numel() else 9)
+          for b in gt_bboxes_3d]
+    dim = max([t.shape[1] for t in ts if t.shape[0] > 0] + [7])
+    ts = [t if t.shape[0] > 0 else t.new_zeros((0, dim)) for t in ts]
+    counts = [t.shape[0] for t in ts]
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    boxes = torch.cat(ts, 0) if sum(counts) else torch.zeros((1, dim))
+    return (boxes.contiguous().to(device, non_blocking=True),
+            torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True), max(counts + [0]))
+
+
+def foreground_scale_mask(student_H, student_W, gt_bboxes_3d, grid_size, point_cloud_range,
+                          voxel_size, device, transpose_mask=False, cell_center=False,
+                          float_out_size_factor=False, return_counts=False):
+    """-> foreground_mask, fg_scale_mask, bg_scale_mask, each [B, 1, H, W] fp32 on `device`."""
+    lib = _lib.load()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("foreground_scale_mask: device must be CUDA (no CPU path)")
+    assert grid_size[0] == grid_size[1] and student_W == student_H
+    if float_out_size_factor:
+        osf = float(grid_size[0]) / student_W        # bevformer_distill.py:397
+    else:
+        assert grid_size[0] % student_W == 0
+        osf = float(int(grid_size[0]) // student_W)  # bevdet_distill.py:764
+    B = len(gt_bboxes_3d)
+    boxes, offs, max_m = pack_boxes(gt_bboxes_3d, device)
+    fg = torch.empty((B, 1, student_H, student_W), dtype=torch.float32, device=device)
+    fg_scale = torch.empty_like(fg)
+    fg_count = torch.empty((B,), dtype=torch.int32, device=device)
+    vs = torch.tensor(voxel_size, dtype=torch.float32)
+    pcr = torch.tensor(point_cloud_range, dtype=torch.float32)
+    with torch.cuda.device(device):
+        rc = lib.dbev_fgd_foreground_mask(
+            _lib.ptr(boxes), boxes.shape[1], _lib.ptr(offs), max_m, B, student_H, student_W,
+            float(vs[0]), float(vs[1]), osf, float(pcr[0]), float(pcr[1]), int(bool(cell_center)),
+            int(bool(transpose_mask)), _lib.ptr(fg), _lib.ptr(fg_scale), _lib.ptr(fg_count),
+            _lib.stream_ptr(device))
+    _lib.check(rc, "dbev_fgd_foreground_mask")
+    hw = float(student_H * student_W)
+    bg_scale = (1.0 / (hw - fg_count.to(torch.float32))).view(B, 1, 1, 1).expand_as(fg)
+    if return_counts:
+        return fg, fg_scale, bg_scale, fg_count
+    return fg, fg_scale, bg_scale
+
+
+def heatmap_class_max(heatmaps, apply_clip_sigmoid=False):
+    """[B, K, H, W] (tensor or list of per-task tensors) -> [B, 1, H, W] max over classes."""
+    lib = _lib.load()
+    if isinstance(heatmaps, (list, tuple)):
+        heatmaps = torch.cat(list(heatmaps), dim=1)
+    _lib.require_cuda(heatmaps, "heatmaps", torch.float32)
+    heatmaps = heatmaps.contiguous()
+    B, K, H, W = heatmaps.shape
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=heatmaps.device)
+    with torch.cuda.device(heatmaps.device):
+        rc = lib.dbev_heatmap_class_max(_lib.ptr(heatmaps), B, K, H, W, int(apply_clip_sigmoid),
+                                        _lib.ptr(out), _lib.stream_ptr(heatmaps.device))
+    _lib.check(rc, "dbev_heatmap_class_max")
+    return out
+
+
+def add_fp_as_fg(mode, fg_mask, gt_hm_max, teacher_hm_max, student_hm_max, thres, gt_thres=None,
+                 return_counts=False):
+    """Class-max maps [B,1,S,S] -> fp_mask, fp_scale_mask [B,1,H,W], fp count [B] (float)."""
+    lib = _lib.load()
+    if mode not in _FP_MODE:
+        raise NotImplementedError(mode)
+    if gt_thres is None:
+        gt_thres = thres
+    _lib.require_cuda(fg_mask, "fg_mask", torch.float32)
+    B, _, R, _ = fg_mask.shape
+    g, t = gt_hm_max.contiguous(), teacher_hm_max.contiguous()
+    s = student_hm_max.contiguous() if student_hm_max is not None else None
+    fp = torch.empty_like(fg_mask)
+    cnt = torch.empty((B,), dtype=torch.int32, device=fg_mask.device)
+    with torch.cuda.device(fg_mask.device):
+        rc = lib.dbev_fgd_fp_mask(_lib.ptr(g), g.shape[2], _lib.ptr(t), t.shape[2], _lib.ptr(s),
+                                  s.shape[2] if s is not None else 0, _lib.ptr(fg_mask.contiguous()),
+                                  R, B, _FP_MODE[mode], float(thres), float(gt_thres), _lib.ptr(fp),
+                                  _lib.ptr(cnt), _lib.stream_ptr(fg_mask.device))
+    _lib.check(rc, "dbev_fgd_fp_mask")
+    cntf = cnt.to(torch.float32)
+    scale = torch.where(cntf > 0, 1.0 / cntf.clamp(min=1.0), torch.zeros_like(cntf)).view(B, 1, 1, 1) * fp
+    if return_counts:
+        return fp, scale, cntf, cnt
+    return fp, scale, cntf
+
+
+def make_config(B, C, H, W, distill_params, index=0, use_fp=None, epoch=0):
+    """dbev_fgd_config from the reference's distill_params dict (…r50.py:50-92)."""
+    p = distill_params
+
+    def pick(key):
+        v = p[key]
+        return v[index] if len(v) > 1 else v[0]
+    fp_mode = p.get("fp_as_foreground", "none")
+    if isinstance(fp_mode, (list, tuple)):
+        fp_mode = fp_mode[index] if len(fp_mode) > 1 else fp_mode[0]
+    if use_fp is None:
+        use_fp = fp_mode != "none" and epoch >= p.get("fp_epoch", 0)
+    att = pick("spatial_attentions")
+    if att not in ("teacher", "teacher_student"):
+        raise NotImplementedError(att)
+    if p.get("scale_mask") not in _SCALE:
+        raise NotImplementedError(p.get("scale_mask"))
+    if p.get("background_mask", "logical_not") not in ("logical_not", "1minus"):
+        raise NotImplementedError(p.get("background_mask"))
+    cfg = _lib.FgdConfig(
+        B, C, H, W, float(p["spatial_t"]), float(p["channel_t"]), float(p["spatial_student_ratio"]),
+        float(pick("fg_feat_loss_weights")), float(pick("bg_feat_loss_weights")),
+        float(p.get("fp_weight", 0.0)), float(pick("channel_loss_weights")),
+        float(pick("spatial_loss_weights")), 0 if att == "teacher" else 1,
+        int(bool(p["spatial_mask"])), int(bool(p["channel_mask"])), _SCALE[p.get("scale_mask")],
+        int(bool(use_fp)))
+    return cfg, fp_mode
+
+
+class _FGDLoss(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, student, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count):
+        lib = _lib.load()
+        _lib.require_cuda(student, "student_feat", torch.float32)
+        _lib.require_cuda(teacher, "teacher_feat", torch.float32)
+        if student.shape != teacher.shape:
+            raise RuntimeError("student %s and teacher %s must have the same shape after adaptation"
+                               % (tuple(student.shape), tuple(teacher.shape)))
+        student, teacher = student.contiguous(), teacher.contiguous()
+        dev = student.device
+        if conv_w is None:
+            conv_w = torch.zeros(9, device=dev)
+            conv_b = torch.zeros(1, device=dev)
+        cw = conv_w.detach().reshape(-1).contiguous().float()
+        cb = conv_b.detach().reshape(-1).contiguous().float()
+        nbytes = lib.dbev_fgd_state_bytes(ctypes.byref(cfg))
+        state = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        losses = torch.empty(5, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.dbev_fgd_loss_forward(
+                ctypes.byref(cfg), _lib.ptr(student), _lib.ptr(teacher), _lib.ptr(fg.contiguous()),
+                _lib.ptr(fg_scale.contiguous()), _lib.ptr(fg_count), _lib.ptr(fp), _lib.ptr(fp_count),
+                _lib.ptr(cw), _lib.ptr(cb), _lib.ptr(state), nbytes, _lib.ptr(losses),
+                _lib.stream_ptr(dev))
+        _lib.check(rc, "dbev_fgd_loss_forward")
+        ctx.cfg = cfg
+        ctx.state = state
+        ctx.conv_shape = (conv_w.shape, conv_b.shape)
+        ctx.save_for_backward(student, teacher, cw, cb)
+        return losses
+
+    @staticmethod
+    def backward(ctx, grad_losses):
+        lib = _lib.load()
+        student, teacher, cw, cb = ctx.saved_tensors
+        dev = student.device
+        gl = grad_losses.contiguous().float()
+        gs = torch.empty_like(student)
+        gw = torch.empty(9, dtype=torch.float32, device=dev)
+        gb = torch.empty(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.dbev_fgd_loss_backward(
+                ctypes.byref(ctx.cfg), _lib.ptr(student), _lib.ptr(teacher), _lib.ptr(cw), _lib.ptr(cb),
+                _lib.ptr(ctx.state), ctx.state.numel() * 4, _lib.ptr(gl), _lib.ptr(gs), _lib.ptr(gw),
+                _lib.ptr(gb), _lib.stream_ptr(dev))
+        _lib.check(rc, "dbev_fgd_loss_backward")
+        return (gs, None, gw.view(ctx.conv_shape[0]), gb.view(ctx.conv_shape[1]),
+                None, None, None, None, None, None)
+
+
+def fgd_loss_terms(student_feat, teacher_feat, cfg, fg, fg_scale, fg_count, fp=None, fp_count=None,
+                   conv_weight=None, conv_bias=None):
+    """losses[5] tensor (order LOSS_KEYS), differentiable w.r.t. student_feat / conv."""
+    return _FGDLoss.apply(student_feat, teacher_feat, conv_weight, conv_bias, cfg, fg, fg_scale,
+                          fg_count, fp, fp_count)
+
+
+def fgd_distill_loss(teacher_feat, student_feat, gt_bboxes_3d, distill_params, train_cfg,
+                     spatial_adaptation=None, heatmaps=None, teacher_heatmaps=None,
+                     student_heatmaps=None, index=0, epoch=0):
+    """Drop-in for the body of ``BEVDetDistill.fgd_distill_loss`` after the adaptation layers
+    (:1006-1293): returns the same loss dict. ``train_cfg`` = pts_bbox_head.train_cfg
+    (grid_size, point_cloud_range, voxel_size); ``spatial_adaptation`` = the
+    ``spatial_wise_adaptations[index]`` Conv2d(1,1,3,padding=1); ``heatmaps`` /
+    ``teacher_heatmaps`` (raw logits) / ``student_heatmaps`` (already sigmoid) are [B,K,h,w]
+    tensors or per-task lists, needed only when fp_as_foreground is active."""
+    B, C, H, W = student_feat.shape
+    cfg, fp_mode = make_config(B, C, H, W, distill_params, index, epoch=epoch)
+    if distill_params.get("foreground_mask", "gt") != "gt":
+        raise NotImplementedError("foreground_mask=%r" % distill_params.get("foreground_mask"))
+    fg, fg_scale, _, fg_count = foreground_scale_mask(
+        H, W, gt_bboxes_3d, train_cfg["grid_size"], train_cfg["point_cloud_range"],
+        train_cfg["voxel_size"], student_feat.device,
+        transpose_mask=distill_params.get("transpose_mask", False), return_counts=True)
+    fp = fp_count = None
+    if cfg.use_fp:
+        if distill_params.get("fp_scale_mode", "average") != "average":
+            raise NotImplementedError("fp_scale_mode=%r" % distill_params.get("fp_scale_mode"))
+        g = heatmap_class_max(heatmaps)
+        t = heatmap_class_max(teacher_heatmaps, apply_clip_sigmoid=True)
+        s = heatmap_class_max(student_heatmaps) if student_heatmaps is not None else None
+        fp, _, _, fp_count = add_fp_as_fg(fp_mode, fg, g, t, s, distill_params["output_threshold"],
+                                          distill_params.get("groundtruth_threshold"), return_counts=True)
+    cw = spatial_adaptation.weight if spatial_adaptation is not None else None
+    cb = spatial_adaptation.bias if spatial_adaptation is not None else None
+    losses = fgd_loss_terms(student_feat, teacher_feat, cfg, fg, fg_scale, fg_count, fp, fp_count, cw, cb)
+    out = {"kd_fg_feat_loss": losses[0], "kd_bg_feat_loss": losses[1]}
+    if cfg.channel_mask:
+        out["kd_channel_loss"] = losses[3]
+    if cfg.spatial_mask:
+        out["kd_spatial_loss"] = losses[4]
+    if cfg.use_fp:
+        out["kd_fp_bg_feat_loss"] = losses[2]
+    return out

@@ -197,6 +197,79 @@ int dbev_dynamic_scatter_backward(const float* grad_reduced, const float* feats,
                                   void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * Cross-modal feature distillation loss (FGD-style), BEVDetDistill
+ * (mmdet3d/models/detectors/bevdet_distill.py). The reference has no native
+ * interface for this path: it is ~20 torch kernels plus numpy/numba on the
+ * host. These entry points are what a maintainer binds instead of the bodies
+ * of foreground_scale_mask (:755-843), add_fp_as_fg (:846-970) and the
+ * attention / mask / loss part of fgd_distill_loss (:1084-1293).
+ * ------------------------------------------------------------------------ */
+
+/* foreground_scale_mask (:755-843; BEVFormer variant bevformer_distill.py:391-482).
+ * boxes[total, box_dim] fp32 rows (x, y, z, x_size, y_size, z_size, yaw, ...) of all
+ * samples back to back, box_offsets[batch + 1] (device int). The sample point of
+ * BEV cell (i, j) is (i*voxel_x*osf + pc_min_x, j*voxel_y*osf + pc_min_y) in fp32
+ * (+ half a cell when cell_center != 0); osf = grid_size // W (BEVDet) or
+ * grid_size / W (BEVFormer). Outputs fg[batch,H,W] in {0,1}, fg_scale[batch,H,W] =
+ * sqrt(cell_area / (w*l)) of the first containing box, fg_count[batch] (int). The
+ * background scale 1 / (H*W - fg_count) is applied inside dbev_fgd_loss_forward. */
+int dbev_fgd_foreground_mask(const float* boxes, int box_dim, const int* box_offsets,
+                             int max_boxes_per_sample, int batch, int H, int W, float voxel_x,
+                             float voxel_y, float out_size_factor, float pc_min_x, float pc_min_y,
+                             int cell_center, int transpose_mask, float* fg, float* fg_scale,
+                             int* fg_count, void* stream);
+
+/* max over the class axis of heatmaps[batch, K, H, W]; apply_clip_sigmoid != 0 applies
+ * clamp(sigmoid(x), 1e-4, 1 - 1e-4) first (models/utils/clip_sigmoid.py:17; :855-858). */
+int dbev_heatmap_class_max(const float* heatmaps, int batch, int K, int H, int W,
+                           int apply_clip_sigmoid, float* out, void* stream);
+
+/* add_fp_as_fg (:846-925) on class-max maps: gt_max[batch,Sg,Sg], teacher_max[batch,St,St],
+ * student_max[batch,Ss,Ss] (may be NULL for mode 0), fg[batch,R,R]. mode: 0 teacher,
+ * 1 student, 2 teacher_selected_student, 3 teacher+teacher_selected_student (:893-903).
+ * Resampling between resolutions = max-pool / repeat as in the reference. Outputs
+ * fp[batch,R,R] in {0,1} (already cleared where fg != 0) and fp_count[batch] (int);
+ * fp_scale_mode 'average' (1 / fp_count) is applied inside dbev_fgd_loss_forward. */
+int dbev_fgd_fp_mask(const float* gt_max, int Sg, const float* teacher_max, int St,
+                     const float* student_max, int Ss, const float* fg, int R, int batch,
+                     int mode, float thres, float gt_thres, float* fp, int* fp_count,
+                     void* stream);
+
+typedef struct dbev_fgd_config {
+  int B, C, H, W;
+  float spatial_t;             /* distill_params['spatial_t'] */
+  float channel_t;             /* distill_params['channel_t'] */
+  float spatial_student_ratio; /* distill_params['spatial_student_ratio'] */
+  float w_fg, w_bg, w_fp, w_channel, w_spatial; /* loss weights (fp_weight for w_fp) */
+  int spatial_att;     /* 0 'teacher', 1 'teacher_student' */
+  int spatial_mask;    /* distill_params['spatial_mask'] */
+  int channel_mask;    /* distill_params['channel_mask'] */
+  int scale_mask;      /* 0 none, 1 'combine_gt', 2 'separate_gt', 3 'bg_only' */
+  int use_fp;          /* fp_as_foreground != 'none' and epoch >= fp_epoch */
+} dbev_fgd_config;
+
+/* bytes of the opaque state that links forward and backward */
+size_t dbev_fgd_state_bytes(const dbev_fgd_config* cfg);
+
+/* Losses of fgd_distill_loss (:1252-1293) for already-adapted student[B,C,H,W] and
+ * teacher[B,C,H,W] (NCHW fp32, H*W % 4 == 0): losses[5] = kd_fg_feat_loss,
+ * kd_bg_feat_loss, kd_fp_bg_feat_loss, kd_channel_loss, kd_spatial_loss (terms the
+ * configuration disables are 0). conv_w[9] / conv_b[1]: spatial_wise_adaptations
+ * Conv2d(1,1,3,padding=1) (:348-351), device pointers. 3 tensor reads in total. */
+int dbev_fgd_loss_forward(const dbev_fgd_config* cfg, const float* student, const float* teacher,
+                          const float* fg, const float* fg_scale, const int* fg_count,
+                          const float* fp, const int* fp_count, const float* conv_w,
+                          const float* conv_b, void* state, size_t state_bytes, float* losses,
+                          void* stream);
+
+/* Gradient of sum_k grad_losses[k] * losses[k] w.r.t. student (attention masks and the
+ * teacher are detached as in the reference, :1100,1104,1108), conv_w[9] and conv_b[1]. */
+int dbev_fgd_loss_backward(const dbev_fgd_config* cfg, const float* student, const float* teacher,
+                           const float* conv_w, const float* conv_b, void* state,
+                           size_t state_bytes, const float* grad_losses, float* grad_student,
+                           float* grad_conv_w, float* grad_conv_b, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Primitives exposed for testing (stable LSD radix sort, exclusive scan).
  * They stand in for argsort / at::unique_dim / cumsum on the reference path.
  * ------------------------------------------------------------------------ */

@@ -1,0 +1,157 @@
+"""GPU parity: distillation-loss CUDA path (through the C-ABI shims) vs the committed
+reference fixtures (unmodified reference method bodies) and the numpy oracle.
+
+Masks are exact (0/1 and counts); fg_scale is fp32-exact; losses within 1e-4 relative
+(north_star bound 1e-3; the reference itself sums 50k+ fp32 terms); gradients within 1e-4
+relative to the largest gradient entry.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import distill_bev_b200  # noqa: F401
+from distill_bev_b200 import synthetic
+from distill_bev_b200.plugin.distill import fgd
+from oracle import fgd_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _boxes(g):
+    out, o = [], 0
+    for n in g["n_boxes"]:
+        out.append(torch.from_numpy(g["boxes"][o:o + n]))
+        o += n
+    return out
+
+
+@pytest.fixture(scope="module")
+def g(golden_dir):
+    return np.load(os.path.join(golden_dir, "fgd_small.npz"))
+
+
+def _train_cfg(g):
+    return dict(grid_size=g["grid"].tolist(), point_cloud_range=g["pc_range"].tolist(),
+                voxel_size=g["voxel"].tolist())
+
+
+def test_foreground_mask_golden(cuda, g):
+    H = g["teacher"].shape[2]
+    tc = _train_cfg(g)
+    fg, fgs, bgs, cnt = fgd.foreground_scale_mask(H, H, _boxes(g), tc["grid_size"], tc["point_cloud_range"],
+                                                  tc["voxel_size"], cuda, return_counts=True)
+    np.testing.assert_array_equal(fg.cpu().numpy(), g["recipe_fg"])
+    np.testing.assert_array_equal(fgs.cpu().numpy(), g["recipe_fg_scale"])
+    np.testing.assert_allclose(bgs.cpu().numpy(), g["recipe_bg_scale"], rtol=1e-6)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), g["recipe_fg"].sum(axis=(1, 2, 3)).astype(np.int32))
+
+
+@pytest.mark.parametrize("name", ["recipe", "separate"])
+def test_fp_mask_golden(cuda, g, name):
+    p = json.loads(str(g[name + "_params"]))
+    gm = fgd.heatmap_class_max(_t(g["gt_hm"], cuda))
+    tm = fgd.heatmap_class_max(_t(g["teacher_logit"], cuda), apply_clip_sigmoid=True)
+    sm = fgd.heatmap_class_max(_t(g["student_prob"], cuda))
+    fp, fps, cnt = fgd.add_fp_as_fg(p["fp_as_foreground"][0], _t(g[name + "_fg"], cuda), gm, tm, sm,
+                                    p["output_threshold"], p["groundtruth_threshold"])
+    np.testing.assert_array_equal(fp.cpu().numpy(), g[name + "_fp"])
+    np.testing.assert_allclose(fps.cpu().numpy(), g[name + "_fp_scale"], rtol=1e-6)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), g[name + "_fp_count"])
+
+
+@pytest.mark.parametrize("name", ["recipe", "baseconfig", "separate"])
+def test_fgd_loss_and_grads_golden(cuda, g, name):
+    p = json.loads(str(g[name + "_params"]))
+    conv = torch.nn.Conv2d(1, 1, 3, padding=1).to(cuda)
+    with torch.no_grad():
+        conv.weight.copy_(_t(g[name + "_conv_w"], cuda).view(1, 1, 3, 3))
+        conv.bias.copy_(_t(g[name + "_conv_b"], cuda))
+    student = _t(g["student"], cuda).requires_grad_(True)
+    losses = fgd.fgd_distill_loss(_t(g["teacher"], cuda), student, _boxes(g), p, _train_cfg(g),
+                                  spatial_adaptation=conv, heatmaps=_t(g["gt_hm"], cuda),
+                                  teacher_heatmaps=_t(g["teacher_logit"], cuda),
+                                  student_heatmaps=_t(g["student_prob"], cuda), index=0, epoch=5)
+    keys = json.loads(str(g[name + "_loss_keys"]))
+    assert sorted(losses) == keys                       # same loss-dict keys as the reference
+    for k, v in zip(keys, g[name + "_loss_vals"]):
+        assert abs(float(losses[k]) - v) <= 1e-4 * max(abs(v), 1e-3), (k, float(losses[k]), v)
+    sum(losses.values()).backward()
+    gs = g[name + "_grad_student"]
+    np.testing.assert_allclose(student.grad.cpu().numpy(), gs, rtol=1e-4, atol=1e-4 * np.abs(gs).max())
+    np.testing.assert_allclose(conv.weight.grad.cpu().numpy().reshape(3, 3), g[name + "_grad_conv_w"],
+                               rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(conv.bias.grad.cpu().numpy(), g[name + "_grad_conv_b"], rtol=1e-3, atol=1e-5)
+
+
+def _recipe_params():
+    return dict(spatial_t=0.5, spatial_student_ratio=1.0, channel_t=0.5, fg_feat_loss_weights=[6e-3],
+                bg_feat_loss_weights=[4e-2], channel_loss_weights=[0.25], spatial_loss_weights=[2.5e-3],
+                spatial_attentions=["teacher_student"], transpose_mask=False, foreground_mask="gt",
+                background_mask="logical_not", scale_mask="combine_gt", spatial_mask=True,
+                channel_mask=False, output_threshold=0.1, groundtruth_threshold=None,
+                fp_as_foreground=["teacher"], fp_weight=6e-2, fp_epoch=0, fp_scale_mode="average")
+
+
+@pytest.mark.parametrize("B,C,H", [(2, 384, 128), (1, 256, 200), (2, 64, 64)])
+def test_fgd_full_size_vs_oracle(cuda, B, C, H):
+    """configs[1] head position (384 ch, 128x128) and the BEVFormer 200x200x256 shape."""
+    rng = np.random.RandomState(B * 7 + C)
+    teacher = np.maximum(rng.randn(B, C, H, H), 0).astype(np.float32)
+    student = np.maximum(rng.randn(B, C, H, H), 0).astype(np.float32)
+    boxes = [b for b, _ in synthetic.make_gt_boxes(B, seed=3)]
+    grid = [H * 8, H * 8, 40]
+    vox = 102.4 / (H * 8)
+    tc = dict(grid_size=grid, point_cloud_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], voxel_size=[vox, vox, 0.2])
+    p = _recipe_params()
+    K = 10
+    gt_hm = (rng.random_sample((B, K, H, H)) ** 12).astype(np.float32)
+    t_logit = (rng.randn(B, K, H, H) * 1.5 - 3.0).astype(np.float32)
+    conv = torch.nn.Conv2d(1, 1, 3, padding=1).to(cuda)
+    st = _t(student, cuda).requires_grad_(True)
+    losses = fgd.fgd_distill_loss(_t(teacher, cuda), st, [torch.from_numpy(b) for b in boxes], p, tc,
+                                  spatial_adaptation=conv, heatmaps=_t(gt_hm, cuda),
+                                  teacher_heatmaps=_t(t_logit, cuda), student_heatmaps=None, epoch=1)
+    sum(losses.values()).backward()
+    # oracle
+    fg, fgs, bgs = fo.foreground_scale_mask(H, H, boxes, grid, tc["point_cloud_range"], tc["voxel_size"])
+    sig = np.clip(1 / (1 + np.exp(-t_logit.astype(np.float64))), 1e-4, 1 - 1e-4).astype(np.float32)
+    fp, fps, cnt = fo.add_fp_as_fg("teacher", fg, gt_hm, sig, np.zeros_like(sig), 0.1)
+    op = dict(spatial_t=0.5, spatial_student_ratio=1.0, channel_t=0.5, w_fg=6e-3, w_bg=4e-2, w_channel=0.25,
+              w_spatial=2.5e-3, w_fp=6e-2, spatial_att="teacher_student", spatial_mask=True,
+              channel_mask=False, scale_mask="combine_gt")
+    ref = fo.fgd_loss(teacher, student, fg, fgs, bgs, op, conv_w=conv.weight.detach().cpu().numpy().reshape(3, 3),
+                      conv_b=float(conv.bias), fp=fp, fp_scale=fps, fp_count=cnt, want_grad=True)
+    for k in losses:
+        assert abs(float(losses[k]) - ref[k]) <= 1e-4 * abs(ref[k]) + 1e-9, (k, float(losses[k]), ref[k])
+    gref = ref["grad_student"]
+    np.testing.assert_allclose(st.grad.cpu().numpy(), gref, rtol=1e-3, atol=1e-4 * np.abs(gref).max())
+
+
+def test_bevformer_mask_variant_and_transpose(cuda):
+    boxes = [b for b, _ in synthetic.make_gt_boxes(2, seed=8)]
+    pcr, vs, grid = [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], [0.2, 0.2, 8.0], [512, 512, 1]
+    for kw, okw in ((dict(cell_center=True, float_out_size_factor=True), dict(center=True, float_osf=True)),
+                    (dict(transpose_mask=True), dict(transpose_mask=True))):
+        H = 200 if "cell_center" in kw else 128
+        fg, fgs, _ = fgd.foreground_scale_mask(H, H, [torch.from_numpy(b) for b in boxes], grid, pcr, vs, cuda, **kw)
+        ofg, ofgs, _ = fo.foreground_scale_mask(H, H, boxes, grid, pcr, vs, **okw)
+        assert (fg.cpu().numpy() != ofg).sum() <= 2      # fp32 vs fp64 edge test, see oracle header
+        same = fg.cpu().numpy() == ofg
+        np.testing.assert_array_equal(fgs.cpu().numpy()[same], ofgs[same])
+
+
+def test_empty_boxes_and_cpu_rejection(cuda):
+    fg, fgs, bgs = fgd.foreground_scale_mask(64, 64, [torch.zeros(0, 9), torch.zeros(0, 9)], [512, 512, 1],
+                                             [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], [0.2, 0.2, 8.0], cuda)
+    assert float(fg.sum()) == 0 and float(fgs.sum()) == 0
+    assert abs(float(bgs[0, 0, 0, 0]) - 1.0 / 4096) < 1e-12
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fgd.foreground_scale_mask(64, 64, [torch.zeros(0, 9)], [512, 512, 1], [-51.2] * 2 + [-5, 51.2, 51.2, 3],
+                                  [0.2, 0.2, 8.0], "cpu")

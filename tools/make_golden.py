@@ -19,6 +19,9 @@ Fixtures
   quickcumsum.npz  QuickCumsum of mmdet3d/ops/bev_pool/bev_pool.py (pure torch)
   voxel_small.npz  reference voxel_layer CPU extension (oracle/_ref): dynamic_voxelize,
                    hard_voxelize x3 configs; dynamic scatter via torch.unique(dim=0)
+  fgd_small.npz    BEVDetDistill.foreground_scale_mask / add_fp_as_fg / fgd_distill_loss /
+                   affinity_distill_loss method bodies (ast-extracted, unmodified): masks,
+                   losses, autograd gradients for three option sets
 Also prints (not stored) the full-size config-1 comparison oracle vs reference.
 """
 import json
@@ -210,6 +213,117 @@ def voxel_small():
     print("voxel_small: invalid points", int((coors[:, 0] < 0).sum()), "unique voxels", m)
 
 
+def _fgd_self(methods, AttrDict, params, C, grid, pc_range, voxel):
+    """Fake `self` carrying exactly what the reference methods read."""
+    class Head(object):
+        train_cfg = dict(grid_size=grid, point_cloud_range=pc_range, voxel_size=voxel)
+
+    class Fake(object):
+        pass
+    for name, fn in methods.items():
+        setattr(Fake, name, fn)
+    me = Fake()
+    me.distill_params = AttrDict(params)
+    me.pts_bbox_head = Head()
+    me._epoch = 5
+    me.count = 0
+    me.teacher_adaptations = [torch.nn.Identity()]
+    me.channel_wise_adaptations = [torch.nn.Identity()]
+    torch.manual_seed(11)
+    me.spatial_wise_adaptations = [torch.nn.Conv2d(1, 1, kernel_size=3, stride=1, padding=1)]
+    return me
+
+
+class _Boxes(object):   # LiDARInstance3DBoxes stand-in: the methods only read .tensor
+    def __init__(self, t):
+        self.tensor = t
+
+
+def fgd_golden():
+    methods, AttrDict = ref_import.load_fgd_methods()
+    B, C, H = 3, 12, 32
+    grid, pc_range, voxel = [256, 256, 40], [-12.8, -12.8, -5.0, 12.8, 12.8, 3.0], [0.1, 0.1, 0.2]
+    rng = np.random.RandomState(21)
+    boxes = []
+    for b, m in enumerate([6, 0, 11]):
+        bx = np.zeros((m, 9), dtype=np.float32)
+        bx[:, 0:2] = rng.uniform(-11, 11, (m, 2))
+        bx[:, 2] = rng.uniform(-2, 0, m)
+        bx[:, 3:5] = rng.uniform(0.6, 4.5, (m, 2))
+        bx[:, 5] = rng.uniform(1, 3, m)
+        bx[:, 6] = rng.uniform(-3.14, 3.14, m)
+        boxes.append(bx)
+    g = torch.Generator().manual_seed(4)
+    teacher = torch.relu(torch.randn(B, C, H, H, generator=g))
+    student = torch.relu(torch.randn(B, C, H, H, generator=g))
+    canvas = torch.rand(B, 1, H * 4, H * 4, generator=g)
+    # heatmaps: 2 tasks x (1, 2 classes); gt sparse gaussians, teacher logits, student probs
+    gt_hm = [torch.rand(B, k, H, H, generator=g) ** 8 for k in (1, 2)]
+    t_logit = [torch.randn(B, k, H, H, generator=g) * 1.5 - 2.0 for k in (1, 2)]
+    s_prob = [torch.rand(B, k, H, H, generator=g) * 0.3 for k in (1, 2)]
+    base = dict(spatial_t=0.5, spatial_student_ratio=1.0, channel_t=0.5,
+                fg_feat_loss_weights=[6e-3], bg_feat_loss_weights=[4e-2], channel_loss_weights=[0.25],
+                spatial_loss_weights=[2.5e-3], spatial_attentions=["teacher_student"],
+                feat_criterion=dict(type="MSELoss", reduction="none"),
+                spatial_criterion=dict(type="L1Loss", reduction="none"),
+                channel_criterion=dict(type="L1Loss", reduction="none"),
+                transpose_mask=False, foreground_mask="gt", background_mask="logical_not",
+                scale_mask="combine_gt", spatial_mask=True, channel_mask=False,
+                student_feat_pos=["head"], teacher_feat_pos=["head"], affinity_mode=["none"],
+                non_empty_weight=0, output_threshold=0.1, groundtruth_threshold=None,
+                fp_as_foreground=["teacher"], fp_weight=6e-2, fp_epoch=0, fp_scale_mode="average",
+                context_length=0, context_weight=0)
+    variants = dict(
+        recipe=dict(),                                                 # scripts/teacher_to_bevdepth4d recipe
+        baseconfig=dict(spatial_attentions=["teacher"], channel_mask=True,
+                        fp_as_foreground=["none"], fg_feat_loss_weights=[1.5e-3]),  # shipped .py config
+        separate=dict(scale_mask="separate_gt", channel_mask=True, fp_as_foreground=["student"]),
+    )
+    out = dict(teacher=teacher.numpy(), student=student.numpy(), grid=np.array(grid),
+               pc_range=np.array(pc_range, np.float32), voxel=np.array(voxel, np.float32),
+               n_boxes=np.array([b.shape[0] for b in boxes]),
+               boxes=np.concatenate(boxes), gt_hm=torch.cat(gt_hm, 1).numpy(),
+               teacher_logit=torch.cat(t_logit, 1).numpy(), student_prob=torch.cat(s_prob, 1).numpy())
+    for name, over in variants.items():
+        params = dict(base)
+        params.update(over)
+        me = _fgd_self(methods, AttrDict, params, C, grid, pc_range, voxel)
+        st = student.clone().requires_grad_(True)
+        fg, fgs, bgs = me.foreground_scale_mask(H, H, [_Boxes(torch.from_numpy(b)) for b in boxes], 0, 0)
+        teacher_preds = [[dict(heatmap=t.clone())] for t in t_logit]   # clip_sigmoid is in-place
+        student_preds = [[dict(heatmap=p.clone())] for p in s_prob]
+        losses = me.fgd_distill_loss(teacher.clone(), st, [_Boxes(torch.from_numpy(b)) for b in boxes],
+                                     None, canvas, [h.clone() for h in gt_hm], teacher_preds,
+                                     student_preds, 0)
+        total = sum(losses.values())
+        total.backward()
+        conv = me.spatial_wise_adaptations[0]
+        out.update({name + "_fg": fg.numpy(), name + "_fg_scale": fgs.numpy(), name + "_bg_scale": bgs.numpy(),
+                    name + "_params": json.dumps(params), name + "_loss_keys": json.dumps(sorted(losses)),
+                    name + "_loss_vals": np.array([float(losses[k]) for k in sorted(losses)], np.float64),
+                    name + "_grad_student": st.grad.numpy(),
+                    name + "_conv_w": conv.weight.detach().numpy().reshape(3, 3),
+                    name + "_conv_b": conv.bias.detach().numpy(),
+                    name + "_grad_conv_w": conv.weight.grad.numpy().reshape(3, 3),
+                    name + "_grad_conv_b": conv.bias.grad.numpy()})
+        if params["fp_as_foreground"][0] != "none":
+            fp, fps, cnt = me.add_fp_as_fg(
+                params["fp_as_foreground"][0], fg, [h.clone() for h in gt_hm],
+                [[dict(heatmap=t.clone())] for t in t_logit], [[dict(heatmap=p.clone())] for p in s_prob])
+            out.update({name + "_fp": fp.numpy(), name + "_fp_scale": fps.numpy(), name + "_fp_count": cnt.numpy()})
+        print("fgd", name, {k: float(v) for k, v in losses.items()})
+    # affinity (list branch) on foreground rows of sample 0
+    me = _fgd_self(methods, AttrDict, dict(base, affinity_weights=[0.5], affinity_split=1,
+                                           affinity_criterion=dict(type="SmoothL1Loss")), C, grid, pc_range, voxel)
+    K = 37
+    tf = [torch.randn(K, C, generator=g), torch.randn(5, C, generator=g)]
+    sf = [torch.randn(K, C, generator=g), torch.randn(5, C, generator=g)]
+    aff = me.affinity_distill_loss(tf, sf, 0)
+    out.update(aff_t0=tf[0].numpy(), aff_t1=tf[1].numpy(), aff_s0=sf[0].numpy(), aff_s1=sf[1].numpy(),
+               aff_loss=np.float64(float(aff["kd_affinity_loss"])))
+    np.savez_compressed(os.path.join(GOLDEN, "fgd_small.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     vtm = ref_import.view_transformer_mine()
@@ -219,3 +333,4 @@ if __name__ == "__main__":
     quickcumsum(bp)
     fullsize_check(vtm)
     voxel_small()
+    fgd_golden()

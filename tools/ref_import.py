@@ -118,3 +118,68 @@ def view_transformer_mine():
 
 def bev_pool_py():
     return load_ref_module("mmdet3d.ops.bev_pool.bev_pool", "mmdet3d/ops/bev_pool/bev_pool.py")
+
+
+# --------------------------------------------------------------------------
+# DistillBEV loss methods: the file mmdet3d/models/detectors/bevdet_distill.py
+# cannot be imported (mmcv, mmdet, cv2, sibling detectors ...), so the
+# UNMODIFIED source of the methods we need is cut out of the class with `ast`
+# and compiled in a namespace holding the real reference helpers
+# (box_np_ops, LiDARPoints, clip_sigmoid) plus a stand-in for mmdet's
+# build_loss (third-party mmdet==2.24.0: MSELoss / L1Loss / SmoothL1Loss with
+# reduction='none' are loss_weight * F.{mse,l1,smooth_l1}_loss(..., 'none');
+# parity unpinned for that dependency).
+# --------------------------------------------------------------------------
+
+class _AttrDict(dict):
+    """mmcv ConfigDict stand-in: dict with attribute access, getattr(default) works."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+
+def _build_loss(cfg):
+    import torch.nn.functional as F
+    cfg = dict(cfg)
+    typ = cfg.pop("type")
+    red = cfg.pop("reduction", "mean")
+    lw = cfg.pop("loss_weight", 1.0)
+    fn = {"MSELoss": F.mse_loss, "L1Loss": F.l1_loss, "SmoothL1Loss": F.smooth_l1_loss}[typ]
+    return lambda pred, target: lw * fn(pred, target, reduction=red)
+
+
+def load_fgd_methods(names=("foreground_scale_mask", "add_fp_as_fg", "fgd_distill_loss",
+                            "affinity_distill_loss")):
+    """dict name -> python function(self, ...) compiled from the reference source."""
+    import ast
+    import copy
+    import functools
+    import numpy as np
+    import torch.nn.functional as F
+    install_stubs()
+    box_np_ops = load_ref_module("ref_box_np_ops", "mmdet3d/core/bbox/box_np_ops.py")
+    _pkg("ref_points", os.path.join(REF_ROOT, "mmdet3d/core/points"))
+    load_ref_module("ref_points.base_points", "mmdet3d/core/points/base_points.py")
+    lidar_points = load_ref_module("ref_points.lidar_points", "mmdet3d/core/points/lidar_points.py")
+    clip = load_ref_module("ref_clip_sigmoid", "mmdet3d/models/utils/clip_sigmoid.py")
+    path = os.path.join(REF_ROOT, "mmdet3d/models/detectors/bevdet_distill.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "BEVDetDistill"][0]
+    ns = dict(torch=torch, nn=nn, F=F, np=np, deepcopy=copy.deepcopy, partial=functools.partial,
+              box_np_ops=box_np_ops, LiDARPoints=lidar_points.LiDARPoints,
+              clip_sigmoid=clip.clip_sigmoid, build_loss=_build_loss, os=os)
+    out = {}
+    for node in cls.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            node.decorator_list = []
+            mod = ast.Module(body=[node], type_ignores=[])
+            code = compile(mod, path, "exec")  # keeps reference file:line in tracebacks
+            exec(code, ns)
+            out[node.name] = ns[node.name]
+    missing = set(names) - set(out)
+    assert not missing, missing
+    return out, _AttrDict
