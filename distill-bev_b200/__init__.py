@@ -6,7 +6,7 @@ Import as ``distill_bev_b200`` (alias module at the repository root).
 from . import _lib  # noqa: F401
 from .plugin.ops.bev_pool import (BevPlan, QuickCumsumCuda, bev_plan_from_coords,  # noqa: F401
                                   bev_plan_from_geom, bev_pool, bev_pool_ext, bev_pool_gather,
-                                  voxel_pooling)
+                                  lift_splat, transpose_batched, voxel_pooling)
 
 from .plugin.ops.voxel import (DynamicScatter, Voxelization, dynamic_scatter, voxel_layer,  # noqa: F401
                                voxelization)

@@ -43,8 +43,14 @@ SIGNATURES = {
     "dbev_bev_plan_workspace_bytes": (_c_size, [_c_ll, _c_ll]),
     "dbev_bev_plan_max_items": (_c_ll, [_c_ll, _c_ll, _c_int, _c_int]),
     "dbev_bev_plan_from_geom": (_c_int, [_ptr, _c_ll, _c_int, _fptr, _fptr, _fptr, _iptr, _c_int,
-                                         _c_int, _ptr, _ptr, _ptr, _ptr, _c_ll, _ptr, _ptr,
+                                         _c_int, _ptr, _ptr, _ptr, _ptr, _c_ll, _ptr, _ptr, _ptr,
                                          _c_size, _ptr]),
+    "dbev_lift_splat_forward": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr,
+                                         _ptr, _c_int, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll,
+                                         _ptr, _ptr]),
+    "dbev_lift_splat_backward": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_ll, _c_int, _c_int, _c_int,
+                                          _ptr, _ptr, _ptr]),
+    "dbev_transpose_batched": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr]),
     "dbev_bev_plan_from_coords": (_c_int, [_ptr, _c_int, _c_ll, _c_int, _c_int, _c_int, _c_int,
                                            _c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _c_ll, _ptr,
                                            _ptr, _c_size, _ptr]),

@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256)
 bev_keys_from_geom_kernel(const float* __restrict__ geom, long long n, long long pts_per_batch,
                           float off0, float off1, float off2, float dx0, float dx1, float dx2,
                           float nxf0, float nxf1, float nxf2, int n0, int n1, int nz,
-                          int fast_axis, uint32_t sentinel, uint32_t* __restrict__ keys) {
+                          int fast_axis, uint32_t sentinel, uint32_t* __restrict__ keys,
+                          int* __restrict__ point_cell) {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const float g0 = geom[p * 3 + 0], g1 = geom[p * 3 + 1], g2 = geom[p * 3 + 2];
@@ -68,6 +69,7 @@ bev_keys_from_geom_kernel(const float* __restrict__ geom, long long n, long long
     key = (uint32_t)((((long long)b * nz + i2) * nslow + islow) * nfast + ifast);
   }
   keys[p] = key;
+  if (point_cell) point_cell[p] = ok ? (int)key : -1;
 }
 
 template <typename T>
@@ -197,12 +199,21 @@ __device__ __forceinline__ ItemCtx decode_item(const int4& item, const PoolGeom&
   return ic;
 }
 
-template <int LPR>
+// LIFT = true fuses the "lift" (view_transformer_mine.py:333-335): the row of point p is
+// depth[p] * feat[pixel(p), :] computed on the fly from depth[BN, D, fH, fW] (flat index = p)
+// and channels-last feat[BN * fH * fW, C]; the [B,N,D,fH,fW,C] volume never exists.
+struct LiftArgs {
+  const float* depth;
+  int dfhw;  // D * fH * fW
+  int fhw;   // fH * fW
+};
+
+template <int LPR, bool LIFT>
 __global__ void __launch_bounds__(kPoolBlock)
 bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restrict__ order,
                            const int* __restrict__ cell_start, const int* __restrict__ cell_end,
                            const int4* __restrict__ items, const int* __restrict__ n_items_ptr,
-                           float* __restrict__ out, PoolGeom g) {
+                           float* __restrict__ out, PoolGeom g, LiftArgs la) {
   extern __shared__ float smem[];
   constexpr int NW = 32 / LPR;   // workers per warp
   constexpr int CB = LPR * 4;    // channels per block
@@ -277,8 +288,21 @@ bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restri
       for (int pos = ws; pos < we; pos += U) {
         float4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (lane_active && pos + u < we) v[u] = ld_stream_f4(xb + (size_t)pid[u] * g.C);
+        for (int u = 0; u < U; ++u) {
+          if (lane_active && pos + u < we) {
+            if (LIFT) {
+              const uint32_t p = pid[u];
+              const uint32_t bn = p / (uint32_t)la.dfhw;
+              const uint32_t pix = (p - bn * (uint32_t)la.dfhw) % (uint32_t)la.fhw;
+              const float w = __ldg(la.depth + p);
+              const float4 f = __ldg(reinterpret_cast<const float4*>(
+                  xb + ((size_t)bn * la.fhw + pix) * g.C));
+              v[u] = make_float4(w * f.x, w * f.y, w * f.z, w * f.w);
+            } else {
+              v[u] = ld_stream_f4(xb + (size_t)pid[u] * g.C);
+            }
+          }
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) pid[u] = (pos + U + u < we) ? __ldg(order + pos + U + u) : 0u;
 #pragma unroll
@@ -484,6 +508,75 @@ bev_pool_gather_bwd_generic_kernel(const float* __restrict__ out_grad,
       const uint32_t p = order[i];
       for (int c = lane; c < g.C; c += 32) x_grad[(size_t)p * g.C + c] = tile[c * kTilePitch + ci];
     }
+  }
+}
+
+// out[b][c][r] = in[b][r][c]  (32x32 tiles through shared memory, both sides coalesced)
+__global__ void __launch_bounds__(256)
+transpose_batched_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  __shared__ float t[32][33];
+  const size_t boff = (size_t)blockIdx.z * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = r0 + ty + k * 8, c = c0 + tx;
+    if (r < rows && c < cols) t[ty + k * 8][tx] = in[boff + (size_t)r * cols + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + ty + k * 8, r = r0 + tx;
+    if (r < rows && c < cols) out[boff + (size_t)c * rows + r] = t[tx][ty + k * 8];
+  }
+}
+
+// backward of the fused lift+splat. One group of LPR lanes per image pixel
+// (bn, h, w) walks the D depth bins of its ray:
+//   d_depth[p]     = <feat[pix, :], g[cell(p), :]>
+//   d_feat[pix, :] = sum_d depth[p] * g[cell(p), :]
+// g is the BEV gradient in cells-major layout [n_cells, C] (transposed once),
+// so every access is a contiguous row; everything is read from L2.
+template <int LPR>
+__global__ void __launch_bounds__(256)
+lift_splat_bwd_kernel(const float* __restrict__ g_cl, const float* __restrict__ depth,
+                      const float* __restrict__ feat, const int* __restrict__ point_cell,
+                      long long n_pix, int C, int D, int fhw, float* __restrict__ d_depth,
+                      float* __restrict__ d_feat) {
+  constexpr int CB = LPR * 4;
+  constexpr int GPB = 256 / LPR;  // pixel groups per CTA
+  const int sub = threadIdx.x % LPR;
+  const long long pixrow = (long long)blockIdx.x * GPB + threadIdx.x / LPR;
+  const bool valid = pixrow < n_pix;  // whole groups are valid or not; shuffles stay in-group
+  const long long bn = valid ? pixrow / fhw : 0;
+  const int pix = valid ? (int)(pixrow % fhw) : 0;
+  const int nblocks = (C + CB - 1) / CB;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu
+                                     : (((1u << LPR) - 1u) << ((threadIdx.x & 31) / LPR * LPR));
+  for (int cbk = 0; cbk < nblocks; ++cbk) {
+    const int c = cbk * CB + sub * 4;
+    const bool act = valid && c < C;
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f), acc = f;
+    if (act) f = __ldg(reinterpret_cast<const float4*>(feat + (size_t)pixrow * C + c));
+#pragma unroll 4
+    for (int d = 0; d < D; ++d) {
+      const size_t p = ((size_t)bn * D + d) * fhw + pix;
+      const int cell = valid ? __ldg(point_cell + p) : -1;
+      float dot = 0.f;
+      if (cell >= 0 && act) {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g_cl + (size_t)cell * C + c));
+        const float w = __ldg(depth + p);
+        acc.x += w * gv.x; acc.y += w * gv.y; acc.z += w * gv.z; acc.w += w * gv.w;
+        dot = (f.x * gv.x + f.y * gv.y) + (f.z * gv.z + f.w * gv.w);
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o);
+      if (valid && sub == 0) {
+        if (cbk == 0) d_depth[p] = dot;
+        else d_depth[p] += dot;  // same thread wrote it in the previous channel block
+      }
+    }
+    if (act) *reinterpret_cast<float4*>(d_feat + (size_t)pixrow * C + c) = acc;
   }
 }
 
@@ -728,8 +821,8 @@ static int check_plan_out(const char* who, long long n_points, long long ncells,
 int bev_plan_from_geom(const float* geom, long long n_points, int batch, const float off[3],
                        const float dx[3], const float nx_f[3], const int nx_i[3], int fast_axis,
                        int rows_per_item, uint32_t* order, int* cell_start, int* cell_end,
-                       int4* items, long long max_items, int* n_items, void* ws, size_t ws_bytes,
-                       cudaStream_t stream) {
+                       int4* items, long long max_items, int* n_items, int* point_cell, void* ws,
+                       size_t ws_bytes, cudaStream_t stream) {
   DBEV_CHECK_ARG(batch > 0 && n_points >= 0 && n_points % batch == 0,
                  "bev_plan_from_geom: n_points (%lld) must be a multiple of batch (%d)", n_points,
                  batch);
@@ -748,7 +841,8 @@ int bev_plan_from_geom(const float* geom, long long n_points, int batch, const f
   if (n_points > 0) {
     bev_keys_from_geom_kernel<<<ceil_div(n_points, 256), 256, 0, stream>>>(
         geom, n_points, n_points / batch, off[0], off[1], off[2], dx[0], dx[1], dx[2], nx_f[0],
-        nx_f[1], nx_f[2], nx_i[0], nx_i[1], nx_i[2], fast_axis, (uint32_t)ncells, keys0);
+        nx_f[1], nx_f[2], nx_i[0], nx_i[1], nx_i[2], fast_axis, (uint32_t)ncells, keys0,
+        point_cell);
     DBEV_CHECK_LAUNCH("bev_keys_from_geom_kernel");
   }
   PlanOut po{order, cell_start, cell_end, items, max_items, n_items, rows_per_item, nfast};
@@ -842,23 +936,40 @@ static int pick_lpr(int C) {  // lanes per row of one channel block (<= 64 chann
     }                                    \
   } while (0)
 
-int bev_pool_gather_forward(const float* x, int C, const uint32_t* order, const int* cell_start,
-                            const int* cell_end, const int4* items, const int* n_items, int batch,
-                            int nz, int nslow, int nfast, long long sB, long long sZ, long long sC,
-                            float* out, cudaStream_t stream) {
+static int gather_forward_impl(const float* x, int C, const uint32_t* order, const int* cell_start,
+                               const int* cell_end, const int4* items, const int* n_items,
+                               int batch, int nz, int nslow, int nfast, long long sB, long long sZ,
+                               long long sC, float* out, const LiftArgs* lift,
+                               cudaStream_t stream) {
   PoolGeom g;
   int rc = make_pool_geom(C, batch, nz, nslow, nfast, sB, sZ, sC, &g);
   if (rc != DBEV_OK) return rc;
   const int lpr = pick_lpr(C);
+  if (lift) {
+    DBEV_CHECK_ARG(lpr > 0, "lift_splat: C must be a multiple of 4 (got %d)", C);
+    const int cb = lpr * 4, nw = 32 / lpr;
+    const size_t smem = (size_t)kPoolWarps * (cb * kTilePitch + nw * 2 * cb) * sizeof(float);
+    int grid = 0;
+#define LAUNCH(L)                                                                        \
+  rc = persistent_grid(bev_pool_gather_fwd_kernel<L, true>, smem, &grid);                \
+  if (rc != DBEV_OK) return rc;                                                          \
+  bev_pool_gather_fwd_kernel<L, true><<<grid, kPoolBlock, smem, stream>>>(               \
+      x, order, cell_start, cell_end, items, n_items, out, g, *lift)
+    DBEV_DISPATCH_LPR(lpr, LAUNCH);
+#undef LAUNCH
+    DBEV_CHECK_LAUNCH("lift_splat_fwd_kernel");
+    return DBEV_OK;
+  }
+  const LiftArgs none{nullptr, 1, 1};
   if (lpr > 0) {
     const int cb = lpr * 4, nw = 32 / lpr;
     const size_t smem = (size_t)kPoolWarps * (cb * kTilePitch + nw * 2 * cb) * sizeof(float);
     int grid = 0;
 #define LAUNCH(L)                                                                        \
-  rc = persistent_grid(bev_pool_gather_fwd_kernel<L>, smem, &grid);                      \
+  rc = persistent_grid(bev_pool_gather_fwd_kernel<L, false>, smem, &grid);               \
   if (rc != DBEV_OK) return rc;                                                          \
-  bev_pool_gather_fwd_kernel<L><<<grid, kPoolBlock, smem, stream>>>(                     \
-      x, order, cell_start, cell_end, items, n_items, out, g)
+  bev_pool_gather_fwd_kernel<L, false><<<grid, kPoolBlock, smem, stream>>>(              \
+      x, order, cell_start, cell_end, items, n_items, out, g, none)
     DBEV_DISPATCH_LPR(lpr, LAUNCH);
 #undef LAUNCH
   } else {
@@ -870,6 +981,52 @@ int bev_pool_gather_forward(const float* x, int C, const uint32_t* order, const 
                                                                            cell_end, out, g);
   }
   DBEV_CHECK_LAUNCH("bev_pool_gather_fwd_kernel");
+  return DBEV_OK;
+}
+
+int bev_pool_gather_forward(const float* x, int C, const uint32_t* order, const int* cell_start,
+                            const int* cell_end, const int4* items, const int* n_items, int batch,
+                            int nz, int nslow, int nfast, long long sB, long long sZ, long long sC,
+                            float* out, cudaStream_t stream) {
+  return gather_forward_impl(x, C, order, cell_start, cell_end, items, n_items, batch, nz, nslow,
+                             nfast, sB, sZ, sC, out, nullptr, stream);
+}
+
+int lift_splat_forward(const float* depth, const float* feat_cl, int C, int D, int fhw,
+                       const uint32_t* order, const int* cell_start, const int* cell_end,
+                       const int4* items, const int* n_items, int batch, int nz, int nslow,
+                       int nfast, long long sB, long long sZ, long long sC, float* out,
+                       cudaStream_t stream) {
+  DBEV_CHECK_ARG(D > 0 && fhw > 0, "lift_splat: bad frustum shape D=%d fH*fW=%d", D, fhw);
+  const LiftArgs la{depth, D * fhw, fhw};
+  return gather_forward_impl(feat_cl, C, order, cell_start, cell_end, items, n_items, batch, nz,
+                             nslow, nfast, sB, sZ, sC, out, &la, stream);
+}
+
+int lift_splat_backward(const float* g_cl, const float* depth, const float* feat_cl,
+                        const int* point_cell, long long n_pix, int C, int D, int fhw,
+                        float* d_depth, float* d_feat_cl, cudaStream_t stream) {
+  DBEV_CHECK_ARG(n_pix >= 0 && D > 0 && fhw > 0 && C > 0, "lift_splat_backward: bad sizes");
+  const int lpr = pick_lpr(C);
+  DBEV_CHECK_ARG(lpr > 0, "lift_splat: C must be a multiple of 4 (got %d)", C);
+  if (n_pix == 0) return DBEV_OK;
+#define LAUNCH(L)                                                                         \
+  lift_splat_bwd_kernel<L><<<ceil_div(n_pix, 256 / L), 256, 0, stream>>>(                 \
+      g_cl, depth, feat_cl, point_cell, n_pix, C, D, fhw, d_depth, d_feat_cl)
+  DBEV_DISPATCH_LPR(lpr, LAUNCH);
+#undef LAUNCH
+  DBEV_CHECK_LAUNCH("lift_splat_bwd_kernel");
+  return DBEV_OK;
+}
+
+int transpose_batched(const float* in, float* out, int batch, int rows, int cols,
+                      cudaStream_t stream) {
+  DBEV_CHECK_ARG(batch >= 0 && rows >= 0 && cols >= 0 && batch < 65536, "transpose: bad sizes");
+  if (batch == 0 || rows == 0 || cols == 0) return DBEV_OK;
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), batch);
+  DBEV_CHECK_ARG(grid.y < 65536, "transpose: too many rows (%d)", rows);
+  transpose_batched_kernel<<<grid, 256, 0, stream>>>(in, out, rows, cols);
+  DBEV_CHECK_LAUNCH("transpose_batched_kernel");
   return DBEV_OK;
 }
 

@@ -12,8 +12,8 @@ long long bev_plan_max_items(long long n_points, long long n_cells, int nfast, i
 int bev_plan_from_geom(const float* geom, long long n_points, int batch, const float off[3],
                        const float dx[3], const float nx_f[3], const int nx_i[3], int fast_axis,
                        int rows_per_item, uint32_t* order, int* cell_start, int* cell_end,
-                       int4* items, long long max_items, int* n_items, void* ws, size_t ws_bytes,
-                       cudaStream_t stream);
+                       int4* items, long long max_items, int* n_items, int* point_cell, void* ws,
+                       size_t ws_bytes, cudaStream_t stream);
 
 int bev_plan_from_coords(const void* coords, int coords_i64, long long n_points, int batch, int n0,
                          int n1, int nz, int fast_axis, int rows_per_item, uint32_t* order,
@@ -30,6 +30,19 @@ int bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* order
                              const int* n_items, int batch, int nz, int nslow, int nfast,
                              long long sB, long long sZ, long long sC, float* x_grad,
                              cudaStream_t stream);
+
+int lift_splat_forward(const float* depth, const float* feat_cl, int C, int D, int fhw,
+                       const uint32_t* order, const int* cell_start, const int* cell_end,
+                       const int4* items, const int* n_items, int batch, int nz, int nslow,
+                       int nfast, long long sB, long long sZ, long long sC, float* out,
+                       cudaStream_t stream);
+
+int lift_splat_backward(const float* g_cl, const float* depth, const float* feat_cl,
+                        const int* point_cell, long long n_pix, int C, int D, int fhw,
+                        float* d_depth, float* d_feat_cl, cudaStream_t stream);
+
+int transpose_batched(const float* in, float* out, int batch, int rows, int cols,
+                      cudaStream_t stream);
 
 int bev_pool_interval_forward(int b, int d, int h, int w, int n, int c, int n_intervals,
                               const float* x, const int* geom_feats, const int* interval_starts,

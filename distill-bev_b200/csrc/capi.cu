@@ -59,12 +59,34 @@ int dbev_bev_plan_from_geom(const float* geom, long long n_points, int batch,
                             const float* off_host3, const float* dx_host3,
                             const float* nx_float_host3, const int* nx_int_host3, int fast_axis,
                             int rows_per_item, uint32_t* order, int* cell_start, int* cell_end,
-                            int* items, long long max_items, int* n_items, void* workspace,
-                            size_t workspace_bytes, void* stream) {
+                            int* items, long long max_items, int* n_items, int* point_cell,
+                            void* workspace, size_t workspace_bytes, void* stream) {
   return bev_plan_from_geom(geom, n_points, batch, off_host3, dx_host3, nx_float_host3,
                             nx_int_host3, fast_axis, rows_per_item, order, cell_start, cell_end,
-                            (int4*)items, max_items, n_items, workspace, workspace_bytes,
-                            (cudaStream_t)stream);
+                            (int4*)items, max_items, n_items, point_cell, workspace,
+                            workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_lift_splat_forward(const float* depth, const float* feat_cl, int C, int D, int fhw,
+                            const uint32_t* order, const int* cell_start, const int* cell_end,
+                            const int* items, const int* n_items, int batch, int nz, int nslow,
+                            int nfast, long long stride_b, long long stride_z, long long stride_c,
+                            float* out, void* stream) {
+  return lift_splat_forward(depth, feat_cl, C, D, fhw, order, cell_start, cell_end,
+                            (const int4*)items, n_items, batch, nz, nslow, nfast, stride_b,
+                            stride_z, stride_c, out, (cudaStream_t)stream);
+}
+
+int dbev_lift_splat_backward(const float* grad_cl, const float* depth, const float* feat_cl,
+                             const int* point_cell, long long n_pixels, int C, int D, int fhw,
+                             float* d_depth, float* d_feat_cl, void* stream) {
+  return lift_splat_backward(grad_cl, depth, feat_cl, point_cell, n_pixels, C, D, fhw, d_depth,
+                             d_feat_cl, (cudaStream_t)stream);
+}
+
+int dbev_transpose_batched(const float* in, float* out, int batch, int rows, int cols,
+                           void* stream) {
+  return transpose_batched(in, out, batch, rows, cols, (cudaStream_t)stream);
 }
 
 int dbev_bev_plan_from_coords(const void* coords, int coords_is_i64, long long n_points,

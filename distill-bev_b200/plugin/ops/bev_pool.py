@@ -22,7 +22,7 @@ class BevPlan(object):
     """
 
     __slots__ = ("order", "cell_start", "cell_end", "items", "n_items", "rows_per_item", "n_points",
-                 "batch", "nz", "nslow", "nfast", "fast_axis", "device")
+                 "batch", "nz", "nslow", "nfast", "fast_axis", "device", "point_cell")
 
     def __init__(self, order, cell_start, cell_end, items, n_items, rows_per_item, n_points, batch,
                  nz, nslow, nfast, fast_axis):
@@ -39,6 +39,7 @@ class BevPlan(object):
         self.nfast = nfast
         self.fast_axis = fast_axis
         self.device = order.device
+        self.point_cell = None        # [n_points] int32 cell id / -1 (lift_splat backward)
 
     @property
     def n_cells(self):
@@ -67,7 +68,7 @@ def _alloc_plan(n_points, batch, n0, n1, nz, fast_axis, device, rows_per_item=0)
                    nslow, nfast, fast_axis)
 
 
-def bev_plan_from_geom(geom, batch, bx, dx, nx, fast_axis=0, rows_per_item=0):
+def bev_plan_from_geom(geom, batch, bx, dx, nx, fast_axis=0, rows_per_item=0, with_point_cell=False):
     """Plan from ego-frame frustum coordinates.
 
     geom: [..., 3] fp32 CUDA tensor, batch-major (e.g. [B, N, D, fH, fW, 3]);
@@ -85,6 +86,8 @@ def bev_plan_from_geom(geom, batch, bx, dx, nx, fast_axis=0, rows_per_item=0):
     nx_i = nx32.to(torch.long)          # nx.to(torch.long) truncates
     plan = _alloc_plan(n_points, batch, int(nx_i[0]), int(nx_i[1]), int(nx_i[2]), fast_axis,
                        geom.device, rows_per_item)
+    if with_point_cell:
+        plan.point_cell = torch.empty(max(n_points, 1), dtype=torch.int32, device=geom.device)
     with torch.cuda.device(geom.device):
         ws_bytes = lib.dbev_bev_plan_workspace_bytes(n_points, plan.n_cells)
         ws = _lib.workspace(ws_bytes, geom.device)
@@ -93,7 +96,7 @@ def bev_plan_from_geom(geom, batch, bx, dx, nx, fast_axis=0, rows_per_item=0):
             _lib.host_f3(nx32.tolist()), _lib.host_i3(nx_i.tolist()), fast_axis, rows_per_item,
             _lib.ptr(plan.order), _lib.ptr(plan.cell_start), _lib.ptr(plan.cell_end),
             _lib.ptr(plan.items), plan.items.shape[0], _lib.ptr(plan.n_items),
-            _lib.ptr(ws), ws_bytes, _lib.stream_ptr(geom.device))
+            _lib.ptr(plan.point_cell), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(geom.device))
     _lib.check(rc, "dbev_bev_plan_from_geom")
     return plan
 
@@ -169,6 +172,83 @@ class _BevPoolGather(torch.autograd.Function):
                 _lib.ptr(x_grad), _lib.stream_ptr(out_grad.device))
         _lib.check(rc, "dbev_bev_pool_gather_backward")
         return x_grad, None, None
+
+
+def transpose_batched(x, batch, rows, cols):
+    """[batch, rows, cols] -> [batch, cols, rows] (NCHW <-> channels-last helper kernel)."""
+    lib = _lib.load()
+    _lib.require_cuda(x, "x", torch.float32)
+    x = x.contiguous()
+    out = torch.empty((batch, cols, rows), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.dbev_transpose_batched(_lib.ptr(x), _lib.ptr(out), batch, rows, cols,
+                                        _lib.stream_ptr(x.device))
+    _lib.check(rc, "dbev_transpose_batched")
+    return out
+
+
+class _LiftSplat(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, depth, feat, plan):
+        lib = _lib.load()
+        _lib.require_cuda(depth, "depth", torch.float32)
+        _lib.require_cuda(feat, "feat", torch.float32)
+        BN, D, fH, fW = depth.shape
+        C = feat.shape[1]
+        if tuple(feat.shape) != (BN, C, fH, fW):
+            raise RuntimeError("feat must be [%d, C, %d, %d], got %s" % (BN, fH, fW, tuple(feat.shape)))
+        if plan.n_points != BN * D * fH * fW:
+            raise RuntimeError("plan was built for %d points, frustum has %d"
+                               % (plan.n_points, BN * D * fH * fW))
+        depth = depth.contiguous()
+        fhw = fH * fW
+        feat_cl = transpose_batched(feat, BN, C, fhw)            # [BN, fH*fW, C]
+        shape, sB, sZ, sC = _out_strides(plan, C, "bz_c")
+        out = torch.empty(shape, dtype=torch.float32, device=depth.device)
+        with torch.cuda.device(depth.device):
+            rc = lib.dbev_lift_splat_forward(
+                _lib.ptr(depth), _lib.ptr(feat_cl), C, D, fhw, _lib.ptr(plan.order),
+                _lib.ptr(plan.cell_start), _lib.ptr(plan.cell_end), _lib.ptr(plan.items),
+                _lib.ptr(plan.n_items), plan.batch, plan.nz, plan.nslow, plan.nfast, sB, sZ, sC,
+                _lib.ptr(out), _lib.stream_ptr(depth.device))
+        _lib.check(rc, "dbev_lift_splat_forward")
+        ctx.plan = plan
+        ctx.dims = (BN, C, D, fH, fW)
+        ctx.save_for_backward(depth, feat_cl)
+        return out
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        lib = _lib.load()
+        plan = ctx.plan
+        if plan.point_cell is None:
+            raise RuntimeError("lift_splat backward needs a plan built with with_point_cell=True")
+        depth, feat_cl = ctx.saved_tensors
+        BN, C, D, fH, fW = ctx.dims
+        fhw = fH * fW
+        plane = plan.nslow * plan.nfast
+        # [B, nz*C, ny, nx] -> cells-major [B*nz, plane, C]
+        g_cl = transpose_batched(out_grad.contiguous().float(), plan.batch * plan.nz, C, plane)
+        d_depth = torch.empty_like(depth)
+        d_feat_cl = torch.empty_like(feat_cl)
+        with torch.cuda.device(depth.device):
+            rc = lib.dbev_lift_splat_backward(
+                _lib.ptr(g_cl), _lib.ptr(depth), _lib.ptr(feat_cl), _lib.ptr(plan.point_cell),
+                BN * fhw, C, D, fhw, _lib.ptr(d_depth), _lib.ptr(d_feat_cl),
+                _lib.stream_ptr(depth.device))
+        _lib.check(rc, "dbev_lift_splat_backward")
+        d_feat = transpose_batched(d_feat_cl, BN, fhw, C).view(BN, C, fH, fW)
+        return d_depth, d_feat, None
+
+
+def lift_splat(depth_prob, img_feat, plan):
+    """Fused lift + splat: depth_prob [B*N, D, fH, fW] (softmax depth), img_feat
+    [B*N, C, fH, fW] -> BEV [B, C*nz, ny, nx], identical to
+    ``voxel_pooling(geom, (depth.unsqueeze(1) * feat.unsqueeze(2)).view(B,N,C,D,fH,fW)
+    .permute(0,1,3,4,5,2))`` (bevdet_distill_more.py:413-421) without materialising the
+    volume. ``plan`` = bev_plan_from_geom(geom, B, ..., with_point_cell=True)."""
+    return _LiftSplat.apply(depth_prob, img_feat, plan)
 
 
 def bev_pool_gather(x, plan, layout="bz_c"):

@@ -96,8 +96,10 @@ int dbev_bev_plan_from_geom(const float* geom, long long n_points, int batch,
                             const float* off_host3, const float* dx_host3,
                             const float* nx_float_host3, const int* nx_int_host3, int fast_axis,
                             int rows_per_item, uint32_t* order, int* cell_start, int* cell_end,
-                            int* items, long long max_items, int* n_items, void* workspace,
-                            size_t workspace_bytes, void* stream);
+                            int* items, long long max_items, int* n_items, int* point_cell,
+                            void* workspace, size_t workspace_bytes, void* stream);
+/* point_cell (nullable): [n_points] cell id of every point, -1 when dropped; needed by
+ * dbev_lift_splat_backward. */
 
 /* Replaces the rank + argsort + kept/where prelude of bev_pool()
  * (mmdet3d/ops/bev_pool/bev_pool.py:86-93,40-46). coords[n,4] = (c0,c1,c2,b),
@@ -129,6 +131,32 @@ int dbev_bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* 
                                   const int* n_items, int batch, int nz, int nslow, int nfast,
                                   long long stride_b, long long stride_z, long long stride_c,
                                   float* x_grad, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Fused lift + splat. Replaces, in one kernel, the outer
+ * product volume = depth.unsqueeze(1) * img_feat.unsqueeze(2), its permute to
+ * channels-last (view_transformer_mine.py:333-335 = bevdet_distill_more.py:413-416)
+ * and voxel_pooling (:141-181): the [B,N,D,fH,fW,C] volume (64-510 MB per
+ * sample and frame) is never written or read.
+ *   depth    [BN, D, fH, fW] fp32 depth distribution (flat index = point id)
+ *   feat_cl  [BN * fH * fW, C] fp32 image features, channels-last
+ * plan: from dbev_bev_plan_from_geom on the same frustum (n_points = BN*D*fH*fW).
+ * ------------------------------------------------------------------------ */
+int dbev_lift_splat_forward(const float* depth, const float* feat_cl, int C, int D, int fhw,
+                            const uint32_t* order, const int* cell_start, const int* cell_end,
+                            const int* items, const int* n_items, int batch, int nz, int nslow,
+                            int nfast, long long stride_b, long long stride_z, long long stride_c,
+                            float* out, void* stream);
+
+/* grad_cl [n_cells, C]: BEV gradient in cells-major layout (dbev_transpose_batched of the
+ * NCHW gradient). Writes d_depth[BN*D*fH*fW] and d_feat_cl[BN*fH*fW, C] completely. */
+int dbev_lift_splat_backward(const float* grad_cl, const float* depth, const float* feat_cl,
+                             const int* point_cell, long long n_pixels, int C, int D, int fhw,
+                             float* d_depth, float* d_feat_cl, void* stream);
+
+/* out[b][c][r] = in[b][r][c] for b < batch: NCHW <-> channels-last helper. */
+int dbev_transpose_batched(const float* in, float* out, int batch, int rows, int cols,
+                           void* stream);
 
 /* ------------------------------------------------------------------------ *
  * LiDAR voxelization — replaces the pybind module mmdet3d.ops.voxel.voxel_layer

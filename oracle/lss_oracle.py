@@ -140,6 +140,35 @@ def voxel_pooling(geom, x, bx, dx, nx):
     return out.astype(np.float32)
 
 
+def lift(depth, feat, B, N):
+    """view_transformer_mine.py:333-335 (= bevdet_distill_more.py:413-416): outer product of
+    the depth distribution [BN, D, fH, fW] and image features [BN, C, fH, fW], permuted to
+    channels-last -> [B, N, D, fH, fW, C] float32."""
+    d = np.asarray(depth, dtype=np.float32)
+    f = np.asarray(feat, dtype=np.float32)
+    vol = d[:, None] * f[:, :, None]                       # [BN, C, D, fH, fW]
+    BN, C, D, fH, fW = vol.shape
+    return vol.reshape(B, N, C, D, fH, fW).transpose(0, 1, 3, 4, 5, 2)
+
+
+def lift_splat(geom, depth, feat, B, N, bx, dx, nx):
+    """lift followed by voxel_pooling."""
+    return voxel_pooling(geom, lift(depth, feat, B, N), bx, dx, nx)
+
+
+def lift_splat_backward(geom, depth, feat, out_grad, B, N, bx, dx, nx):
+    """Gradients of lift_splat w.r.t. depth and feat (float64 accumulation)."""
+    d = np.asarray(depth, dtype=np.float64)
+    f = np.asarray(feat, dtype=np.float64)
+    BN, C, fH, fW = f.shape
+    D = d.shape[1]
+    gx = voxel_pooling_backward(geom, out_grad, C, bx, dx, nx).astype(np.float64)  # [Nprime, C]
+    gx = gx.reshape(BN, D, fH, fW, C)
+    d_depth = np.einsum("bdhwc,bchw->bdhw", gx, f)
+    d_feat = np.einsum("bdhwc,bdhw->bchw", gx, d)
+    return d_depth.astype(np.float32), d_feat.astype(np.float32)
+
+
 def voxel_pooling_backward(geom, out_grad, C, bx, dx, nx):
     """Gradient of voxel_pooling w.r.t. x: every kept point receives its cell's
     gradient row, dropped points receive zero (x[kept] indexing :160 and

@@ -216,3 +216,53 @@ def test_voxel_pooling_sweep_vs_oracle(cuda, bev, dstep, C):
     out = dbev.voxel_pooling(_t(geom, cuda), _t(x, cuda), bx, dx, nx)
     ref = lss_oracle.voxel_pooling(geom, x, bx, dx, nx)
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+
+
+def test_lift_splat_golden_small(cuda, golden_dir):
+    """Fused lift+splat vs the reference's own lift (outer product, permute) + voxel_pooling."""
+    g = np.load(os.path.join(golden_dir, "lss_small.npz"))
+    B = g["rots"].shape[0]
+    plan = dbev.bev_plan_from_geom(_t(g["geom"], cuda), B, g["bx"], g["dx"], g["nx"], with_point_cell=True)
+    depth = _t(g["lift_depth"], cuda).requires_grad_(True)
+    feat = _t(g["lift_feat"], cuda).requires_grad_(True)
+    out = dbev.lift_splat(depth, feat, plan)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["lift_out"], rtol=RTOL, atol=ATOL)
+    (out * _t(g["out_weight"], cuda)).sum().backward()
+    np.testing.assert_allclose(depth.grad.cpu().numpy(), g["lift_ddepth"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(feat.grad.cpu().numpy(), g["lift_dfeat"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("C,frames", [(64, 2), (80, 1), (256, 1)])
+def test_lift_splat_full_size_equals_materialised_path(cuda, C, frames):
+    """configs[0]/[1] frustum (6 cams, D=59, 16x44): fused result == voxel_pooling of the
+    materialised volume (same kernels, same summation order -> tight), grads vs oracle."""
+    geom, _, bx, dx, nx = _config1_inputs(frames, seed=4, C=4)
+    rng = np.random.RandomState(C)
+    BN, D, fH, fW = frames * 6, 59, 16, 44
+    dl = rng.randn(BN, D, fH, fW).astype(np.float32)
+    depth = np.exp(dl) / np.exp(dl).sum(1, keepdims=True)
+    feat = rng.randn(BN, C, fH, fW).astype(np.float32)
+    gt = _t(geom, cuda)
+    plan = dbev.bev_plan_from_geom(gt, frames, bx, dx, nx, with_point_cell=True)
+    dt, ft = _t(depth, cuda).requires_grad_(True), _t(feat, cuda).requires_grad_(True)
+    out = dbev.lift_splat(dt, ft, plan)
+    vol = (dt.detach().unsqueeze(1) * ft.detach().unsqueeze(2)).view(frames, 6, C, D, fH, fW).permute(0, 1, 3, 4, 5, 2)
+    ref = dbev.voxel_pooling(gt, vol, bx, dx, nx, plan=plan)
+    torch.testing.assert_close(out.detach(), ref, rtol=1e-5, atol=1e-5)
+    w = rng.random_sample(tuple(out.shape)).astype(np.float32)
+    (out * _t(w, cuda)).sum().backward()
+    if C == 64:
+        dd, df = lss_oracle.lift_splat_backward(geom, depth, feat, w, frames, 6, bx, dx, nx)
+        np.testing.assert_allclose(dt.grad.cpu().numpy(), dd, rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(ft.grad.cpu().numpy(), df, rtol=1e-3, atol=1e-4)
+    else:
+        vol2 = vol.clone().requires_grad_(True)
+        (dbev.voxel_pooling(gt, vol2, bx, dx, nx, plan=plan) * _t(w, cuda)).sum().backward()
+        gx = vol2.grad.reshape(BN, D, fH, fW, C)
+        torch.testing.assert_close(dt.grad, torch.einsum("bdhwc,bchw->bdhw", gx, ft.detach()), rtol=1e-3, atol=1e-3)
+        torch.testing.assert_close(ft.grad, torch.einsum("bdhwc,bdhw->bchw", gx, dt.detach()), rtol=1e-3, atol=1e-3)
+
+
+def test_transpose_batched(cuda):
+    x = torch.rand(3, 70, 45, device=cuda)
+    assert torch.equal(dbev.transpose_batched(x, 3, 70, 45), x.transpose(1, 2).contiguous())

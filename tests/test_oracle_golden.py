@@ -96,3 +96,14 @@ def test_fullsize_report_pins_oracle(golden_dir):
     assert rep["idx_equal_on_kept"] is True
     assert rep["rel_oracle_vs_accelerated"] < 1e-5
     assert rep["rel_oracle_vs_cumsum"] < 1e-3
+
+
+def test_lift_splat_matches_reference_small(golden_dir):
+    g = _load(golden_dir, "lss_small.npz")
+    B, N = g["rots"].shape[:2]
+    out = lss_oracle.lift_splat(g["geom"], g["lift_depth"], g["lift_feat"], B, N, g["bx"], g["dx"], g["nx"])
+    np.testing.assert_allclose(out, g["lift_out"], rtol=1e-5, atol=1e-5)
+    dd, df = lss_oracle.lift_splat_backward(g["geom"], g["lift_depth"], g["lift_feat"], g["out_weight"],
+                                            B, N, g["bx"], g["dx"], g["nx"])
+    np.testing.assert_allclose(dd, g["lift_ddepth"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(df, g["lift_dfeat"], rtol=1e-4, atol=1e-5)

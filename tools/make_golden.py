@@ -72,8 +72,18 @@ def lss_small(vtm):
     w = torch.rand(out.shape, generator=g)
     (out * w).sum().backward()
     out_acc = vt.voxel_pooling_accelerated(geom, x.detach())
+    # lift + splat exactly as ViewTransformerLiftSplatShoot.forward does it (:250-262)
+    depth = torch.rand(B * N, D, fH, fW, generator=g).softmax(dim=1).requires_grad_(True)
+    feat = torch.randn(B * N, C, fH, fW, generator=g).requires_grad_(True)
+    volume = depth.unsqueeze(1) * feat.unsqueeze(2)
+    volume = volume.view(B, N, C, D, fH, fW).permute(0, 1, 3, 4, 5, 2)
+    lift_out = vt.voxel_pooling_accelerated(geom, volume)
+    (lift_out * w).sum().backward()
     np.savez_compressed(
         os.path.join(GOLDEN, "lss_small.npz"),
+        lift_depth=depth.detach().numpy(), lift_feat=feat.detach().numpy(),
+        lift_out=lift_out.detach().numpy(), lift_ddepth=depth.grad.numpy(),
+        lift_dfeat=feat.grad.numpy(),
         grid=json.dumps(grid), input_size=np.array(input_size), downsample=down,
         rots=rots, trans=trans, intrins=intrins, post_rots=post_rots, post_trans=post_trans,
         frustum=vt.frustum.detach().numpy(), geom=geom.detach().numpy(),
