@@ -11,6 +11,10 @@ from .plugin.ops.bev_pool import (BevPlan, QuickCumsumCuda, bev_plan_from_coords
 from .plugin.ops.voxel import (DynamicScatter, Voxelization, dynamic_scatter, voxel_layer,  # noqa: F401
                                voxelization)
 
+from .plugin.pillars import DynamicPillarFeatureNet, PointPillarsScatter, pillar_canvas  # noqa: F401
+from .plugin.view_transformer import ViewTransformerLiftSplatShoot, lss_geometry  # noqa: F401
+from .plugin.distill import fgd  # noqa: F401
+
 __version__ = "0.1.0"
 
 

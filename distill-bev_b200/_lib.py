@@ -81,6 +81,14 @@ SIGNATURES = {
                                        _ptr, _c_size, _ptr, _ptr]),
     "dbev_fgd_loss_backward": (_c_int, [_cfgp, _ptr, _ptr, _ptr, _ptr, _ptr, _c_size, _ptr, _ptr,
                                         _ptr, _ptr, _ptr]),
+    "dbev_pillar_encode_workspace_bytes": (_c_size, [_c_ll]),
+    "dbev_pillar_encode": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _fptr, _fptr, _c_float,
+                                    _c_float, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                    _c_size, _ptr]),
+    "dbev_pillar_scatter": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                     _c_int, _ptr, _ptr]),
+    "dbev_lss_geometry": (_c_int, [_ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr,
+                                   _ptr]),
     "dbev_sort_workspace_bytes": (_c_size, [_c_ll]),
     "dbev_sort_keys_iota": (_c_int, [_ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _c_size, _ptr]),
     "dbev_scan_workspace_bytes": (_c_size, [_c_ll]),

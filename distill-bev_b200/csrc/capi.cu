@@ -6,6 +6,7 @@
 
 #include "bev_pool.cuh"
 #include "distill_loss.cuh"
+#include "pillar.cuh"
 #include "sort.cuh"
 #include "voxelize.cuh"
 
@@ -207,6 +208,36 @@ int dbev_fgd_loss_backward(const dbev_fgd_config* cfg, const float* student, con
   DBEV_CHECK_ARG(cfg != nullptr, "fgd: null config");
   return fgd_loss_backward(*cfg, student, teacher, conv_w, conv_b, state, state_bytes, grad_losses,
                            grad_student, grad_conv_w, grad_conv_b, (cudaStream_t)stream);
+}
+
+size_t dbev_pillar_encode_workspace_bytes(long long n) { return pillar_encode_ws_bytes(n); }
+
+int dbev_pillar_encode(const float* points, const int* batch_offsets, const int* coors_in,
+                       int batch, int n, int nfeat, const float* voxel_size_host3,
+                       const float* coors_range_host6, float x_offset, float y_offset,
+                       const float* weight, int nout, const float* bn_scale,
+                       const float* bn_shift, float* voxel_feats, int* voxel_coors,
+                       int* num_voxels, int* point_coors, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  return pillar_encode(points, batch_offsets, coors_in, batch, n, nfeat, voxel_size_host3,
+                       coors_range_host6, x_offset, y_offset, weight, nout, bn_scale, bn_shift,
+                       voxel_feats, voxel_coors, num_voxels, point_coors, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_pillar_scatter(const float* voxel_feats, const int* coors, const int* m_dev, int m_max,
+                        int C, int batch, int ny, int nx, int channels_last, int zero_canvas,
+                        float* canvas, void* stream) {
+  return pillar_scatter(voxel_feats, coors, m_dev, m_max, C, batch, ny, nx, channels_last,
+                        zero_canvas, canvas, (cudaStream_t)stream);
+}
+
+int dbev_lss_geometry(const float* frustum, int pts_per_cam, const float* rots,
+                      const float* trans, const float* intrins, const float* post_rots,
+                      const float* post_trans, int n_cams, float* mats_ws, float* geom,
+                      void* stream) {
+  return lss_geometry(frustum, pts_per_cam, rots, trans, intrins, post_rots, post_trans, n_cams,
+                      mats_ws, geom, (cudaStream_t)stream);
 }
 
 size_t dbev_sort_workspace_bytes(long long n) {

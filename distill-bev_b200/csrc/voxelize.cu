@@ -303,6 +303,26 @@ struct SortedSegments {
   int* nseg;      // device scalar: number of valid segments
 };
 
+}  // namespace
+
+// sorted keys -> head flags, exclusive scan (segment ordinal), head positions [nseg + 1]
+// (last entry = one past the last valid row), *nseg = number of valid segments
+int segment_sorted_keys(const uint32_t* skeys, const uint32_t* sidx, int n, uint32_t sentinel,
+                        int* flags, int* excl, int* head_pos, int* nseg, void* sub, size_t sub_bytes,
+                        cudaStream_t stream) {
+  const int grid = ceil_div(n, 256);
+  head_flags_kernel<<<grid, 256, 0, stream>>>(skeys, n, sentinel, flags);
+  int rc = exclusive_scan_i32(flags, excl, n, nseg, sub, sub_bytes, stream);
+  if (rc != DBEV_OK) return rc;
+  segment_heads_kernel<<<grid, 256, 0, stream>>>(skeys, sidx, flags, excl, n, sentinel, head_pos,
+                                                 nullptr);
+  set_tail_marker_kernel<<<1, 32, 0, stream>>>(skeys, n, sentinel, nseg, head_pos);
+  DBEV_CHECK_LAUNCH("segment_sorted_keys");
+  return DBEV_OK;
+}
+
+namespace {
+
 // keys0 holds the unsorted keys (taken from `w` by the caller)
 int sort_and_segment(uint32_t* keys0, int n, unsigned long long nkeys, uint32_t sentinel,
                      Workspace& w, void* ws, size_t ws_bytes, cudaStream_t stream,

@@ -10,6 +10,10 @@ int voxel_grid_size(const float* voxel_size, const float* coors_range, int* grid
 int dynamic_voxelize(const float* points, int n, int nfeat, const float* voxel_size,
                      const float* coors_range, int* coors, cudaStream_t stream);
 
+int segment_sorted_keys(const uint32_t* skeys, const uint32_t* sidx, int n, uint32_t sentinel,
+                        int* flags, int* excl, int* head_pos, int* nseg, void* sub, size_t sub_bytes,
+                        cudaStream_t stream);
+
 size_t hard_voxelize_ws_bytes(long long n);
 int hard_voxelize(const float* points, int n, int nfeat, const float* voxel_size,
                   const float* coors_range, int max_points, int max_voxels, float* voxels,

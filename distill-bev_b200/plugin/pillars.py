@@ -1,0 +1,176 @@
+"""Teacher pillar path on the B200 kernels (csrc/pillar.cu).
+
+Mirrors (same constructor arguments, parameter names and return shapes):
+  * ``DynamicPillarFeatureNet``  mmdet3d/models/voxel_encoders/pillar_encoder.py:165-338
+  * ``PointPillarsScatter``      mmdet3d/models/middle_encoders/pillar_scatter.py:10-102
+  * ``DynamicCenterPoint.voxelize`` + ``extract_pts_feat`` up to the canvas
+    (mmdet3d/models/detectors/dynamic_centerpoint.py:43-93) as ``pillar_canvas``.
+
+In eval mode (the DistillBEV teacher is always frozen / eval,
+bevdet_distill.py:1591-1597) the whole encoder is one fused kernel sequence; in
+training mode (batch-norm needs batch statistics over all points) the forward is
+composed from this package's DynamicScatter kernels plus the module's own
+Linear / BatchNorm1d / ReLU, exactly the reference's data flow.
+"""
+import torch
+from torch import nn
+
+from .. import _lib
+from .ops.voxel import DynamicScatter, grid_size as _grid_size
+
+
+def fold_bn(bn):
+    """eval-mode BatchNorm1d -> per-channel (scale, shift)."""
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    shift = bn.bias - bn.running_mean * scale
+    return scale.detach().float().contiguous(), shift.detach().float().contiguous()
+
+
+def pillar_encode(points, weight, bn_scale, bn_shift, voxel_size, point_cloud_range, batch_size,
+                  coors=None, batch_offsets=None, return_point_coors=False, sync=True):
+    """Fused eval-mode DynamicPillarFeatureNet. points [N, F] of the whole batch; either
+    ``coors`` [N, 4] int32 (b, z, y, x) or ``batch_offsets`` [B + 1] int32 (voxelized on the fly).
+    -> voxel_feats [M, nout], voxel_coors [M, 4] int32 (and point coors / device count)."""
+    lib = _lib.load()
+    _lib.require_cuda(points, "points", torch.float32)
+    points = points.contiguous()
+    n, f = points.shape
+    nout = weight.shape[0]
+    if weight.shape[1] != f + 5:
+        raise RuntimeError("PFN weight must be [%d, %d] (raw + cluster(3) + center(2)), got %s"
+                           % (nout, f + 5, tuple(weight.shape)))
+    dev = points.device
+    w = weight.detach().float().contiguous()
+    vf = torch.empty((max(n, 1), nout), dtype=torch.float32, device=dev)
+    vc = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev)
+    cnt = torch.empty(1, dtype=torch.int32, device=dev)
+    pc = torch.empty((max(n, 1), 4), dtype=torch.int32, device=dev) if return_point_coors else None
+    if coors is not None:
+        _lib.require_cuda(coors, "coors", torch.int32)
+        coors = coors.contiguous()
+    if batch_offsets is not None:
+        batch_offsets = batch_offsets.to(device=dev, dtype=torch.int32).contiguous()
+    x_off = float(voxel_size[0]) / 2 + float(point_cloud_range[0])   # python doubles, :88-89
+    y_off = float(voxel_size[1]) / 2 + float(point_cloud_range[1])
+    with torch.cuda.device(dev):
+        wsb = lib.dbev_pillar_encode_workspace_bytes(n)
+        ws = _lib.workspace(wsb, dev)
+        rc = lib.dbev_pillar_encode(
+            _lib.ptr(points), _lib.ptr(batch_offsets), _lib.ptr(coors), int(batch_size), n, f,
+            _lib.host_floats(voxel_size), _lib.host_floats(point_cloud_range), x_off, y_off,
+            _lib.ptr(w), nout, _lib.ptr(bn_scale), _lib.ptr(bn_shift), _lib.ptr(vf), _lib.ptr(vc),
+            _lib.ptr(cnt), _lib.ptr(pc), _lib.ptr(ws), wsb, _lib.stream_ptr(dev))
+    _lib.check(rc, "dbev_pillar_encode")
+    if not sync:
+        return vf, vc, cnt, pc
+    m = int(cnt.item())
+    out = (vf[:m], vc[:m])
+    return out + ((pc[:n],) if return_point_coors else ())
+
+
+def pillar_scatter(voxel_features, coors, batch_size, ny, nx, channels_last=False, count=None):
+    """canvas [B, C, ny, nx] (NCHW, or the same shape in channels_last memory format)."""
+    lib = _lib.load()
+    _lib.require_cuda(voxel_features, "voxel_features", torch.float32)
+    _lib.require_cuda(coors, "coors")
+    voxel_features = voxel_features.contiguous()
+    coors = coors.to(torch.int32).contiguous()
+    m, c = voxel_features.shape
+    dev = voxel_features.device
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
+    canvas = torch.empty((batch_size, c, ny, nx), dtype=torch.float32, device=dev, memory_format=fmt)
+    with torch.cuda.device(dev):
+        rc = lib.dbev_pillar_scatter(_lib.ptr(voxel_features), _lib.ptr(coors), _lib.ptr(count), m, c,
+                                     batch_size, ny, nx, int(channels_last), 1, _lib.ptr(canvas),
+                                     _lib.stream_ptr(dev))
+    _lib.check(rc, "dbev_pillar_scatter")
+    return canvas
+
+
+class DynamicPillarFeatureNet(nn.Module):
+    """pillar_encoder.py:165-338 with one PFN layer (the only case the reference supports,
+    ':219 TODO: currently only support one PFNLayer')."""
+
+    def __init__(self, in_channels=4, feat_channels=(64,), with_distance=False,
+                 with_cluster_center=True, with_voxel_center=True, voxel_size=(0.2, 0.2, 4),
+                 point_cloud_range=(0, -40, -3, 70.4, 40, 1),
+                 norm_cfg=dict(type='BN1d', eps=1e-3, momentum=0.01), mode='max', virtual=False,
+                 act_cfg=dict(type='ReLU', inplace=True), use_checkpoint=False):
+        super(DynamicPillarFeatureNet, self).__init__()
+        if len(feat_channels) != 1 or with_distance or not with_cluster_center or not with_voxel_center \
+                or virtual or mode != 'max':
+            raise NotImplementedError("only the shipped teacher configuration is implemented: one PFN "
+                                      "layer, cluster + voxel centre decorations, max pooling")
+        self.in_channels = in_channels + 5
+        self.voxel_size = voxel_size
+        self.point_cloud_range = point_cloud_range
+        self.vx, self.vy = voxel_size[0], voxel_size[1]
+        self.x_offset = self.vx / 2 + point_cloud_range[0]
+        self.y_offset = self.vy / 2 + point_cloud_range[1]
+        bn = nn.BatchNorm1d(feat_channels[0], eps=norm_cfg.get('eps', 1e-5),
+                            momentum=norm_cfg.get('momentum', 0.1))
+        self.pfn_layers = nn.ModuleList([nn.Sequential(
+            nn.Linear(self.in_channels, feat_channels[0], bias=False), bn, nn.ReLU(inplace=True))])
+        self.pfn_scatter = DynamicScatter(voxel_size, point_cloud_range, False)
+        self.cluster_scatter = DynamicScatter(voxel_size, point_cloud_range, True)
+
+    def forward(self, features, coors):
+        batch_size = int(coors[-1, 0] + 1)
+        lin, bn = self.pfn_layers[0][0], self.pfn_layers[0][1]
+        if not self.training:
+            scale, shift = fold_bn(bn)
+            return pillar_encode(features, lin.weight, scale, shift, self.voxel_size,
+                                 self.point_cloud_range, batch_size, coors=coors.to(torch.int32))
+        # training mode: reference data flow on this package's scatter kernels
+        coors = coors.to(torch.int32)
+        voxel_mean, mean_coors = self.cluster_scatter(features, coors, batch_size)
+        gx, gy, gz = _grid_size(self.voxel_size, self.point_cloud_range)
+        key = lambda c: ((c[:, 0].long() * gz + c[:, 1].long()) * gy + c[:, 2].long()) * gx + c[:, 3].long()
+        valid = (coors >= 0).all(dim=1)
+        idx = torch.searchsorted(key(mean_coors), key(coors.clamp(min=0)))
+        points_mean = voxel_mean[idx.clamp(max=max(voxel_mean.shape[0] - 1, 0))]
+        points_mean = torch.where(valid[:, None], points_mean, torch.zeros_like(points_mean))
+        f_cluster = features[:, :3] - points_mean[:, :3]
+        f_center = torch.stack([features[:, 0] - (coors[:, 3].type_as(features) * self.vx + self.x_offset),
+                                features[:, 1] - (coors[:, 2].type_as(features) * self.vy + self.y_offset)], 1)
+        point_feats = self.pfn_layers[0](torch.cat([features, f_cluster, f_center], dim=-1))
+        return self.pfn_scatter(point_feats, coors, batch_size)
+
+
+class PointPillarsScatter(nn.Module):
+    """pillar_scatter.py:10-102. ``channels_last=True`` returns the same [B, C, ny, nx] tensor in
+    NHWC memory order (one contiguous 4*C-byte row per pillar; what cuDNN prefers downstream)."""
+
+    def __init__(self, in_channels, output_shape, channels_last=False):
+        super().__init__()
+        self.output_shape = output_shape
+        self.ny, self.nx = output_shape[0], output_shape[1]
+        self.in_channels = in_channels
+        self.channels_last = channels_last
+
+    def forward(self, voxel_features, coors, batch_size=None):
+        if batch_size is not None:
+            return pillar_scatter(voxel_features, coors, batch_size, self.ny, self.nx, self.channels_last)
+        # forward_single: coors = (y, x) at columns 1, 2 (:47); returns a list like the reference
+        c4 = torch.zeros((coors.shape[0], 4), dtype=torch.int32, device=coors.device)
+        c4[:, 2], c4[:, 3] = coors[:, 1], coors[:, 2]
+        return [pillar_scatter(voxel_features, c4, 1, self.ny, self.nx, self.channels_last)]
+
+
+def pillar_canvas(points_list, encoder, scatter):
+    """points (list of [N_b, F] CUDA tensors) -> teacher pseudo image [B, C, ny, nx] with no host
+    synchronisation: voxelization, pillar encoding and scatter are enqueued back to back
+    (DynamicCenterPoint.voxelize + extract_pts_feat, dynamic_centerpoint.py:43-93)."""
+    B = len(points_list)
+    offs = [0]
+    for p in points_list:
+        offs.append(offs[-1] + p.shape[0])
+    points = torch.cat(points_list, 0) if B > 1 else points_list[0]
+    offsets = torch.tensor(offs, dtype=torch.int32)
+    lin, bn = encoder.pfn_layers[0][0], encoder.pfn_layers[0][1]
+    if encoder.training:
+        raise RuntimeError("pillar_canvas is the frozen-teacher (eval) path")
+    scale, shift = fold_bn(bn)
+    vf, vc, cnt, _ = pillar_encode(points, lin.weight, scale, shift, encoder.voxel_size,
+                                   encoder.point_cloud_range, B, batch_offsets=offsets, sync=False)
+    return pillar_scatter(vf, vc, B, scatter.ny, scatter.nx, scatter.channels_last, count=cnt)

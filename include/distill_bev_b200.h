@@ -225,6 +225,47 @@ int dbev_dynamic_scatter_backward(const float* grad_reduced, const float* feats,
                                   void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * Teacher pillar encoder (eval mode) and pseudo-image scatter.
+ * ------------------------------------------------------------------------ */
+
+/* DynamicPillarFeatureNet.forward with one PFN layer, eval-mode BN
+ * (mmdet3d/models/voxel_encoders/pillar_encoder.py:282-338): cluster mean,
+ * f_cluster / f_center decorations, Linear(nfeat+5 -> nout, no bias) + BN + ReLU,
+ * max over the pillar - fused, the decorated / per-point features never reach HBM.
+ *   points[n, nfeat] of the whole batch back to back; either coors_in[n,4] = (b,z,y,x)
+ *   (the reference's call shape) or batch_offsets[batch+1] (device int; voxelization is
+ *   then done on the fly and optionally written to point_coors[n,4]).
+ *   weight[nout, nfeat+5] = pfn_layers[0][0].weight; bn_scale/shift[nout] = folded BN.
+ *   x_offset = vx/2 + pc_min_x, y_offset likewise (host doubles rounded to float, :88-89).
+ * Outputs (sized for n rows): voxel_feats[M, nout], voxel_coors[M, 4] in lexicographic
+ * (b,z,y,x) order = the order pfn_scatter returns; *num_voxels is a DEVICE int. */
+size_t dbev_pillar_encode_workspace_bytes(long long n);
+int dbev_pillar_encode(const float* points, const int* batch_offsets, const int* coors_in,
+                       int batch, int n, int nfeat, const float* voxel_size_host3,
+                       const float* coors_range_host6, float x_offset, float y_offset,
+                       const float* weight, int nout, const float* bn_scale,
+                       const float* bn_shift, float* voxel_feats, int* voxel_coors,
+                       int* num_voxels, int* point_coors, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* PointPillarsScatter.forward_batch (mmdet3d/models/middle_encoders/pillar_scatter.py:62-102):
+ * canvas[b, :, y, x] = voxel_feats[m, :] for coors[m] = (b, z, y, x). The canvas is
+ * [batch, C, ny, nx] (channels_last = 0) or the same tensor in NHWC memory order
+ * (channels_last = 1: one contiguous row per pillar). m_dev (nullable): device count
+ * clamp; zero_canvas != 0 enqueues the zero fill. One launch for the whole batch. */
+int dbev_pillar_scatter(const float* voxel_feats, const int* coors, const int* m_dev, int m_max,
+                        int C, int batch, int ny, int nx, int channels_last, int zero_canvas,
+                        float* canvas, void* stream);
+
+/* get_geometry (mmdet3d/models/necks/view_transformer_mine.py:111-139): frustum[pts_per_cam, 3]
+ * (x_px, y_px, depth), per camera rots/intrins/post_rots [n_cams,3,3], trans/post_trans
+ * [n_cams,3] -> geom[n_cams * pts_per_cam, 3] ego-frame xyz. mats_ws: n_cams * 18 floats. */
+int dbev_lss_geometry(const float* frustum, int pts_per_cam, const float* rots,
+                      const float* trans, const float* intrins, const float* post_rots,
+                      const float* post_trans, int n_cams, float* mats_ws, float* geom,
+                      void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Cross-modal feature distillation loss (FGD-style), BEVDetDistill
  * (mmdet3d/models/detectors/bevdet_distill.py). The reference has no native
  * interface for this path: it is ~20 torch kernels plus numpy/numba on the

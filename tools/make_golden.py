@@ -22,6 +22,8 @@ Fixtures
   fgd_small.npz    BEVDetDistill.foreground_scale_mask / add_fp_as_fg / fgd_distill_loss /
                    affinity_distill_loss method bodies (ast-extracted, unmodified): masks,
                    losses, autograd gradients for three option sets
+  pillar_small.npz reference DynamicPillarFeatureNet (eval) + PointPillarsScatter, unmodified
+                   files; DynamicScatter (CUDA-only) replaced by its host sequence on torch CPU
 Also prints (not stored) the full-size config-1 comparison oracle vs reference.
 """
 import json
@@ -334,6 +336,49 @@ def fgd_golden():
     np.savez_compressed(os.path.join(GOLDEN, "fgd_small.npz"), **out)
 
 
+def pillar_golden():
+    """Unmodified reference DynamicPillarFeatureNet (eval) + PointPillarsScatter on a small batch."""
+    from oracle import voxel_oracle
+    DPFN, PPS = ref_import.pillar_modules()
+    vs, pcr = [0.5, 0.5, 8.0], [-16.0, -16.0, -5.0, 16.0, 16.0, 3.0]
+    torch.manual_seed(5)
+    enc = DPFN(in_channels=5, feat_channels=(64,), voxel_size=vs, point_cloud_range=pcr,
+               norm_cfg=dict(type="BN1d", eps=1e-3, momentum=0.01))
+    bn = enc.pfn_layers[0][1]
+    with torch.no_grad():
+        bn.running_mean.copy_(torch.randn(64) * 0.3)
+        bn.running_var.copy_(torch.rand(64) + 0.5)
+        bn.weight.copy_(torch.rand(64) + 0.5)
+        bn.bias.copy_(torch.randn(64) * 0.2)
+    enc.eval()
+    rng = np.random.RandomState(17)
+    pts, coors = [], []
+    for b, n in enumerate([1500, 900]):
+        p = np.zeros((n, 5), dtype=np.float32)
+        p[:, :2] = rng.normal(0, 7.0, (n, 2))
+        p[:, 2] = rng.uniform(-4.5, 2.5, n)
+        p[:, 3] = rng.uniform(0, 255, n)
+        p[:, 4] = rng.randint(0, 10, n) * 0.05
+        p[:30, 0] += 40.0                      # out of range -> coors -1
+        c = voxel_oracle.dynamic_voxelize(p, vs, pcr)
+        pts.append(p)
+        coors.append(np.concatenate([np.full((n, 1), b, np.int32), c], 1))
+    pts, coors = np.concatenate(pts), np.concatenate(coors)
+    with torch.no_grad():
+        vf, vc = enc(torch.from_numpy(pts), torch.from_numpy(coors))
+        scat = PPS(64, [64, 64])
+        canvas = scat(vf, vc, 2)
+    np.savez_compressed(
+        os.path.join(GOLDEN, "pillar_small.npz"), points=pts, coors=coors,
+        voxel_size=np.array(vs, np.float32), coors_range=np.array(pcr, np.float32),
+        weight=enc.pfn_layers[0][0].weight.detach().numpy(), bn_weight=bn.weight.detach().numpy(),
+        bn_bias=bn.bias.detach().numpy(), bn_mean=bn.running_mean.numpy(), bn_var=bn.running_var.numpy(),
+        bn_eps=np.float32(bn.eps), voxel_feats=vf.numpy(), voxel_coors=vc.numpy(),
+        canvas_nonzero=np.stack(np.nonzero(canvas.numpy().sum(1))).astype(np.int32),
+        canvas_checksum=np.float64(canvas.double().sum().item()))
+    print("pillar_small: pillars", vf.shape[0], "canvas", tuple(canvas.shape))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     vtm = ref_import.view_transformer_mine()
@@ -344,3 +389,4 @@ if __name__ == "__main__":
     fullsize_check(vtm)
     voxel_small()
     fgd_golden()
+    pillar_golden()

@@ -66,7 +66,17 @@ def install_stubs():
         return nn.Conv2d(*args, **kwargs)
 
     def build_norm_layer(cfg, num_features, postfix=""):
-        return "bn", nn.BatchNorm2d(num_features)
+        cfg = dict(cfg)
+        typ = cfg.pop("type")
+        cfg.pop("requires_grad", None)
+        cls = {"BN": nn.BatchNorm2d, "BN2d": nn.BatchNorm2d, "BN1d": nn.BatchNorm1d}[typ]
+        return "bn", cls(num_features, **cfg)
+
+    def build_activation_layer(cfg):
+        assert cfg["type"] == "ReLU"
+        return nn.ReLU(inplace=cfg.get("inplace", False))
+
+    cnn.build_activation_layer = build_activation_layer
 
     cnn.build_conv_layer = build_conv_layer
     cnn.build_norm_layer = build_norm_layer
@@ -109,6 +119,60 @@ def load_ref_module(qualname, relpath):
     sys.modules[qualname] = mod
     spec.loader.exec_module(mod)
     return mod
+
+
+class _CpuDynamicScatter(nn.Module):
+    """CPU stand-in for mmdet3d.ops.DynamicScatter (CUDA-only in the reference,
+    voxelization.h:118): the host sequence of scatter_points_cuda.cu:183-239 executed with
+    torch CPU ops (masked_fill, torch.unique(dim=0) = at::unique_dim, scatter amax / index_add),
+    wrapped in the reference's own per-sample loop (scatter_points.py:75-100)."""
+
+    def __init__(self, voxel_size, point_cloud_range, average_points):
+        super().__init__()
+        self.average_points = average_points
+
+    def forward_single(self, points, coors):
+        clean = coors.masked_fill(coors.lt(0).any(-1, True), -1)
+        oc, inv, cnt = torch.unique(clean, dim=0, sorted=True, return_inverse=True, return_counts=True)
+        if oc[0, 0] < 0:
+            oc, cnt, inv = oc[1:], cnt[1:], inv - 1
+        valid = inv >= 0
+        m, c = oc.shape[0], points.shape[1]
+        if self.average_points:
+            red = torch.zeros(m, c).index_add_(0, inv[valid], points[valid]) / cnt[:, None].float()
+        else:
+            red = torch.full((m, c), -float("inf")).scatter_reduce(
+                0, inv[valid][:, None].expand(-1, c), points[valid], "amax")
+        return red, oc
+
+    def forward(self, points, coors):
+        if coors.size(-1) == 3:
+            return self.forward_single(points, coors)
+        batch_size = int(coors[-1, 0] + 1)
+        voxels, voxel_coors = [], []
+        for i in range(batch_size):
+            inds = torch.where(coors[:, 0] == i)
+            voxel, voxel_coor = self.forward_single(points[inds], coors[inds][:, 1:])
+            voxel_coors.append(nn.functional.pad(voxel_coor, (1, 0), mode="constant", value=i))
+            voxels.append(voxel)
+        return torch.cat(voxels, dim=0), torch.cat(voxel_coors, dim=0)
+
+
+def pillar_modules():
+    """(DynamicPillarFeatureNet, PointPillarsScatter) classes from the unmodified reference files."""
+    install_stubs()
+    sys.modules["mmdet3d.ops"].DynamicScatter = _CpuDynamicScatter
+    builder = sys.modules["mmdet3d.models.builder"]
+    builder.VOXEL_ENCODERS = _Registry("voxel encoder")
+    builder.MIDDLE_ENCODERS = _Registry("middle encoder")
+    _pkg("mmdet3d.models.voxel_encoders", os.path.join(REF_ROOT, "mmdet3d/models/voxel_encoders"))
+    _pkg("mmdet3d.models.middle_encoders", os.path.join(REF_ROOT, "mmdet3d/models/middle_encoders"))
+    load_ref_module("mmdet3d.models.voxel_encoders.utils", "mmdet3d/models/voxel_encoders/utils.py")
+    pe = load_ref_module("mmdet3d.models.voxel_encoders.pillar_encoder",
+                         "mmdet3d/models/voxel_encoders/pillar_encoder.py")
+    ps = load_ref_module("mmdet3d.models.middle_encoders.pillar_scatter",
+                         "mmdet3d/models/middle_encoders/pillar_scatter.py")
+    return pe.DynamicPillarFeatureNet, ps.PointPillarsScatter
 
 
 def view_transformer_mine():
