@@ -204,8 +204,8 @@ __device__ __forceinline__ ItemCtx decode_item(const int4& item, const PoolGeom&
 // and channels-last feat[BN * fH * fW, C]; the [B,N,D,fH,fW,C] volume never exists.
 struct LiftArgs {
   const float* depth;
-  int dfhw;  // D * fH * fW
-  int fhw;   // fH * fW
+  FastDiv dfhw;  // D * fH * fW
+  FastDiv fhw;   // fH * fW
 };
 
 template <int LPR, bool LIFT>
@@ -292,11 +292,11 @@ bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restri
           if (lane_active && pos + u < we) {
             if (LIFT) {
               const uint32_t p = pid[u];
-              const uint32_t bn = p / (uint32_t)la.dfhw;
-              const uint32_t pix = (p - bn * (uint32_t)la.dfhw) % (uint32_t)la.fhw;
+              const uint32_t bn = la.dfhw.div(p);
+              const uint32_t pix = la.fhw.mod(p - bn * la.dfhw.d);
               const float w = __ldg(la.depth + p);
               const float4 f = __ldg(reinterpret_cast<const float4*>(
-                  xb + ((size_t)bn * la.fhw + pix) * g.C));
+                  xb + ((size_t)bn * la.fhw.d + pix) * g.C));
               v[u] = make_float4(w * f.x, w * f.y, w * f.z, w * f.w);
             } else {
               v[u] = ld_stream_f4(xb + (size_t)pid[u] * g.C);
@@ -545,6 +545,7 @@ lift_splat_bwd_kernel(const float* __restrict__ g_cl, const float* __restrict__ 
                       float* __restrict__ d_feat) {
   constexpr int CB = LPR * 4;
   constexpr int GPB = 256 / LPR;  // pixel groups per CTA
+  constexpr int U = 8;            // depth bins in flight per group
   const int sub = threadIdx.x % LPR;
   const long long pixrow = (long long)blockIdx.x * GPB + threadIdx.x / LPR;
   const bool valid = pixrow < n_pix;  // whole groups are valid or not; shuffles stay in-group
@@ -553,27 +554,40 @@ lift_splat_bwd_kernel(const float* __restrict__ g_cl, const float* __restrict__ 
   const int nblocks = (C + CB - 1) / CB;
   const unsigned gmask = (LPR == 32) ? 0xffffffffu
                                      : (((1u << LPR) - 1u) << ((threadIdx.x & 31) / LPR * LPR));
+  const size_t p0 = (size_t)bn * D * fhw + pix;  // point id of depth bin 0 of this ray
   for (int cbk = 0; cbk < nblocks; ++cbk) {
     const int c = cbk * CB + sub * 4;
     const bool act = valid && c < C;
     float4 f = make_float4(0.f, 0.f, 0.f, 0.f), acc = f;
     if (act) f = __ldg(reinterpret_cast<const float4*>(feat + (size_t)pixrow * C + c));
-#pragma unroll 4
-    for (int d = 0; d < D; ++d) {
-      const size_t p = ((size_t)bn * D + d) * fhw + pix;
-      const int cell = valid ? __ldg(point_cell + p) : -1;
-      float dot = 0.f;
-      if (cell >= 0 && act) {
-        const float4 gv = __ldg(reinterpret_cast<const float4*>(g_cl + (size_t)cell * C + c));
-        const float w = __ldg(depth + p);
-        acc.x += w * gv.x; acc.y += w * gv.y; acc.z += w * gv.z; acc.w += w * gv.w;
-        dot = (f.x * gv.x + f.y * gv.y) + (f.z * gv.z + f.w * gv.w);
+    for (int d0 = 0; d0 < D; d0 += U) {
+      int cell[U];
+      float w[U];
+      float4 gv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool in = valid && d0 + u < D;
+        cell[u] = in ? __ldg(point_cell + p0 + (size_t)(d0 + u) * fhw) : -1;
+        w[u] = in ? __ldg(depth + p0 + (size_t)(d0 + u) * fhw) : 0.f;
       }
 #pragma unroll
-      for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o);
-      if (valid && sub == 0) {
-        if (cbk == 0) d_depth[p] = dot;
-        else d_depth[p] += dot;  // same thread wrote it in the previous channel block
+      for (int u = 0; u < U; ++u) {
+        gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cell[u] >= 0 && act)
+          gv[u] = __ldg(reinterpret_cast<const float4*>(g_cl + (size_t)cell[u] * C + c));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc.x += w[u] * gv[u].x; acc.y += w[u] * gv[u].y;
+        acc.z += w[u] * gv[u].z; acc.w += w[u] * gv[u].w;
+        float dot = (f.x * gv[u].x + f.y * gv[u].y) + (f.z * gv[u].z + f.w * gv[u].w);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o);
+        if (valid && sub == 0 && d0 + u < D) {
+          float* dd = d_depth + p0 + (size_t)(d0 + u) * fhw;
+          if (cbk == 0) *dd = dot;
+          else *dd += dot;  // same thread wrote it in the previous channel block
+        }
       }
     }
     if (act) *reinterpret_cast<float4*>(d_feat + (size_t)pixrow * C + c) = acc;
@@ -960,7 +974,7 @@ static int gather_forward_impl(const float* x, int C, const uint32_t* order, con
     DBEV_CHECK_LAUNCH("lift_splat_fwd_kernel");
     return DBEV_OK;
   }
-  const LiftArgs none{nullptr, 1, 1};
+  const LiftArgs none{nullptr, FastDiv(1), FastDiv(1)};
   if (lpr > 0) {
     const int cb = lpr * 4, nw = 32 / lpr;
     const size_t smem = (size_t)kPoolWarps * (cb * kTilePitch + nw * 2 * cb) * sizeof(float);
@@ -998,7 +1012,8 @@ int lift_splat_forward(const float* depth, const float* feat_cl, int C, int D, i
                        int nfast, long long sB, long long sZ, long long sC, float* out,
                        cudaStream_t stream) {
   DBEV_CHECK_ARG(D > 0 && fhw > 0, "lift_splat: bad frustum shape D=%d fH*fW=%d", D, fhw);
-  const LiftArgs la{depth, D * fhw, fhw};
+  DBEV_CHECK_ARG((long long)D * fhw < (1LL << 30), "lift_splat: frustum too large");
+  const LiftArgs la{depth, FastDiv((unsigned)(D * fhw)), FastDiv((unsigned)fhw)};
   return gather_forward_impl(feat_cl, C, order, cell_start, cell_end, items, n_items, batch, nz,
                              nslow, nfast, sB, sZ, sC, out, &la, stream);
 }

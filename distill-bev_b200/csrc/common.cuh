@@ -42,6 +42,28 @@ struct Workspace {
   bool ok() const { return base != nullptr && used <= size; }
 };
 
+// Exact unsigned division by a runtime constant for numerators n < 2^31
+// (Granlund-Montgomery round-up method): with l = ceil(log2 d), shift = 31 + l and
+// mul = ceil(2^shift / d) < 2^32, floor(n / d) == (n * mul) >> shift for every n < 2^31
+// because mul * d - 2^shift <= 2^l. One IMAD.WIDE + one funnel shift instead of ~25
+// instructions for a hardware-less 32-bit division.
+struct FastDiv {
+  unsigned mul;
+  int shift;
+  unsigned d;
+  FastDiv() : mul(1u << 31), shift(31), d(1) {}
+  explicit FastDiv(unsigned div) : d(div) {
+    int l = 0;
+    while ((1ull << l) < div) ++l;
+    shift = 31 + l;
+    mul = (unsigned)(((1ull << shift) + div - 1) / div);
+  }
+  __host__ __device__ __forceinline__ unsigned div(unsigned n) const {
+    return (unsigned)(((unsigned long long)n * mul) >> shift);
+  }
+  __host__ __device__ __forceinline__ unsigned mod(unsigned n) const { return n - div(n) * d; }
+};
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 
 __device__ __forceinline__ unsigned lanemask_lt() {

@@ -272,25 +272,31 @@ fgd_teacher_stats_kernel(const float* __restrict__ t, FgdDims d, float* __restri
   }
 }
 
-// per-channel finalize: means over HW (fixed tile order), channel attention
-// softmax(mean|t| / C_T) * C (:1094-1097). One CTA per sample.
+// per-channel means over HW from the tile partials (fixed tile order): one thread per (b, c)
 __global__ void __launch_bounds__(256)
-fgd_channel_finalize_kernel(FgdDims d, float channel_t, const float* __restrict__ cta_p,
-                            const float* __restrict__ ctm_p, float* __restrict__ catt,
-                            float* __restrict__ ctm) {
+fgd_channel_means_kernel(FgdDims d, const float* __restrict__ part_a, const float* __restrict__ part_b,
+                         float* __restrict__ mean_a, float* __restrict__ mean_b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.B * d.C) return;
+  const size_t o = (size_t)i * d.ntiles;
+  float sa = 0.f, sb = 0.f;
+  for (int k = 0; k < d.ntiles; ++k) {
+    sa += part_a[o + k];
+    if (part_b) sb += part_b[o + k];
+  }
+  mean_a[i] = sa / (float)d.HW;
+  if (part_b) mean_b[i] = sb / (float)d.HW;
+}
+
+// channel attention softmax(mean|t| / C_T) * C (:1094-1097), in place. One CTA per sample.
+__global__ void __launch_bounds__(256)
+fgd_channel_softmax_kernel(FgdDims d, float channel_t, float* __restrict__ catt) {
   __shared__ float red[256];
   const int b = blockIdx.x;
   float lmax = -INFINITY;
   for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
-    const size_t o = ((size_t)b * d.C + c) * d.ntiles;
-    float sa = 0.f, sm = 0.f;
-    for (int k = 0; k < d.ntiles; ++k) {
-      sa += cta_p[o + k];
-      sm += ctm_p[o + k];
-    }
-    const float v = (sa / (float)d.HW) / channel_t;
+    const float v = catt[(size_t)b * d.C + c] / channel_t;
     catt[(size_t)b * d.C + c] = v;
-    ctm[(size_t)b * d.C + c] = sm / (float)d.HW;
     lmax = fmaxf(lmax, v);
   }
   red[threadIdx.x] = lmax;
@@ -384,16 +390,6 @@ fgd_spatial_softmax_kernel(FgdDims d, float spatial_t, float* __restrict__ ta,
   }
   const float inv = (float)d.HW / red[0];
   for (int i = threadIdx.x; i < d.HW; i += blockDim.x) a[i] = expf(a[i] * scale - mx) * inv;
-}
-
-__global__ void __launch_bounds__(256)
-fgd_student_channel_mean_kernel(FgdDims d, const float* __restrict__ csm_p,
-                                float* __restrict__ csm) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.B * d.C) return;
-  float s = 0.f;
-  for (int k = 0; k < d.ntiles; ++k) s += csm_p[(size_t)i * d.ntiles + k];
-  csm[i] = s / (float)d.HW;
 }
 
 struct FgdCfg {
@@ -754,12 +750,14 @@ int fgd_loss_forward(const FgdConfig& c, const float* student, const float* teac
   FgdState st = carve_state((float*)state, d);
   dim3 grid(d.ntiles, d.B);
   fgd_teacher_stats_kernel<<<grid, kBlock, 0, stream>>>(teacher, d, st.ta, st.tm, st.cta_p, st.ctm_p);
-  fgd_channel_finalize_kernel<<<d.B, 256, 0, stream>>>(d, k.channel_t, st.cta_p, st.ctm_p, st.catt,
-                                                       st.ctm);
+  fgd_channel_means_kernel<<<ceil_div(d.B * d.C, 256), 256, 0, stream>>>(d, st.cta_p, st.ctm_p,
+                                                                         st.catt, st.ctm);
+  fgd_channel_softmax_kernel<<<d.B, 256, 0, stream>>>(d, k.channel_t, st.catt);
   fgd_student_pass_kernel<<<grid, kBlock, 0, stream>>>(student, teacher, d, st.catt, st.sa, st.sm,
                                                        st.d1, st.d2, st.csm_p);
   fgd_spatial_softmax_kernel<<<dim3(d.B, 2), 1024, 0, stream>>>(d, k.spatial_t, st.ta, st.sa);
-  fgd_student_channel_mean_kernel<<<ceil_div(d.B * d.C, 256), 256, 0, stream>>>(d, st.csm_p, st.csm);
+  fgd_channel_means_kernel<<<ceil_div(d.B * d.C, 256), 256, 0, stream>>>(d, st.csm_p, nullptr,
+                                                                         st.csm, nullptr);
   fgd_combine_kernel<<<grid, kTile, 0, stream>>>(d, k, fg, fg_scale, fg_count, fp, fp_count, st.ta,
                                                  st.sa, st.tm, st.sm, st.d1, st.d2, conv_w, conv_b,
                                                  st.fgw, st.bgw, st.fpw, st.loss_p);

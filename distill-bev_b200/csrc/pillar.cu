@@ -39,49 +39,41 @@ struct PillarGeom {
   int nx, ny, nz; // grid (keys are ((b*nz + z)*ny + y)*nx + x)
 };
 
-// one group of `nout` threads per pillar; blockDim.x = groups * nout
+// one group of `nout` threads per pillar (thread = output channel); blockDim.x = groups * nout.
+// Groups are independent (no block barrier inside the loop): every thread recomputes the
+// pillar mean from the L1-resident point rows, so thousands of pillars are in flight.
 __global__ void __launch_bounds__(256)
 pillar_encode_kernel(const float* __restrict__ points, const uint32_t* __restrict__ skeys,
                      const uint32_t* __restrict__ sidx, const int* __restrict__ head_pos,
                      const int* __restrict__ nseg_ptr, PillarGeom g, const float* __restrict__ weight,
                      const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
                      float* __restrict__ voxel_feats, int* __restrict__ voxel_coors) {
-  extern __shared__ float sh[];
-  float* w_s = sh;                              // [nin][nout]
-  float* mean_s = sh + g.nin * g.nout;          // [groups][4]
+  extern __shared__ float w_s[];  // [nin][nout]
   const int groups = blockDim.x / g.nout;
   for (int i = threadIdx.x; i < g.nin * g.nout; i += blockDim.x) {
     // nn.Linear weight is [nout, nin]; stage transposed so threads of a group read consecutively
     const int c = i % g.nout, k = i / g.nout;
     w_s[i] = weight[c * g.nin + k];
   }
+  __syncthreads();
   const int grp = threadIdx.x / g.nout, c = threadIdx.x % g.nout;
-  const bool grp_ok = grp < groups;
   const int nseg = *nseg_ptr;
-  const float sc = grp_ok ? bn_scale[c] : 0.f, shf = grp_ok ? bn_shift[c] : 0.f;
-  for (int base = blockIdx.x * groups; base < nseg; base += gridDim.x * groups) {
-    const int seg = base + grp;
-    const bool ok = grp_ok && seg < nseg;
-    __syncthreads();  // weights staged / previous iteration done with mean_s
-    int s = 0, e = 0;
-    uint32_t key = 0;
-    if (ok) {
-      s = head_pos[seg];
-      e = head_pos[seg + 1];
-      key = skeys[s];
-      if (c < 3) {  // pillar mean of x, y, z in point order (cluster_scatter, average_points=True)
-        float acc = 0.f;
-        for (int j = s; j < e; ++j) acc += points[(size_t)sidx[j] * g.nfeat + c];
-        mean_s[grp * 4 + c] = acc / (float)(e - s);
-      }
+  const float sc = bn_scale[c], shf = bn_shift[c];
+  for (int seg = blockIdx.x * groups + grp; seg < nseg; seg += gridDim.x * groups) {
+    const int s = head_pos[seg], e = head_pos[seg + 1];
+    const uint32_t key = skeys[s];
+    // pillar mean of x, y, z in point order (cluster_scatter, average_points=True)
+    float mx = 0.f, my = 0.f, mz = 0.f;
+    for (int j = s; j < e; ++j) {
+      const float* p = points + (size_t)sidx[j] * g.nfeat;
+      mx += p[0]; my += p[1]; mz += p[2];
     }
-    __syncthreads();
-    if (!ok) continue;
+    const float cnt = (float)(e - s);
+    mx /= cnt; my /= cnt; mz /= cnt;
     const int cx = (int)(key % (uint32_t)g.nx);
     const int cy = (int)((key / (uint32_t)g.nx) % (uint32_t)g.ny);
     const float ctr_x = __fadd_rn(__fmul_rn((float)cx, g.vx), g.x_offset);
     const float ctr_y = __fadd_rn(__fmul_rn((float)cy, g.vy), g.y_offset);
-    const float mx = mean_s[grp * 4 + 0], my = mean_s[grp * 4 + 1], mz = mean_s[grp * 4 + 2];
     float best = -INFINITY;
     for (int j = s; j < e; ++j) {
       const float* p = points + (size_t)sidx[j] * g.nfeat;
@@ -288,8 +280,9 @@ int pillar_encode(const float* points, const int* batch_offsets, const int* coor
   g.y_offset = y_offset;
   g.nfeat = nfeat; g.nin = nfeat + 5; g.nout = nout;
   g.nx = grid3[0]; g.ny = grid3[1]; g.nz = grid3[2];
-  const size_t smem = ((size_t)g.nin * nout + (256 / nout) * 4) * sizeof(float);
-  pillar_encode_kernel<<<kNumSMs * 4, 256, smem, stream>>>(points, keys[sel], vals[sel], head_pos,
+  const size_t smem = (size_t)g.nin * nout * sizeof(float);
+  const int egrid = min(kNumSMs * 16, ceil_div((long long)n * nout, 256));
+  pillar_encode_kernel<<<egrid, 256, smem, stream>>>(points, keys[sel], vals[sel], head_pos,
                                                           num_voxels, g, weight, bn_scale, bn_shift,
                                                           voxel_feats, voxel_coors);
   DBEV_CHECK_LAUNCH("pillar_encode_kernel");

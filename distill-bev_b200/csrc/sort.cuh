@@ -22,7 +22,7 @@ constexpr int kSortTile = kSortBlock * kSortItems;   // 4096 keys per CTA
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 
-// Workspace for radix_sort_pairs over n keys (per-pass digit table + totals).
+// Workspace for radix_sort_pairs over n keys (per-pass tile descriptors + histograms).
 size_t radix_sort_ws_bytes(long long n);
 
 // Stable sort by key bits [0, num_bits). Input is keys[0] (+ vals[0] unless

@@ -68,22 +68,39 @@ def _alloc_plan(n_points, batch, n0, n1, nz, fast_axis, device, rows_per_item=0)
                    nslow, nfast, fast_axis)
 
 
-def bev_plan_from_geom(geom, batch, bx, dx, nx, fast_axis=0, rows_per_item=0, with_point_cell=False):
+class GridSpec(object):
+    """Host copy of the BEV grid constants (off = bx - dx/2, dx, nx as fp32 and nx.to(long)).
+
+    Built once per view transformer: reading ``bx/dx/nx`` CUDA parameters back on every call
+    would put a device synchronisation on the hot path."""
+
+    __slots__ = ("off", "dx", "nx_f", "nx_i")
+
+    def __init__(self, bx, dx, nx):
+        bx32 = torch.as_tensor(bx, dtype=torch.float32).detach().cpu()
+        dx32 = torch.as_tensor(dx, dtype=torch.float32).detach().cpu()
+        nx32 = torch.as_tensor(nx, dtype=torch.float32).detach().cpu()
+        self.off = (bx32 - dx32 / 2.0).tolist()   # fp32, exactly as (self.bx - self.dx / 2.)
+        self.dx = dx32.tolist()
+        self.nx_f = nx32.tolist()
+        self.nx_i = nx32.to(torch.long).tolist()   # nx.to(torch.long) truncates
+
+
+def bev_plan_from_geom(geom, batch, bx=None, dx=None, nx=None, fast_axis=0, rows_per_item=0,
+                       with_point_cell=False, grid=None):
     """Plan from ego-frame frustum coordinates.
 
     geom: [..., 3] fp32 CUDA tensor, batch-major (e.g. [B, N, D, fH, fW, 3]);
-    bx, dx, nx: the float triples of ``gen_dx_bx`` (view_transformer_mine.py:14-18).
-    Index math, bounds test and batch index follow voxel_pooling :150-161.
+    bx, dx, nx: the float triples of ``gen_dx_bx`` (view_transformer_mine.py:14-18), or a
+    cached ``GridSpec``. Index math, bounds test and batch index follow voxel_pooling :150-161.
     """
     lib = _lib.load()
     _lib.require_cuda(geom, "geom", torch.float32)
     geom = geom.contiguous()
     n_points = geom.numel() // 3
-    bx32 = torch.as_tensor(bx, dtype=torch.float32).cpu()
-    dx32 = torch.as_tensor(dx, dtype=torch.float32).cpu()
-    nx32 = torch.as_tensor(nx, dtype=torch.float32).cpu()
-    off = bx32 - dx32 / 2.0            # fp32, exactly as (self.bx - self.dx / 2.)
-    nx_i = nx32.to(torch.long)          # nx.to(torch.long) truncates
+    if grid is None:
+        grid = GridSpec(bx, dx, nx)
+    nx_i = grid.nx_i
     plan = _alloc_plan(n_points, batch, int(nx_i[0]), int(nx_i[1]), int(nx_i[2]), fast_axis,
                        geom.device, rows_per_item)
     if with_point_cell:
@@ -92,8 +109,8 @@ def bev_plan_from_geom(geom, batch, bx, dx, nx, fast_axis=0, rows_per_item=0, wi
         ws_bytes = lib.dbev_bev_plan_workspace_bytes(n_points, plan.n_cells)
         ws = _lib.workspace(ws_bytes, geom.device)
         rc = lib.dbev_bev_plan_from_geom(
-            _lib.ptr(geom), n_points, batch, _lib.host_f3(off.tolist()), _lib.host_f3(dx32.tolist()),
-            _lib.host_f3(nx32.tolist()), _lib.host_i3(nx_i.tolist()), fast_axis, rows_per_item,
+            _lib.ptr(geom), n_points, batch, _lib.host_f3(grid.off), _lib.host_f3(grid.dx),
+            _lib.host_f3(grid.nx_f), _lib.host_i3(grid.nx_i), fast_axis, rows_per_item,
             _lib.ptr(plan.order), _lib.ptr(plan.cell_start), _lib.ptr(plan.cell_end),
             _lib.ptr(plan.items), plan.items.shape[0], _lib.ptr(plan.n_items),
             _lib.ptr(plan.point_cell), _lib.ptr(ws), ws_bytes, _lib.stream_ptr(geom.device))
@@ -266,7 +283,7 @@ def bev_pool(feats, coords, B, D, H, W):
     return bev_pool_gather(feats, plan, layout="b_c_z")
 
 
-def voxel_pooling(geom_feats, x, bx, dx, nx, plan=None):
+def voxel_pooling(geom_feats, x, bx=None, dx=None, nx=None, plan=None, grid=None):
     """Drop-in for ``ViewTransformerLiftSplatShoot.voxel_pooling`` (:141-181).
 
     geom_feats [B, N, D, H, W, 3] fp32 ego-frame xyz, x [B, N, D, H, W, C] ->
@@ -275,7 +292,7 @@ def voxel_pooling(geom_feats, x, bx, dx, nx, plan=None):
     B, N, D, H, W, C = x.shape
     Nprime = B * N * D * H * W
     if plan is None:
-        plan = bev_plan_from_geom(geom_feats, B, bx, dx, nx, fast_axis=0)
+        plan = bev_plan_from_geom(geom_feats, B, bx, dx, nx, fast_axis=0, grid=grid)
     x = x.reshape(Nprime, C)
     return bev_pool_gather(x, plan, layout="bz_c")
 

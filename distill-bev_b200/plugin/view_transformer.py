@@ -67,6 +67,7 @@ class ViewTransformerLiftSplatShoot(nn.Module):
         self.numC_Trans = numC_Trans
         self.depthnet = nn.Conv2d(numC_input, self.D + numC_Trans, kernel_size=1, padding=0)
         self.accelerate = accelerate
+        self._grid = _bp.GridSpec(bx, dx, nx)   # host copy: no device read-back per call
 
     def get_depth_dist(self, x):
         return x.softmax(dim=1)
@@ -87,11 +88,11 @@ class ViewTransformerLiftSplatShoot(nn.Module):
 
     def make_plan(self, geom, batch, with_point_cell=True):
         """Sort the frustum over the BEV grid once; reuse for every tensor sharing `geom`."""
-        return _bp.bev_plan_from_geom(geom, batch, self.bx, self.dx, self.nx, fast_axis=0,
-                                      with_point_cell=with_point_cell)
+        return _bp.bev_plan_from_geom(geom, batch, fast_axis=0, with_point_cell=with_point_cell,
+                                      grid=self._grid)
 
     def voxel_pooling(self, geom_feats, x, plan=None):
-        return _bp.voxel_pooling(geom_feats, x, self.bx, self.dx, self.nx, plan=plan)
+        return _bp.voxel_pooling(geom_feats, x, plan=plan, grid=self._grid)
 
     voxel_pooling_accelerated = voxel_pooling   # same result as the scatter_sum path (:184-240)
 
