@@ -297,7 +297,8 @@ bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restri
               const float w = __ldg(la.depth + p);
               const float4 f = __ldg(reinterpret_cast<const float4*>(
                   xb + ((size_t)bn * la.fhw.d + pix) * g.C));
-              v[u] = make_float4(w * f.x, w * f.y, w * f.z, w * f.w);
+              // rounded product first, like the reference's materialised volume (no FMA contraction)
+              v[u] = make_float4(__fmul_rn(w, f.x), __fmul_rn(w, f.y), __fmul_rn(w, f.z), __fmul_rn(w, f.w));
             } else {
               v[u] = ld_stream_f4(xb + (size_t)pid[u] * g.C);
             }
