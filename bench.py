@@ -109,6 +109,27 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def aggregate_step_time(ms_local, world, dist=None, device=None):
+    """MAX over ranks of the per-rank device time (the contract's max-over-ranks rule) and the
+    whole-job throughput: every rank processes its own BATCH samples per step (weak scaling, no
+    data-path collective), so value = BATCH * world / max_ms. Works with any backend (tested with
+    gloo on CPU, world_size 2)."""
+    import torch
+    t = torch.tensor([float(ms_local)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def samples_per_sec(total_ms, steps, world):
+    return BATCH * world / (total_ms / steps * 1e-3)
+
+
+def rank_seed(rank):
+    """Each rank draws its own synthetic batch (independent samples, like a DistributedSampler)."""
+    return 1000 + rank
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -274,7 +295,7 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
-    hp = HotPath(device, seed=1000 + rank)
+    hp = HotPath(device, seed=rank_seed(rank))
 
     def barrier():
         if world > 1:
@@ -291,11 +312,9 @@ def run_ours(args):
             hp.step(e2e)
         b.record()
         torch.cuda.synchronize()
-        ms = torch.tensor([a.elapsed_time(b)], device=device)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = aggregate_step_time(a.elapsed_time(b), world, dist, device)
         barrier()
-        return float(ms.item())
+        return ms
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -309,8 +328,8 @@ def run_ours(args):
         return
     ours, all_k = count_our_kernels(hp)
     ms_per_step = total_ms / args.steps
-    value = BATCH * world / (ms_per_step * 1e-3)
-    e2e_value = BATCH * world / (e2e_ms / args.steps * 1e-3)
+    value = samples_per_sec(total_ms, args.steps, world)
+    e2e_value = samples_per_sec(e2e_ms, args.steps, world)
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
