@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include "adapt_gemm.cuh"
 #include "bev_pool.cuh"
 #include "distill_loss.cuh"
 #include "pillar.cuh"
@@ -238,6 +239,11 @@ int dbev_lss_geometry(const float* frustum, int pts_per_cam, const float* rots,
                       void* stream) {
   return lss_geometry(frustum, pts_per_cam, rots, trans, intrins, post_rots, post_trans, n_cams,
                       mats_ws, geom, (cudaStream_t)stream);
+}
+
+int dbev_adapt_conv1x1_forward(const float* x_cl, const float* w, const float* bias, int batch,
+                               int c_in, int c_out, int hw, float* y, void* stream) {
+  return adapt_conv1x1_forward(x_cl, w, bias, batch, c_in, c_out, hw, y, (cudaStream_t)stream);
 }
 
 size_t dbev_sort_workspace_bytes(long long n) {

@@ -266,6 +266,19 @@ int dbev_lss_geometry(const float* frustum, int pts_per_cam, const float* rots,
                       void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * '1x1conv' student adaptation layer on tcgen05 tensor cores (TF32 inputs, fp32 accumulate
+ * in TMEM, operands fed by TMA straight from the NCHW tensors): replaces
+ * nn.Conv2d(student_channel, teacher_channel, 1) of BEVDetDistill
+ * (mmdet3d/models/detectors/bevdet_distill.py:216-351, applied at :1004).
+ *   x_cl[batch, hw, c_in] CHANNELS-LAST (the memory of a torch.channels_last NCHW tensor; an
+ *   NCHW-contiguous tensor goes through dbev_transpose_batched first), w[c_out, c_in],
+ *   bias[c_out] (nullable) -> y[batch, c_out, hw] NCHW-contiguous.
+ * c_in % 32 == 0, c_out in {128, 256, 384, 512}, hw % 4 == 0, 16-byte aligned pointers.
+ * ------------------------------------------------------------------------ */
+int dbev_adapt_conv1x1_forward(const float* x_cl, const float* w, const float* bias, int batch,
+                               int c_in, int c_out, int hw, float* y, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Cross-modal feature distillation loss (FGD-style), BEVDetDistill
  * (mmdet3d/models/detectors/bevdet_distill.py). The reference has no native
  * interface for this path: it is ~20 torch kernels plus numpy/numba on the
