@@ -12,7 +12,8 @@ One "step" = one pass of the hot path over one synthetic nuScenes-shaped batch p
   B  frozen teacher LiDAR path: voxelize -> fused DynamicPillarFeatureNet -> PointPillarsScatter
      (512x512x64 pseudo image), 8 clouds
   C  head-position distillation loss: fg / fp masks from GT boxes and heat maps, 1x1 adaptation
-     conv (cuDNN, library), fused fgd loss forward and backward
+     conv (tcgen05 TF32 forward; its backward GEMMs still go through cuDNN), fused fgd loss
+     forward and backward
 The dense conv stacks around these stages (image backbone, SECOND/SECONDFPN, BEV encoder) are
 library code (cuDNN) that this repository does not replace yet; they are NOT in the step and
 `config.workload` says so.
@@ -47,7 +48,7 @@ N_POINTS = 30000
 C_STUDENT, C_TEACHER = 256, 384
 WORKLOAD = ("hotpath-ops-v1: lift+splat fwd/bwd (B=8 x 2 frames, 6 cams, D=59, 16x44, C=64 -> 128x128) "
             "+ teacher voxelize/pillar-encode/scatter (8 x 30k pts -> 512x512x64) "
-            "+ fgd distill loss fwd/bwd at head (256->384 ch, 128x128, fg+fp masks); "
+            "+ 1x1 adaptation conv (tcgen05 fwd, cuDNN bwd) + fgd distill loss fwd/bwd at head (256->384 ch, 128x128, fg+fp masks); "
             "dense conv stacks (cuDNN) not in step")
 PILLAR_VS, PILLAR_RANGE = [0.2, 0.2, 8.0], [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
 DISTILL_PARAMS = dict(
@@ -171,7 +172,8 @@ class HotPath(object):
         self.enc = dbev.DynamicPillarFeatureNet(in_channels=5, feat_channels=(64,), voxel_size=PILLAR_VS,
                                                 point_cloud_range=PILLAR_RANGE).to(device).eval()
         self.scat = dbev.PointPillarsScatter(64, [512, 512], channels_last=True)
-        self.adapt = torch.nn.Conv2d(C_STUDENT, C_TEACHER, 1).to(device)          # '1x1conv' adaptation
+        from distill_bev_b200.plugin.distill.adaptation import Conv1x1Adaptation
+        self.adapt = Conv1x1Adaptation(C_STUDENT, C_TEACHER).to(device)            # '1x1conv' adaptation, tcgen05 fwd
         self.spatial = torch.nn.Conv2d(1, 1, 3, padding=1).to(device)            # spatial_wise_adaptations
         self.d_calib = [t.to(device) for t in self.h_calib]
         self.d_points = [t.to(device) for t in self.h_points]

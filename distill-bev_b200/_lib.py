@@ -146,6 +146,13 @@ def require_cuda(t, name, dtype=None):
     return t
 
 
+def h2d_async(host_tensor, device):
+    """Small host tensor -> device without stalling the stream: a pageable cudaMemcpyAsync makes the
+    driver synchronise the stream first, a pinned source does not (torch's pinned cache keeps the
+    staging block alive until the copy has run)."""
+    return host_tensor.contiguous().pin_memory().to(device, non_blocking=True)
+
+
 def workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
 

@@ -272,20 +272,26 @@ fgd_teacher_stats_kernel(const float* __restrict__ t, FgdDims d, float* __restri
   }
 }
 
-// per-channel means over HW from the tile partials (fixed tile order): one thread per (b, c)
+// per-channel means over HW from the tile partials: one WARP per (b, c), lanes stride over the
+// tiles (coalesced), fixed shuffle tree -> deterministic
 __global__ void __launch_bounds__(256)
 fgd_channel_means_kernel(FgdDims d, const float* __restrict__ part_a, const float* __restrict__ part_b,
                          float* __restrict__ mean_a, float* __restrict__ mean_b) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= d.B * d.C) return;
   const size_t o = (size_t)i * d.ntiles;
   float sa = 0.f, sb = 0.f;
-  for (int k = 0; k < d.ntiles; ++k) {
+  for (int k = lane; k < d.ntiles; k += 32) {
     sa += part_a[o + k];
     if (part_b) sb += part_b[o + k];
   }
-  mean_a[i] = sa / (float)d.HW;
-  if (part_b) mean_b[i] = sb / (float)d.HW;
+  sa = warp_sum(sa);
+  sb = warp_sum(sb);
+  if (lane == 0) {
+    mean_a[i] = sa / (float)d.HW;
+    if (part_b) mean_b[i] = sb / (float)d.HW;
+  }
 }
 
 // channel attention softmax(mean|t| / C_T) * C (:1094-1097), in place. One CTA per sample.
@@ -603,12 +609,20 @@ fgd_bwd_small_kernel(FgdDims d, FgdCfg cfg, const float* __restrict__ go_map,
     }
     gc[i] = g;
   }
-  if (blockIdx.x == 0 && threadIdx.x < 10) {
-    double acc = 0.0;
-    if (cfg.spatial_mask)
-      for (int i = 0; i < d.B * d.ntiles; ++i) acc += conv_p[(size_t)i * 10 + threadIdx.x];
-    if (threadIdx.x < 9) grad_conv_w[threadIdx.x] = (float)acc;
-    else grad_conv_b[0] = (float)acc;
+  if (blockIdx.x == 0) {
+    // conv weight / bias gradients: one warp per output, lanes stride over the tile partials
+    const int lane = threadIdx.x & 31;
+    for (int k = threadIdx.x >> 5; k < 10; k += blockDim.x >> 5) {
+      double acc = 0.0;
+      if (cfg.spatial_mask)
+        for (int i = lane; i < d.B * d.ntiles; i += 32) acc += conv_p[(size_t)i * 10 + k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        if (k < 9) grad_conv_w[k] = (float)acc;
+        else grad_conv_b[0] = (float)acc;
+      }
+    }
   }
 }
 
@@ -750,13 +764,13 @@ int fgd_loss_forward(const FgdConfig& c, const float* student, const float* teac
   FgdState st = carve_state((float*)state, d);
   dim3 grid(d.ntiles, d.B);
   fgd_teacher_stats_kernel<<<grid, kBlock, 0, stream>>>(teacher, d, st.ta, st.tm, st.cta_p, st.ctm_p);
-  fgd_channel_means_kernel<<<ceil_div(d.B * d.C, 256), 256, 0, stream>>>(d, st.cta_p, st.ctm_p,
+  fgd_channel_means_kernel<<<ceil_div((long long)d.B * d.C * 32, 256), 256, 0, stream>>>(d, st.cta_p, st.ctm_p,
                                                                          st.catt, st.ctm);
   fgd_channel_softmax_kernel<<<d.B, 256, 0, stream>>>(d, k.channel_t, st.catt);
   fgd_student_pass_kernel<<<grid, kBlock, 0, stream>>>(student, teacher, d, st.catt, st.sa, st.sm,
                                                        st.d1, st.d2, st.csm_p);
   fgd_spatial_softmax_kernel<<<dim3(d.B, 2), 1024, 0, stream>>>(d, k.spatial_t, st.ta, st.sa);
-  fgd_channel_means_kernel<<<ceil_div(d.B * d.C, 256), 256, 0, stream>>>(d, st.csm_p, nullptr,
+  fgd_channel_means_kernel<<<ceil_div((long long)d.B * d.C * 32, 256), 256, 0, stream>>>(d, st.csm_p, nullptr,
                                                                          st.csm, nullptr);
   fgd_combine_kernel<<<grid, kTile, 0, stream>>>(d, k, fg, fg_scale, fg_count, fp, fp_count, st.ta,
                                                  st.sa, st.tm, st.sm, st.d1, st.d2, conv_w, conv_b,

@@ -38,8 +38,11 @@ def pack_boxes(gt_bboxes_3d, device):
     for c in counts:
         offs.append(offs[-1] + c)
     boxes = torch.cat(ts, 0) if sum(counts) else torch.zeros((1, dim))
-    return (boxes.contiguous().to(device, non_blocking=True),
-            torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True), max(counts + [0]))
+    if boxes.is_cuda:
+        boxes = boxes.contiguous()
+    else:
+        boxes = _lib.h2d_async(boxes, device)
+    return boxes, _lib.h2d_async(torch.tensor(offs, dtype=torch.int32), device), max(counts + [0])
 
 
 def foreground_scale_mask(student_H, student_W, gt_bboxes_3d, grid_size, point_cloud_range,

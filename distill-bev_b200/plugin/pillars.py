@@ -49,7 +49,8 @@ def pillar_encode(points, weight, bn_scale, bn_shift, voxel_size, point_cloud_ra
         _lib.require_cuda(coors, "coors", torch.int32)
         coors = coors.contiguous()
     if batch_offsets is not None:
-        batch_offsets = batch_offsets.to(device=dev, dtype=torch.int32).contiguous()
+        batch_offsets = batch_offsets.to(torch.int32)
+        batch_offsets = batch_offsets.contiguous() if batch_offsets.is_cuda else _lib.h2d_async(batch_offsets, dev)
     x_off = float(voxel_size[0]) / 2 + float(point_cloud_range[0])   # python doubles, :88-89
     y_off = float(voxel_size[1]) / 2 + float(point_cloud_range[1])
     with torch.cuda.device(dev):
