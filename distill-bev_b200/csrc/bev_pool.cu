@@ -280,44 +280,118 @@ bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restri
         dst[(c + 3) * pitch] = acc.w;
       };
 
-      // software pipeline: the point ids of batch i+1 are fetched while the rows of
-      // batch i are in flight, so only one global latency per batch is exposed
-      uint32_t pid[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) pid[u] = (ws + u < we) ? __ldg(order + ws + u) : 0u;
-      for (int pos = ws; pos < we; pos += U) {
-        float4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (lane_active && pos + u < we) {
-            if (LIFT) {
-              const uint32_t p = pid[u];
-              const uint32_t bn = la.dfhw.div(p);
-              const uint32_t pix = la.fhw.mod(p - bn * la.dfhw.d);
-              const float w = __ldg(la.depth + p);
-              const float4 f = __ldg(reinterpret_cast<const float4*>(
-                  xb + ((size_t)bn * la.fhw.d + pix) * g.C));
-              // rounded product first, like the reference's materialised volume (no FMA contraction)
-              v[u] = make_float4(__fmul_rn(w, f.x), __fmul_rn(w, f.y), __fmul_rn(w, f.z), __fmul_rn(w, f.w));
-            } else {
+      if constexpr (!LIFT) {
+        // streaming gather of materialised rows (HBM-bound): every lane keeps its own point ids,
+        // fewest registers -> most warps in flight
+        // software pipeline: the point ids of batch i+1 are fetched while the rows of
+        // batch i are in flight, so only one global latency per batch is exposed
+        uint32_t pid[U];
+  #pragma unroll
+        for (int u = 0; u < U; ++u) pid[u] = (ws + u < we) ? __ldg(order + ws + u) : 0u;
+        for (int pos = ws; pos < we; pos += U) {
+          float4 v[U];
+  #pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (lane_active && pos + u < we) {
               v[u] = ld_stream_f4(xb + (size_t)pid[u] * g.C);
             }
           }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) pid[u] = (pos + U + u < we) ? __ldg(order + pos + U + u) : 0u;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int r = pos + u;
-          if (r < we) {
-            if (r >= cur_end) {
-              flush(cur);
-              ++cur;
-              while (ce[cur] <= r) ++cur;
-              cur_end = ce[cur];
-              acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  #pragma unroll
+          for (int u = 0; u < U; ++u) pid[u] = (pos + U + u < we) ? __ldg(order + pos + U + u) : 0u;
+  #pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int r = pos + u;
+            if (r < we) {
+              if (r >= cur_end) {
+                flush(cur);
+                ++cur;
+                while (ce[cur] <= r) ++cur;
+                cur_end = ce[cur];
+                acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              if (lane_active) f4_add(acc, v[u]);
             }
-            if (lane_active) f4_add(acc, v[u]);
+          }
+        }
+      } else {
+        // Cooperative addressing: per batch of RB rows every lane of the worker resolves ONE row
+        // (point id -> source row, + depth weight when LIFT) and the 16 lanes then exchange them
+        // with shuffles, instead of all lanes redoing the same integer work per row. Software
+        // pipeline: ids are fetched two batches ahead, offsets / depth weights one batch ahead.
+        constexpr int K = (LPR >= 8) ? 1 : 8 / LPR;  // rows resolved per lane and batch
+        constexpr int RB = LPR * K;                   // rows per batch (8 or 16)
+        const uint32_t c4 = (uint32_t)(g.C >> 2);
+        const float4* xb4 = reinterpret_cast<const float4*>(xb);
+        const unsigned wmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (worker * LPR));
+        auto load_ids = [&](int base, uint32_t (&pp)[K]) {
+  #pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const int r = base + k * LPR + sub;
+            pp[k] = (r < we) ? __ldg(order + r) : 0u;
+          }
+        };
+        auto resolve = [&](const uint32_t (&pp)[K], int base, uint32_t (&off)[K], float (&wg)[K]) {
+  #pragma unroll
+          for (int k = 0; k < K; ++k) {
+            if (LIFT) {
+              const uint32_t bn = la.dfhw.div(pp[k]);
+              const uint32_t pix = la.fhw.mod(pp[k] - bn * la.dfhw.d);
+              off[k] = bn * la.fhw.d + pix;  // row of channels-last feat
+              wg[k] = (base + k * LPR + sub < we) ? __ldg(la.depth + pp[k]) : 0.f;
+            } else {
+              off[k] = pp[k];
+              wg[k] = 0.f;
+            }
+          }
+        };
+        uint32_t pid[K], off_c[K];
+        float w_c[K];
+        load_ids(ws, pid);
+        resolve(pid, ws, off_c, w_c);
+        load_ids(ws + RB, pid);
+        for (int pos = ws; pos < we; pos += RB) {
+          uint32_t off_n[K];
+          float w_n[K];
+          resolve(pid, pos + RB, off_n, w_n);
+          load_ids(pos + 2 * RB, pid);
+  #pragma unroll
+          for (int j0 = 0; j0 < RB; j0 += U) {
+            float4 v[U];
+  #pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int j = j0 + u;
+              const uint32_t o = __shfl_sync(wmask, off_c[j / LPR], j % LPR, LPR);
+              float w = 0.f;
+              if (LIFT) w = __shfl_sync(wmask, w_c[j / LPR], j % LPR, LPR);
+              if (lane_active && pos + j < we) {
+                if (LIFT) {
+                  const float4 f = __ldg(xb4 + (size_t)o * c4);
+                  // rounded product first, like the reference's materialised volume (no FMA contraction)
+                  v[u] = make_float4(__fmul_rn(w, f.x), __fmul_rn(w, f.y), __fmul_rn(w, f.z), __fmul_rn(w, f.w));
+                } else {
+                  v[u] = ld_stream_f4(reinterpret_cast<const float*>(xb4 + (size_t)o * c4));
+                }
+              }
+            }
+  #pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int r = pos + j0 + u;
+              if (r < we) {
+                if (r >= cur_end) {
+                  flush(cur);
+                  ++cur;
+                  while (ce[cur] <= r) ++cur;
+                  cur_end = ce[cur];
+                  acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (lane_active) f4_add(acc, v[u]);
+              }
+            }
+          }
+  #pragma unroll
+          for (int k = 0; k < K; ++k) {
+            off_c[k] = off_n[k];
+            w_c[k] = w_n[k];
           }
         }
       }
@@ -538,6 +612,10 @@ transpose_batched_kernel(const float* __restrict__ in, float* __restrict__ out, 
 //   d_feat[pix, :] = sum_d depth[p] * g[cell(p), :]
 // g is the BEV gradient in cells-major layout [n_cells, C] (transposed once),
 // so every access is a contiguous row; everything is read from L2.
+// Cooperative addressing as in the forward: per batch of DB depth bins each lane of the group
+// fetches (cell, depth weight) of ITS bins and the lanes exchange them with shuffles; the per-bin
+// dot products are reduced with one transposed butterfly per batch (DB - K shuffles instead of
+// DB * log2(LPR)), which leaves bin `sub * K + k` on lane `sub` - the lane that then stores it.
 template <int LPR>
 __global__ void __launch_bounds__(256)
 lift_splat_bwd_kernel(const float* __restrict__ g_cl, const float* __restrict__ depth,
@@ -545,8 +623,10 @@ lift_splat_bwd_kernel(const float* __restrict__ g_cl, const float* __restrict__ 
                       long long n_pix, int C, int D, int fhw, float* __restrict__ d_depth,
                       float* __restrict__ d_feat) {
   constexpr int CB = LPR * 4;
-  constexpr int GPB = 256 / LPR;  // pixel groups per CTA
-  constexpr int U = 8;            // depth bins in flight per group
+  constexpr int GPB = 256 / LPR;                 // pixel groups per CTA
+  constexpr int K = (LPR >= 8) ? 1 : 8 / LPR;    // bins owned per lane and batch
+  constexpr int DB = LPR * K;                    // depth bins per batch (8, 16 or 32)
+  constexpr int U = 8;                           // gradient rows in flight per group
   const int sub = threadIdx.x % LPR;
   const long long pixrow = (long long)blockIdx.x * GPB + threadIdx.x / LPR;
   const bool valid = pixrow < n_pix;  // whole groups are valid or not; shuffles stay in-group
@@ -556,38 +636,64 @@ lift_splat_bwd_kernel(const float* __restrict__ g_cl, const float* __restrict__ 
   const unsigned gmask = (LPR == 32) ? 0xffffffffu
                                      : (((1u << LPR) - 1u) << ((threadIdx.x & 31) / LPR * LPR));
   const size_t p0 = (size_t)bn * D * fhw + pix;  // point id of depth bin 0 of this ray
+  const float4* g4 = reinterpret_cast<const float4*>(g_cl);
+  const uint32_t c4 = (uint32_t)(C >> 2);
   for (int cbk = 0; cbk < nblocks; ++cbk) {
     const int c = cbk * CB + sub * 4;
     const bool act = valid && c < C;
     float4 f = make_float4(0.f, 0.f, 0.f, 0.f), acc = f;
     if (act) f = __ldg(reinterpret_cast<const float4*>(feat + (size_t)pixrow * C + c));
-    for (int d0 = 0; d0 < D; d0 += U) {
-      int cell[U];
-      float w[U];
-      float4 gv[U];
+    for (int d0 = 0; d0 < D; d0 += DB) {
+      int cellv[K];
+      float wv[K];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool in = valid && d0 + u < D;
-        cell[u] = in ? __ldg(point_cell + p0 + (size_t)(d0 + u) * fhw) : -1;
-        w[u] = in ? __ldg(depth + p0 + (size_t)(d0 + u) * fhw) : 0.f;
+      for (int k = 0; k < K; ++k) {
+        const int d = d0 + sub * K + k;
+        const bool in = valid && d < D;
+        cellv[k] = in ? __ldg(point_cell + p0 + (size_t)d * fhw) : -1;
+        wv[k] = in ? __ldg(depth + p0 + (size_t)d * fhw) : 0.f;
+      }
+      float dot[DB];
+#pragma unroll
+      for (int j0 = 0; j0 < DB; j0 += U) {
+        float4 gv[U];
+        float wj[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + u;
+          const int cj = __shfl_sync(gmask, cellv[j % K], j / K, LPR);
+          wj[u] = __shfl_sync(gmask, wv[j % K], j / K, LPR);
+          gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cj >= 0 && act) gv[u] = __ldg(g4 + (size_t)cj * c4 + (c >> 2));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          acc.x += wj[u] * gv[u].x; acc.y += wj[u] * gv[u].y;
+          acc.z += wj[u] * gv[u].z; acc.w += wj[u] * gv[u].w;
+          dot[j0 + u] = (f.x * gv[u].x + f.y * gv[u].y) + (f.z * gv[u].z + f.w * gv[u].w);
+        }
+      }
+      // transposed butterfly: after the step with distance s, lanes with bit s set keep the
+      // upper half of the remaining bins (same pairing order as a per-bin xor butterfly)
+#pragma unroll
+      for (int s = LPR / 2, half = DB / 2; s > 0; s >>= 1, half >>= 1) {
+        const bool up = (sub & s) != 0;
+#pragma unroll
+        for (int i = 0; i < DB / 2; ++i) {
+          if (i < half) {
+            const float send = up ? dot[i] : dot[i + half];
+            const float keep = up ? dot[i + half] : dot[i];
+            dot[i] = keep + __shfl_xor_sync(gmask, send, s);
+          }
+        }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cell[u] >= 0 && act)
-          gv[u] = __ldg(reinterpret_cast<const float4*>(g_cl + (size_t)cell[u] * C + c));
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        acc.x += w[u] * gv[u].x; acc.y += w[u] * gv[u].y;
-        acc.z += w[u] * gv[u].z; acc.w += w[u] * gv[u].w;
-        float dot = (f.x * gv[u].x + f.y * gv[u].y) + (f.z * gv[u].z + f.w * gv[u].w);
-#pragma unroll
-        for (int o = LPR / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(gmask, dot, o);
-        if (valid && sub == 0 && d0 + u < D) {
-          float* dd = d_depth + p0 + (size_t)(d0 + u) * fhw;
-          if (cbk == 0) *dd = dot;
-          else *dd += dot;  // same thread wrote it in the previous channel block
+      for (int k = 0; k < K; ++k) {
+        const int d = d0 + sub * K + k;
+        if (valid && d < D) {
+          float* dd = d_depth + p0 + (size_t)d * fhw;
+          if (cbk == 0) *dd = dot[k];
+          else *dd += dot[k];  // same lane wrote it in the previous channel block
         }
       }
     }
