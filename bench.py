@@ -200,7 +200,7 @@ class HotPath(object):
             canvas = dbev.pillar_canvas(points, self.enc, self.scat)
         # C: head-position distillation loss
         losses = dbev.fgd.fgd_distill_loss(
-            self.teacher, self.adapt(self.student), self.boxes, DISTILL_PARAMS, TRAIN_CFG,
+            self.teacher, self.student, self.boxes, DISTILL_PARAMS, TRAIN_CFG, channel_adaptation=self.adapt,
             spatial_adaptation=self.spatial, heatmaps=gt_hm, teacher_heatmaps=self.teacher_logit, epoch=1)
         total = losses["kd_fg_feat_loss"] + losses["kd_bg_feat_loss"] + losses["kd_spatial_loss"] \
             + losses["kd_fp_bg_feat_loss"]

@@ -80,10 +80,13 @@ SIGNATURES = {
     "dbev_fgd_loss_forward": (_c_int, [_cfgp, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
                                        _ptr, _c_size, _ptr, _ptr]),
     "dbev_fgd_loss_backward": (_c_int, [_cfgp, _ptr, _ptr, _ptr, _ptr, _ptr, _c_size, _ptr, _ptr,
-                                        _ptr, _ptr, _ptr]),
+                                        _ptr, _ptr, _ptr, _ptr]),
     "dbev_pillar_encode_workspace_bytes": (_c_size, [_c_ll]),
     "dbev_pillar_encode": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _fptr, _fptr, _c_float,
                                     _c_float, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                    _c_size, _ptr]),
+    "dbev_pillar_canvas": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _fptr, _fptr, _c_float,
+                                    _c_float, _ptr, _c_int, _ptr, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr,
                                     _c_size, _ptr]),
     "dbev_pillar_scatter": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                      _c_int, _ptr, _ptr]),
@@ -127,7 +130,10 @@ def check(rc, what):
 
 
 def stream_ptr(device):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """torch's current stream on `device` as a cudaStream_t (raw query: no Stream object)."""
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(idx))
 
 
 def ptr(t):

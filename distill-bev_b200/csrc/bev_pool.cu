@@ -17,6 +17,8 @@
 // HBM traffic = n*C*4 (rows) + n*4 (ids) + cells*8 + out  ~ algorithmic bytes.
 #include "bev_pool.cuh"
 
+#include <atomic>
+
 #include "sort.cuh"
 
 namespace dbev {
@@ -208,12 +210,35 @@ struct LiftArgs {
   FastDiv fhw;   // fH * fW
 };
 
+// Dynamic work distribution for the persistent gather kernels: warps pull item indices from a
+// device counter (items differ 100x in row count, a static round-robin leaves a long tail). Each
+// launch takes the next of kSchedSlots counter pairs {next item, warps done}; the last warp to
+// finish re-zeroes its pair, so a slot is clean again long before the host wraps around to it.
+constexpr int kSchedSlots = 256;
+__device__ int g_sched[kSchedSlots * 2];
+
+struct WorkQueue {
+  int* ctr;
+  __device__ __forceinline__ explicit WorkQueue(int slot) : ctr(g_sched + 2 * slot) {}
+  __device__ __forceinline__ long long next(int lane) const {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(ctr, 1);
+    return __shfl_sync(0xffffffffu, v, 0);
+  }
+  __device__ __forceinline__ void finish(int lane, int total_warps) const {
+    if (lane == 0 && atomicAdd(ctr + 1, 1) == total_warps - 1) {
+      ctr[0] = 0;
+      ctr[1] = 0;
+    }
+  }
+};
+
 template <int LPR, bool LIFT>
 __global__ void __launch_bounds__(kPoolBlock)
 bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restrict__ order,
                            const int* __restrict__ cell_start, const int* __restrict__ cell_end,
                            const int4* __restrict__ items, const int* __restrict__ n_items_ptr,
-                           float* __restrict__ out, PoolGeom g, LiftArgs la) {
+                           float* __restrict__ out, PoolGeom g, LiftArgs la, int sched_slot) {
   extern __shared__ float smem[];
   constexpr int NW = 32 / LPR;   // workers per warp
   constexpr int CB = LPR * 4;    // channels per block
@@ -231,9 +256,11 @@ bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restri
 
   const int nblocks = (g.C + CB - 1) / CB;
   const long long n_virtual = (long long)(*n_items_ptr) * nblocks;
-  const long long stride = (long long)gridDim.x * kPoolWarps;
+  const WorkQueue queue(sched_slot);
 
-  for (long long vit = (long long)warp * gridDim.x + blockIdx.x; vit < n_virtual; vit += stride) {
+  for (;;) {
+    const long long vit = queue.next(lane);
+    if (vit >= n_virtual) break;
     const int4 item = items[vit / nblocks];
     const int cb = (int)(vit % nblocks) * CB;  // first channel of this block
     const ItemCtx ic = decode_item(item, g);
@@ -430,6 +457,7 @@ bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restri
         if (wr) ob[(long long)(cb + c) * g.sC] = empty ? 0.f : tile[c * kTilePitch + cell];
     }
   }
+  queue.finish(lane, gridDim.x * kPoolWarps);
 }
 
 // scalar fallback for C % 4 != 0 (one row per warp step, lanes over channels)
@@ -476,7 +504,7 @@ __global__ void __launch_bounds__(kPoolBlock)
 bev_pool_gather_bwd_kernel(const float* __restrict__ out_grad, const uint32_t* __restrict__ order,
                            const int* __restrict__ cell_start, const int* __restrict__ cell_end,
                            const int4* __restrict__ items, const int* __restrict__ n_items_ptr,
-                           float* __restrict__ x_grad, PoolGeom g) {
+                           float* __restrict__ x_grad, PoolGeom g, int sched_slot) {
   extern __shared__ float smem[];
   constexpr int NW = 32 / LPR;
   constexpr int CB = LPR * 4;
@@ -487,9 +515,11 @@ bev_pool_gather_bwd_kernel(const float* __restrict__ out_grad, const uint32_t* _
   int* ce = cend_s[warp];
   const int nblocks = (g.C + CB - 1) / CB;
   const long long n_virtual = (long long)(*n_items_ptr) * nblocks;
-  const long long stride = (long long)gridDim.x * kPoolWarps;
+  const WorkQueue queue(sched_slot);
 
-  for (long long vit = (long long)warp * gridDim.x + blockIdx.x; vit < n_virtual; vit += stride) {
+  for (;;) {
+    const long long vit = queue.next(lane);
+    if (vit >= n_virtual) break;
     const int4 item = items[vit / nblocks];
     const int cb = (int)(vit % nblocks) * CB;
     const ItemCtx ic = decode_item(item, g);
@@ -555,6 +585,7 @@ bev_pool_gather_bwd_kernel(const float* __restrict__ out_grad, const uint32_t* _
       }
     }
   }
+  queue.finish(lane, gridDim.x * kPoolWarps);
 }
 
 __global__ void __launch_bounds__(kPoolBlock)
@@ -1057,6 +1088,11 @@ static int pick_lpr(int C) {  // lanes per row of one channel block (<= 64 chann
     }                                    \
   } while (0)
 
+static int next_sched_slot() {
+  static std::atomic<unsigned> n{0};
+  return (int)(n.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
+}
+
 static int gather_forward_impl(const float* x, int C, const uint32_t* order, const int* cell_start,
                                const int* cell_end, const int4* items, const int* n_items,
                                int batch, int nz, int nslow, int nfast, long long sB, long long sZ,
@@ -1075,7 +1111,7 @@ static int gather_forward_impl(const float* x, int C, const uint32_t* order, con
   rc = persistent_grid(bev_pool_gather_fwd_kernel<L, true>, smem, &grid);                \
   if (rc != DBEV_OK) return rc;                                                          \
   bev_pool_gather_fwd_kernel<L, true><<<grid, kPoolBlock, smem, stream>>>(               \
-      x, order, cell_start, cell_end, items, n_items, out, g, *lift)
+      x, order, cell_start, cell_end, items, n_items, out, g, *lift, next_sched_slot())
     DBEV_DISPATCH_LPR(lpr, LAUNCH);
 #undef LAUNCH
     DBEV_CHECK_LAUNCH("lift_splat_fwd_kernel");
@@ -1090,7 +1126,7 @@ static int gather_forward_impl(const float* x, int C, const uint32_t* order, con
   rc = persistent_grid(bev_pool_gather_fwd_kernel<L, false>, smem, &grid);               \
   if (rc != DBEV_OK) return rc;                                                          \
   bev_pool_gather_fwd_kernel<L, false><<<grid, kPoolBlock, smem, stream>>>(              \
-      x, order, cell_start, cell_end, items, n_items, out, g, none)
+      x, order, cell_start, cell_end, items, n_items, out, g, none, next_sched_slot())
     DBEV_DISPATCH_LPR(lpr, LAUNCH);
 #undef LAUNCH
   } else {
@@ -1169,7 +1205,7 @@ int bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* order
   rc = persistent_grid(bev_pool_gather_bwd_kernel<L>, smem, &grid);                      \
   if (rc != DBEV_OK) return rc;                                                          \
   bev_pool_gather_bwd_kernel<L><<<grid, kPoolBlock, smem, stream>>>(                     \
-      out_grad, order, cell_start, cell_end, items, n_items, x_grad, g)
+      out_grad, order, cell_start, cell_end, items, n_items, x_grad, g, next_sched_slot())
     DBEV_DISPATCH_LPR(lpr, LAUNCH);
 #undef LAUNCH
   } else {

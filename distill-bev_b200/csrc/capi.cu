@@ -205,10 +205,12 @@ int dbev_fgd_loss_forward(const dbev_fgd_config* cfg, const float* student, cons
 int dbev_fgd_loss_backward(const dbev_fgd_config* cfg, const float* student, const float* teacher,
                            const float* conv_w, const float* conv_b, void* state,
                            size_t state_bytes, const float* grad_losses, float* grad_student,
-                           float* grad_conv_w, float* grad_conv_b, void* stream) {
+                           float* grad_conv_w, float* grad_conv_b, float* grad_channel_sum,
+                           void* stream) {
   DBEV_CHECK_ARG(cfg != nullptr, "fgd: null config");
   return fgd_loss_backward(*cfg, student, teacher, conv_w, conv_b, state, state_bytes, grad_losses,
-                           grad_student, grad_conv_w, grad_conv_b, (cudaStream_t)stream);
+                           grad_student, grad_conv_w, grad_conv_b, grad_channel_sum,
+                           (cudaStream_t)stream);
 }
 
 size_t dbev_pillar_encode_workspace_bytes(long long n) { return pillar_encode_ws_bytes(n); }
@@ -222,8 +224,21 @@ int dbev_pillar_encode(const float* points, const int* batch_offsets, const int*
                        void* stream) {
   return pillar_encode(points, batch_offsets, coors_in, batch, n, nfeat, voxel_size_host3,
                        coors_range_host6, x_offset, y_offset, weight, nout, bn_scale, bn_shift,
-                       voxel_feats, voxel_coors, num_voxels, point_coors, workspace,
+                       voxel_feats, voxel_coors, num_voxels, point_coors, nullptr, 0, 0, workspace,
                        workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_pillar_canvas(const float* points, const int* batch_offsets, const int* coors_in,
+                       int batch, int n, int nfeat, const float* voxel_size_host3,
+                       const float* coors_range_host6, float x_offset, float y_offset,
+                       const float* weight, int nout, const float* bn_scale,
+                       const float* bn_shift, int channels_last, int zero_canvas, float* canvas,
+                       int* num_voxels, void* workspace, size_t workspace_bytes, void* stream) {
+  DBEV_CHECK_ARG(canvas != nullptr, "pillar_canvas: null canvas");
+  return pillar_encode(points, batch_offsets, coors_in, batch, n, nfeat, voxel_size_host3,
+                       coors_range_host6, x_offset, y_offset, weight, nout, bn_scale, bn_shift,
+                       nullptr, nullptr, num_voxels, nullptr, canvas, channels_last, zero_canvas,
+                       workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int dbev_pillar_scatter(const float* voxel_feats, const int* coors, const int* m_dev, int m_max,

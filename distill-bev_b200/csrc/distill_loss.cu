@@ -632,12 +632,14 @@ fgd_bwd_main_kernel(const float* __restrict__ s, const float* __restrict__ t, Fg
                     FgdCfg cfg, const float* __restrict__ fgw, const float* __restrict__ bgw,
                     const float* __restrict__ fpw, const float* __restrict__ catt,
                     const float* __restrict__ gc, const float* __restrict__ gsp,
-                    const float* __restrict__ gl, float* __restrict__ ds) {
+                    const float* __restrict__ gl, float* __restrict__ ds,
+                    float* __restrict__ chan_p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile = blockIdx.x, b = blockIdx.y;
   const int hw0 = tile * kTile + lane * 4;
-  if (hw0 >= d.HW) return;
-  const size_t o = (size_t)b * d.HW + hw0;
+  if (hw0 >= d.HW && chan_p == nullptr) return;
+  const bool in = hw0 < d.HW;  // (whole warps stay alive for the per-channel tile sums)
+  const size_t o = (size_t)b * d.HW + (in ? hw0 : 0);
   const float ib = 1.f / (float)d.B;
   const float kf = 2.f * cfg.w_fg * ib * gl[0], kb = 2.f * cfg.w_bg * ib * gl[1];
   const float kp = cfg.use_fp ? 2.f * cfg.w_fp * ib * gl[2] : 0.f;
@@ -653,7 +655,7 @@ fgd_bwd_main_kernel(const float* __restrict__ s, const float* __restrict__ t, Fg
     wa = base;
     wb = fpk;
   }
-  const size_t boff = (size_t)b * d.C * d.HW + hw0;
+  const size_t boff = (size_t)b * d.C * d.HW + (in ? hw0 : 0);
 #pragma unroll 4
   for (int c = warp; c < d.C; c += kWarps) {
     const float4 sv = ld4(s + boff + (size_t)c * d.HW);
@@ -664,8 +666,27 @@ fgd_bwd_main_kernel(const float* __restrict__ s, const float* __restrict__ t, Fg
     r.y = (sv.y - tv.y) * (wa.y + ca * wb.y) + g + g4.y;
     r.z = (sv.z - tv.z) * (wa.z + ca * wb.z) + g + g4.z;
     r.w = (sv.w - tv.w) * (wa.w + ca * wb.w) + g + g4.w;
-    st_stream_f4(ds + boff + (size_t)c * d.HW, r);
+    if (in) st_stream_f4(ds + boff + (size_t)c * d.HW, r);
+    if (chan_p) {  // per-channel sum of ds over this tile (bias gradient of a 1x1 adaptation conv)
+      const float v = warp_sum(in ? (r.x + r.y) + (r.z + r.w) : 0.f);
+      if (lane == 0) chan_p[((size_t)b * d.C + c) * d.ntiles + tile] = v;
+    }
   }
+}
+
+// out[c] = sum over samples and tiles of the per-tile channel sums: one warp per channel
+__global__ void __launch_bounds__(256)
+fgd_channel_total_kernel(FgdDims d, const float* __restrict__ chan_p, float* __restrict__ out) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= d.C) return;
+  float acc = 0.f;
+  for (int i = lane; i < d.B * d.ntiles; i += 32) {
+    const int b = i / d.ntiles, tile = i - b * d.ntiles;
+    acc += chan_p[((size_t)b * d.C + c) * d.ntiles + tile];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[c] = acc;
 }
 
 int make_dims(const FgdConfig& c, FgdDims* d) {
@@ -783,7 +804,8 @@ int fgd_loss_forward(const FgdConfig& c, const float* student, const float* teac
 int fgd_loss_backward(const FgdConfig& c, const float* student, const float* teacher,
                       const float* conv_w, const float* conv_b, void* state, size_t state_bytes,
                       const float* grad_losses, float* grad_student, float* grad_conv_w,
-                      float* grad_conv_b, cudaStream_t stream) {
+                      float* grad_conv_b, float* grad_channel_sum,
+                      cudaStream_t stream) {
   FgdDims d;
   int rc = make_dims(c, &d);
   if (rc != DBEV_OK) return rc;
@@ -797,8 +819,14 @@ int fgd_loss_backward(const FgdConfig& c, const float* student, const float* tea
   fgd_bwd_small_kernel<<<kNumSMs, 256, 0, stream>>>(d, k, st.d1, conv_w, st.ctm, st.csm, grad_losses,
                                                     st.conv_p, st.gsp, st.gc, grad_conv_w,
                                                     grad_conv_b);
+  // the student's per-tile channel sums are dead after the forward: reuse them as scratch
+  float* chan_p = grad_channel_sum ? st.csm_p : nullptr;
   fgd_bwd_main_kernel<<<grid, kBlock, 0, stream>>>(student, teacher, d, k, st.fgw, st.bgw, st.fpw,
-                                                   st.catt, st.gc, st.gsp, grad_losses, grad_student);
+                                                   st.catt, st.gc, st.gsp, grad_losses, grad_student,
+                                                   chan_p);
+  if (grad_channel_sum)
+    fgd_channel_total_kernel<<<ceil_div((long long)d.C * 32, 256), 256, 0, stream>>>(d, chan_p,
+                                                                                     grad_channel_sum);
   DBEV_CHECK_LAUNCH("fgd_loss_backward");
   return DBEV_OK;
 }

@@ -30,6 +30,7 @@ int fgd_loss_forward(const FgdConfig& c, const float* student, const float* teac
 int fgd_loss_backward(const FgdConfig& c, const float* student, const float* teacher,
                       const float* conv_w, const float* conv_b, void* state, size_t state_bytes,
                       const float* grad_losses, float* grad_student, float* grad_conv_w,
-                      float* grad_conv_b, cudaStream_t stream);
+                      float* grad_conv_b, float* grad_channel_sum,
+                      cudaStream_t stream);
 
 }  // namespace dbev

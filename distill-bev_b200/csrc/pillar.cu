@@ -53,7 +53,8 @@ pillar_encode_kernel(const float* __restrict__ points, const uint32_t* __restric
                      const uint32_t* __restrict__ sidx, const int* __restrict__ head_pos,
                      const int* __restrict__ nseg_ptr, PillarGeom g, const float* __restrict__ weight,
                      const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
-                     float* __restrict__ voxel_feats, int* __restrict__ voxel_coors) {
+                     float* __restrict__ voxel_feats, int* __restrict__ voxel_coors,
+                     float* __restrict__ canvas, int canvas_cl) {
   extern __shared__ __align__(16) float sh[];
   const int nout_p = (g.nout + 3) & ~3;   // padded row so every lane's 8 weights are 16B aligned
   float* w_s = sh;                        // [nin][nout_p]
@@ -86,7 +87,8 @@ pillar_encode_kernel(const float* __restrict__ points, const uint32_t* __restric
     const int cx = (int)(r % (uint32_t)g.nx); r /= (uint32_t)g.nx;
     const int cy = (int)(r % (uint32_t)g.ny); r /= (uint32_t)g.ny;
     const int cz = (int)(r % (uint32_t)g.nz); r /= (uint32_t)g.nz;
-    if (sub == 0) *reinterpret_cast<int4*>(voxel_coors + (size_t)seg * 4) = make_int4((int)r, cz, cy, cx);
+    if (sub == 0 && voxel_coors)
+      *reinterpret_cast<int4*>(voxel_coors + (size_t)seg * 4) = make_int4((int)r, cz, cy, cx);
     const float ctr_x = __fadd_rn(__fmul_rn((float)cx, g.vx), g.x_offset);
     const float ctr_y = __fadd_rn(__fmul_rn((float)cy, g.vy), g.y_offset);
     for (int c0 = 0; c0 < g.nout; c0 += kLanesPerPillar * kChPerLane) {
@@ -121,14 +123,29 @@ pillar_encode_kernel(const float* __restrict__ points, const uint32_t* __restric
           best[i] = fmaxf(best[i], fmaxf(acc[i] * sc_s[c] + sf_s[c], 0.f));  // folded BN, ReLU, max
         }
       }
-      float* o = voxel_feats + (size_t)seg * g.nout + cb;
-      if ((g.nout & 3) == 0) {
-        *reinterpret_cast<float4*>(o) = make_float4(best[0], best[1], best[2], best[3]);
-        if (cb + 4 < g.nout) *reinterpret_cast<float4*>(o + 4) = make_float4(best[4], best[5], best[6], best[7]);
-      } else {
+      // destinations: the [M, nout] pillar table and / or straight into the BEV canvas
+      // (PointPillarsScatter fused: with nz == 1 the key IS the canvas cell)
+      float* rows[2] = {voxel_feats ? voxel_feats + (size_t)seg * g.nout + cb : nullptr,
+                        (canvas && canvas_cl) ? canvas + (size_t)key * g.nout + cb : nullptr};
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float* o = rows[t];
+        if (!o) continue;
+        if ((g.nout & 3) == 0) {
+          *reinterpret_cast<float4*>(o) = make_float4(best[0], best[1], best[2], best[3]);
+          if (cb + 4 < g.nout) *reinterpret_cast<float4*>(o + 4) = make_float4(best[4], best[5], best[6], best[7]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < kChPerLane; ++i)
+            if (cb + i < g.nout) o[i] = best[i];
+        }
+      }
+      if (canvas && !canvas_cl) {  // NCHW canvas: one strided store per channel
+        const size_t plane = (size_t)g.ny * g.nx;
+        float* o = canvas + ((size_t)r * g.nout + cb) * plane + (size_t)cy * g.nx + cx;
 #pragma unroll
         for (int i = 0; i < kChPerLane; ++i)
-          if (cb + i < g.nout) o[i] = best[i];
+          if (cb + i < g.nout) o[(size_t)i * plane] = best[i];
       }
     }
   }
@@ -257,16 +274,24 @@ int pillar_encode(const float* points, const int* batch_offsets, const int* coor
                   int n, int nfeat, const float* voxel_size, const float* coors_range,
                   float x_offset, float y_offset, const float* weight, int nout,
                   const float* bn_scale, const float* bn_shift, float* voxel_feats,
-                  int* voxel_coors, int* num_voxels, int* point_coors, void* ws, size_t ws_bytes,
+                  int* voxel_coors, int* num_voxels, int* point_coors, float* canvas,
+                  int canvas_channels_last, int zero_canvas, void* ws, size_t ws_bytes,
                   cudaStream_t stream) {
   DBEV_CHECK_ARG(n >= 0 && batch > 0 && nfeat >= 3 && nfeat + 5 <= kMaxIn,
                  "pillar_encode: bad sizes n=%d batch=%d nfeat=%d", n, batch, nfeat);
+  DBEV_CHECK_ARG(canvas != nullptr || (voxel_feats != nullptr && voxel_coors != nullptr),
+                 "pillar_encode: no output given");
   DBEV_CHECK_ARG(nout > 0, "pillar_encode: output channels must be positive (got %d)", nout);
   int grid3[3];
   int rc = voxel_grid_size(voxel_size, coors_range, grid3);
   if (rc != DBEV_OK) return rc;
   const unsigned long long nkeys = (unsigned long long)batch * grid3[0] * grid3[1] * grid3[2];
   DBEV_CHECK_ARG(nkeys < 0xfffffff0ULL, "pillar_encode: key space exceeds 32 bits");
+  if (canvas) {
+    DBEV_CHECK_ARG(grid3[2] == 1, "pillar_canvas: pillars need a single z bin (got nz=%d)", grid3[2]);
+    if (zero_canvas)
+      DBEV_CUDA(cudaMemsetAsync(canvas, 0, (size_t)nkeys * nout * sizeof(float), stream));
+  }
   if (n == 0) {
     DBEV_CUDA(cudaMemsetAsync(num_voxels, 0, sizeof(int), stream));
     return DBEV_OK;
@@ -320,7 +345,8 @@ int pillar_encode(const float* points, const int* batch_offsets, const int* coor
 #define DBEV_LAUNCH_ENCODE(RAW)                                                                       \
   pillar_encode_kernel<RAW><<<egrid, 256, smem, stream>>>(points, keys[sel], vals[sel], head_pos,     \
                                                           num_voxels, g, weight, bn_scale, bn_shift,  \
-                                                          voxel_feats, voxel_coors)
+                                                          voxel_feats, voxel_coors, canvas,           \
+                                                          canvas_channels_last)
   if (nfeat <= 5) DBEV_LAUNCH_ENCODE(5);
   else if (nfeat <= 8) DBEV_LAUNCH_ENCODE(8);
   else DBEV_LAUNCH_ENCODE(kMaxIn - 5);

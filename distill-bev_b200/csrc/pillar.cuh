@@ -11,7 +11,8 @@ int pillar_encode(const float* points, const int* batch_offsets, const int* coor
                   int n, int nfeat, const float* voxel_size, const float* coors_range,
                   float x_offset, float y_offset, const float* weight, int nout,
                   const float* bn_scale, const float* bn_shift, float* voxel_feats,
-                  int* voxel_coors, int* num_voxels, int* point_coors, void* ws, size_t ws_bytes,
+                  int* voxel_coors, int* num_voxels, int* point_coors, float* canvas,
+                  int canvas_channels_last, int zero_canvas, void* ws, size_t ws_bytes,
                   cudaStream_t stream);
 
 int pillar_scatter(const float* voxel_feats, const int* coors, const int* m_dev, int m_max, int C,

@@ -13,27 +13,35 @@ from ... import _lib
 from ..ops.bev_pool import transpose_batched
 
 
+def conv1x1_forward(x, weight, bias):
+    """y = conv1x1(x) [B, Cout, H, W] on the tcgen05 GEMM (no autograd); also returns the x that
+    a backward should save."""
+    lib = _lib.load()
+    _lib.require_cuda(x, "x", torch.float32)
+    _lib.require_cuda(weight, "weight", torch.float32)
+    x, weight = x.detach(), weight.detach()
+    B, Cin, H, W = x.shape
+    Cout = weight.shape[0]
+    if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
+        x_cl = x                                   # [B, HW, Cin] in memory already
+    else:
+        x = x.contiguous()
+        x_cl = transpose_batched(x, B, Cin, H * W)  # NCHW -> channels-last rows
+    w2 = weight.reshape(Cout, Cin).contiguous()
+    y = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device)
+    b = bias.detach().contiguous() if bias is not None else None
+    with torch.cuda.device(x.device):
+        rc = lib.dbev_adapt_conv1x1_forward(_lib.ptr(x_cl), _lib.ptr(w2), _lib.ptr(b), B, Cin, Cout,
+                                            H * W, _lib.ptr(y), _lib.stream_ptr(x.device))
+    _lib.check(rc, "dbev_adapt_conv1x1_forward")
+    return y, x
+
+
 class _Conv1x1(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        lib = _lib.load()
-        _lib.require_cuda(x, "x", torch.float32)
-        _lib.require_cuda(weight, "weight", torch.float32)
-        B, Cin, H, W = x.shape
-        Cout = weight.shape[0]
-        if x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous():
-            x_cl = x                                   # [B, HW, Cin] in memory already
-        else:
-            x = x.contiguous()
-            x_cl = transpose_batched(x, B, Cin, H * W)  # NCHW -> channels-last rows
-        w2 = weight.reshape(Cout, Cin).contiguous()
-        y = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device)
-        b = bias.contiguous() if bias is not None else None
-        with torch.cuda.device(x.device):
-            rc = lib.dbev_adapt_conv1x1_forward(_lib.ptr(x_cl), _lib.ptr(w2), _lib.ptr(b), B, Cin, Cout,
-                                                H * W, _lib.ptr(y), _lib.stream_ptr(x.device))
-        _lib.check(rc, "dbev_adapt_conv1x1_forward")
+        y, x = conv1x1_forward(x, weight, bias)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         return y

@@ -152,75 +152,129 @@ def make_config(B, C, H, W, distill_params, index=0, use_fp=None, epoch=0):
     return cfg, fp_mode
 
 
+def _loss_forward(student, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count):
+    lib = _lib.load()
+    _lib.require_cuda(student, "student_feat", torch.float32)
+    _lib.require_cuda(teacher, "teacher_feat", torch.float32)
+    if student.shape != teacher.shape:
+        raise RuntimeError("student %s and teacher %s must have the same shape after adaptation"
+                           % (tuple(student.shape), tuple(teacher.shape)))
+    student, teacher = student.contiguous(), teacher.contiguous()
+    dev = student.device
+    if conv_w is None:
+        conv_w = torch.zeros(9, device=dev)
+        conv_b = torch.zeros(1, device=dev)
+    cw = conv_w.detach().reshape(-1).contiguous().float()
+    cb = conv_b.detach().reshape(-1).contiguous().float()
+    nbytes = lib.dbev_fgd_state_bytes(ctypes.byref(cfg))
+    state = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+    losses = torch.empty(5, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.dbev_fgd_loss_forward(
+            ctypes.byref(cfg), _lib.ptr(student), _lib.ptr(teacher), _lib.ptr(fg.contiguous()),
+            _lib.ptr(fg_scale.contiguous()), _lib.ptr(fg_count), _lib.ptr(fp), _lib.ptr(fp_count),
+            _lib.ptr(cw), _lib.ptr(cb), _lib.ptr(state), nbytes, _lib.ptr(losses),
+            _lib.stream_ptr(dev))
+    _lib.check(rc, "dbev_fgd_loss_forward")
+    return losses, state, student, teacher, cw, cb, (conv_w.shape, conv_b.shape)
+
+
+def _loss_backward(cfg, state, student, teacher, cw, cb, grad_losses, conv_shape, channel_sum=False):
+    lib = _lib.load()
+    dev = student.device
+    gl = grad_losses.contiguous().float()
+    gs = torch.empty_like(student)
+    gw = torch.empty(9, dtype=torch.float32, device=dev)
+    gb = torch.empty(1, dtype=torch.float32, device=dev)
+    gc = torch.empty(student.shape[1], dtype=torch.float32, device=dev) if channel_sum else None
+    with torch.cuda.device(dev):
+        rc = lib.dbev_fgd_loss_backward(
+            ctypes.byref(cfg), _lib.ptr(student), _lib.ptr(teacher), _lib.ptr(cw), _lib.ptr(cb),
+            _lib.ptr(state), state.numel() * 4, _lib.ptr(gl), _lib.ptr(gs), _lib.ptr(gw),
+            _lib.ptr(gb), _lib.ptr(gc), _lib.stream_ptr(dev))
+    _lib.check(rc, "dbev_fgd_loss_backward")
+    return gs, gw.view(conv_shape[0]), gb.view(conv_shape[1]), gc
+
+
 class _FGDLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, student, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count):
-        lib = _lib.load()
-        _lib.require_cuda(student, "student_feat", torch.float32)
-        _lib.require_cuda(teacher, "teacher_feat", torch.float32)
-        if student.shape != teacher.shape:
-            raise RuntimeError("student %s and teacher %s must have the same shape after adaptation"
-                               % (tuple(student.shape), tuple(teacher.shape)))
-        student, teacher = student.contiguous(), teacher.contiguous()
-        dev = student.device
-        if conv_w is None:
-            conv_w = torch.zeros(9, device=dev)
-            conv_b = torch.zeros(1, device=dev)
-        cw = conv_w.detach().reshape(-1).contiguous().float()
-        cb = conv_b.detach().reshape(-1).contiguous().float()
-        nbytes = lib.dbev_fgd_state_bytes(ctypes.byref(cfg))
-        state = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
-        losses = torch.empty(5, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            rc = lib.dbev_fgd_loss_forward(
-                ctypes.byref(cfg), _lib.ptr(student), _lib.ptr(teacher), _lib.ptr(fg.contiguous()),
-                _lib.ptr(fg_scale.contiguous()), _lib.ptr(fg_count), _lib.ptr(fp), _lib.ptr(fp_count),
-                _lib.ptr(cw), _lib.ptr(cb), _lib.ptr(state), nbytes, _lib.ptr(losses),
-                _lib.stream_ptr(dev))
-        _lib.check(rc, "dbev_fgd_loss_forward")
-        ctx.cfg = cfg
-        ctx.state = state
-        ctx.conv_shape = (conv_w.shape, conv_b.shape)
+        losses, state, student, teacher, cw, cb, shp = _loss_forward(
+            student, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count)
+        ctx.cfg, ctx.state, ctx.conv_shape = cfg, state, shp
         ctx.save_for_backward(student, teacher, cw, cb)
         return losses
 
     @staticmethod
     def backward(ctx, grad_losses):
-        lib = _lib.load()
         student, teacher, cw, cb = ctx.saved_tensors
-        dev = student.device
-        gl = grad_losses.contiguous().float()
-        gs = torch.empty_like(student)
-        gw = torch.empty(9, dtype=torch.float32, device=dev)
-        gb = torch.empty(1, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            rc = lib.dbev_fgd_loss_backward(
-                ctypes.byref(ctx.cfg), _lib.ptr(student), _lib.ptr(teacher), _lib.ptr(cw), _lib.ptr(cb),
-                _lib.ptr(ctx.state), ctx.state.numel() * 4, _lib.ptr(gl), _lib.ptr(gs), _lib.ptr(gw),
-                _lib.ptr(gb), _lib.stream_ptr(dev))
-        _lib.check(rc, "dbev_fgd_loss_backward")
-        return (gs, None, gw.view(ctx.conv_shape[0]), gb.view(ctx.conv_shape[1]),
-                None, None, None, None, None, None)
+        gs, gw, gb, _ = _loss_backward(ctx.cfg, ctx.state, student, teacher, cw, cb, grad_losses,
+                                       ctx.conv_shape)
+        return (gs, None, gw, gb, None, None, None, None, None, None)
+
+
+class _AdaptFGDLoss(torch.autograd.Function):
+    """channel_wise_adaptations[index] (1x1 conv, :1004) + the loss as ONE autograd node: the
+    adapted student never leaves this node and the conv's bias gradient falls out of the loss
+    backward kernel (per-channel sums of d loss / d adapted student)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count):
+        from .adaptation import conv1x1_forward
+        adapted, x = conv1x1_forward(x, weight, bias)
+        losses, state, adapted, teacher, cw, cb, shp = _loss_forward(
+            adapted, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count)
+        ctx.cfg, ctx.state, ctx.conv_shape, ctx.has_bias = cfg, state, shp, bias is not None
+        ctx.save_for_backward(x, weight, adapted, teacher, cw, cb)
+        return losses
+
+    @staticmethod
+    def backward(ctx, grad_losses):
+        x, weight, adapted, teacher, cw, cb = ctx.saved_tensors
+        want_bias = ctx.has_bias and ctx.needs_input_grad[2]
+        gs, gw, gb, gsum = _loss_backward(ctx.cfg, ctx.state, adapted, teacher, cw, cb, grad_losses,
+                                          ctx.conv_shape, channel_sum=want_bias)
+        gx = torch.nn.grad.conv2d_input(x.shape, weight, gs) if ctx.needs_input_grad[0] else None
+        gwt = torch.nn.grad.conv2d_weight(x, weight.shape, gs) if ctx.needs_input_grad[1] else None
+        return (gx, gwt, gsum, None, gw, gb, None, None, None, None, None, None)
 
 
 def fgd_loss_terms(student_feat, teacher_feat, cfg, fg, fg_scale, fg_count, fp=None, fp_count=None,
-                   conv_weight=None, conv_bias=None):
-    """losses[5] tensor (order LOSS_KEYS), differentiable w.r.t. student_feat / conv."""
+                   conv_weight=None, conv_bias=None, adapt_weight=None, adapt_bias=None):
+    """losses[5] tensor (order LOSS_KEYS), differentiable w.r.t. student_feat / conv. With
+    ``adapt_weight`` [Ct, Cs, 1, 1] (+ ``adapt_bias``) the 1x1 adaptation conv is applied to
+    ``student_feat`` [B, Cs, H, W] inside the same autograd node."""
+    if adapt_weight is not None:
+        return _AdaptFGDLoss.apply(student_feat, adapt_weight, adapt_bias, teacher_feat, conv_weight,
+                                   conv_bias, cfg, fg, fg_scale, fg_count, fp, fp_count)
     return _FGDLoss.apply(student_feat, teacher_feat, conv_weight, conv_bias, cfg, fg, fg_scale,
                           fg_count, fp, fp_count)
 
 
 def fgd_distill_loss(teacher_feat, student_feat, gt_bboxes_3d, distill_params, train_cfg,
                      spatial_adaptation=None, heatmaps=None, teacher_heatmaps=None,
-                     student_heatmaps=None, index=0, epoch=0):
+                     student_heatmaps=None, index=0, epoch=0, channel_adaptation=None):
     """Drop-in for the body of ``BEVDetDistill.fgd_distill_loss`` after the adaptation layers
     (:1006-1293): returns the same loss dict. ``train_cfg`` = pts_bbox_head.train_cfg
     (grid_size, point_cloud_range, voxel_size); ``spatial_adaptation`` = the
     ``spatial_wise_adaptations[index]`` Conv2d(1,1,3,padding=1); ``heatmaps`` /
     ``teacher_heatmaps`` (raw logits) / ``student_heatmaps`` (already sigmoid) are [B,K,h,w]
-    tensors or per-task lists, needed only when fp_as_foreground is active."""
-    B, C, H, W = student_feat.shape
+    tensors or per-task lists, needed only when fp_as_foreground is active.
+    ``channel_adaptation`` = ``channel_wise_adaptations[index]`` (:1004), applied to ``student_feat``
+    here as the reference does; a 1x1 conv is fused with the loss (tcgen05 forward, bias gradient
+    from the loss backward), any other module is simply called."""
+    adapt_w = adapt_b = None
+    if channel_adaptation is not None:
+        conv = channel_adaptation
+        if (isinstance(conv, torch.nn.Conv2d) and conv.kernel_size == (1, 1) and conv.stride == (1, 1)
+                and conv.padding == (0, 0) and conv.groups == 1 and conv.dilation == (1, 1)
+                and student_feat.is_cuda and student_feat.dtype == torch.float32):
+            adapt_w, adapt_b = conv.weight, conv.bias
+        else:
+            student_feat = channel_adaptation(student_feat)
+    B, _, H, W = student_feat.shape
+    C = adapt_w.shape[0] if adapt_w is not None else student_feat.shape[1]
     cfg, fp_mode = make_config(B, C, H, W, distill_params, index, epoch=epoch)
     if distill_params.get("foreground_mask", "gt") != "gt":
         raise NotImplementedError("foreground_mask=%r" % distill_params.get("foreground_mask"))
@@ -239,7 +293,8 @@ def fgd_distill_loss(teacher_feat, student_feat, gt_bboxes_3d, distill_params, t
                                           distill_params.get("groundtruth_threshold"), return_counts=True)
     cw = spatial_adaptation.weight if spatial_adaptation is not None else None
     cb = spatial_adaptation.bias if spatial_adaptation is not None else None
-    losses = fgd_loss_terms(student_feat, teacher_feat, cfg, fg, fg_scale, fg_count, fp, fp_count, cw, cb)
+    losses = fgd_loss_terms(student_feat, teacher_feat, cfg, fg, fg_scale, fg_count, fp, fp_count, cw, cb,
+                            adapt_w, adapt_b)
     out = {"kd_fg_feat_loss": losses[0], "kd_bg_feat_loss": losses[1]}
     if cfg.channel_mask:
         out["kd_channel_loss"] = losses[3]

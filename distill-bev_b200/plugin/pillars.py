@@ -172,6 +172,29 @@ def pillar_canvas(points_list, encoder, scatter):
     if encoder.training:
         raise RuntimeError("pillar_canvas is the frozen-teacher (eval) path")
     scale, shift = fold_bn(bn)
-    vf, vc, cnt, _ = pillar_encode(points, lin.weight, scale, shift, encoder.voxel_size,
-                                   encoder.point_cloud_range, B, batch_offsets=offsets, sync=False)
-    return pillar_scatter(vf, vc, B, scatter.ny, scatter.nx, scatter.channels_last, count=cnt)
+    lib = _lib.load()
+    _lib.require_cuda(points, "points", torch.float32)
+    points = points.contiguous()
+    n, f = points.shape
+    dev = points.device
+    w = lin.weight.detach().float().contiguous()
+    nout = w.shape[0]
+    gx, gy, gz = _grid_size(encoder.voxel_size, encoder.point_cloud_range)
+    if (gy, gx) != (scatter.ny, scatter.nx) or gz != 1:
+        raise RuntimeError("pillar_canvas: encoder grid %s does not match the scatter output_shape %s"
+                           % ((gz, gy, gx), (scatter.ny, scatter.nx)))
+    fmt = torch.channels_last if scatter.channels_last else torch.contiguous_format
+    canvas = torch.empty((B, nout, gy, gx), dtype=torch.float32, device=dev, memory_format=fmt)
+    cnt = torch.empty(1, dtype=torch.int32, device=dev)
+    x_off = float(encoder.voxel_size[0]) / 2 + float(encoder.point_cloud_range[0])
+    y_off = float(encoder.voxel_size[1]) / 2 + float(encoder.point_cloud_range[1])
+    with torch.cuda.device(dev):
+        wsb = lib.dbev_pillar_encode_workspace_bytes(n)
+        ws = _lib.workspace(wsb, dev)
+        rc = lib.dbev_pillar_canvas(
+            _lib.ptr(points), _lib.ptr(_lib.h2d_async(offsets, dev)), None, B, n, f,
+            _lib.host_floats(encoder.voxel_size), _lib.host_floats(encoder.point_cloud_range), x_off, y_off,
+            _lib.ptr(w), nout, _lib.ptr(scale), _lib.ptr(shift), int(scatter.channels_last), 1,
+            _lib.ptr(canvas), _lib.ptr(cnt), _lib.ptr(ws), wsb, _lib.stream_ptr(dev))
+    _lib.check(rc, "dbev_pillar_canvas")
+    return canvas

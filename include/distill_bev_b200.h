@@ -248,6 +248,19 @@ int dbev_pillar_encode(const float* points, const int* batch_offsets, const int*
                        int* num_voxels, int* point_coors, void* workspace, size_t workspace_bytes,
                        void* stream);
 
+/* Voxel encoder + middle encoder of the pillar teacher in one pass
+ * (DynamicCenterPoint.extract_pts_feat, mmdet3d/models/detectors/dynamic_centerpoint.py:43-93:
+ * pts_voxel_encoder -> pts_middle_encoder): dbev_pillar_encode whose pillar rows are stored
+ * straight into the BEV canvas [batch, nout, ny, nx] (channels_last as for dbev_pillar_scatter),
+ * so the [M, nout] table is never written or re-read. Needs a single z bin. Same workspace as
+ * dbev_pillar_encode; *num_voxels (DEVICE int) = number of non-empty pillars. */
+int dbev_pillar_canvas(const float* points, const int* batch_offsets, const int* coors_in,
+                       int batch, int n, int nfeat, const float* voxel_size_host3,
+                       const float* coors_range_host6, float x_offset, float y_offset,
+                       const float* weight, int nout, const float* bn_scale,
+                       const float* bn_shift, int channels_last, int zero_canvas, float* canvas,
+                       int* num_voxels, void* workspace, size_t workspace_bytes, void* stream);
+
 /* PointPillarsScatter.forward_batch (mmdet3d/models/middle_encoders/pillar_scatter.py:62-102):
  * canvas[b, :, y, x] = voxel_feats[m, :] for coors[m] = (b, z, y, x). The canvas is
  * [batch, C, ny, nx] (channels_last = 0) or the same tensor in NHWC memory order
@@ -345,11 +358,14 @@ int dbev_fgd_loss_forward(const dbev_fgd_config* cfg, const float* student, cons
                           void* stream);
 
 /* Gradient of sum_k grad_losses[k] * losses[k] w.r.t. student (attention masks and the
- * teacher are detached as in the reference, :1100,1104,1108), conv_w[9] and conv_b[1]. */
+ * teacher are detached as in the reference, :1100,1104,1108), conv_w[9] and conv_b[1].
+ * grad_channel_sum (optional, [C]) receives sum over (b, h, w) of grad_student: the bias gradient
+ * of the 1x1 channel_wise_adaptations conv that produced `student` (:1004), for free. */
 int dbev_fgd_loss_backward(const dbev_fgd_config* cfg, const float* student, const float* teacher,
                            const float* conv_w, const float* conv_b, void* state,
                            size_t state_bytes, const float* grad_losses, float* grad_student,
-                           float* grad_conv_w, float* grad_conv_b, void* stream);
+                           float* grad_conv_w, float* grad_conv_b, float* grad_channel_sum,
+                           void* stream);
 
 /* ------------------------------------------------------------------------ *
  * Primitives exposed for testing (stable LSD radix sort, exclusive scan).

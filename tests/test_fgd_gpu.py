@@ -155,3 +155,53 @@ def test_empty_boxes_and_cpu_rejection(cuda):
     with pytest.raises(RuntimeError, match="no CPU path"):
         fgd.foreground_scale_mask(64, 64, [torch.zeros(0, 9)], [512, 512, 1], [-51.2] * 2 + [-5, 51.2, 51.2, 3],
                                   [0.2, 0.2, 8.0], "cpu")
+
+
+@pytest.mark.parametrize("B,Cs,Ct,H", [(2, 256, 384, 128), (1, 64, 128, 50)])
+def test_fused_channel_adaptation_matches_composition(cuda, B, Cs, Ct, H):
+    """channel_adaptation= (1x1 conv inside the loss node, bias gradient from the loss backward)
+    == adaptation module followed by the loss; the bias gradient == sum of d loss / d adapted."""
+    from distill_bev_b200.plugin.distill.adaptation import Conv1x1Adaptation
+    rng = np.random.RandomState(B + Cs + Ct)
+    teacher = _t(np.maximum(rng.randn(B, Ct, H, H), 0).astype(np.float32), cuda)
+    student = np.maximum(rng.randn(B, Cs, H, H), 0).astype(np.float32)
+    boxes = [torch.from_numpy(b) for b, _ in synthetic.make_gt_boxes(B, seed=5)]
+    grid = [H * 8, H * 8, 40]
+    vox = 102.4 / (H * 8)
+    tc = dict(grid_size=grid, point_cloud_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], voxel_size=[vox, vox, 0.2])
+    p = _recipe_params()
+    gt_hm = _t((rng.random_sample((B, 10, H, H)) ** 12).astype(np.float32), cuda)
+    t_logit = _t((rng.randn(B, 10, H, H) * 1.5 - 3.0).astype(np.float32), cuda)
+    torch.manual_seed(1)
+    spatial = torch.nn.Conv2d(1, 1, 3, padding=1).to(cuda)
+    adapt = Conv1x1Adaptation(Cs, Ct).to(cuda)
+    kw = dict(spatial_adaptation=spatial, heatmaps=gt_hm, teacher_heatmaps=t_logit, epoch=1)
+
+    s1 = _t(student, cuda).requires_grad_(True)
+    l1 = fgd.fgd_distill_loss(teacher, s1, boxes, p, tc, channel_adaptation=adapt, **kw)
+    sum(l1.values()).backward()
+    g1 = [s1.grad.clone(), adapt.weight.grad.clone(), adapt.bias.grad.clone(), spatial.weight.grad.clone()]
+    adapt.zero_grad()
+    spatial.zero_grad()
+
+    s2 = _t(student, cuda).requires_grad_(True)
+    adapted = adapt(s2)
+    adapted.retain_grad()
+    l2 = fgd.fgd_distill_loss(teacher, adapted, boxes, p, tc, **kw)
+    sum(l2.values()).backward()
+    for k in l1:
+        assert torch.equal(l1[k], l2[k]), k                     # same kernels, same order
+    assert torch.equal(g1[0], s2.grad) and torch.equal(g1[1], adapt.weight.grad)
+    assert torch.equal(g1[3], spatial.weight.grad)
+    ref_bias = adapted.grad.double().sum(dim=(0, 2, 3))
+    err = (g1[2].double() - ref_bias).abs().max().item()
+    assert err <= 1e-5 * ref_bias.abs().max().item() + 1e-12, err
+    # rerun: bit-reproducible (fixed-order tile sums)
+    adapt.zero_grad()
+    s3 = _t(student, cuda).requires_grad_(True)
+    sum(fgd.fgd_distill_loss(teacher, s3, boxes, p, tc, channel_adaptation=adapt, **kw).values()).backward()
+    assert torch.equal(adapt.bias.grad, g1[2])
+    # a non-1x1 adaptation module is simply applied
+    conv3 = torch.nn.Conv2d(Cs, Ct, 3, padding=1).to(cuda)
+    l3 = fgd.fgd_distill_loss(teacher, _t(student, cuda), boxes, p, tc, channel_adaptation=conv3, **kw)
+    assert set(l3) == set(l1)

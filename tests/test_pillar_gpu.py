@@ -79,6 +79,28 @@ def test_pillar_canvas_full_size_vs_oracle(cuda, B, n):
     np.testing.assert_allclose(got, ref, rtol=1e-4, atol=2e-4)
 
 
+@pytest.mark.parametrize("channels_last", [False, True])
+@pytest.mark.parametrize("nout,nfeat", [(64, 5), (32, 4), (20, 4)])
+def test_pillar_canvas_equals_encode_then_scatter(cuda, channels_last, nout, nfeat):
+    """The fused canvas entry point stores the same bits as dbev_pillar_encode + dbev_pillar_scatter."""
+    vs, pcr = [0.4, 0.4, 8.0], [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
+    clouds = [c[:, :nfeat].copy() for c in synthetic.make_lidar(3, 20000, seed=4)]
+    torch.manual_seed(nout)
+    enc = pillars.DynamicPillarFeatureNet(in_channels=nfeat, feat_channels=(nout,), voxel_size=vs,
+                                          point_cloud_range=pcr).to(cuda).eval()
+    scat = pillars.PointPillarsScatter(nout, [256, 256], channels_last=channels_last)
+    pts = [_t(c, cuda) for c in clouds]
+    canvas = pillars.pillar_canvas(pts, enc, scat)
+    lin, bn = enc.pfn_layers[0][0], enc.pfn_layers[0][1]
+    scale, shift = pillars.fold_bn(bn)
+    offs = torch.tensor([0, 20000, 40000, 60000], dtype=torch.int32)
+    vf, vc = pillars.pillar_encode(torch.cat(pts), lin.weight, scale, shift, vs, pcr, 3, batch_offsets=offs)
+    two_step = pillars.pillar_scatter(vf, vc, 3, 256, 256, channels_last)
+    assert canvas.shape == two_step.shape and canvas.stride() == two_step.stride()
+    assert torch.equal(canvas, two_step)
+    assert int((canvas != 0).any(1).sum()) <= vf.shape[0]
+
+
 def test_lss_geometry_vs_reference_golden(cuda, golden_dir):
     g = np.load(os.path.join(golden_dir, "lss_small.npz"))
     geom = vtm.lss_geometry(_t(g["frustum"], cuda), _t(g["rots"], cuda), _t(g["trans"], cuda),

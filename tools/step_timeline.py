@@ -53,13 +53,10 @@ def phases(hp):
             return dbev.pillar_canvas(hp.d_points, hp.enc, hp.scat)
     timed("B.pillar_canvas", pillars)
 
-    def adapt():
-        state["s"] = hp.adapt(hp.student)
-
     def loss():
         losses = dbev.fgd.fgd_distill_loss(
-            hp.teacher, state["s"], hp.boxes, bench.DISTILL_PARAMS, bench.TRAIN_CFG,
-            spatial_adaptation=hp.spatial, heatmaps=hp.d_gt_hm, teacher_heatmaps=hp.teacher_logit, epoch=1)
+            hp.teacher, hp.student, hp.boxes, bench.DISTILL_PARAMS, bench.TRAIN_CFG,
+            channel_adaptation=hp.adapt, spatial_adaptation=hp.spatial, heatmaps=hp.d_gt_hm, teacher_heatmaps=hp.teacher_logit, epoch=1)
         state["total"] = losses["kd_fg_feat_loss"] + losses["kd_bg_feat_loss"] + losses["kd_spatial_loss"] \
             + losses["kd_fp_bg_feat_loss"]
 
@@ -68,8 +65,7 @@ def phases(hp):
         hp.student.grad = None
         hp.adapt.zero_grad(set_to_none=True)
         hp.spatial.zero_grad(set_to_none=True)
-    timed("C.adapt_fwd", adapt)
-    timed("C.loss_fwd", loss)
+    timed("C.adapt+loss_fwd", loss)
     timed("C.loss_bwd", lbwd)
     return res
 
