@@ -15,6 +15,7 @@ from .plugin.pillars import DynamicPillarFeatureNet, PointPillarsScatter, pillar
 from .plugin.view_transformer import ViewTransformerLiftSplatShoot, lss_geometry  # noqa: F401
 from .plugin.distill import fgd  # noqa: F401
 from .plugin.distill.adaptation import Conv1x1Adaptation, conv1x1  # noqa: F401
+from .graph import CapturedStep  # noqa: F401
 
 __version__ = "0.1.0"
 

@@ -27,8 +27,27 @@ def _box_tensor(b):
     return torch.as_tensor(t, dtype=torch.float32)
 
 
+class PackedBoxes(object):
+    """Ground-truth boxes of a batch already on the device: ``boxes`` [capacity, D >= 7] fp32 with
+    the samples back to back, ``offsets`` [B + 1] int32 (device), ``max_per_sample`` an upper bound
+    of boxes in one sample (host int; sizes the rasteriser's shared memory). Accepted wherever
+    ``gt_bboxes_3d`` is; lets a step be CUDA-graph captured: refill the two tensors in place."""
+
+    def __init__(self, boxes, offsets, max_per_sample):
+        _lib.require_cuda(boxes, "boxes", torch.float32)
+        _lib.require_cuda(offsets, "offsets", torch.int32)
+        if boxes.dim() != 2 or boxes.shape[1] < 7:
+            raise RuntimeError("boxes must be [n, >=7], got %s" % (tuple(boxes.shape),))
+        self.boxes, self.offsets, self.max_per_sample = boxes.contiguous(), offsets.contiguous(), int(max_per_sample)
+
+    def __len__(self):
+        return self.offsets.numel() - 1
+
+
 def pack_boxes(gt_bboxes_3d, device):
     """list of per-sample boxes [M_b, >=7] -> (boxes [sum M, D] cuda, offsets [B+1] cuda int32, max M)."""
+    if isinstance(gt_bboxes_3d, PackedBoxes):
+        return gt_bboxes_3d.boxes, gt_bboxes_3d.offsets, gt_bboxes_3d.max_per_sample
     ts = [_box_tensor(b).reshape(-1, _box_tensor(b).shape[-1] if _box_tensor(b).numel() else 9)
           for b in gt_bboxes_3d]
     dim = max([t.shape[1] for t in ts if t.shape[0] > 0] + [7])

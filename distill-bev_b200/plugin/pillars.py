@@ -158,6 +158,22 @@ class PointPillarsScatter(nn.Module):
         return [pillar_scatter(voxel_features, c4, 1, self.ny, self.nx, self.channels_last)]
 
 
+_OFFSETS_CACHE = {}
+
+
+def _device_offsets(offs, device):
+    """Batch offsets [B + 1] int32 on the device; cached per (offsets, device): fixed-size clouds
+    then cost no copy per step, and the call is CUDA-graph capturable."""
+    key = (offs, str(device))
+    t = _OFFSETS_CACHE.get(key)
+    if t is None:
+        if len(_OFFSETS_CACHE) > 256:
+            _OFFSETS_CACHE.clear()
+        t = _lib.h2d_async(torch.tensor(offs, dtype=torch.int32), device)
+        _OFFSETS_CACHE[key] = t
+    return t
+
+
 def pillar_canvas(points_list, encoder, scatter):
     """points (list of [N_b, F] CUDA tensors) -> teacher pseudo image [B, C, ny, nx] with no host
     synchronisation: voxelization, pillar encoding and scatter are enqueued back to back
@@ -167,7 +183,7 @@ def pillar_canvas(points_list, encoder, scatter):
     for p in points_list:
         offs.append(offs[-1] + p.shape[0])
     points = torch.cat(points_list, 0) if B > 1 else points_list[0]
-    offsets = torch.tensor(offs, dtype=torch.int32)
+    offsets = _device_offsets(tuple(offs), points.device)
     lin, bn = encoder.pfn_layers[0][0], encoder.pfn_layers[0][1]
     if encoder.training:
         raise RuntimeError("pillar_canvas is the frozen-teacher (eval) path")
@@ -192,7 +208,7 @@ def pillar_canvas(points_list, encoder, scatter):
         wsb = lib.dbev_pillar_encode_workspace_bytes(n)
         ws = _lib.workspace(wsb, dev)
         rc = lib.dbev_pillar_canvas(
-            _lib.ptr(points), _lib.ptr(_lib.h2d_async(offsets, dev)), None, B, n, f,
+            _lib.ptr(points), _lib.ptr(offsets), None, B, n, f,
             _lib.host_floats(encoder.voxel_size), _lib.host_floats(encoder.point_cloud_range), x_off, y_off,
             _lib.ptr(w), nout, _lib.ptr(scale), _lib.ptr(shift), int(scatter.channels_last), 1,
             _lib.ptr(canvas), _lib.ptr(cnt), _lib.ptr(ws), wsb, _lib.stream_ptr(dev))
