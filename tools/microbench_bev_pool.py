@@ -40,12 +40,13 @@ def main():
     ap.add_argument("--dstep", type=float, default=1.0)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--rpi", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=0)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     grid = synthetic.grid_config(a.bev, a.dstep)
     dx, bx, nx = lss_oracle.gen_dx_bx(grid["xbound"], grid["ybound"], grid["zbound"])
     frustum = lss_oracle.create_frustum(synthetic.NUSC_INPUT_SIZE, 16, grid["dbound"])
-    calib = synthetic.make_calibration(a.frames, 6, seed=0)
+    calib = synthetic.make_calibration(a.frames, 6, seed=a.seed)
     geom = torch.from_numpy(lss_oracle.get_geometry(frustum, *calib)).to(dev)
     n = geom.numel() // 3
     x = torch.rand(n, a.C, device=dev)
