@@ -93,6 +93,36 @@ SIGNATURES = {
     "dbev_lss_geometry": (_c_int, [_ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _c_int, _ptr, _ptr,
                                    _ptr]),
     "dbev_adapt_conv1x1_forward": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr]),
+    "dbev_spconv_max_out": (_c_ll, [_c_ll, _iptr]),
+    "dbev_spconv_workspace_bytes": (_c_size, [_c_ll, _c_ll]),
+    "dbev_spconv_table": (_c_int, [_ptr, _c_int, _ptr, _c_int, _iptr, _ptr, _ptr, _c_size, _ptr]),
+    "dbev_spconv_out_candidates": (_c_int, [_ptr, _c_int, _iptr, _ptr, _c_ll, _ptr, _ptr, _c_size,
+                                            _ptr]),
+    "dbev_spconv_out_table": (_c_int, [_ptr, _c_int, _iptr, _ptr, _c_int, _ptr, _ptr, _ptr, _c_size,
+                                       _ptr]),
+    "dbev_spconv_pairs_from_table": (_c_int, [_ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr]),
+    "dbev_spconv_table_from_pairs": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr,
+                                              _ptr]),
+    "dbev_spconv_forward": (_c_int, [_ptr, _c_int, _ptr, _c_int, _ptr, _c_int, _c_int, _ptr, _ptr,
+                                     _ptr, _c_int, _ptr, _ptr]),
+    "dbev_spconv_dense": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr,
+                                   _ptr]),
+    "dbev_hard_simple_vfe": (_c_int, [_ptr, _ptr, _c_ll, _c_int, _c_int, _c_int, _ptr, _ptr]),
+    "dbev_dynvoxel_coords": (_c_int, [_ptr, _c_int, _c_int, _ptr, _c_int, _fptr, _fptr, _c_int, _ptr,
+                                      _ptr]),
+    "dbev_dynvoxel_virtual_rows": (_c_int, [_ptr, _c_int, _c_int, _ptr, _ptr]),
+    "dbev_dynvoxel_virtual_fix": (_c_int, [_ptr, _ptr, _c_int, _ptr, _ptr]),
+    "dbev_affinity_select_workspace_bytes": (_c_size, [_c_int, _c_int]),
+    "dbev_affinity_select": (_c_int, [_ptr, _ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _c_size, _ptr]),
+    "dbev_affinity_gather_rows": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr,
+                                           _ptr]),
+    "dbev_affinity_partial_floats": (_c_size, [_iptr, _c_int]),
+    "dbev_affinity_forward": (_c_int, [_ptr, _ptr, _iptr, _c_int, _c_int, _c_int, _c_float, _c_float,
+                                       _ptr, _ptr, _ptr]),
+    "dbev_affinity_backward": (_c_int, [_ptr, _ptr, _iptr, _c_int, _c_int, _c_int, _c_float,
+                                        _c_float, _ptr, _ptr, _ptr]),
+    "dbev_affinity_scatter_rows": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _ptr,
+                                            _ptr]),
     "dbev_sort_workspace_bytes": (_c_size, [_c_ll]),
     "dbev_sort_keys_iota": (_c_int, [_ptr, _c_int, _c_int, _ptr, _ptr, _ptr, _c_size, _ptr]),
     "dbev_scan_workspace_bytes": (_c_size, [_c_ll]),

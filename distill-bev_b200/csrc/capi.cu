@@ -5,10 +5,13 @@
 #include <string.h>
 
 #include "adapt_gemm.cuh"
+#include "affinity.cuh"
 #include "bev_pool.cuh"
 #include "distill_loss.cuh"
 #include "pillar.cuh"
 #include "sort.cuh"
+#include "spconv.cuh"
+#include "voxel_encoders.cuh"
 #include "voxelize.cuh"
 
 namespace dbev {
@@ -259,6 +262,134 @@ int dbev_lss_geometry(const float* frustum, int pts_per_cam, const float* rots,
 int dbev_adapt_conv1x1_forward(const float* x_cl, const float* w, const float* bias, int batch,
                                int c_in, int c_out, int hw, float* y, void* stream) {
   return adapt_conv1x1_forward(x_cl, w, bias, batch, c_in, c_out, hw, y, (cudaStream_t)stream);
+}
+
+static SpConvGeom geom_from_host(const int* g) {
+  SpConvGeom r;
+  for (int i = 0; i < 3; ++i) {
+    r.k[i] = g[i], r.s[i] = g[3 + i], r.p[i] = g[6 + i], r.d[i] = g[9 + i];
+    r.in_shape[i] = g[12 + i], r.out_shape[i] = g[15 + i];
+  }
+  r.batch = g[18];
+  return r;
+}
+
+long long dbev_spconv_max_out(long long n_in, const int* geom_host19) {
+  return spconv_max_out(n_in, geom_from_host(geom_host19));
+}
+
+size_t dbev_spconv_workspace_bytes(long long n_in, long long max_out) {
+  return spconv_ws_bytes(n_in, max_out);
+}
+
+int dbev_spconv_table(const int* in_coors, int n_in, const int* out_coors, int n_out,
+                      const int* geom_host19, int* nbr, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  return spconv_table(in_coors, n_in, out_coors, n_out, geom_from_host(geom_host19), nbr,
+                      workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_spconv_out_candidates(const int* in_coors, int n_in, const int* geom_host19,
+                               uint32_t* out_keys, long long max_out, int* n_out,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  return spconv_out_candidates(in_coors, n_in, geom_from_host(geom_host19), out_keys, max_out,
+                               n_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_spconv_out_table(const int* in_coors, int n_in, const int* geom_host19,
+                          uint32_t* out_keys, int n_out, int* out_coors, int* nbr,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  return spconv_out_table(in_coors, n_in, geom_from_host(geom_host19), out_keys, n_out, out_coors,
+                          nbr, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_spconv_pairs_from_table(const int* nbr, int kvol, int n_out, int pair_stride,
+                                 int* indice_pairs, int* indice_num, void* stream) {
+  return spconv_pairs_from_table(nbr, kvol, n_out, pair_stride, indice_pairs, indice_num,
+                                 (cudaStream_t)stream);
+}
+
+int dbev_spconv_table_from_pairs(const int* indice_pairs, const int* indice_num, int kvol,
+                                 int pair_stride, int inverse, int n_out, int* nbr, void* stream) {
+  return spconv_table_from_pairs(indice_pairs, indice_num, kvol, pair_stride, inverse, n_out, nbr,
+                                 (cudaStream_t)stream);
+}
+
+int dbev_spconv_forward(const float* in_feats, int c_in, const float* weight, int c_out,
+                        const int* nbr, int kvol, int n_out, const float* scale,
+                        const float* shift, const float* residual, int relu, float* out,
+                        void* stream) {
+  return spconv_forward(in_feats, c_in, weight, c_out, nbr, kvol, n_out, scale, shift, residual,
+                        relu, out, (cudaStream_t)stream);
+}
+
+int dbev_spconv_dense(const float* feats, const int* coors, int m, int C, int batch, int Z,
+                      int Y, int X, float* dense, void* stream) {
+  return spconv_dense(feats, coors, m, C, batch, Z, Y, X, dense, (cudaStream_t)stream);
+}
+
+int dbev_hard_simple_vfe(const float* voxels, const int* num_points, long long m, int max_points,
+                         int nfeat, int num_features, float* out, void* stream) {
+  return hard_simple_vfe(voxels, num_points, m, max_points, nfeat, num_features, out,
+                         (cudaStream_t)stream);
+}
+
+int dbev_dynvoxel_coords(const float* points, int n, int nfeat, const int* batch_offsets,
+                         int batch, const float* pc_range_host6, const float* voxel_size_host3,
+                         int check_flag, int* coors, void* stream) {
+  return dynvoxel_coords(points, n, nfeat, batch_offsets, batch, pc_range_host6, voxel_size_host3,
+                         check_flag, coors, (cudaStream_t)stream);
+}
+
+int dbev_dynvoxel_virtual_rows(const float* points, int n, int nfeat, float* rows24,
+                               void* stream) {
+  return dynvoxel_virtual_rows(points, n, nfeat, rows24, (cudaStream_t)stream);
+}
+
+int dbev_dynvoxel_virtual_fix(const float* mean24, const int* m_dev, int m_max, float* out23,
+                              void* stream) {
+  return dynvoxel_virtual_fix(mean24, m_dev, m_max, out23, (cudaStream_t)stream);
+}
+
+size_t dbev_affinity_select_workspace_bytes(int batch, int hw) {
+  return affinity_select_ws_bytes(batch, hw);
+}
+
+int dbev_affinity_select(const float* mask_a, const float* mask_b, int batch, int hw,
+                         int* row_cell, int* row_offsets, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  return affinity_select(mask_a, mask_b, batch, hw, row_cell, row_offsets, workspace,
+                         workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_affinity_gather_rows(const float* feat, const int* row_cell, const int* row_offsets,
+                              int batch, int C, int hw, int k_total, float* rows, void* stream) {
+  return affinity_gather_rows(feat, row_cell, row_offsets, batch, C, hw, k_total, rows,
+                              (cudaStream_t)stream);
+}
+
+size_t dbev_affinity_partial_floats(const int* row_offsets_host, int batch) {
+  return affinity_partial_floats(row_offsets_host, batch);
+}
+
+int dbev_affinity_forward(const float* t_rows, const float* s_rows, const int* row_offsets_host,
+                          int batch, int C, int kind, float beta, float weight, float* partial,
+                          float* loss, void* stream) {
+  return affinity_forward(t_rows, s_rows, row_offsets_host, batch, C, kind, beta, weight, partial,
+                          loss, (cudaStream_t)stream);
+}
+
+int dbev_affinity_backward(const float* t_rows, const float* s_rows, const int* row_offsets_host,
+                           int batch, int C, int kind, float beta, float weight,
+                           const float* grad_loss, float* d_s_rows, void* stream) {
+  return affinity_backward(t_rows, s_rows, row_offsets_host, batch, C, kind, beta, weight,
+                           grad_loss, d_s_rows, (cudaStream_t)stream);
+}
+
+int dbev_affinity_scatter_rows(const float* d_rows, const int* row_cell, const int* row_offsets,
+                               int batch, int C, int hw, int k_total, float* grad, void* stream) {
+  return affinity_scatter_rows(d_rows, row_cell, row_offsets, batch, C, hw, k_total, grad,
+                               (cudaStream_t)stream);
 }
 
 size_t dbev_sort_workspace_bytes(long long n) {

@@ -368,6 +368,131 @@ int dbev_fgd_loss_backward(const dbev_fgd_config* cfg, const float* student, con
                            void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * Sparse 3D convolution of the sparse LiDAR teachers (LidarFormer / MVPFormer middle
+ * encoder). Replaces the pybind module mmdet3d.ops.spconv.sparse_conv_ext
+ * (mmdet3d/ops/spconv/src/all.cc:21-51): get_indice_pairs_3d
+ * (include/spconv/spconv_ops.h:28-141, geometry.h:24-84,141-199,259-311) and
+ * indice_conv_fp32 (spconv_ops.h:261-361), plus SparseConvTensor.dense
+ * (mmdet3d/ops/spconv/structure.py:53-64).
+ *
+ * The rulebook is an OUTPUT-major neighbour table nbr[kvol][n_out] (int32): row of the
+ * input voxel that feeds output o through kernel offset k, or -1. Offsets are numbered
+ * like the reference (geometry.h:64-66): k = (kz*Ky + ky)*Kx + kx with
+ * in = out*stride - padding + k*dilation per axis; weight is [Kz,Ky,Kx,Cin,Cout]
+ * (conv.py:109-110). Coordinates are int32 rows (batch, z, y, x), 16-byte aligned.
+ * geom_host[19] = ksize[3], stride[3], padding[3], dilation[3], in_shape[3],
+ * out_shape[3] (all z,y,x) and batch — HOST ints. For a submanifold conv pass
+ * stride 1, padding = ksize/2 (spconv_ops.h:75-78) and out_shape = in_shape.
+ * ------------------------------------------------------------------------ */
+long long dbev_spconv_max_out(long long n_in, const int* geom_host19);
+size_t dbev_spconv_workspace_bytes(long long n_in, long long max_out);
+
+/* Neighbour table for known output coordinates (SubMConv3d: out_coors = in_coors;
+ * replaces getIndicePairsSubM, geometry.h:259-311). */
+int dbev_spconv_table(const int* in_coors, int n_in, const int* out_coors, int n_out,
+                      const int* geom_host19, int* nbr, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* SparseConv3d step 1: the distinct output cells (getValidOutPos, geometry.h:24-84) as
+ * unsorted linear keys out_keys[max_out] and their count *n_out (DEVICE int). The caller
+ * reads *n_out back (the reference synchronises in the same place, spconv_ops.h:130-137). */
+int dbev_spconv_out_candidates(const int* in_coors, int n_in, const int* geom_host19,
+                               uint32_t* out_keys, long long max_out, int* n_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* SparseConv3d step 2: sorts the keys (lexicographic (b,z,y,x) output order = what
+ * torch::_unique gives the reference's CUDA path, spconv_ops.h:131), writes
+ * out_coors[n_out,4] and nbr[kvol][n_out]. out_keys is clobbered. */
+int dbev_spconv_out_table(const int* in_coors, int n_in, const int* geom_host19,
+                          uint32_t* out_keys, int n_out, int* out_coors, int* nbr,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Neighbour table -> the reference's rulebook tensors indice_pairs[kvol,2,pair_stride]
+ * (-1 filled) and indice_num[kvol] (what get_indice_pairs returns, spconv_ops.h:56-59),
+ * pairs of every offset in ascending output order; and back (inverse != 0 swaps the two
+ * rows, as indice_conv's `inverse` flag does, spconv_ops.h:323-352). */
+int dbev_spconv_pairs_from_table(const int* nbr, int kvol, int n_out, int pair_stride,
+                                 int* indice_pairs, int* indice_num, void* stream);
+int dbev_spconv_table_from_pairs(const int* indice_pairs, const int* indice_num, int kvol,
+                                 int pair_stride, int inverse, int n_out, int* nbr, void* stream);
+
+/* out[o,:] = act((sum_k in_feats[nbr[k][o],:] . weight[k]) * scale + shift + residual[o,:])
+ * One kernel instead of kvol x (gather, mm, scatter-add) (spconv_ops.h:308-356); scale /
+ * shift [c_out] fold the eval-mode BatchNorm1d that follows every sparse conv of
+ * SparseEncoder (sparse_encoder.py:97-128) and a conv bias (conv.py:223-224); residual
+ * [n_out,c_out] is SparseBasicBlock's identity (sparse_block.py:116-117). All three are
+ * nullable; relu != 0 applies max(., 0). c_out in {16, 32, 64, 128}. */
+int dbev_spconv_forward(const float* in_feats, int c_in, const float* weight, int c_out,
+                        const int* nbr, int kvol, int n_out, const float* scale,
+                        const float* shift, const float* residual, int relu, float* out,
+                        void* stream);
+
+/* SparseConvTensor.dense() + view(N, C*D, H, W) (structure.py:53-64,
+ * sparse_encoder.py:122-126): dense[b, c*Z + z, y, x] = feats[m, c]; the whole tensor is
+ * written (zero fill included). */
+int dbev_spconv_dense(const float* feats, const int* coors, int m, int C, int batch, int Z,
+                      int Y, int X, float* dense, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Voxel encoders of the sparse teachers.
+ * ------------------------------------------------------------------------ */
+
+/* HardSimpleVFE.forward (mmdet3d/models/voxel_encoders/voxel_encoder.py:29-45):
+ * out[m, :nf] = voxels[m, :, :nf].sum(1) / num_points[m]. */
+int dbev_hard_simple_vfe(const float* voxels, const int* num_points, long long m, int max_points,
+                         int nfeat, int num_features, float* out, void* stream);
+
+/* voxelization() of DynamicVoxelEncoder (voxel_encoders/dynamic_voxel_encoder.py:8-17): keep
+ * lo <= p <= hi (both ends inclusive), coords = trunc((p - lo) / voxel) in fp32, stored
+ * (batch, z, y, x); dropped points get -1 in every column. points of the whole batch back to
+ * back, batch_offsets[batch+1] device ints. The per-voxel mean (coords.unique(dim=0) +
+ * scatter_mean) is dbev_dynamic_scatter_forward(reduce_type = mean, ncol = 4).
+ * check_flag != 0 (voxelization_virtual, :19-68) also drops points whose flag column
+ * points[:, -2] is not 1 / 0 / -1. */
+int dbev_dynvoxel_coords(const float* points, int n, int nfeat, const int* batch_offsets,
+                         int batch, const float* pc_range_host6, const float* voxel_size_host3,
+                         int check_flag, int* coors, void* stream);
+
+/* voxelization_virtual (:27-50): 17-column MVP points -> the 24-channel rows whose per-voxel
+ * mean the reference takes; dbev_dynvoxel_virtual_fix (:56-66) re-normalises voxels mixing
+ * real and painted/virtual points and drops the indicator channel: mean24[m,24] -> out23[m,23]
+ * (m_dev: nullable DEVICE count clamp). */
+int dbev_dynvoxel_virtual_rows(const float* points, int n, int nfeat, float* rows24, void* stream);
+int dbev_dynvoxel_virtual_fix(const float* mean24, const int* m_dev, int m_max, float* out23,
+                              void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Affinity distillation loss — BEVDetDistill.affinity_distill_loss, list branch
+ * (mmdet3d/models/detectors/bevdet_distill.py:735-748) and the masked-cell gather that
+ * feeds it (:1294-1321):
+ *   loss = sum_b weight * mean_{K_b x K_b} criterion(T_b T_b^T - S_b S_b^T)
+ * criterion kind: 0 SmoothL1(beta), 1 L1, 2 MSE (mmdet losses, reduction 'mean'). The
+ * K x K gram matrices are never materialised.
+ * ------------------------------------------------------------------------ */
+size_t dbev_affinity_select_workspace_bytes(int batch, int hw);
+/* Cells with mask_a != 0 (or mask_b != 0, nullable) of every sample in ascending cell
+ * order: row_cell[batch*hw] (compact), row_offsets[batch+1] — DEVICE ints. */
+int dbev_affinity_select(const float* mask_a, const float* mask_b, int batch, int hw,
+                         int* row_cell, int* row_offsets, void* workspace, size_t workspace_bytes,
+                         void* stream);
+/* rows[r, :] = feat[b, :, cell(r)] for feat [batch, C, hw] NCHW (the feat[c][mask] gather). */
+int dbev_affinity_gather_rows(const float* feat, const int* row_cell, const int* row_offsets,
+                              int batch, int C, int hw, int k_total, float* rows, void* stream);
+/* number of floats of `partial` for dbev_affinity_forward */
+size_t dbev_affinity_partial_floats(const int* row_offsets_host, int batch);
+/* t_rows / s_rows [k_total, C]; row_offsets_host[batch+1] HOST ints; loss: DEVICE float[1]. */
+int dbev_affinity_forward(const float* t_rows, const float* s_rows, const int* row_offsets_host,
+                          int batch, int C, int kind, float beta, float weight, float* partial,
+                          float* loss, void* stream);
+/* d_s_rows[k_total, C] = d(loss * *grad_loss)/d(s_rows); grad_loss: DEVICE float[1]. */
+int dbev_affinity_backward(const float* t_rows, const float* s_rows, const int* row_offsets_host,
+                           int batch, int C, int kind, float beta, float weight,
+                           const float* grad_loss, float* d_s_rows, void* stream);
+/* grad[batch, C, hw] = 0 except grad[b, :, cell(r)] = d_rows[r, :]. */
+int dbev_affinity_scatter_rows(const float* d_rows, const int* row_cell, const int* row_offsets,
+                               int batch, int C, int hw, int k_total, float* grad, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Primitives exposed for testing (stable LSD radix sort, exclusive scan).
  * They stand in for argsort / at::unique_dim / cumsum on the reference path.
  * ------------------------------------------------------------------------ */

@@ -9,6 +9,10 @@
        mmdet3d/ops/voxel/src/voxelization.cpp
        mmdet3d/ops/voxel/src/voxelization_cpu.cpp
        mmdet3d/ops/voxel/src/scatter_points_cpu.cpp
+3. Likewise the reference's vendored spconv extension (all 7 sources of
+   mmdet3d/ops/spconv/src with mmdet3d/ops/spconv/include; its CPU and CUDA functors
+   live in one module, so nvcc compiles the .cu files for sm_100) into
+   oracle/_ref/ref_sparse_conv_ext*.so. Its CPU path pins oracle/spconv_oracle.py.
    oracle/_ref/ is git-ignored but travels to the GPU box with the snapshot.
    No reference source is copied into this repository.
 """
@@ -56,10 +60,37 @@ def build_ref():
     return dst
 
 
+def build_ref_spconv():
+    src_dir = "/root/reference/mmdet3d/ops/spconv"
+    if not os.path.isdir(src_dir):
+        return None
+    os.makedirs(REF_OUT, exist_ok=True)
+    existing = glob.glob(os.path.join(REF_OUT, "ref_sparse_conv_ext*.so"))
+    if existing:
+        return existing[0]
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
+    from torch.utils.cpp_extension import load
+    tmp = os.path.join(REF_OUT, "_jit_spconv")
+    os.makedirs(tmp, exist_ok=True)
+    srcs = [os.path.join(src_dir, "src", f) for f in
+            ("all.cc", "reordering.cc", "reordering_cuda.cu", "indice.cc", "indice_cuda.cu",
+             "maxpool.cc", "maxpool_cuda.cu")]
+    load(name="ref_sparse_conv_ext", sources=srcs,
+         extra_include_paths=[os.path.join(src_dir, "include")],
+         extra_cflags=["-O2", "-w", "-DWITH_CUDA", "-std=c++17"],
+         extra_cuda_cflags=["-w", "-DWITH_CUDA", "-std=c++17"], build_directory=tmp, verbose=False)
+    so = glob.glob(os.path.join(tmp, "ref_sparse_conv_ext*.so"))[0]
+    dst = os.path.join(REF_OUT, os.path.basename(so))
+    shutil.copy(so, dst)
+    shutil.rmtree(tmp, ignore_errors=True)
+    return dst
+
+
 if __name__ == "__main__":
     print(build_c())
     try:
         print(build_ref())
+        print(build_ref_spconv())
     except Exception as e:  # the reference build is optional evidence, not a dependency
         print("reference CPU build unavailable: %s" % e)
         sys.exit(0)

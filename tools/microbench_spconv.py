@@ -1,0 +1,89 @@
+"""GPU microbench of the sparse teacher path at LidarFormer size (41 x 1600 x 1600 grid,
+configs/teacher_transformer/lidarformer.py:43-51): rulebooks, every conv of the encoder, dense.
+Prints one JSON object; per-layer times come from CUDA events around each call."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import distill_bev_b200 as dbev  # noqa: E402
+from distill_bev_b200 import synthetic  # noqa: E402
+from distill_bev_b200.plugin.ops import spconv as sp  # noqa: E402
+
+LF = dict(in_channels=5, sparse_shape=[41, 1600, 1600], output_channels=128,
+          encoder_channels=((16, 16, 32), (32, 32, 64), (64, 64, 128), (128, 128)),
+          encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)),
+          block_type="basicblock")
+
+
+def make_voxels(batch, n_points, dev, seed=0):
+    """Hard-voxelize synthetic clouds with the LidarFormer voxel size -> mean VFE features."""
+    vox = dbev.Voxelization([0.064, 0.064, 0.2], [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], 10, (90000, 120000)).eval()
+    vfe = dbev.HardSimpleVFE(5)
+    feats, coors = [], []
+    for b, pts in enumerate(synthetic.make_lidar_scene(batch, n_points, seed=seed)):
+        v, c, n = vox(torch.from_numpy(pts).to(dev))
+        feats.append(vfe(v, n, c))
+        coors.append(torch.nn.functional.pad(c, (1, 0), value=b))
+    return torch.cat(feats), torch.cat(coors).contiguous()
+
+
+def timed(fn, iters=5):
+    for _ in range(2):
+        fn()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record(); r = fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return sorted(ts)[len(ts) // 2], r
+
+
+def main(batch=4, n_points=240000):
+    dev = torch.device("cuda:0")
+    feats, coors = make_voxels(batch, n_points, dev)
+    enc = dbev.SparseEncoder(**LF).to(dev).eval()
+    res = dict(batch=batch, n_points=n_points, n_voxels=int(feats.shape[0]))
+    t, out = timed(lambda: enc(feats, coors, batch))
+    res["encoder_ms"] = t
+    res["out_shape"] = list(out.shape)
+    # per-layer breakdown: hook every conv's rulebook + kernel
+    layers = []
+    orig_build, orig_conv = sp.build_rulebook, sp.conv_table
+
+    def build(*a, **k):
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(); rb = orig_build(*a, **k); e1.record(); torch.cuda.synchronize()
+        layers.append(dict(op="rulebook", subm=bool(a[-1]), n_in=int(a[0].shape[0]), n_out=int(rb.n_out),
+                           ms=e0.elapsed_time(e1)))
+        return rb
+
+    def conv(features, weight, nbr, n_out, *a, **k):
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(); y = orig_conv(features, weight, nbr, n_out, *a, **k); e1.record(); torch.cuda.synchronize()
+        pairs = int((nbr >= 0).sum())
+        cin, cout = weight.shape[-2], weight.shape[-1]
+        ms = e0.elapsed_time(e1)
+        layers.append(dict(op="conv", cin=cin, cout=cout, kvol=int(nbr.shape[0]), n_out=int(n_out), pairs=pairs,
+                           ms=ms, gflops=2.0 * pairs * cin * cout / ms / 1e6,
+                           gbs=(pairs * cin + n_out * cout) * 4 / ms / 1e6))
+        return y
+
+    sp.build_rulebook, sp.conv_table = build, conv
+    try:
+        enc(feats, coors, batch)
+    finally:
+        sp.build_rulebook, sp.conv_table = orig_build, orig_conv
+    res["layers"] = layers
+    res["sum_rulebook_ms"] = sum(l["ms"] for l in layers if l["op"] == "rulebook")
+    res["sum_conv_ms"] = sum(l["ms"] for l in layers if l["op"] == "conv")
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main(*(int(a) for a in sys.argv[1:]))
