@@ -105,6 +105,10 @@ SIGNATURES = {
                                               _ptr]),
     "dbev_spconv_forward": (_c_int, [_ptr, _c_int, _ptr, _c_int, _ptr, _c_int, _c_int, _ptr, _ptr,
                                      _ptr, _c_int, _ptr, _ptr]),
+    "dbev_spconv_tc_supported": (_c_int, [_c_int, _c_int, _c_int]),
+    "dbev_spconv_pack_weights": (_c_int, [_ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr]),
+    "dbev_spconv_forward_tc": (_c_int, [_ptr, _c_int, _ptr, _ptr, _c_int, _ptr, _c_int, _c_int, _ptr,
+                                        _ptr, _ptr, _c_int, _ptr, _ptr]),
     "dbev_spconv_dense": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr,
                                    _ptr]),
     "dbev_hard_simple_vfe": (_c_int, [_ptr, _ptr, _c_ll, _c_int, _c_int, _c_int, _ptr, _ptr]),

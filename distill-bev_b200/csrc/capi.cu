@@ -323,6 +323,23 @@ int dbev_spconv_forward(const float* in_feats, int c_in, const float* weight, in
                         relu, out, (cudaStream_t)stream);
 }
 
+int dbev_spconv_tc_supported(int c_in, int c_out, int kvol) {
+  return spconv_tc_supported(c_in, c_out, kvol) ? 1 : 0;
+}
+
+int dbev_spconv_pack_weights(const float* weight, int kvol, int c_in, int c_out, float* wt_hi,
+                             float* wt_lo, void* stream) {
+  return spconv_pack_weights(weight, kvol, c_in, c_out, wt_hi, wt_lo, (cudaStream_t)stream);
+}
+
+int dbev_spconv_forward_tc(const float* in_feats, int c_in, const float* wt_hi, const float* wt_lo,
+                           int c_out, const int* nbr, int kvol, int n_out, const float* scale,
+                           const float* shift, const float* residual, int relu, float* out,
+                           void* stream) {
+  return spconv_forward_tc(in_feats, c_in, wt_hi, wt_lo, c_out, nbr, kvol, n_out, scale, shift,
+                           residual, relu, out, (cudaStream_t)stream);
+}
+
 int dbev_spconv_dense(const float* feats, const int* coors, int m, int C, int batch, int Z,
                       int Y, int X, float* dense, void* stream) {
   return spconv_dense(feats, coors, m, C, batch, Z, Y, X, dense, (cudaStream_t)stream);

@@ -284,6 +284,108 @@ sp_conv_fma_kernel(const float* __restrict__ in_feats, int c_in, const float* __
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Narrow layers (C_in * C_out <= 512: 5->16, 16->16, 16->32 of the LidarFormer encoder). These
+// are gather-bound, and a LiDAR voxel has only ~4-6 of its 27 neighbours, so a tile kernel that
+// walks all 27 offsets wastes >80 % of its work. Here FOUR lanes own one output row (each lane
+// C_out/4 channels); the row's present offsets are a 27-bit mask and the lanes walk only the set
+// bits, so every group of the warp does useful work in every iteration. All kvol weight slabs
+// live in shared memory (slab stride padded by 4 words: groups of a warp read different slabs).
+// ---------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256)
+sp_conv_rows_kernel(const float* __restrict__ in_feats, int c_in, const float* __restrict__ w,
+                    const int* __restrict__ nbr, int n_out, int kvol,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ residual, int relu, float* __restrict__ out) {
+  constexpr int OPL = COUT / 4;  // output channels per lane
+  extern __shared__ __align__(16) float W_s[];
+  const int slab = c_in * COUT + 4;
+  for (int e = threadIdx.x; e < kvol * c_in * (COUT / 4); e += blockDim.x) {
+    const int k = e / (c_in * (COUT / 4)), r = e % (c_in * (COUT / 4));
+    *reinterpret_cast<float4*>(&W_s[k * slab + r * 4]) =
+        __ldg(reinterpret_cast<const float4*>(w + (long long)k * c_in * COUT) + r);
+  }
+  __syncthreads();
+  const int q = threadIdx.x & 3;
+  const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const int group_in_warp = (threadIdx.x & 31) >> 2;
+  const int n_groups = (gridDim.x * blockDim.x) >> 2;
+  const bool vec = (c_in & 3) == 0;
+  for (int base = group - group_in_warp; base < n_out; base += n_groups) {
+    const int row = base + group_in_warp;
+    const bool valid = row < n_out;
+    unsigned m = 0;
+    if (valid)
+      for (int k = q; k < kvol; k += 4)
+        if (__ldg(nbr + (long long)k * n_out + row) >= 0) m |= 1u << k;
+    m |= __shfl_xor_sync(0xffffffffu, m, 1);
+    m |= __shfl_xor_sync(0xffffffffu, m, 2);
+    float acc[OPL];
+#pragma unroll
+    for (int j = 0; j < OPL; ++j) acc[j] = 0.f;
+    while (__any_sync(0xffffffffu, m != 0)) {
+      if (m != 0) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1;
+        const int idx = __ldg(nbr + (long long)k * n_out + row);
+        const float* src = in_feats + (long long)idx * c_in;
+        const float* wk = W_s + k * slab + q * OPL;
+        if (vec) {
+          for (int c4 = 0; c4 < c_in; c4 += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + c4));
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+              for (int j = 0; j < OPL; j += 4) {
+                const float4 wv = *reinterpret_cast<const float4*>(wk + (c4 + u) * COUT + j);
+                acc[j + 0] = fmaf(av[u], wv.x, acc[j + 0]);
+                acc[j + 1] = fmaf(av[u], wv.y, acc[j + 1]);
+                acc[j + 2] = fmaf(av[u], wv.z, acc[j + 2]);
+                acc[j + 3] = fmaf(av[u], wv.w, acc[j + 3]);
+              }
+            }
+          }
+        } else {
+          for (int ci = 0; ci < c_in; ++ci) {
+            const float a = __ldg(src + ci);
+#pragma unroll
+            for (int j = 0; j < OPL; j += 4) {
+              const float4 wv = *reinterpret_cast<const float4*>(wk + ci * COUT + j);
+              acc[j + 0] = fmaf(a, wv.x, acc[j + 0]);
+              acc[j + 1] = fmaf(a, wv.y, acc[j + 1]);
+              acc[j + 2] = fmaf(a, wv.z, acc[j + 2]);
+              acc[j + 3] = fmaf(a, wv.w, acc[j + 3]);
+            }
+          }
+        }
+      }
+    }
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < OPL; j += 4) {
+        const int c = q * OPL + j;
+        float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        if (scale) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + c));
+          v.x *= sc.x, v.y *= sc.y, v.z *= sc.z, v.w *= sc.w;
+        }
+        if (shift) {
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + c));
+          v.x += sh.x, v.y += sh.y, v.z += sh.z, v.w += sh.w;
+        }
+        if (residual) {
+          const float4 rr = __ldg(reinterpret_cast<const float4*>(residual + (long long)row * COUT + c));
+          v.x += rr.x, v.y += rr.y, v.z += rr.z, v.w += rr.w;
+        }
+        if (relu) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+        *reinterpret_cast<float4*>(out + (long long)row * COUT + c) = v;
+      }
+    }
+  }
+}
+
 // dense[b][c*Z + z][y][x] = feats[m][c]. 32 consecutive (sorted) voxels per CTA: rows are read
 // coalesced into shared memory, then lane <-> voxel so that neighbouring x land in one sector.
 __global__ void __launch_bounds__(256)
@@ -494,6 +596,30 @@ int spconv_forward(const float* in_feats, int c_in, const float* weight, int c_o
                      ((uintptr_t)shift & 15) == 0,
                  "spconv_forward: pointers must be 16-byte aligned");
   if (n_out == 0) return DBEV_OK;
+  if (kvol <= 32 && (c_out == 16 || c_out == 32) && c_in * c_out <= 512) {
+    // narrow, gather-bound layers: lane-group-per-row kernel, persistent grid
+    const size_t smem = (size_t)kvol * (c_in * c_out + 4) * sizeof(float);
+    int dev = 0, sms = 0;
+    DBEV_CUDA(cudaGetDevice(&dev));
+    DBEV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int per_sm = smem > 56 * 1024 ? 2 : (smem > 36 * 1024 ? 4 : 6);
+    int grid_r = sms * per_sm;
+    const int need = ceil_div((long long)n_out * 4, 256);
+    if (grid_r > need) grid_r = need;
+    if (c_out == 16) {
+      DBEV_CUDA(cudaFuncSetAttribute(sp_conv_rows_kernel<16>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sp_conv_rows_kernel<16><<<grid_r, 256, smem, stream>>>(in_feats, c_in, weight, nbr, n_out, kvol,
+                                                             scale, shift, residual, relu, out);
+    } else {
+      DBEV_CUDA(cudaFuncSetAttribute(sp_conv_rows_kernel<32>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      sp_conv_rows_kernel<32><<<grid_r, 256, smem, stream>>>(in_feats, c_in, weight, nbr, n_out, kvol,
+                                                             scale, shift, residual, relu, out);
+    }
+    DBEV_CHECK_LAUNCH("sp_conv_rows_kernel");
+    return DBEV_OK;
+  }
   const int grid = ceil_div(n_out, kConvTM);
 #define DBEV_SP_LAUNCH(CO)                                                                   \
   sp_conv_fma_kernel<CO><<<grid, 256, 0, stream>>>(in_feats, c_in, weight, nbr, n_out, kvol, \

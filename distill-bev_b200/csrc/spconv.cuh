@@ -63,6 +63,16 @@ int spconv_forward(const float* in_feats, int c_in, const float* weight, int c_o
                    const int* nbr, int kvol, int n_out, const float* scale, const float* shift,
                    const float* residual, int relu, float* out, cudaStream_t stream);
 
+// Tensor-core path (spconv_tc.cu): tcgen05 3xTF32 implicit GEMM for C_in, C_out in {32,64,128}.
+bool spconv_tc_supported(int c_in, int c_out, int kvol);
+// weight [kvol][c_in][c_out] -> wt_hi / wt_lo [kvol][c_out][c_in] (TF32 head / remainder)
+int spconv_pack_weights(const float* weight, int kvol, int c_in, int c_out, float* wt_hi,
+                        float* wt_lo, cudaStream_t stream);
+int spconv_forward_tc(const float* in_feats, int c_in, const float* wt_hi, const float* wt_lo,
+                      int c_out, const int* nbr, int kvol, int n_out, const float* scale,
+                      const float* shift, const float* residual, int relu, float* out,
+                      cudaStream_t stream);
+
 // dense[b, c*Z + z, y, x] = feats[m, c]; the whole tensor is written (zero fill included).
 int spconv_dense(const float* feats, const int* coors, int m, int C, int batch, int Z, int Y,
                  int X, float* dense, cudaStream_t stream);

@@ -1,0 +1,379 @@
+// Sparse convolution on the 5th-gen tensor cores (tcgen05, 3xTF32) for B200 — the wide layers of
+// the sparse LiDAR teacher (C_in, C_out in {32, 64, 128}); SURVEY.md §8 row E4.
+//
+// Reference behaviour: indiceConv (mmdet3d/ops/spconv/include/spconv/spconv_ops.h:261-361) —
+// per kernel offset a gather into an [nHot, C_in] buffer, an fp32 cuBLAS mm and a scatter-add —
+// followed in SparseEncoder by BatchNorm1d(eval) / residual / ReLU as separate kernels.
+//
+// Design: an implicit GEMM per tile of 128 output voxels, D[128 voxels, C_out] accumulated in
+// TMEM over all (kernel offset k, 32-channel chunk) steps:
+//   A = rows gathered through the output-major neighbour table nbr[k][o] (zeros where the
+//       neighbour is absent), written by 4 producer warps straight into the 128-byte-swizzled
+//       K-major layout the tensor core reads (one thread = one voxel row = one 128 B smem row);
+//   B = W[k]^T chunk [C_out, 32] (K-major), fetched by TMA from the pre-transposed weights.
+// Offsets with no neighbour in the whole tile are skipped. fp32 parity with the reference's
+// cuBLAS-fp32 path is kept by the 3xTF32 split  a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
+// (hi = value rounded to TF32, lo = remainder): the tensor core sees only TF32 operands, the
+// result is accurate to ~1e-6 relative. Warp roles: 0-3 gather producers (+ thread 0 issues the
+// weight TMA), 4-7 epilogue (tcgen05.ld -> BN scale/shift, residual, ReLU -> row-contiguous
+// stores; the TMEM lane is the voxel), warp 8 = MMA issuer + TMEM owner. Two TMEM accumulator
+// buffers let the epilogue of tile t overlap the MMAs of tile t+1; persistent over tiles.
+#include "spconv.cuh"
+
+#include "umma.cuh"
+
+namespace dbev {
+
+namespace {
+
+constexpr int kTileM = 128;                   // output voxels per tile (UMMA M, TMEM lanes)
+constexpr int kChunk = 32;                    // input channels per stage (one 128 B swizzle row)
+constexpr int kABytes = kTileM * kChunk * 4;  // 16 KB: one A operand tile (hi or lo)
+constexpr int kProducers = 128;
+constexpr int kTcThreads = 288;               // 9 warps
+
+// value rounded to the nearest TF32 (10-bit mantissa); the remainder v - head is exact in fp32
+__device__ __forceinline__ float tf32_head(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+struct TcShape {
+  int c_in, c_out, n_out, n_tiles, chunks, kvol;
+};
+
+template <int COUT, int KVOL, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
+                  const __grid_constant__ CUtensorMap tmap_wlo, const float* __restrict__ in_feats,
+                  const int* __restrict__ nbr, const float* __restrict__ scale,
+                  const float* __restrict__ shift, const float* __restrict__ residual, int relu,
+                  float* __restrict__ out, TcShape s) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int kWBytes = COUT * kChunk * 4;
+  constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2],
+      tmem_empty_bar[2];
+  __shared__ uint32_t stage_flags[STAGES];  // bit 0: first step of a tile, bit 1: last step
+  __shared__ uint32_t mask_s[2];
+  __shared__ int idx_s[KVOL * kTileM];  // neighbour rows of the current tile, [k][row]
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], kProducers + 1);  // 128 gather arrivals + the expect_tx arrival
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&tmem_full_bar[0], 1);
+    mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 4);
+    mbar_init(&tmem_empty_bar[1], 4);
+    mask_s[0] = mask_s[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_whi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_wlo) : "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_addr(&tmem_base_s)),
+                 "r"(256u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ gather producers
+    // Steps of a tile = (active offset k) x (32-channel chunk kc). The rows of step i+1 are
+    // requested from L2 BEFORE the thread waits for / fills the stage of step i, so two steps of
+    // loads are in flight per thread (the producers are latency-bound, not bandwidth-bound).
+    const int t = threadIdx.x;  // row of the tile
+    uint32_t stage = 0, phase = 0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
+      const int o = tile * kTileM + t;
+      uint32_t bits = 0;
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's idx_s / mask_s reads are done
+#pragma unroll
+      for (int k = 0; k < KVOL; ++k) {
+        const int v = o < s.n_out ? __ldg(nbr + (long long)k * s.n_out + o) : -1;
+        idx_s[k * kTileM + t] = v;
+        bits |= (v >= 0 ? 1u : 0u) << k;
+      }
+      const uint32_t par = it & 1u;
+      if (t == 0) mask_s[par ^ 1u] = 0;
+      bits = __reduce_or_sync(0xffffffffu, bits);
+      if (lane == 0 && bits) atomicOr(&mask_s[par], bits);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      uint32_t mask = mask_s[par];
+      if (mask == 0) mask = 1u;  // keep producer and MMA issuer in step on an (impossible) empty tile
+      const int n_steps = __popc(mask) * s.chunks;
+
+      float4 cur[8], nxt[8];
+      int cur_row, nxt_row = -1;
+      uint32_t rest = mask;       // offsets not yet started
+      int k_cur = __ffs(rest) - 1, kc_cur = 0;
+      rest &= rest - 1;
+      // prologue: request step 0
+      cur_row = idx_s[k_cur * kTileM + t];
+      if (cur_row >= 0) {
+        const float4* src = reinterpret_cast<const float4*>(in_feats + (long long)cur_row * s.c_in);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) cur[c] = __ldg(src + c);
+      }
+      for (int step = 0; step < n_steps; ++step) {
+        // coordinates of the next step and its loads
+        int k_nxt = k_cur, kc_nxt = kc_cur + 1;
+        if (kc_nxt == s.chunks) {
+          kc_nxt = 0;
+          k_nxt = rest ? __ffs(rest) - 1 : -1;
+          rest &= rest - 1;
+        }
+        if (step + 1 < n_steps) {
+          nxt_row = idx_s[k_nxt * kTileM + t];
+          if (nxt_row >= 0) {
+            const float4* src = reinterpret_cast<const float4*>(in_feats + (long long)nxt_row * s.c_in +
+                                                                kc_nxt * kChunk);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) nxt[c] = __ldg(src + c);
+          }
+        }
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* st = base + (size_t)stage * kStageBytes;
+        if (t == 0) {
+          stage_flags[stage] = (step == 0 ? 1u : 0u) | (step == n_steps - 1 ? 2u : 0u);
+          mbar_expect_tx(&full_bar[stage], 2u * kWBytes);
+          tma_load_2d(st + 2 * kABytes, &tmap_whi, kc_cur * kChunk, k_cur * COUT, &full_bar[stage]);
+          tma_load_2d(st + 2 * kABytes + kWBytes, &tmap_wlo, kc_cur * kChunk, k_cur * COUT,
+                      &full_bar[stage]);
+        }
+        uint8_t* row_hi = st + (t >> 3) * 1024 + (t & 7) * 128;
+        uint8_t* row_lo = row_hi + kABytes;
+        if (cur_row >= 0) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 hi, lo;
+            hi.x = tf32_head(cur[c].x), hi.y = tf32_head(cur[c].y);
+            hi.z = tf32_head(cur[c].z), hi.w = tf32_head(cur[c].w);
+            lo.x = cur[c].x - hi.x, lo.y = cur[c].y - hi.y, lo.z = cur[c].z - hi.z, lo.w = cur[c].w - hi.w;
+            const int off = ((c ^ (t & 7)) << 4);
+            *reinterpret_cast<float4*>(row_hi + off) = hi;
+            *reinterpret_cast<float4*>(row_lo + off) = lo;
+          }
+        } else {
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            *reinterpret_cast<float4*>(row_hi + (c << 4)) = z;
+            *reinterpret_cast<float4*>(row_lo + (c << 4)) = z;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic -> async proxy
+        mbar_arrive(&full_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        cur_row = nxt_row;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
+        k_cur = k_nxt, kc_cur = kc_nxt;
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(kTileM, COUT);
+      uint32_t stage = 0, phase = 0;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u, use = it >> 1;
+        mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);  // epilogue has drained this buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + buf * 128u;
+        uint32_t accumulate = 0;
+        while (true) {
+          mbar_wait(&full_bar[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t flags = stage_flags[stage];
+          const uint32_t a_hi = smem_addr(base + (size_t)stage * kStageBytes);
+          const uint32_t a_lo = a_hi + kABytes;
+          const uint32_t w_hi = a_hi + 2 * kABytes;
+          const uint32_t w_lo = w_hi + kWBytes;
+#pragma unroll
+          for (int kk = 0; kk < kChunk / 8; ++kk) {
+            const uint64_t d_ahi = umma_desc(a_hi + kk * 32, 16, 1024);
+            const uint64_t d_alo = umma_desc(a_lo + kk * 32, 16, 1024);
+            const uint64_t d_whi = umma_desc(w_hi + kk * 32, 16, 1024);
+            const uint64_t d_wlo = umma_desc(w_lo + kk * 32, 16, 1024);
+            umma_tf32(d_tmem, d_ahi, d_whi, idesc, accumulate);
+            accumulate = 1;
+            umma_tf32(d_tmem, d_alo, d_whi, idesc, 1u);
+            umma_tf32(d_tmem, d_ahi, d_wlo, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (flags & 2u) break;
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 4..7)
+    const int q = warp & 3;  // TMEM lane quarter
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u, use = it >> 1;
+      const int o = tile * kTileM + q * 32 + lane;
+      mbar_wait(&tmem_full_bar[buf], use & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int cc = 0; cc < COUT / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u + (uint32_t)(cc * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (o < s.n_out) {
+          float* orow = out + (long long)o * COUT + cc * 32;
+          const float* rrow = residual ? residual + (long long)o * COUT + cc * 32 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 r = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (scale) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cc * 32 + j));
+              r.x *= sc.x, r.y *= sc.y, r.z *= sc.z, r.w *= sc.w;
+            }
+            if (shift) {
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cc * 32 + j));
+              r.x += sh.x, r.y += sh.y, r.z += sh.z, r.w += sh.w;
+            }
+            if (rrow) {
+              const float4 rr = __ldg(reinterpret_cast<const float4*>(rrow + j));
+              r.x += rr.x, r.y += rr.y, r.z += rr.z, r.w += rr.w;
+            }
+            if (relu) r.x = fmaxf(r.x, 0.f), r.y = fmaxf(r.y, 0.f), r.z = fmaxf(r.z, 0.f), r.w = fmaxf(r.w, 0.f);
+            *reinterpret_cast<float4*>(orow + j) = r;
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u)
+                 : "memory");
+  }
+}
+
+int encode_w(CUtensorMap* map, const float* w_t, int kvol, int c_in, int c_out) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) {
+    set_last_error("spconv_forward_tc: cuTensorMapEncodeTiled not available from the driver");
+    return DBEV_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)c_in, (cuuint64_t)kvol * c_out};
+  cuuint64_t strides[1] = {(cuuint64_t)c_in * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)c_out};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w_t, dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("spconv_forward_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return DBEV_ERR_CUDA;
+  }
+  return DBEV_OK;
+}
+
+// wt_hi[k][co][ci] = W[k][ci][co] truncated to TF32, wt_lo = remainder
+__global__ void sp_pack_weights_kernel(const float* __restrict__ w, int kvol, int c_in, int c_out,
+                                       float* __restrict__ wt_hi, float* __restrict__ wt_lo) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)kvol * c_in * c_out;
+  if (t >= total) return;
+  const int ci = (int)(t % c_in);
+  const int co = (int)((t / c_in) % c_out);
+  const int k = (int)(t / ((long long)c_in * c_out));
+  const float v = w[((long long)k * c_in + ci) * c_out + co];
+  const float hi = tf32_head(v);
+  wt_hi[t] = hi;
+  wt_lo[t] = v - hi;
+}
+
+}  // namespace
+
+bool spconv_tc_supported(int c_in, int c_out, int kvol) {
+  return (c_in == 32 || c_in == 64 || c_in == 128) && (c_out == 32 || c_out == 64 || c_out == 128) &&
+         (kvol == 27 || kvol == 3);
+}
+
+int spconv_pack_weights(const float* weight, int kvol, int c_in, int c_out, float* wt_hi,
+                        float* wt_lo, cudaStream_t stream) {
+  DBEV_CHECK_ARG(kvol >= 1 && c_in >= 1 && c_out >= 1, "spconv_pack_weights: bad sizes");
+  const long long total = (long long)kvol * c_in * c_out;
+  sp_pack_weights_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(weight, kvol, c_in, c_out, wt_hi,
+                                                                   wt_lo);
+  DBEV_CHECK_LAUNCH("sp_pack_weights_kernel");
+  return DBEV_OK;
+}
+
+int spconv_forward_tc(const float* in_feats, int c_in, const float* wt_hi, const float* wt_lo,
+                      int c_out, const int* nbr, int kvol, int n_out, const float* scale,
+                      const float* shift, const float* residual, int relu, float* out,
+                      cudaStream_t stream) {
+  DBEV_CHECK_ARG(spconv_tc_supported(c_in, c_out, kvol),
+                 "spconv_forward_tc: needs C_in, C_out in {32, 64, 128} and a 27- or 3-tap kernel "
+                 "(got %d -> %d, %d taps)", c_in, c_out, kvol);
+  DBEV_CHECK_ARG(n_out >= 0, "spconv_forward_tc: negative n_out");
+  DBEV_CHECK_ARG(((uintptr_t)in_feats & 15) == 0 && ((uintptr_t)wt_hi & 15) == 0 &&
+                     ((uintptr_t)wt_lo & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
+                     ((uintptr_t)residual & 15) == 0 && ((uintptr_t)scale & 15) == 0 &&
+                     ((uintptr_t)shift & 15) == 0,
+                 "spconv_forward_tc: pointers must be 16-byte aligned");
+  if (n_out == 0) return DBEV_OK;
+  CUtensorMap map_hi, map_lo;
+  int rc = encode_w(&map_hi, wt_hi, kvol, c_in, c_out);
+  if (rc != DBEV_OK) return rc;
+  rc = encode_w(&map_lo, wt_lo, kvol, c_in, c_out);
+  if (rc != DBEV_OK) return rc;
+  TcShape s;
+  s.c_in = c_in, s.c_out = c_out, s.n_out = n_out, s.kvol = kvol;
+  s.n_tiles = ceil_div(n_out, kTileM);
+  s.chunks = c_in / kChunk;
+  int dev = 0, sms = 0;
+  DBEV_CUDA(cudaGetDevice(&dev));
+  DBEV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = s.n_tiles < sms ? s.n_tiles : sms;
+#define DBEV_TC_LAUNCH(CO, KV, STG)                                                             \
+  do {                                                                                          \
+    const size_t smem = (size_t)STG * (2 * kABytes + 2 * CO * kChunk * 4) + 1024;               \
+    DBEV_CUDA(cudaFuncSetAttribute(sp_conv_tc_kernel<CO, KV, STG>,                              \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    sp_conv_tc_kernel<CO, KV, STG><<<grid, kTcThreads, smem, stream>>>(                         \
+        map_hi, map_lo, in_feats, nbr, scale, shift, residual, relu, out, s);                   \
+  } while (0)
+  if (kvol == 27) {
+    if (c_out == 32) DBEV_TC_LAUNCH(32, 27, 4);
+    else if (c_out == 64) DBEV_TC_LAUNCH(64, 27, 4);
+    else DBEV_TC_LAUNCH(128, 27, 3);
+  } else {
+    if (c_out == 32) DBEV_TC_LAUNCH(32, 3, 4);
+    else if (c_out == 64) DBEV_TC_LAUNCH(64, 3, 4);
+    else DBEV_TC_LAUNCH(128, 3, 3);
+  }
+#undef DBEV_TC_LAUNCH
+  DBEV_CHECK_LAUNCH("sp_conv_tc_kernel");
+  return DBEV_OK;
+}
+
+}  // namespace dbev

@@ -127,8 +127,29 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, d
     return Rulebook(out_indices, nbr, kvol, n_in, out_shape)
 
 
-def conv_table(features, weight, nbr, n_out, scale=None, shift=None, residual=None, relu=False):
-    """out = act((sum_k features[nbr[k]] @ weight[k]) * scale + shift + residual): one kernel."""
+def pack_weights(weight):
+    """[*k, Cin, Cout] fp32 -> (wt_hi, wt_lo) [kvol, Cout, Cin]: transposed TF32 head / remainder,
+    the operand format of the tensor-core kernel (done once per layer: the teacher is frozen)."""
+    lib = _lib.load()
+    _lib.require_cuda(weight, "filters", torch.float32)
+    c_in, c_out = weight.shape[-2], weight.shape[-1]
+    w = weight.detach().reshape(-1, c_in, c_out).contiguous()
+    kvol = w.shape[0]
+    hi = torch.empty((kvol, c_out, c_in), dtype=torch.float32, device=w.device)
+    lo = torch.empty_like(hi)
+    with torch.cuda.device(w.device):
+        rc = lib.dbev_spconv_pack_weights(_lib.ptr(w), kvol, c_in, c_out, _lib.ptr(hi), _lib.ptr(lo),
+                                          _lib.stream_ptr(w.device))
+    _lib.check(rc, "dbev_spconv_pack_weights")
+    return hi, lo
+
+
+def conv_table(features, weight, nbr, n_out, scale=None, shift=None, residual=None, relu=False,
+               impl=None, packed=None):
+    """out = act((sum_k features[nbr[k]] @ weight[k]) * scale + shift + residual): one kernel.
+
+    impl: None = automatic (tcgen05 3xTF32 kernel when C_in, C_out in {32, 64, 128}, else the fp32
+    FMA kernels), "fma" / "tc" force one. `packed` = pack_weights(weight) cached by the caller."""
     lib = _lib.load()
     _lib.require_cuda(features, "features", torch.float32)
     _lib.require_cuda(weight, "filters", torch.float32)
@@ -140,18 +161,27 @@ def conv_table(features, weight, nbr, n_out, scale=None, shift=None, residual=No
     if features.shape[1] != c_in:
         raise RuntimeError("features have %d channels, filters expect %d" % (features.shape[1], c_in))
     kvol = nbr.shape[0]
-    w = weight.detach().reshape(kvol, c_in, c_out).contiguous()
     out = torch.empty((n_out, c_out), dtype=torch.float32, device=features.device)
     for t in (scale, shift, residual):
         if t is not None:
             _lib.require_cuda(t, "epilogue operand", torch.float32)
     if residual is not None:
         residual = residual.contiguous()
+    use_tc = bool(lib.dbev_spconv_tc_supported(c_in, c_out, kvol)) if impl is None else impl == "tc"
     with torch.cuda.device(features.device):
-        rc = lib.dbev_spconv_forward(_lib.ptr(features), c_in, _lib.ptr(w), c_out, _lib.ptr(nbr), kvol,
-                                     n_out, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(residual),
-                                     1 if relu else 0, _lib.ptr(out), _lib.stream_ptr(features.device))
-    _lib.check(rc, "dbev_spconv_forward")
+        sp = _lib.stream_ptr(features.device)
+        if use_tc:
+            hi, lo = packed if packed is not None else pack_weights(weight)
+            rc = lib.dbev_spconv_forward_tc(_lib.ptr(features), c_in, _lib.ptr(hi), _lib.ptr(lo), c_out,
+                                            _lib.ptr(nbr), kvol, n_out, _lib.ptr(scale), _lib.ptr(shift),
+                                            _lib.ptr(residual), 1 if relu else 0, _lib.ptr(out), sp)
+            _lib.check(rc, "dbev_spconv_forward_tc")
+        else:
+            w = weight.detach().reshape(kvol, c_in, c_out).contiguous()
+            rc = lib.dbev_spconv_forward(_lib.ptr(features), c_in, _lib.ptr(w), c_out, _lib.ptr(nbr), kvol,
+                                         n_out, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(residual),
+                                         1 if relu else 0, _lib.ptr(out), sp)
+            _lib.check(rc, "dbev_spconv_forward")
     return out
 
 
@@ -288,13 +318,38 @@ class SparseConvolution(SparseModule):
             bound = 1 / math.sqrt(fan_in)
             init.uniform_(self.bias, -bound, bound)
 
+    impl = None     # None = automatic kernel choice; "fma" / "tc" force one (tests, benchmarks)
+
+    def _packed_weights(self, kvol):
+        """TF32 hi/lo operands of the tensor-core kernel, rebuilt only when the weight changes."""
+        lib = _lib.load()
+        if self.impl == "fma" or not self.weight.is_cuda or not (
+                self.impl == "tc" or lib.dbev_spconv_tc_supported(self.in_channels, self.out_channels, kvol)):
+            return None
+        key = (self.weight.data_ptr(), self.weight._version)
+        cache = getattr(self, "_packed", None)
+        if cache is None or cache[0] != key:
+            cache = (key, pack_weights(self.weight))
+            self._packed = cache
+        return cache[1]
+
     def rulebook(self, input):
         datas = input.find_indice_pair(self.indice_key)
         if self.indice_key is not None and datas is not None:
             return datas
+        # A submanifold rulebook depends only on the active coordinates and the kernel, so un-keyed
+        # SubM convs over the same voxel set (SparseBasicBlock's conv1 / conv2, and every block of a
+        # stage) share one table; the reference rebuilds it per conv (indice_key=None, conv.py:165-183).
+        auto_key = None
+        if self.subm and self.indice_key is None:
+            auto_key = ("subm", tuple(self.kernel_size), tuple(self.dilation), input.indices.data_ptr(),
+                        int(input.indices.shape[0]))
+            rb = input.indice_dict.get(auto_key)
+            if rb is not None:
+                return rb
         rb = build_rulebook(input.indices, input.batch_size, input.spatial_shape, self.kernel_size,
                             self.stride, self.padding, self.dilation, self.subm)
-        input.indice_dict[self.indice_key] = rb
+        input.indice_dict[self.indice_key if auto_key is None else auto_key] = rb
         return rb
 
     def forward(self, input, scale=None, shift=None, residual=None, relu=False):
@@ -311,7 +366,8 @@ class SparseConvolution(SparseModule):
         rb = self.rulebook(input)
         if scale is None and shift is None and self.bias is not None:
             shift = self.bias.detach()
-        feats = conv_table(input.features, self.weight, rb.nbr, rb.n_out, scale, shift, residual, relu)
+        feats = conv_table(input.features, self.weight, rb.nbr, rb.n_out, scale, shift, residual, relu,
+                           impl=self.impl, packed=self._packed_weights(rb.kvol))
         out = SparseConvTensor(feats, rb.out_indices, rb.out_shape, input.batch_size)
         out.indice_dict, out.grid = input.indice_dict, input.grid
         return out

@@ -427,6 +427,20 @@ int dbev_spconv_forward(const float* in_feats, int c_in, const float* weight, in
                         const float* shift, const float* residual, int relu, float* out,
                         void* stream);
 
+/* Tensor-core variant of dbev_spconv_forward for the wide layers: tcgen05 implicit GEMM per tile
+ * of 128 outputs (gathered rows written into the swizzled smem operand layout, weights by TMA,
+ * accumulators in TMEM), 3xTF32 split so that results match the reference's fp32 cuBLAS mm
+ * (spconv_ops.h:333) to ~1e-6. dbev_spconv_tc_supported: c_in, c_out in {32, 64, 128} and
+ * kvol in {27, 3}. Weights are pre-packed once per layer (frozen teacher) by
+ * dbev_spconv_pack_weights: weight [kvol, c_in, c_out] -> wt_hi / wt_lo [kvol, c_out, c_in]. */
+int dbev_spconv_tc_supported(int c_in, int c_out, int kvol);
+int dbev_spconv_pack_weights(const float* weight, int kvol, int c_in, int c_out, float* wt_hi,
+                             float* wt_lo, void* stream);
+int dbev_spconv_forward_tc(const float* in_feats, int c_in, const float* wt_hi, const float* wt_lo,
+                           int c_out, const int* nbr, int kvol, int n_out, const float* scale,
+                           const float* shift, const float* residual, int relu, float* out,
+                           void* stream);
+
 /* SparseConvTensor.dense() + view(N, C*D, H, W) (structure.py:53-64,
  * sparse_encoder.py:122-126): dense[b, c*Z + z, y, x] = feats[m, c]; the whole tensor is
  * written (zero fill included). */

@@ -200,6 +200,64 @@ def test_full_size_lidarformer_grid(cuda):
     assert torch.equal(ya, sp.conv_table(xa, w, rb2.nbr, rb2.n_out))   # fixed summation order
 
 
+@pytest.mark.parametrize("cin,cout,kshape", [(32, 32, (3, 3, 3)), (32, 64, (3, 3, 3)), (64, 64, (3, 3, 3)),
+                                             (64, 128, (3, 3, 3)), (128, 128, (3, 3, 3)),
+                                             (128, 128, (3, 1, 1)), (5, 16, (3, 3, 3)),
+                                             (16, 16, (3, 3, 3)), (16, 32, (3, 3, 3)), (23, 16, (3, 3, 3))])
+def test_kernel_variants_agree_with_fp64(cuda, cin, cout, kshape):
+    """Every kernel variant (tcgen05 3xTF32 / lane-group rows / tile FMA) against an fp64 gather-matmul
+    on a clustered cloud: 1e-5 of the largest output (the 3xTF32 split must keep fp32 accuracy)."""
+    rs = np.random.RandomState(cin * 1000 + cout)
+    B, shape, n = 2, [11, 40, 40], 2500
+    c = np.unique(np.stack([rs.randint(0, 11, n), rs.randint(5, 30, n), rs.randint(5, 30, n)], 1), axis=0)
+    coors = np.concatenate([np.concatenate([np.full((len(c), 1), b), c], 1) for b in range(B)], 0)
+    coors = coors[rs.permutation(len(coors))].astype(np.int32)
+    subm = kshape == (3, 3, 3)
+    rb = sp.build_rulebook(_t(coors, cuda), B, shape, list(kshape), [2, 1, 1], 0, 1, subm)
+    feats = rs.standard_normal((len(coors), cin)).astype(np.float32)
+    w = (rs.standard_normal(kshape + (cin, cout)) / np.sqrt(cin * 4)).astype(np.float32)
+    nbr = rb.nbr.cpu().numpy()
+    f64 = np.concatenate([feats.astype(np.float64), np.zeros((1, cin))], 0)
+    want = np.zeros((rb.n_out, cout))
+    w64 = w.reshape(-1, cin, cout).astype(np.float64)
+    for k in range(nbr.shape[0]):
+        want += f64[nbr[k]] @ w64[k]      # index -1 hits the appended zero row
+    scale = rs.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rs.standard_normal(cout).astype(np.float32)
+    res = rs.standard_normal((rb.n_out, cout)).astype(np.float32)
+    want_ep = np.maximum(want * scale + shift + res, 0)
+    impls = ["fma"] + (["tc"] if cin % 32 == 0 and cout % 32 == 0 else [])
+    for impl in impls + [None]:
+        y = sp.conv_table(_t(feats, cuda), _t(w, cuda), rb.nbr, rb.n_out, impl=impl).cpu().numpy()
+        # fp32 FMA ~1e-6; 3xTF32 drops the lo*lo term and keeps ~2^-20 per product
+        tol = 5e-5 if impl != "fma" and cin % 32 == 0 and cout % 32 == 0 else 1e-5
+        assert np.abs(y - want).max() <= tol * np.abs(want).max(), (impl, np.abs(y - want).max())
+        y = sp.conv_table(_t(feats, cuda), _t(w, cuda), rb.nbr, rb.n_out, _t(scale, cuda), _t(shift, cuda),
+                          _t(res, cuda), True, impl=impl).cpu().numpy()
+        assert np.abs(y - want_ep).max() <= tol * np.abs(want_ep).max() + 1e-6, impl
+
+
+def test_tc_many_tiles_deterministic(cuda):
+    """More tiles than SMs (persistent loop, both TMEM buffers, stage ring wrap-around)."""
+    rs = np.random.RandomState(9)
+    B, shape = 2, [21, 400, 400]
+    coors = []
+    for b in range(B):
+        xy = np.clip(rs.standard_normal((40000, 2)) * 60 + 200, 0, 399).astype(np.int64)
+        c = np.unique(np.stack([rs.randint(8, 12, 40000), xy[:, 0], xy[:, 1]], 1), axis=0)
+        coors.append(np.concatenate([np.full((len(c), 1), b), c], 1))
+    coors = np.concatenate(coors, 0).astype(np.int32)
+    rb = sp.build_rulebook(_t(coors, cuda), B, shape, 3, 1, 1, 1, True)
+    assert rb.n_out > 148 * 128 * 2
+    feats = _t(rs.standard_normal((len(coors), 64)).astype(np.float32), cuda)
+    w = _t((rs.standard_normal((3, 3, 3, 64, 64)) / 16).astype(np.float32), cuda)
+    a = sp.conv_table(feats, w, rb.nbr, rb.n_out, impl="tc")
+    b = sp.conv_table(feats, w, rb.nbr, rb.n_out, impl="tc")
+    ref = sp.conv_table(feats, w, rb.nbr, rb.n_out, impl="fma")
+    assert torch.equal(a, b)
+    assert (a - ref).abs().max() <= 2e-5 * ref.abs().max()
+
+
 def test_errors(cuda):
     with pytest.raises(RuntimeError):
         sp.build_rulebook(torch.zeros((4, 4), dtype=torch.int32), 1, [4, 4, 4], 3, 1, 1, 1, True)  # CPU tensor

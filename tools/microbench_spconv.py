@@ -44,11 +44,12 @@ def timed(fn, iters=5):
     return sorted(ts)[len(ts) // 2], r
 
 
-def main(batch=4, n_points=240000):
+def main(batch=4, n_points=240000, impl="auto"):
     dev = torch.device("cuda:0")
     feats, coors = make_voxels(batch, n_points, dev)
     enc = dbev.SparseEncoder(**LF).to(dev).eval()
-    res = dict(batch=batch, n_points=n_points, n_voxels=int(feats.shape[0]))
+    sp.SparseConvolution.impl = None if impl == "auto" else impl
+    res = dict(batch=batch, n_points=n_points, n_voxels=int(feats.shape[0]), impl=impl)
     t, out = timed(lambda: enc(feats, coors, batch))
     res["encoder_ms"] = t
     res["out_shape"] = list(out.shape)
@@ -86,4 +87,5 @@ def main(batch=4, n_points=240000):
 
 
 if __name__ == "__main__":
-    main(*(int(a) for a in sys.argv[1:]))
+    a = sys.argv[1:]
+    main(int(a[0]) if a else 4, int(a[1]) if len(a) > 1 else 240000, a[2] if len(a) > 2 else "auto")
