@@ -8,8 +8,11 @@
 // Design: an implicit GEMM per tile of 128 output voxels, D[128 voxels, C_out] accumulated in
 // TMEM over all (kernel offset k, 32-channel chunk) steps:
 //   A = rows gathered through the output-major neighbour table nbr[k][o] (zeros where the
-//       neighbour is absent), written by 4 producer warps straight into the 128-byte-swizzled
-//       K-major layout the tensor core reads (one thread = one voxel row = one 128 B smem row);
+//       neighbour is absent). The 4 producer warps load them into registers and write them with
+//       tcgen05.st straight into TENSOR MEMORY (one thread = one voxel row = one TMEM lane, one
+//       column per channel): the MMA reads A from TMEM, so the gathered rows never touch shared
+//       memory - with 3xTF32 the shared-memory pipe (STS + TMA writes + operand reads of 12 MMAs
+//       per step) was the measured limiter of the first version (profiles/r01_spconv_tc.json);
 //   B = W[k]^T chunk [C_out, 32] (K-major), fetched by TMA from the pre-transposed weights.
 // Offsets with no neighbour in the whole tile are skipped. fp32 parity with the reference's
 // cuBLAS-fp32 path is kept by the 3xTF32 split  a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
@@ -52,7 +55,10 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
                   float* __restrict__ out, TcShape s) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kWBytes = COUT * kChunk * 4;
-  constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
+  constexpr int kStageBytes = 2 * kWBytes;            // W hi + lo; A lives in TMEM
+  constexpr uint32_t kAccCols = 256;                  // 2 accumulator buffers x 128 columns
+  constexpr uint32_t kAStageCols = 64;                // A hi (32 columns) + A lo (32 columns)
+  static_assert(STAGES * kAStageCols + kAccCols <= 512, "TMEM budget");
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2],
       tmem_empty_bar[2];
@@ -81,7 +87,7 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_addr(&tmem_base_s)),
-                 "r"(256u)
+                 "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -151,32 +157,28 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
         if (t == 0) {
           stage_flags[stage] = (step == 0 ? 1u : 0u) | (step == n_steps - 1 ? 2u : 0u);
           mbar_expect_tx(&full_bar[stage], 2u * kWBytes);
-          tma_load_2d(st + 2 * kABytes, &tmap_whi, kc_cur * kChunk, k_cur * COUT, &full_bar[stage]);
-          tma_load_2d(st + 2 * kABytes + kWBytes, &tmap_wlo, kc_cur * kChunk, k_cur * COUT,
-                      &full_bar[stage]);
+          tma_load_2d(st, &tmap_whi, kc_cur * kChunk, k_cur * COUT, &full_bar[stage]);
+          tma_load_2d(st + kWBytes, &tmap_wlo, kc_cur * kChunk, k_cur * COUT, &full_bar[stage]);
         }
-        uint8_t* row_hi = st + (t >> 3) * 1024 + (t & 7) * 128;
-        uint8_t* row_lo = row_hi + kABytes;
-        if (cur_row >= 0) {
+        // absent neighbours contribute zero rows (the store is warp-collective: no divergence)
+        const bool present = cur_row >= 0;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float4 hi, lo;
-            hi.x = tf32_head(cur[c].x), hi.y = tf32_head(cur[c].y);
-            hi.z = tf32_head(cur[c].z), hi.w = tf32_head(cur[c].w);
-            lo.x = cur[c].x - hi.x, lo.y = cur[c].y - hi.y, lo.z = cur[c].z - hi.z, lo.w = cur[c].w - hi.w;
-            const int off = ((c ^ (t & 7)) << 4);
-            *reinterpret_cast<float4*>(row_hi + off) = hi;
-            *reinterpret_cast<float4*>(row_lo + off) = lo;
-          }
-        } else {
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 8; ++c) {
+          const float v4[4] = {cur[c].x, cur[c].y, cur[c].z, cur[c].w};
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            *reinterpret_cast<float4*>(row_hi + (c << 4)) = z;
-            *reinterpret_cast<float4*>(row_lo + (c << 4)) = z;
+          for (int e = 0; e < 4; ++e) {
+            const float h = present ? tf32_head(v4[e]) : 0.f;
+            hi[c * 4 + e] = __float_as_uint(h);
+            lo[c * 4 + e] = __float_as_uint(present ? v4[e] - h : 0.f);
           }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic -> async proxy
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");  // after the empty-barrier wait
+        const uint32_t a_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + kAccCols + stage * kAStageCols;
+        tmem_st32(a_addr, hi);
+        tmem_st32(a_addr + 32, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(&full_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         cur_row = nxt_row;
@@ -201,20 +203,18 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
           mbar_wait(&full_bar[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t flags = stage_flags[stage];
-          const uint32_t a_hi = smem_addr(base + (size_t)stage * kStageBytes);
-          const uint32_t a_lo = a_hi + kABytes;
-          const uint32_t w_hi = a_hi + 2 * kABytes;
+          const uint32_t w_hi = smem_addr(base + (size_t)stage * kStageBytes);
           const uint32_t w_lo = w_hi + kWBytes;
+          const uint32_t a_hi = tmem_base + kAccCols + stage * kAStageCols;  // lane 0, A columns
+          const uint32_t a_lo = a_hi + 32;
 #pragma unroll
           for (int kk = 0; kk < kChunk / 8; ++kk) {
-            const uint64_t d_ahi = umma_desc(a_hi + kk * 32, 16, 1024);
-            const uint64_t d_alo = umma_desc(a_lo + kk * 32, 16, 1024);
             const uint64_t d_whi = umma_desc(w_hi + kk * 32, 16, 1024);
             const uint64_t d_wlo = umma_desc(w_lo + kk * 32, 16, 1024);
-            umma_tf32(d_tmem, d_ahi, d_whi, idesc, accumulate);
+            umma_tf32_ts(d_tmem, a_hi + kk * 8, d_whi, idesc, accumulate);
             accumulate = 1;
-            umma_tf32(d_tmem, d_alo, d_whi, idesc, 1u);
-            umma_tf32(d_tmem, d_ahi, d_wlo, idesc, 1u);
+            umma_tf32_ts(d_tmem, a_lo + kk * 8, d_whi, idesc, 1u);
+            umma_tf32_ts(d_tmem, a_hi + kk * 8, d_wlo, idesc, 1u);
           }
           umma_commit(&empty_bar[stage]);  // frees the stage when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -270,7 +270,7 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 8) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
                  : "memory");
   }
 }
@@ -356,7 +356,7 @@ int spconv_forward_tc(const float* in_feats, int c_in, const float* wt_hi, const
   const int grid = s.n_tiles < sms ? s.n_tiles : sms;
 #define DBEV_TC_LAUNCH(CO, KV, STG)                                                             \
   do {                                                                                          \
-    const size_t smem = (size_t)STG * (2 * kABytes + 2 * CO * kChunk * 4) + 1024;               \
+    const size_t smem = (size_t)STG * (2 * CO * kChunk * 4) + 1024;               \
     DBEV_CUDA(cudaFuncSetAttribute(sp_conv_tc_kernel<CO, KV, STG>,                              \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
     sp_conv_tc_kernel<CO, KV, STG><<<grid, kTcThreads, smem, stream>>>(                         \
@@ -365,11 +365,11 @@ int spconv_forward_tc(const float* in_feats, int c_in, const float* wt_hi, const
   if (kvol == 27) {
     if (c_out == 32) DBEV_TC_LAUNCH(32, 27, 4);
     else if (c_out == 64) DBEV_TC_LAUNCH(64, 27, 4);
-    else DBEV_TC_LAUNCH(128, 27, 3);
+    else DBEV_TC_LAUNCH(128, 27, 4);
   } else {
     if (c_out == 32) DBEV_TC_LAUNCH(32, 3, 4);
     else if (c_out == 64) DBEV_TC_LAUNCH(64, 3, 4);
-    else DBEV_TC_LAUNCH(128, 3, 3);
+    else DBEV_TC_LAUNCH(128, 3, 4);
   }
 #undef DBEV_TC_LAUNCH
   DBEV_CHECK_LAUNCH("sp_conv_tc_kernel");
