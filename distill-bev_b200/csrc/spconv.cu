@@ -101,19 +101,25 @@ __global__ void sp_table_kernel(const int4* __restrict__ out_coors, int n_out, G
 
 // Every (input, kernel offset) pair names one output cell when (in + p - k*d) is a multiple of
 // the stride (getValidOutPos, geometry.h:24-84). Distinct cells are collected through a hash set.
-__global__ void sp_candidates_kernel(const int4* __restrict__ coors, int n_in, Geom g,
-                                     uint32_t* hset, uint32_t mask, uint32_t* __restrict__ out_keys,
-                                     long long max_out, int* counter) {
+__global__ void sp_candidates_kernel(const int4* __restrict__ coors, int n_in, Geom g, int cz, int cy,
+                                     int cx, uint32_t* hset, uint32_t mask,
+                                     uint32_t* __restrict__ out_keys, long long max_out, int* counter) {
+  // One thread per (input, j): only offsets with (in + p - k) % stride == 0 can name an output, at
+  // most cz*cy*cx = prod ceil(K/stride) of the K^3 per input (8 of 27 for a 3x3x3 stride-2 conv).
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int kvol = g.kz * g.ky * g.kx;
-  if (t >= (long long)kvol * n_in) return;
-  const int k = (int)(t / n_in);
-  const int i = (int)(t - (long long)k * n_in);
+  const int per = cz * cy * cx;
+  if (t >= (long long)per * n_in) return;
+  const int j = (int)(t / n_in);
+  const int i = (int)(t - (long long)j * n_in);
   const int4 c = coors[i];
   if ((unsigned)c.x >= (unsigned)g.batch || (unsigned)c.y >= (unsigned)g.iz ||
       (unsigned)c.z >= (unsigned)g.iy || (unsigned)c.w >= (unsigned)g.ix)
     return;
-  const int kx = k % g.kx, ky = (k / g.kx) % g.ky, kz = k / (g.kx * g.ky);
+  const int jx = j % cx, jy = (j / cx) % cy, jz = j / (cx * cy);
+  const int kz = g.sz == 1 ? jz : (c.y + g.pz) % g.sz + jz * g.sz;
+  const int ky = g.sy == 1 ? jy : (c.z + g.py) % g.sy + jy * g.sy;
+  const int kx = g.sx == 1 ? jx : (c.w + g.px) % g.sx + jx * g.sx;
+  if (kz >= g.kz || ky >= g.ky || kx >= g.kx) return;
   const int nz = c.y + g.pz - kz * g.dz, ny = c.z + g.py - ky * g.dy, nx = c.w + g.px - kx * g.dx;
   if (nz < 0 || ny < 0 || nx < 0) return;
   if (nz % g.sz || ny % g.sy || nx % g.sx) return;
@@ -515,9 +521,12 @@ int spconv_out_candidates(const int* in_coors, int n_in, const SpConvGeom& g, ui
     return DBEV_ERR_WORKSPACE;
   }
   DBEV_CUDA(cudaMemsetAsync(hset, 0xFF, (size_t)cap * 4, stream));
-  const long long total = (long long)g.kvol() * n_in;
+  int cnt[3];
+  for (int i = 0; i < 3; ++i) cnt[i] = g.s[i] == 1 ? g.k[i] : (g.k[i] + g.s[i] - 1) / g.s[i];
+  const long long total = (long long)cnt[0] * cnt[1] * cnt[2] * n_in;
   sp_candidates_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(
-      (const int4*)in_coors, n_in, to_dev(g), hset, cap - 1, out_keys, max_out, n_out_dev);
+      (const int4*)in_coors, n_in, to_dev(g), cnt[0], cnt[1], cnt[2], hset, cap - 1, out_keys, max_out,
+      n_out_dev);
   DBEV_CHECK_LAUNCH("sp_candidates_kernel");
   return DBEV_OK;
 }

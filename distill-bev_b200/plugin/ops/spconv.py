@@ -271,15 +271,25 @@ class SparseModule(nn.Module):
 
 
 def _fold_bn(bn, bias=None):
-    """eval-mode BatchNorm1d (+ conv bias) as per-channel scale / shift."""
-    scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps) if bn.affine else \
-        1.0 / torch.sqrt(bn.running_var + bn.eps)
-    shift = -bn.running_mean * scale
-    if bn.affine:
-        shift = shift + bn.bias.detach()
-    if bias is not None:
-        shift = shift + bias.detach() * scale
-    return scale.float().contiguous(), shift.float().contiguous()
+    """eval-mode BatchNorm1d (+ conv bias) as per-channel scale / shift. Cached on the module and
+    rebuilt only when a parameter / running statistic changes (the teacher is frozen)."""
+    ts = [t for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var, bias) if t is not None]
+    key = tuple((t.data_ptr(), t._version) for t in ts)
+    cache = getattr(bn, "_dbev_folded", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    with torch.no_grad():
+        scale = 1.0 / torch.sqrt(bn.running_var + bn.eps)
+        if bn.affine:
+            scale = scale * bn.weight
+        shift = -bn.running_mean * scale
+        if bn.affine:
+            shift = shift + bn.bias
+        if bias is not None:
+            shift = shift + bias * scale
+        folded = (scale.float().contiguous(), shift.float().contiguous())
+    bn._dbev_folded = (key, folded)
+    return folded
 
 
 class SparseConvolution(SparseModule):

@@ -44,6 +44,55 @@ def timed(fn, iters=5):
     return sorted(ts)[len(ts) // 2], r
 
 
+def reference_kernels(enc, feats, coors, batch, dev):
+    """The kernels to beat: the reference's own spconv CUDA extension (mmdet3d/ops/spconv, compiled
+    unmodified for sm_100 into oracle/_ref by oracle/build_oracle.py) on the same inputs — rulebook
+    (get_indice_pairs_3d) and indice_conv_fp32 of the first SubM layers, a strided layer and a
+    128-channel SubM layer. Skipped when the extension is not in the snapshot."""
+    import glob
+    import importlib.util
+    so = glob.glob(os.path.join(ROOT, "oracle", "_ref", "ref_sparse_conv_ext*.so"))
+    if not so:
+        return None
+    spec = importlib.util.spec_from_file_location("ref_sparse_conv_ext", so[0])
+    ext = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ext)
+    out = []
+    shape = LF["sparse_shape"]
+
+    def pairs(indices, in_shape, k, s, p, subm):
+        o_shape = in_shape if subm else sp.get_conv_output_size(in_shape, k, s, p, [1, 1, 1])
+        fn = lambda: ext.get_indice_pairs_3d(indices, batch, o_shape, in_shape, k, s, p, [1, 1, 1],
+                                             [0, 0, 0], int(subm), 0)
+        ms, r = timed(fn, 3)
+        return ms, r, o_shape
+
+    def conv(x, cin, cout, r, subm, n_out):
+        w = torch.randn(3, 3, 3, cin, cout, device=dev) * 0.05
+        fn = lambda: ext.indice_conv_fp32(x, w, r[1], r[2], n_out, 0, int(subm))
+        ms, y = timed(fn, 3)
+        return ms, y
+
+    ms_rb, r, _ = pairs(coors, shape, [3, 3, 3], [1, 1, 1], [1, 1, 1], True)
+    x16 = torch.randn(coors.shape[0], 16, device=dev)
+    ms_c, _ = conv(x16, 16, 16, r, True, coors.shape[0])
+    out.append(dict(layer="subm 16->16 stage 1", n_out=int(coors.shape[0]), rulebook_ms=ms_rb, conv_ms=ms_c))
+    ms_rb2, r2, s2 = pairs(coors, shape, [3, 3, 3], [2, 2, 2], [1, 1, 1], False)
+    n2 = int(r2[0].shape[0])
+    ms_c2, _ = conv(x16, 16, 32, r2, False, n2)
+    out.append(dict(layer="sparse 16->32 stride 2", n_out=n2, rulebook_ms=ms_rb2, conv_ms=ms_c2))
+    # deeper stages: downsample the coordinates the way the encoder does to get realistic sets
+    ind = r2[0]
+    for cin, cout in ((32, 64), (64, 128)):
+        ms_rb3, r3, s3 = pairs(ind, s2, [3, 3, 3], [2, 2, 2], [1, 1, 1], False)
+        ind, s2 = r3[0], s3
+    ms_rb4, r4, _ = pairs(ind, s2, [3, 3, 3], [1, 1, 1], [1, 1, 1], True)
+    x128 = torch.randn(ind.shape[0], 128, device=dev)
+    ms_c4, _ = conv(x128, 128, 128, r4, True, ind.shape[0])
+    out.append(dict(layer="subm 128->128 stage 4", n_out=int(ind.shape[0]), rulebook_ms=ms_rb4, conv_ms=ms_c4))
+    return out
+
+
 def main(batch=4, n_points=240000, impl="auto"):
     dev = torch.device("cuda:0")
     feats, coors = make_voxels(batch, n_points, dev)
@@ -81,6 +130,9 @@ def main(batch=4, n_points=240000, impl="auto"):
     finally:
         sp.build_rulebook, sp.conv_table = orig_build, orig_conv
     res["layers"] = layers
+    ref = reference_kernels(enc, feats, coors, batch, dev)
+    if ref:
+        res["reference_cuda_ext"] = ref
     res["sum_rulebook_ms"] = sum(l["ms"] for l in layers if l["op"] == "rulebook")
     res["sum_conv_ms"] = sum(l["ms"] for l in layers if l["op"] == "conv")
     print(json.dumps(res))

@@ -216,7 +216,8 @@ def _build_loss(cfg):
 
 
 def load_fgd_methods(names=("foreground_scale_mask", "add_fp_as_fg", "fgd_distill_loss",
-                            "affinity_distill_loss")):
+                            "affinity_distill_loss"), cls_name="BEVDetDistill",
+                     relpath="mmdet3d/models/detectors/bevdet_distill.py"):
     """dict name -> python function(self, ...) compiled from the reference source."""
     import ast
     import copy
@@ -229,10 +230,10 @@ def load_fgd_methods(names=("foreground_scale_mask", "add_fp_as_fg", "fgd_distil
     load_ref_module("ref_points.base_points", "mmdet3d/core/points/base_points.py")
     lidar_points = load_ref_module("ref_points.lidar_points", "mmdet3d/core/points/lidar_points.py")
     clip = load_ref_module("ref_clip_sigmoid", "mmdet3d/models/utils/clip_sigmoid.py")
-    path = os.path.join(REF_ROOT, "mmdet3d/models/detectors/bevdet_distill.py")
+    path = os.path.join(REF_ROOT, relpath)
     src = open(path).read()
     tree = ast.parse(src)
-    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "BEVDetDistill"][0]
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls_name][0]
     ns = dict(torch=torch, nn=nn, F=F, np=np, deepcopy=copy.deepcopy, partial=functools.partial,
               box_np_ops=box_np_ops, LiDARPoints=lidar_points.LiDARPoints,
               clip_sigmoid=clip.clip_sigmoid, build_loss=_build_loss, os=os)
