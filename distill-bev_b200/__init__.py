@@ -14,7 +14,7 @@ from .plugin.ops.voxel import (DynamicScatter, Voxelization, dynamic_scatter, vo
 from .plugin.pillars import DynamicPillarFeatureNet, PointPillarsScatter, pillar_canvas  # noqa: F401
 from .plugin.view_transformer import ViewTransformerLiftSplatShoot, lss_geometry  # noqa: F401
 from .plugin.distill import fgd  # noqa: F401
-from .plugin.distill import affinity, bevformer  # noqa: F401
+from .plugin.distill import affinity, bevformer, detector  # noqa: F401
 from .plugin.distill.adaptation import Conv1x1Adaptation, conv1x1  # noqa: F401
 from .plugin.ops import spconv  # noqa: F401
 from .plugin.sparse_teacher import DynamicVoxelEncoder, HardSimpleVFE, SparseEncoder  # noqa: F401

@@ -321,4 +321,24 @@ def fgd_distill_loss(teacher_feat, student_feat, gt_bboxes_3d, distill_params, t
         out["kd_spatial_loss"] = losses[4]
     if cfg.use_fp:
         out["kd_fp_bg_feat_loss"] = losses[2]
+    # affinity branch of fgd_distill_loss (:1294-1321)
+    mode = distill_params.get("affinity_mode", "none")
+    if isinstance(mode, (list, tuple)):
+        mode = mode[index] if len(mode) > 1 else mode[0]
+    if mode != "none":
+        from . import affinity as _aff
+        if mode not in ("foreground", "foreground+fp"):
+            raise NotImplementedError("affinity_mode=%r" % mode)   # 'attention' needs the top-k of the attention map
+        if mode == "foreground+fp":
+            assert fp_mode != "none"                                # :1297
+        aw = distill_params["affinity_weights"]
+        aw = aw[index] if len(aw) > 1 else aw[0]
+        adapted = student_feat
+        if adapt_w is not None:
+            from .adaptation import conv1x1
+            adapted = conv1x1(student_feat, adapt_w, adapt_b)
+        out.update(_aff.affinity_distill_loss(
+            teacher_feat, adapted, fg, fp if (mode == "foreground+fp" and cfg.use_fp) else None, weight=aw,
+            criterion=distill_params.get("affinity_criterion", dict(type="SmoothL1Loss")),
+            split=int(distill_params.get("affinity_split", 1))))
     return out

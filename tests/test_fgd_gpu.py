@@ -205,3 +205,46 @@ def test_fused_channel_adaptation_matches_composition(cuda, B, Cs, Ct, H):
     conv3 = torch.nn.Conv2d(Cs, Ct, 3, padding=1).to(cuda)
     l3 = fgd.fgd_distill_loss(teacher, _t(student, cuda), boxes, p, tc, channel_adaptation=conv3, **kw)
     assert set(l3) == set(l1)
+
+
+def test_forward_distill_positions_and_affinity_branch(cuda):
+    """Position loop + key suffixing of forward_distill (bevdet_distill.py:1456-1507) and the
+    affinity branch of fgd_distill_loss (:1294-1321): 'foreground' affinity == the standalone
+    affinity loss on the foreground mask; backbone positions are skipped before multi_scale_epoch."""
+    import distill_bev_b200 as dbev
+    from distill_bev_b200.plugin.distill import detector, fgd as F, affinity as A
+    torch.manual_seed(0)
+    B, C, H = 2, 32, 32
+    params = dict(spatial_t=0.5, spatial_student_ratio=1.0, channel_t=0.5, fg_feat_loss_weights=[6e-3],
+                  bg_feat_loss_weights=[4e-2], channel_loss_weights=[0.25], spatial_loss_weights=[2.5e-3],
+                  spatial_attentions=["teacher_student"], transpose_mask=False, foreground_mask="gt",
+                  background_mask="logical_not", scale_mask="combine_gt", spatial_mask=True,
+                  channel_mask=True, student_feat_pos=["head", "backbone1"],
+                  teacher_feat_pos=["head", "backbone1"], affinity_mode=["foreground"],
+                  affinity_weights=[0.5], affinity_criterion=dict(type="SmoothL1Loss"), affinity_split=1,
+                  fp_as_foreground=["none"], fp_weight=0.0, fp_epoch=0, multi_scale_epoch=3)
+    cfg = dict(grid_size=[256, 256, 40], point_cloud_range=[-12.8, -12.8, -5.0, 12.8, 12.8, 3.0],
+               voxel_size=[0.1, 0.1, 0.2])
+    boxes = [torch.tensor([[0.0, 0.0, -1.0, 4.0, 3.0, 1.5, 0.3, 0, 0], [5.0, -4.0, -1.0, 3.0, 5.0, 1.5, 1.0, 0, 0]]),
+             torch.tensor([[-3.0, 2.0, -1.0, 5.0, 4.0, 1.5, -0.7, 0, 0]])]
+    s_head = torch.relu(torch.randn(B, C, H, H, device=cuda)).requires_grad_(True)
+    t_head = torch.relu(torch.randn(B, C, H, H, device=cuda))
+    s_bb = [torch.randn(B, C, H, H, device=cuda) for _ in range(3)]
+    t_bb = [torch.randn(B, C, H, H, device=cuda) for _ in range(3)]
+    ident = [torch.nn.Identity(), torch.nn.Identity()]
+    spat = [torch.nn.Conv2d(1, 1, 3, padding=1).to(cuda) for _ in range(2)]
+    kw = dict(img_feats=[s_head], lss_feat=None, bev_backbone_feats=s_bb, teacher_neck_feat=t_head,
+              teacher_backbone_feats=t_bb, canvas_feat=None, teacher_preds=None, student_preds=None,
+              heatmaps=None, gt_bboxes_3d=boxes, channel_wise_adaptations=ident, teacher_adaptations=ident,
+              spatial_wise_adaptations=spat)
+    early = detector.forward_distill_positions("fgd", params, cfg, epoch=0, **kw)
+    assert sorted(early) == ["kd_affinity_loss_head_head", "kd_bg_feat_loss_head_head",
+                             "kd_channel_loss_head_head", "kd_fg_feat_loss_head_head",
+                             "kd_spatial_loss_head_head"]
+    late = detector.forward_distill_positions("fgd", params, cfg, epoch=5, **kw)
+    assert len(late) == 10 and "kd_fg_feat_loss_backbone1_backbone1" in late
+    fg = F.foreground_scale_mask(H, H, boxes, cfg["grid_size"], cfg["point_cloud_range"], cfg["voxel_size"], cuda)[0]
+    alone = A.affinity_distill_loss(t_head, s_head, fg, weight=0.5)["kd_affinity_loss"]
+    torch.testing.assert_close(early["kd_affinity_loss_head_head"], alone)
+    sum(early.values()).backward()
+    assert torch.isfinite(s_head.grad).all() and s_head.grad.abs().sum() > 0
