@@ -61,6 +61,15 @@ def main():
         dbev.bev_pool_gather(x, plan)
     t_plan = time_ms(lambda: dbev.bev_plan_from_geom(geom, a.frames, bx, dx, nx), a.iters, flush)
     t_fwd = time_ms(lambda: dbev.bev_pool_gather(x, plan), a.iters, flush)
+    # back-to-back launches without a flush (what bench.py's roofline leg times)
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(30):
+        dbev.bev_pool_gather(x, plan)
+    e1.record()
+    torch.cuda.synchronize()
+    b2b = e0.elapsed_time(e1) / 30
 
     def bwd():
         o = dbev.bev_pool_gather(xr, plan)
@@ -74,7 +83,7 @@ def main():
                fwd_GBps_med=fwd_bytes / t_fwd[0] / 1e6, fwd_GBps_best=fwd_bytes / t_fwd[1] / 1e6,
                fwdbwd_ms_med=t_fb[0], bwd_ms_est=t_fb[0] - t_fwd[0],
                bwd_GBps_est=bwd_bytes / max(t_fb[0] - t_fwd[0], 1e-6) / 1e6,
-               fwd_alg_bytes=fwd_bytes)
+               fwd_alg_bytes=fwd_bytes, fwd_ms_b2b=b2b, fwd_GBps_b2b=fwd_bytes / b2b / 1e6)
     print(json.dumps(rep))
 
 
