@@ -278,6 +278,52 @@ def count_our_kernels(hp):
         hp.captured = captured
 
 
+def sparse_teacher_probe(device, batch=2, n_points=240000):
+    """Not part of the timed step (configs[1] uses the pillar teacher): the sparse LiDAR teacher of
+    configs[3] — hard voxelize (0.064 m voxels, 41 x 1600 x 1600 grid) + HardSimpleVFE + the LidarFormer
+    SparseEncoder (20 sparse convs: lane-group kernels for the narrow layers, tcgen05 3xTF32 implicit
+    GEMM for C >= 32) -> dense [B, 256, 200, 200], timed with CUDA events (median of 5)."""
+    import torch
+    import distill_bev_b200 as dbev
+    from distill_bev_b200 import synthetic
+    vox = dbev.Voxelization([0.064, 0.064, 0.2], [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], 10, (90000, 120000)).eval()
+    vfe = dbev.HardSimpleVFE(5)
+    enc = dbev.SparseEncoder(
+        in_channels=5, sparse_shape=[41, 1600, 1600], output_channels=128,
+        encoder_channels=((16, 16, 32), (32, 32, 64), (64, 64, 128), (128, 128)),
+        encoder_paddings=((0, 0, 1), (0, 0, 1), (0, 0, [0, 1, 1]), (0, 0)), block_type="basicblock").to(device).eval()
+    clouds = [torch.from_numpy(c).to(device) for c in synthetic.make_lidar_scene(batch, n_points, seed=3)]
+
+    def front():
+        feats, coors = [], []
+        for b, pts in enumerate(clouds):
+            v, c, n = vox(pts)
+            feats.append(vfe(v, n, c))
+            coors.append(torch.nn.functional.pad(c, (1, 0), value=b))
+        return torch.cat(feats), torch.cat(coors).contiguous()
+
+    def timed_ms(fn, iters=5):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+            a.record()
+            r = fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2], r
+
+    t_front, (feats, coors) = timed_ms(front)
+    t_enc, out = timed_ms(lambda: enc(feats, coors, batch))
+    return {"workload": "LidarFormer sparse teacher front end: %d x %d-point clouds -> %d voxels -> %s"
+                        % (batch, n_points, feats.shape[0], list(out.shape)),
+            "voxelize_vfe_ms": round(t_front, 3), "sparse_encoder_ms": round(t_enc, 3),
+            "samples_per_sec": round(batch / ((t_front + t_enc) * 1e-3), 1),
+            "note": "includes the host read-backs of voxel / output counts the reference API implies"}
+
+
 def bev_pool_roofline(device):
     """Live roofline of the dominant bev_pool kernel: gather-forward over materialised frustum
     features at the configs[1] shape (16 sample-frames, C=64): kernel timed alone with CUDA events
@@ -407,6 +453,10 @@ def run_ours(args):
     if world == 1:
         line["roofline"] = bev_pool_roofline(device)
         line["cpu_baseline"] = cpu_baseline(samples=3, procs=1)
+        try:
+            line["sparse_teacher"] = sparse_teacher_probe(device)
+        except Exception as exc:  # extra evidence only: never lose the headline line over it
+            line["sparse_teacher"] = {"error": str(exc)[:200]}
     else:
         line["roofline"] = bev_pool_roofline(device)
     print(json.dumps(line))

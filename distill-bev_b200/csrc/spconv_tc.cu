@@ -21,9 +21,14 @@
 // weight TMA), 4-7 epilogue (tcgen05.ld -> BN scale/shift, residual, ReLU -> row-contiguous
 // stores; the TMEM lane is the voxel), warp 8 = MMA issuer + TMEM owner. Two TMEM accumulator
 // buffers let the epilogue of tile t overlap the MMAs of tile t+1; persistent over tiles.
+// Measured dead ends (B200, round 1): separate accumulators per 3xTF32 term (no gain: the step time
+// is not an accumulate-dependency chain), 8 producer warps with half a chunk each (slower: more
+// barrier traffic), prefetch distance 1 vs 2 (equal), cvt.rna.tf32 (conversion pipe: -15 %).
 #include "spconv.cuh"
 
 #include "umma.cuh"
+
+#include <stdlib.h>
 
 namespace dbev {
 
@@ -32,21 +37,29 @@ namespace {
 constexpr int kTileM = 128;                   // output voxels per tile (UMMA M, TMEM lanes)
 constexpr int kChunk = 32;                    // input channels per stage (one 128 B swizzle row)
 constexpr int kABytes = kTileM * kChunk * 4;  // 16 KB: one A operand tile (hi or lo)
-constexpr int kProducers = 128;
-constexpr int kTcThreads = 288;               // 9 warps
+constexpr int kProdWarps = 4;                  // one warp per TMEM lane quarter (8 warps measured slower)
+constexpr int kEpiWarp0 = kProdWarps;          // warps 8..11: epilogue (warp % 4 = lane quarter)
+constexpr int kMmaWarp = kProdWarps + 4;       // warp 12: MMA issuer + TMEM owner
+constexpr int kTcThreads = (kMmaWarp + 1) * 32;  // 416
 
-// value rounded to the nearest TF32 (10-bit mantissa); the remainder v - head is exact in fp32
+// value rounded to the nearest TF32 (10-bit mantissa, ties away from zero); the remainder v - head
+// is exact in fp32. Integer add + mask (full-rate ALU) instead of cvt.rna.tf32.f32, which issues at
+// the conversion-pipe rate (a quarter of the ALU rate) and made the producers ALU-bound.
 __device__ __forceinline__ float tf32_head(float v) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
 
 struct TcShape {
   int c_in, c_out, n_out, n_tiles, chunks, kvol;
+  int debug;  // experiments only (DBEV_TC_DEBUG): 1 = skip row loads, 2 = skip TMEM stores, 4 = skip W TMA
 };
 
-template <int COUT, int KVOL, int STAGES>
+// NACC accumulators per tile: the three 3xTF32 terms go to different TMEM accumulators (summed by
+// the epilogue) so that consecutive MMAs do not form one read-modify-write dependency chain on the
+// same accumulator - with K = 8 per instruction and N <= 128 the chain latency, not the tensor
+// throughput, set the step time of the single-accumulator version (same ~1550 clk per step for
+// N = 32, 64 and 128). NBUF = accumulator sets (2 = epilogue overlaps the next tile).
+template <int COUT, int KVOL, int STAGES, int NACC, int NBUF>
 __global__ void __launch_bounds__(kTcThreads, 1)
 sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
                   const __grid_constant__ CUtensorMap tmap_wlo, const float* __restrict__ in_feats,
@@ -56,12 +69,12 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kWBytes = COUT * kChunk * 4;
   constexpr int kStageBytes = 2 * kWBytes;            // W hi + lo; A lives in TMEM
-  constexpr uint32_t kAccCols = 256;                  // 2 accumulator buffers x 128 columns
+  constexpr uint32_t kAccCols = NBUF * NACC * COUT;   // accumulator columns
   constexpr uint32_t kAStageCols = 64;                // A hi (32 columns) + A lo (32 columns)
   static_assert(STAGES * kAStageCols + kAccCols <= 512, "TMEM budget");
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2],
-      tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[NBUF],
+      tmem_empty_bar[NBUF];
   __shared__ uint32_t stage_flags[STAGES];  // bit 0: first step of a tile, bit 1: last step
   __shared__ uint32_t mask_s[2];
   __shared__ int idx_s[KVOL * kTileM];  // neighbour rows of the current tile, [k][row]
@@ -72,19 +85,20 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], kProducers + 1);  // 128 gather arrivals + the expect_tx arrival
+      mbar_init(&full_bar[i], kProdWarps + 1);  // one arrival per producer warp + the expect_tx arrival
       mbar_init(&empty_bar[i], 1);
     }
-    mbar_init(&tmem_full_bar[0], 1);
-    mbar_init(&tmem_full_bar[1], 1);
-    mbar_init(&tmem_empty_bar[0], 4);
-    mbar_init(&tmem_empty_bar[1], 4);
+#pragma unroll
+    for (int i = 0; i < NBUF; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);
+    }
     mask_s[0] = mask_s[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_whi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_wlo) : "memory");
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_addr(&tmem_base_s)),
                  "r"(512u)
@@ -96,12 +110,12 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < 4) {
+  if (warp < kProdWarps) {
     // ------------------------------------------------------------ gather producers
     // Steps of a tile = (active offset k) x (32-channel chunk kc). The rows of step i+1 are
     // requested from L2 BEFORE the thread waits for / fills the stage of step i, so two steps of
     // loads are in flight per thread (the producers are latency-bound, not bandwidth-bound).
-    const int t = threadIdx.x;  // row of the tile
+    const int t = threadIdx.x;  // row of the tile = TMEM lane
     uint32_t stage = 0, phase = 0;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
@@ -115,7 +129,7 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
         bits |= (v >= 0 ? 1u : 0u) << k;
       }
       const uint32_t par = it & 1u;
-      if (t == 0) mask_s[par ^ 1u] = 0;
+      if (threadIdx.x == 0) mask_s[par ^ 1u] = 0;
       bits = __reduce_or_sync(0xffffffffu, bits);
       if (lane == 0 && bits) atomicOr(&mask_s[par], bits);
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -123,82 +137,104 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
       if (mask == 0) mask = 1u;  // keep producer and MMA issuer in step on an (impossible) empty tile
       const int n_steps = __popc(mask) * s.chunks;
 
-      float4 cur[8], nxt[8];
-      int cur_row, nxt_row = -1;
-      uint32_t rest = mask;       // offsets not yet started
-      int k_cur = __ffs(rest) - 1, kc_cur = 0;
-      rest &= rest - 1;
-      // prologue: request step 0
-      cur_row = idx_s[k_cur * kTileM + t];
-      if (cur_row >= 0) {
-        const float4* src = reinterpret_cast<const float4*>(in_feats + (long long)cur_row * s.c_in);
+      // Rows of steps i+1 and i+2 are in flight while step i is converted and stored: the producers
+      // are bound by L2 latency x loads in flight (128 threads x 8 x 16 B per step), so the prefetch
+      // distance sets the gather bandwidth.
+      float4 b0[8], b1[8], b2[8];  // step i is consumed from b[i % 3] while i+1, i+2 are in flight
+      uint32_t ld_rest = mask;    // load iterator: runs two steps ahead of the consume iterator
+      int ld_k = __ffs(ld_rest) - 1, ld_kc = 0, ld_step = 0;
+      ld_rest &= ld_rest - 1;
+      auto load_step = [&](float4 (&buf)[8]) {
+        if (ld_step < n_steps) {
+          int row = idx_s[ld_k * kTileM + t];
+          if (s.debug & 1) row = -1;
+          if (row >= 0) {
+            const float4* src = reinterpret_cast<const float4*>(in_feats + (long long)row * s.c_in +
+                                                                ld_kc * kChunk);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) cur[c] = __ldg(src + c);
-      }
-      for (int step = 0; step < n_steps; ++step) {
-        // coordinates of the next step and its loads
-        int k_nxt = k_cur, kc_nxt = kc_cur + 1;
-        if (kc_nxt == s.chunks) {
-          kc_nxt = 0;
-          k_nxt = rest ? __ffs(rest) - 1 : -1;
-          rest &= rest - 1;
-        }
-        if (step + 1 < n_steps) {
-          nxt_row = idx_s[k_nxt * kTileM + t];
-          if (nxt_row >= 0) {
-            const float4* src = reinterpret_cast<const float4*>(in_feats + (long long)nxt_row * s.c_in +
-                                                                kc_nxt * kChunk);
+            for (int c = 0; c < 8; ++c) buf[c] = __ldg(src + c);
+          } else {  // absent neighbour: a zero row
 #pragma unroll
-            for (int c = 0; c < 8; ++c) nxt[c] = __ldg(src + c);
+            for (int c = 0; c < 8; ++c) buf[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          ++ld_step;
+          if (++ld_kc == s.chunks) {
+            ld_kc = 0;
+            ld_k = ld_rest ? __ffs(ld_rest) - 1 : 0;
+            ld_rest &= ld_rest - 1;
           }
         }
+      };
+      uint32_t rest = mask;       // consume iterator
+      int k_cur = __ffs(rest) - 1, kc_cur = 0;
+      rest &= rest - 1;
+      int step = 0;
+      // consume `cur` (step `step`), refill `nxt2` with step + 2
+      auto do_step = [&](float4 (&cur)[8], float4 (&nxt2)[8]) {
+        load_step(nxt2);
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* st = base + (size_t)stage * kStageBytes;
-        if (t == 0) {
+        if (threadIdx.x == 0) {
           stage_flags[stage] = (step == 0 ? 1u : 0u) | (step == n_steps - 1 ? 2u : 0u);
-          mbar_expect_tx(&full_bar[stage], 2u * kWBytes);
-          tma_load_2d(st, &tmap_whi, kc_cur * kChunk, k_cur * COUT, &full_bar[stage]);
-          tma_load_2d(st + kWBytes, &tmap_wlo, kc_cur * kChunk, k_cur * COUT, &full_bar[stage]);
+          if (s.debug & 4) {
+            mbar_arrive(&full_bar[stage]);
+          } else {
+            mbar_expect_tx(&full_bar[stage], 2u * kWBytes);
+            tma_load_2d(st, &tmap_whi, kc_cur * kChunk, k_cur * COUT, &full_bar[stage]);
+            tma_load_2d(st + kWBytes, &tmap_wlo, kc_cur * kChunk, k_cur * COUT, &full_bar[stage]);
+          }
         }
-        // absent neighbours contribute zero rows (the store is warp-collective: no divergence)
-        const bool present = cur_row >= 0;
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const float v4[4] = {cur[c].x, cur[c].y, cur[c].z, cur[c].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float h = present ? tf32_head(v4[e]) : 0.f;
+            const float h = tf32_head(v4[e]);
             hi[c * 4 + e] = __float_as_uint(h);
-            lo[c * 4 + e] = __float_as_uint(present ? v4[e] - h : 0.f);
+            lo[c * 4 + e] = __float_as_uint(v4[e] - h);
           }
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");  // after the empty-barrier wait
         const uint32_t a_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + kAccCols + stage * kAStageCols;
-        tmem_st32(a_addr, hi);
-        tmem_st32(a_addr + 32, lo);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (!(s.debug & 2)) {
+          tmem_st32(a_addr, hi);
+          tmem_st32(a_addr + 32, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(&full_bar[stage]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[stage]);  // one arrival per producer warp
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-        cur_row = nxt_row;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) cur[c] = nxt[c];
-        k_cur = k_nxt, kc_cur = kc_nxt;
+        if (++kc_cur == s.chunks) {
+          kc_cur = 0;
+          k_cur = rest ? __ffs(rest) - 1 : 0;
+          rest &= rest - 1;
+        }
+        ++step;
+      };
+      load_step(b0);
+      load_step(b1);
+      while (step < n_steps) {   // statically rotated buffers: no register copies per step
+        do_step(b0, b2);
+        if (step < n_steps) do_step(b1, b0);
+        if (step < n_steps) do_step(b2, b1);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(kTileM, COUT);
       uint32_t stage = 0, phase = 0;
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1u, use = it >> 1;
+        const uint32_t buf = it % NBUF, use = it / NBUF;
         mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);  // epilogue has drained this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + buf * 128u;
-        uint32_t accumulate = 0;
+        const uint32_t d0 = tmem_base + buf * (NACC * COUT);
+        const uint32_t d1 = d0 + (NACC > 1 ? COUT : 0);
+        const uint32_t d2 = d0 + (NACC > 2 ? 2 * COUT : (NACC > 1 ? COUT : 0));
+        uint32_t acc0 = 0, acc1 = 0, acc2 = 0;   // 0 until the accumulator has been written
         while (true) {
           mbar_wait(&full_bar[stage], phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -209,12 +245,17 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
           const uint32_t a_lo = a_hi + 32;
 #pragma unroll
           for (int kk = 0; kk < kChunk / 8; ++kk) {
+            if (s.debug & 16) break;
             const uint64_t d_whi = umma_desc(w_hi + kk * 32, 16, 1024);
             const uint64_t d_wlo = umma_desc(w_lo + kk * 32, 16, 1024);
-            umma_tf32_ts(d_tmem, a_hi + kk * 8, d_whi, idesc, accumulate);
-            accumulate = 1;
-            umma_tf32_ts(d_tmem, a_lo + kk * 8, d_whi, idesc, 1u);
-            umma_tf32_ts(d_tmem, a_hi + kk * 8, d_wlo, idesc, 1u);
+            umma_tf32_ts(d0, a_hi + kk * 8, d_whi, idesc, acc0);
+            acc0 = 1;
+            if (NACC == 1) acc1 = acc2 = 1;
+            umma_tf32_ts(d1, a_lo + kk * 8, d_whi, idesc, acc1);
+            acc1 = 1;
+            if (NACC == 2) acc2 = 1;
+            umma_tf32_ts(d2, a_hi + kk * 8, d_wlo, idesc, acc2);
+            acc2 = 1;
           }
           umma_commit(&empty_bar[stage]);  // frees the stage when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -224,19 +265,29 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 4..7)
+    // ------------------------------------------------------------ epilogue (4 warps after the producers)
     const int q = warp & 3;  // TMEM lane quarter
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
-      const uint32_t buf = it & 1u, use = it >> 1;
+      const uint32_t buf = it % NBUF, use = it / NBUF;
       const int o = tile * kTileM + q * 32 + lane;
       mbar_wait(&tmem_full_bar[buf], use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (int cc = 0; cc < COUT / 32; ++cc) {
+        if (s.debug & 32) break;
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 128u + (uint32_t)(cc * 32), v);
+        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (NACC * COUT) + (uint32_t)(cc * 32);
+        tmem_ld32(tcol, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j2 = 1; j2 < NACC; ++j2) {   // sum of the 3xTF32 term accumulators
+          uint32_t u[32];
+          tmem_ld32(tcol + j2 * COUT, u);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        }
         if (o < s.n_out) {
           float* orow = out + (long long)o * COUT + cc * 32;
           const float* rrow = residual ? residual + (long long)o * COUT + cc * 32 : nullptr;
@@ -269,7 +320,7 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u)
                  : "memory");
   }
@@ -350,26 +401,32 @@ int spconv_forward_tc(const float* in_feats, int c_in, const float* wt_hi, const
   s.c_in = c_in, s.c_out = c_out, s.n_out = n_out, s.kvol = kvol;
   s.n_tiles = ceil_div(n_out, kTileM);
   s.chunks = c_in / kChunk;
+  {
+    const char* e = getenv("DBEV_TC_DEBUG");
+    s.debug = e ? atoi(e) : 0;
+  }
   int dev = 0, sms = 0;
   DBEV_CUDA(cudaGetDevice(&dev));
   DBEV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = s.n_tiles < sms ? s.n_tiles : sms;
-#define DBEV_TC_LAUNCH(CO, KV, STG)                                                             \
+#define DBEV_TC_LAUNCH(CO, KV, STG, NA, NB)                                                     \
   do {                                                                                          \
-    const size_t smem = (size_t)STG * (2 * CO * kChunk * 4) + 1024;               \
-    DBEV_CUDA(cudaFuncSetAttribute(sp_conv_tc_kernel<CO, KV, STG>,                              \
+    const size_t smem = (size_t)STG * (2 * CO * kChunk * 4) + 1024;                             \
+    DBEV_CUDA(cudaFuncSetAttribute(sp_conv_tc_kernel<CO, KV, STG, NA, NB>,                      \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    sp_conv_tc_kernel<CO, KV, STG><<<grid, kTcThreads, smem, stream>>>(                         \
+    sp_conv_tc_kernel<CO, KV, STG, NA, NB><<<grid, kTcThreads, smem, stream>>>(                 \
         map_hi, map_lo, in_feats, nbr, scale, shift, residual, relu, out, s);                   \
   } while (0)
   if (kvol == 27) {
-    if (c_out == 32) DBEV_TC_LAUNCH(32, 27, 4);
-    else if (c_out == 64) DBEV_TC_LAUNCH(64, 27, 4);
-    else DBEV_TC_LAUNCH(128, 27, 4);
+    // TMEM budget (512 columns): NBUF * NACC * C_out accumulator columns + STAGES * 64 A columns
+    // (splitting the three 3xTF32 terms over separate accumulators, NACC = 3, was measured: no gain)
+    if (c_out == 32) DBEV_TC_LAUNCH(32, 27, 4, 1, 2);
+    else if (c_out == 64) DBEV_TC_LAUNCH(64, 27, 4, 1, 2);
+    else DBEV_TC_LAUNCH(128, 27, 4, 1, 2);
   } else {
-    if (c_out == 32) DBEV_TC_LAUNCH(32, 3, 4);
-    else if (c_out == 64) DBEV_TC_LAUNCH(64, 3, 4);
-    else DBEV_TC_LAUNCH(128, 3, 4);
+    if (c_out == 32) DBEV_TC_LAUNCH(32, 3, 4, 1, 2);
+    else if (c_out == 64) DBEV_TC_LAUNCH(64, 3, 4, 1, 2);
+    else DBEV_TC_LAUNCH(128, 3, 4, 1, 2);
   }
 #undef DBEV_TC_LAUNCH
   DBEV_CHECK_LAUNCH("sp_conv_tc_kernel");
