@@ -239,6 +239,29 @@ __device__ __forceinline__ float4 cta_reduce4(float4 v, float4* sh, int warp, in
   return r;
 }
 
+// Sum over the 32 lanes of EIGHT independent per-lane values with 9 shuffles (instead of 8 x 5):
+// every exchange halves the number of values a lane carries. Returns, in every lane, the total of
+// v[(lane >> 2) & 7]; fixed tree -> deterministic.
+__device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
+  const bool u16 = (lane & 16) != 0, u8 = (lane & 8) != 0, u4 = (lane & 4) != 0;
+  float a[4], b[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = u16 ? v[i] : v[i + 4], keep = u16 ? v[i + 4] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = u8 ? a[i] : a[i + 2], keep = u8 ? a[i + 2] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const float send = u4 ? b[0] : b[1], keep = u4 ? b[1] : b[0];
+  float c = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  return c;
+}
+
 // pass T: teacher statistics. grid (ntiles, B), CTA tile = 128 consecutive cells.
 __global__ void __launch_bounds__(kBlock)
 fgd_teacher_stats_kernel(const float* __restrict__ t, FgdDims d, float* __restrict__ ta,
@@ -251,17 +274,29 @@ fgd_teacher_stats_kernel(const float* __restrict__ t, FgdDims d, float* __restri
   const bool in = hw0 < d.HW;  // HW % 4 == 0 is required by the host wrapper
   const float* base = t + (size_t)b * d.C * d.HW + hw0;
   float4 a_abs = make_float4(0.f, 0.f, 0.f, 0.f), a_sum = a_abs;
-#pragma unroll 4
-  for (int c = warp; c < d.C; c += kWarps) {
-    float4 v = in ? ld4(base + (size_t)c * d.HW) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 av = make_float4(fabsf(v.x), fabsf(v.y), fabsf(v.z), fabsf(v.w));
-    a_abs.x += av.x; a_abs.y += av.y; a_abs.z += av.z; a_abs.w += av.w;
-    a_sum.x += v.x; a_sum.y += v.y; a_sum.z += v.z; a_sum.w += v.w;
-    const float pa = warp_sum(hsum4(av)), ps = warp_sum(hsum4(v));
-    if (lane == 0) {
+  // eight channels per round: 8 loads in flight per lane, one 9-shuffle reduction per quantity
+  for (int c0 = warp; c0 < d.C; c0 += 8 * kWarps) {
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j * kWarps;
+      v[j] = (in && c < d.C) ? ld4(base + (size_t)c * d.HW) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float pa[8], ps[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 av = make_float4(fabsf(v[j].x), fabsf(v[j].y), fabsf(v[j].z), fabsf(v[j].w));
+      a_abs.x += av.x; a_abs.y += av.y; a_abs.z += av.z; a_abs.w += av.w;
+      a_sum.x += v[j].x; a_sum.y += v[j].y; a_sum.z += v[j].z; a_sum.w += v[j].w;
+      pa[j] = hsum4(av);
+      ps[j] = hsum4(v[j]);
+    }
+    const float ra = warp_reduce8(pa, lane), rs = warp_reduce8(ps, lane);
+    const int c = c0 + ((lane >> 2) & 7) * kWarps;
+    if ((lane & 3) == 0 && c < d.C) {
       const size_t o = ((size_t)b * d.C + c) * d.ntiles + tile;
-      cta_p[o] = pa;
-      ctm_p[o] = ps;
+      cta_p[o] = ra;
+      ctm_p[o] = rs;
     }
   }
   a_abs = cta_reduce4(a_abs, sh, warp, lane);
@@ -340,20 +375,35 @@ fgd_student_pass_kernel(const float* __restrict__ s, const float* __restrict__ t
   const size_t boff = (size_t)b * d.C * d.HW + hw0;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 a_abs = z, a_sum = z, a_d1 = z, a_d2 = z;
-#pragma unroll 4
-  for (int c = warp; c < d.C; c += kWarps) {
-    const float4 sv = in ? ld4(s + boff + (size_t)c * d.HW) : z;
-    const float4 tv = in ? ld4(t + boff + (size_t)c * d.HW) : z;
-    const float ca = catt[(size_t)b * d.C + c];
-    a_abs.x += fabsf(sv.x); a_abs.y += fabsf(sv.y); a_abs.z += fabsf(sv.z); a_abs.w += fabsf(sv.w);
-    a_sum.x += sv.x; a_sum.y += sv.y; a_sum.z += sv.z; a_sum.w += sv.w;
-    float4 q;
-    q.x = (sv.x - tv.x) * (sv.x - tv.x); q.y = (sv.y - tv.y) * (sv.y - tv.y);
-    q.z = (sv.z - tv.z) * (sv.z - tv.z); q.w = (sv.w - tv.w) * (sv.w - tv.w);
-    a_d1.x += q.x; a_d1.y += q.y; a_d1.z += q.z; a_d1.w += q.w;
-    a_d2.x += ca * q.x; a_d2.y += ca * q.y; a_d2.z += ca * q.z; a_d2.w += ca * q.w;
-    const float ps = warp_sum(hsum4(sv));
-    if (lane == 0) csm_p[((size_t)b * d.C + c) * d.ntiles + tile] = ps;
+  for (int c0 = warp; c0 < d.C; c0 += 8 * kWarps) {
+    float ps[8];
+#pragma unroll
+    for (int j4 = 0; j4 < 8; j4 += 4) {   // 4 channels (8 loads) in flight per lane
+      float4 sv[4], tv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + (j4 + j) * kWarps;
+        const bool ok = in && c < d.C;
+        sv[j] = ok ? ld4(s + boff + (size_t)c * d.HW) : z;
+        tv[j] = ok ? ld4(t + boff + (size_t)c * d.HW) : z;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c0 + (j4 + j) * kWarps;
+        const float ca = c < d.C ? catt[(size_t)b * d.C + c] : 0.f;
+        a_abs.x += fabsf(sv[j].x); a_abs.y += fabsf(sv[j].y); a_abs.z += fabsf(sv[j].z); a_abs.w += fabsf(sv[j].w);
+        a_sum.x += sv[j].x; a_sum.y += sv[j].y; a_sum.z += sv[j].z; a_sum.w += sv[j].w;
+        float4 q;
+        q.x = (sv[j].x - tv[j].x) * (sv[j].x - tv[j].x); q.y = (sv[j].y - tv[j].y) * (sv[j].y - tv[j].y);
+        q.z = (sv[j].z - tv[j].z) * (sv[j].z - tv[j].z); q.w = (sv[j].w - tv[j].w) * (sv[j].w - tv[j].w);
+        a_d1.x += q.x; a_d1.y += q.y; a_d1.z += q.z; a_d1.w += q.w;
+        a_d2.x += ca * q.x; a_d2.y += ca * q.y; a_d2.z += ca * q.z; a_d2.w += ca * q.w;
+        ps[j4 + j] = hsum4(sv[j]);
+      }
+    }
+    const float rs = warp_reduce8(ps, lane);
+    const int c = c0 + ((lane >> 2) & 7) * kWarps;
+    if ((lane & 3) == 0 && c < d.C) csm_p[((size_t)b * d.C + c) * d.ntiles + tile] = rs;
   }
   a_abs = cta_reduce4(a_abs, sh, warp, lane);
   a_sum = cta_reduce4(a_sum, sh, warp, lane);
