@@ -361,6 +361,117 @@ def sparse_teacher_probe(device, batch=2, n_points=240000):
             "note": "includes the host read-backs of voxel / output counts the reference API implies"}
 
 
+def full_path_probe(hp, steps=10):
+    """Extra evidence, NOT the headline: the same step with the dense conv stacks that sit between
+    the hot-path stages put back as plain torch / cuDNN library modules with random weights —
+    teacher SECOND + SECONDFPN on the pillar canvas (frozen, no_grad; backbones/second.py:80-93,
+    necks/second_fpn.py:77-93) and the student BEV encoder ResNetForBEVDet + FPN_LSS on the
+    lift+splat output (backbones/resnet.py:51-62, necks/lss_fpn.py:62-72). Gradients flow from the
+    distillation loss through the encoder into lift+splat (one autograd chain through our custom
+    Functions and cuDNN). Eager, CUDA events."""
+    import torch
+    import torch.nn as nn
+    dbev, dev = hp.dbev, hp.dev
+
+    def cbr(cin, cout, k=3, s=1, p=1):
+        return nn.Sequential(nn.Conv2d(cin, cout, k, s, p, bias=False), nn.BatchNorm2d(cout, eps=1e-3, momentum=0.01),
+                             nn.ReLU(inplace=True))
+
+    class Second(nn.Module):       # layer_nums (3,5,5), strides (2,2,2), 64 -> 64/128/256
+        def __init__(self):
+            super().__init__()
+            blocks, cin = [], 64
+            for n, cout in zip((3, 5, 5), (64, 128, 256)):
+                layers = [cbr(cin, cout, 3, 2, 1)] + [cbr(cout, cout) for _ in range(n)]
+                blocks.append(nn.Sequential(*layers))
+                cin = cout
+            self.blocks = nn.ModuleList(blocks)
+            # SECONDFPN: upsample_strides (0.5, 1, 2) -> 3 x 128 channels at 128 x 128
+            self.de = nn.ModuleList([
+                nn.Sequential(nn.Conv2d(64, 128, 2, 2, bias=False), nn.BatchNorm2d(128), nn.ReLU(inplace=True)),
+                nn.Sequential(nn.ConvTranspose2d(128, 128, 1, 1, bias=False), nn.BatchNorm2d(128), nn.ReLU(inplace=True)),
+                nn.Sequential(nn.ConvTranspose2d(256, 128, 2, 2, bias=False), nn.BatchNorm2d(128), nn.ReLU(inplace=True))])
+
+        def forward(self, x):
+            outs = []
+            for b in self.blocks:
+                x = b(x)
+                outs.append(x)
+            return torch.cat([d(o) for d, o in zip(self.de, outs)], 1)
+
+    class Basic(nn.Module):
+        def __init__(self, cin, cout, stride=1):
+            super().__init__()
+            self.c1, self.c2 = cbr(cin, cout, 3, stride, 1), nn.Sequential(nn.Conv2d(cout, cout, 3, 1, 1, bias=False),
+                                                                            nn.BatchNorm2d(cout))
+            self.down = nn.Conv2d(cin, cout, 3, stride, 1) if (stride != 1 or cin != cout) else None
+
+        def forward(self, x):
+            idt = x if self.down is None else self.down(x)
+            return torch.relu(self.c2(self.c1(x)) + idt)
+
+    class StudentEncoder(nn.Module):   # ResNetForBEVDet (2,2,2 basic blocks, 128 -> 128/256/512) + FPN_LSS
+        def __init__(self):
+            super().__init__()
+            layers, cin = [], 128
+            for cout in (128, 256, 512):
+                layers.append(nn.Sequential(Basic(cin, cout, 2), Basic(cout, cout)))
+                cin = cout
+            self.layers = nn.ModuleList(layers)
+            self.up = nn.Upsample(scale_factor=4, mode="bilinear", align_corners=True)
+            self.conv = nn.Sequential(cbr(640, 512), cbr(512, 512))
+            self.up2 = nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True), cbr(512, 256),
+                                     nn.Conv2d(256, 256, 1))
+
+        def forward(self, x):
+            feats = []
+            for l in self.layers:
+                x = l(x)
+                feats.append(x)
+            x = torch.cat([feats[0], self.up(feats[2])], 1)
+            return self.up2(self.conv(x))
+
+    torch.manual_seed(0)
+    teacher_net = Second().to(dev).eval().to(memory_format=torch.channels_last)
+    student_net = StudentEncoder().to(dev).train().to(memory_format=torch.channels_last)
+    nf = BATCH * FRAMES
+
+    def step():
+        with torch.no_grad():
+            canvas = dbev.pillar_canvas(hp.d_points, hp.enc, hp.scat)
+            t_feat = teacher_net(canvas).contiguous()
+        geom = hp.vt.get_geometry(*hp.d_calib)
+        plan = hp.vt.make_plan(geom, nf)
+        bev = dbev.lift_splat(hp.depth, hp.feat, plan)                    # [B*2, 64, 128, 128]
+        bev = bev.view(BATCH, FRAMES * C_TRANS, BEV, BEV)                 # frames concatenated (bevdet.py:300-320)
+        s_feat = student_net(bev.contiguous(memory_format=torch.channels_last)).contiguous()
+        losses = dbev.fgd.fgd_distill_loss(t_feat, s_feat, hp.boxes, DISTILL_PARAMS, TRAIN_CFG,
+                                           channel_adaptation=hp.adapt, spatial_adaptation=hp.spatial,
+                                           heatmaps=hp.d_gt_hm, teacher_heatmaps=hp.teacher_logit, epoch=1)
+        total = sum(losses.values())
+        total.backward()
+        for p in (hp.depth, hp.feat):
+            p.grad = None
+        student_net.zero_grad(set_to_none=True)
+        hp.adapt.zero_grad(set_to_none=True)
+        hp.spatial.zero_grad(set_to_none=True)
+        return total
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+    a.record()
+    for _ in range(steps):
+        loss = step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return {"workload": "hot path + cuDNN conv stacks (teacher SECOND+SECONDFPN fwd, student ResNetForBEVDet+FPN_LSS "
+                        "fwd/bwd), one autograd chain, eager, TF32 convs, random weights", "ms_per_step": round(ms, 3),
+            "samples_per_sec": round(BATCH / (ms * 1e-3), 1), "loss_finite": bool(torch.isfinite(loss).item())}
+
+
 def bev_pool_roofline(device):
     """Live roofline of the dominant bev_pool kernel: gather-forward over materialised frustum
     features at the configs[1] shape (16 sample-frames, C=64): kernel timed alone with CUDA events
@@ -492,10 +603,12 @@ def run_ours(args):
     if world == 1:
         line["roofline"] = bev_pool_roofline(device)
         line["cpu_baseline"] = cpu_baseline(samples=3, procs=1)
-        try:
-            line["sparse_teacher"] = sparse_teacher_probe(device)
-        except Exception as exc:  # extra evidence only: never lose the headline line over it
-            line["sparse_teacher"] = {"error": str(exc)[:200]}
+        for key, probe in (("sparse_teacher", lambda: sparse_teacher_probe(device)),
+                           ("with_conv_stacks", lambda: full_path_probe(hp))):
+            try:
+                line[key] = probe()
+            except Exception as exc:  # extra evidence only: never lose the headline line over it
+                line[key] = {"error": str(exc)[:200]}
     else:
         line["roofline"] = bev_pool_roofline(device)
     print(json.dumps(line))

@@ -7,6 +7,7 @@
 #include "adapt_gemm.cuh"
 #include "affinity.cuh"
 #include "bev_pool.cuh"
+#include "conv2d_tc.cuh"
 #include "distill_loss.cuh"
 #include "pillar.cuh"
 #include "sort.cuh"
@@ -321,6 +322,16 @@ int dbev_spconv_forward(const float* in_feats, int c_in, const float* weight, in
                         void* stream) {
   return spconv_forward(in_feats, c_in, weight, c_out, nbr, kvol, n_out, scale, shift, residual,
                         relu, out, (cudaStream_t)stream);
+}
+
+int dbev_conv2d_tc_forward(const float* x_nhwc, int n, int h, int w, int c_in, const float* w_packed,
+                           int c_out, int kh, int kw, int stride, int pad, const float* scale,
+                           const float* shift, int relu, float* out, int out_h, int out_w,
+                           int out_ld, int out_c_off, int out_mul, int out_add_y, int out_add_x,
+                           void* stream) {
+  return conv2d_tc_forward(x_nhwc, n, h, w, c_in, w_packed, c_out, kh, kw, stride, pad, scale, shift,
+                           relu, out, out_h, out_w, out_ld, out_c_off, out_mul, out_add_y, out_add_x,
+                           (cudaStream_t)stream);
 }
 
 int dbev_spconv_tc_supported(int c_in, int c_out, int kvol) {

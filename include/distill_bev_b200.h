@@ -292,6 +292,26 @@ int dbev_adapt_conv1x1_forward(const float* x_cl, const float* w, const float* b
                                int c_in, int c_out, int hw, float* y, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * Dense conv + eval BatchNorm + ReLU of the FROZEN LiDAR teacher's BEV backbone / neck on
+ * tcgen05 tensor cores (TF32 inputs, fp32 accumulate): replaces the cuDNN conv + BatchNorm2d +
+ * ReLU kernel triples of SECOND.forward (mmdet3d/models/backbones/second.py:80-93) and
+ * SECONDFPN.forward (mmdet3d/models/necks/second_fpn.py:77-93) by one implicit-GEMM kernel per
+ * layer. NHWC fp32 activations ([n, h, w, c_in], the memory of a torch.channels_last tensor);
+ * w_packed[c_out][(ky*kw + kx)*c_in + ci]; scale / shift [c_out] = folded BN (nullable); the
+ * filter taps are TMA boxes of the input (padding = TMA zero fill, stride 2 = TMA element
+ * strides): no im2col buffer. c_in % 32 == 0, c_out in {64, 128, 256}, kernel 1..3, stride 1 or
+ * 2, padding 0 or 1. Output pixel (oy, ox) channel c goes to
+ *   out[((n*out_h + oy*out_mul + out_add_y)*out_w + ox*out_mul + out_add_x)*out_ld + out_c_off + c]
+ * so a layer can write a channel slice of the FPN concat (out_c_off, out_ld) and a k2/s2
+ * transposed conv is four 1x1 launches with out_mul = 2 and (out_add_y, out_add_x) = (dy, dx).
+ * ------------------------------------------------------------------------ */
+int dbev_conv2d_tc_forward(const float* x_nhwc, int n, int h, int w, int c_in, const float* w_packed,
+                           int c_out, int kh, int kw, int stride, int pad, const float* scale,
+                           const float* shift, int relu, float* out, int out_h, int out_w,
+                           int out_ld, int out_c_off, int out_mul, int out_add_y, int out_add_x,
+                           void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Cross-modal feature distillation loss (FGD-style), BEVDetDistill
  * (mmdet3d/models/detectors/bevdet_distill.py). The reference has no native
  * interface for this path: it is ~20 torch kernels plus numpy/numba on the

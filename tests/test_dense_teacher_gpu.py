@@ -1,0 +1,75 @@
+"""GPU parity: tcgen05 conv + folded BN + ReLU (csrc/conv2d_tc.cu) and the SECOND / SECONDFPN mirrors vs
+plain PyTorch fp32 (cuDNN with TF32 disabled) of the same modules. The kernel multiplies in TF32 (what the
+reference's cuDNN path does under torch's default cudnn.allow_tf32): tolerance 2e-3 of the output range."""
+import numpy as np
+import pytest
+import torch
+
+import distill_bev_b200 as dbev
+from distill_bev_b200.plugin import dense_teacher as dt
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
+
+def _check(got, want, tol=2e-3):
+    err = (got - want).abs().max().item()
+    assert err <= tol * want.abs().max().item() + 1e-6, (err, want.abs().max().item())
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,hw", [(64, 64, 3, 1, 1, (40, 72)), (64, 64, 3, 2, 1, (64, 64)),
+                                                      (64, 128, 3, 2, 1, (48, 80)), (128, 256, 3, 2, 1, (32, 32)),
+                                                      (256, 256, 3, 1, 1, (16, 24)), (64, 128, 2, 2, 0, (64, 96)),
+                                                      (128, 128, 1, 1, 0, (20, 36)), (32, 64, 3, 1, 1, (7, 9))])
+def test_conv_bn_relu_matches_torch(cuda, cin, cout, k, stride, pad, hw):
+    torch.manual_seed(cin + cout + k)
+    conv = torch.nn.Conv2d(cin, cout, k, stride, pad, bias=False).to(cuda)
+    x = torch.randn(3, cin, *hw, device=cuda)
+    scale = torch.rand(cout, device=cuda) + 0.5
+    shift = torch.randn(cout, device=cuda)
+    with torch.no_grad():
+        want = torch.relu(conv(x) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+        wp = conv.weight.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+        got = dt.conv_nhwc(x.permute(0, 2, 3, 1).contiguous(), wp, cout, k, k, stride, pad, scale, shift, True)
+    _check(got.permute(0, 3, 1, 2), want)
+
+
+def test_second_and_fpn_match_torch(cuda):
+    torch.manual_seed(0)
+    net = dbev.SECOND(in_channels=64, out_channels=[64, 128, 256], layer_nums=[3, 5, 5], layer_strides=[2, 2, 2]).to(cuda)
+    fpn = dbev.SECONDFPN(in_channels=[64, 128, 256], out_channels=[128, 128, 128], upsample_strides=[0.5, 1, 2]).to(cuda)
+    for m in list(net.modules()) + list(fpn.modules()):
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5)
+            m.bias.data.normal_(0, 0.1)
+    assert list(net.state_dict())[:3] == ["blocks.0.0.weight", "blocks.0.1.weight", "blocks.0.1.bias"]
+    assert "deblocks.2.0.weight" in fpn.state_dict()
+    x = torch.relu(torch.randn(2, 64, 128, 128, device=cuda))
+    net.eval(), fpn.eval()
+    with torch.no_grad():
+        got = fpn(net(x))[0]
+        # reference: the same torch modules through cuDNN (fp32)
+        h, outs = x, []
+        for b in net.blocks:
+            h = b(h)
+            outs.append(h)
+        want = torch.cat([d(o) for d, o in zip(fpn.deblocks, outs)], 1)
+    assert tuple(got.shape) == (2, 384, 32, 32) == tuple(want.shape)
+    _check(got, want, tol=5e-3)     # 14 TF32 layers deep
+    # training mode runs the torch modules (batch statistics)
+    net.train()
+    assert net(x)[0].shape == (2, 64, 64, 64)
+
+
+def test_cpu_raises():
+    with pytest.raises(RuntimeError):
+        dt.conv_nhwc(torch.zeros(1, 8, 8, 32), torch.zeros(64, 288), 64, 3, 3, 1, 1)

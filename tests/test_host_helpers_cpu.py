@@ -1,0 +1,65 @@
+"""CPU: host-side helpers of the C-ABI that need no GPU (geometry bounds, capability queries,
+buffer sizing) against the oracle / closed forms."""
+import ctypes
+
+import numpy as np
+
+from distill_bev_b200 import _lib
+from oracle import spconv_oracle as so
+
+
+def _geom(k, s, p, in_shape, batch):
+    out = so.conv_output_size(in_shape, k, s, p, [1, 1, 1])
+    return _lib.host_ints(list(k) + list(s) + list(p) + [1, 1, 1] + list(in_shape) + out + [batch]), out
+
+
+def test_spconv_max_out_bounds_the_oracle():
+    lib = _lib.load()
+    rs = np.random.RandomState(0)
+    for k, s, p in (([3, 3, 3], [2, 2, 2], [1, 1, 1]), ([3, 1, 1], [2, 1, 1], [0, 0, 0]),
+                    ([3, 3, 3], [1, 1, 1], [1, 1, 1]), ([3, 3, 3], [2, 2, 2], [0, 1, 1])):
+        shape = [9, 12, 12]
+        c = np.unique(np.stack([rs.randint(0, 9, 120), rs.randint(0, 12, 120), rs.randint(0, 12, 120)], 1), axis=0)
+        coors = np.concatenate([np.zeros((len(c), 1), np.int64), c], 1)
+        g, out_shape = _geom(k, s, p, shape, 1)
+        out, _, _ = so.get_indice_pairs(coors, 1, shape, k, s, p, [1, 1, 1], False)
+        bound = lib.dbev_spconv_max_out(len(coors), g)
+        assert len(out) <= bound <= max(len(coors) * 27, int(np.prod(out_shape)))
+        assert lib.dbev_spconv_workspace_bytes(len(coors), bound) > 0
+
+
+def test_tc_supported_matrix():
+    lib = _lib.load()
+    for cin in (5, 16, 32, 64, 128, 256):
+        for cout in (16, 32, 64, 128, 256):
+            want = cin in (32, 64, 128) and cout in (32, 64, 128)
+            assert bool(lib.dbev_spconv_tc_supported(cin, cout, 27)) == want
+            assert bool(lib.dbev_spconv_tc_supported(cin, cout, 3)) == want
+            assert not lib.dbev_spconv_tc_supported(cin, cout, 9)
+
+
+def test_affinity_partial_floats():
+    lib = _lib.load()
+    offs = _lib.host_ints([0, 100, 100, 1000])           # K = 100, 0, 900 -> 15 tiles of 64
+    assert lib.dbev_affinity_partial_floats(offs, 3) == 3 * 15 * 15 + 1
+    assert lib.dbev_affinity_select_workspace_bytes(8, 128 * 128) >= 2 * 8 * 128 * 128 * 4
+
+
+def test_conv_output_size_matches_reference_formula():
+    from distill_bev_b200.plugin.ops import spconv as sp
+    assert sp.get_conv_output_size([41, 1600, 1600], [3, 3, 3], [2, 2, 2], [1, 1, 1], [1, 1, 1]) == [21, 800, 800]
+    assert sp.get_conv_output_size([11, 400, 400], [3, 3, 3], [2, 2, 2], [0, 1, 1], [1, 1, 1]) == [5, 200, 200]
+    assert sp.get_conv_output_size([5, 200, 200], [3, 1, 1], [2, 1, 1], [0, 0, 0], [1, 1, 1]) == [2, 200, 200]
+
+
+def test_cpu_tensors_are_rejected():
+    import pytest
+    import torch
+    from distill_bev_b200.plugin.ops import spconv as sp
+    import distill_bev_b200 as dbev
+    with pytest.raises(RuntimeError):
+        sp.dense_from_sparse(torch.zeros(4, 8), torch.zeros((4, 4), dtype=torch.int32), [2, 2, 2], 1)
+    with pytest.raises(RuntimeError):
+        dbev.HardSimpleVFE(4)(torch.zeros(3, 5, 4), torch.ones(3, dtype=torch.int32))
+    with pytest.raises(RuntimeError):
+        dbev.affinity.affinity_distill_loss(torch.zeros(1, 8, 4, 4), torch.zeros(1, 8, 4, 4), torch.ones(1, 1, 4, 4))
