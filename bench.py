@@ -46,10 +46,11 @@ FRAMES = 2           # BEVDepth4D: current + adjacent frame
 N_CAMS, D, FH, FW, C_TRANS, BEV = 6, 59, 16, 44, 64, 128
 N_POINTS = 30000
 C_STUDENT, C_TEACHER = 256, 384
-WORKLOAD = ("hotpath-ops-v1: lift+splat fwd/bwd (B=8 x 2 frames, 6 cams, D=59, 16x44, C=64 -> 128x128) "
-            "+ teacher voxelize/pillar-encode/scatter (8 x 30k pts -> 512x512x64) "
-            "+ 1x1 adaptation conv (tcgen05 fwd, cuDNN bwd) + fgd distill loss fwd/bwd at head (256->384 ch, 128x128, fg+fp masks); "
-            "dense conv stacks (cuDNN) not in step")
+WORKLOAD = ("hotpath-ops-v2: lift+splat fwd/bwd (B=8 x 2 frames, 6 cams, D=59, 16x44, C=64 -> 128x128) "
+            "+ frozen LiDAR teacher end to end: voxelize/pillar-encode/scatter (8 x 30k pts -> 512x512x64) -> "
+            "SECOND + SECONDFPN (tcgen05 conv+BN+ReLU, 601 GFLOP) -> teacher BEV feature [8,384,128,128] "
+            "+ 1x1 adaptation conv (tcgen05 fwd, cuDNN bwd) + fgd distill loss fwd/bwd at head against that "
+            "teacher feature (256->384 ch, 128x128, fg+fp masks); student image/BEV conv stacks (cuDNN) not in step")
 PILLAR_VS, PILLAR_RANGE = [0.2, 0.2, 8.0], [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
 DISTILL_PARAMS = dict(
     spatial_t=0.5, spatial_student_ratio=1.0, channel_t=0.5, fg_feat_loss_weights=[6e-3],
@@ -172,6 +173,11 @@ class HotPath(object):
         self.enc = dbev.DynamicPillarFeatureNet(in_channels=5, feat_channels=(64,), voxel_size=PILLAR_VS,
                                                 point_cloud_range=PILLAR_RANGE).to(device).eval()
         self.scat = dbev.PointPillarsScatter(64, [512, 512], channels_last=True)
+        # teacher BEV backbone + neck (centerpoint_02pillar_second_secfpn: SECOND 64 -> 64/128/256, FPN 3 x 128)
+        self.second = dbev.SECOND(in_channels=64, out_channels=[64, 128, 256], layer_nums=[3, 5, 5],
+                                  layer_strides=[2, 2, 2]).to(device).eval()
+        self.secfpn = dbev.SECONDFPN(in_channels=[64, 128, 256], out_channels=[128, 128, 128],
+                                     upsample_strides=[0.5, 1, 2]).to(device).eval()
         from distill_bev_b200.plugin.distill.adaptation import Conv1x1Adaptation
         self.adapt = Conv1x1Adaptation(C_STUDENT, C_TEACHER).to(device)            # '1x1conv' adaptation, tcgen05 fwd
         self.spatial = torch.nn.Conv2d(1, 1, 3, padding=1).to(device)            # spatial_wise_adaptations
@@ -198,13 +204,16 @@ class HotPath(object):
         main = torch.cuda.current_stream(self.dev)
         for st in self.side:
             st.wait_stream(main)
-        # B: frozen teacher pillar path
+        # B: frozen teacher, points -> BEV feature (pillar path, then SECOND + SECONDFPN on tcgen05)
         with torch.cuda.stream(self.side[0]), torch.no_grad():
             canvas = dbev.pillar_canvas(points, self.enc, self.scat)
-        # C: head-position distillation loss (1x1 channel adaptation inside, as in the reference)
+            teacher = self.secfpn(self.second(canvas))[0].contiguous()      # NCHW for the loss kernels
+        # C: head-position distillation loss against that teacher feature (1x1 channel adaptation
+        # inside, as in the reference); depends on B
+        self.side[1].wait_stream(self.side[0])
         with torch.cuda.stream(self.side[1]):
             losses = dbev.fgd.fgd_distill_loss(
-                self.teacher, self.student, boxes, DISTILL_PARAMS, TRAIN_CFG, channel_adaptation=self.adapt,
+                teacher, self.student, boxes, DISTILL_PARAMS, TRAIN_CFG, channel_adaptation=self.adapt,
                 spatial_adaptation=self.spatial, heatmaps=gt_hm, teacher_heatmaps=self.teacher_logit, epoch=1)
             total = losses["kd_fg_feat_loss"] + losses["kd_bg_feat_loss"] + losses["kd_spatial_loss"] \
                 + losses["kd_fp_bg_feat_loss"]
@@ -219,7 +228,7 @@ class HotPath(object):
             main.wait_stream(st)
         grads = [self.depth.grad, self.feat.grad, self.student.grad, self.adapt.weight.grad,
                  self.adapt.bias.grad, self.spatial.weight.grad]
-        for t in [canvas, loss_vec] + grads:
+        for t in [canvas, teacher, loss_vec] + grads:
             t.record_stream(main)
         for p in (self.depth, self.feat, self.student):
             p.grad = None
@@ -362,11 +371,10 @@ def sparse_teacher_probe(device, batch=2, n_points=240000):
 
 
 def full_path_probe(hp, steps=10):
-    """Extra evidence, NOT the headline: the same step with the dense conv stacks that sit between
-    the hot-path stages put back as plain torch / cuDNN library modules with random weights —
-    teacher SECOND + SECONDFPN on the pillar canvas (frozen, no_grad; backbones/second.py:80-93,
-    necks/second_fpn.py:77-93) and the student BEV encoder ResNetForBEVDet + FPN_LSS on the
-    lift+splat output (backbones/resnet.py:51-62, necks/lss_fpn.py:62-72). Gradients flow from the
+    """Extra evidence, NOT the headline: the same step with the student BEV encoder that sits between
+    lift+splat and the loss put back as a plain torch / cuDNN library module with random weights
+    (ResNetForBEVDet + FPN_LSS, backbones/resnet.py:51-62, necks/lss_fpn.py:62-72); the teacher side
+    is the headline's own tcgen05 SECOND + SECONDFPN. Gradients flow from the
     distillation loss through the encoder into lift+splat (one autograd chain through our custom
     Functions and cuDNN). Eager, CUDA events."""
     import torch
@@ -432,14 +440,13 @@ def full_path_probe(hp, steps=10):
             return self.up2(self.conv(x))
 
     torch.manual_seed(0)
-    teacher_net = Second().to(dev).eval().to(memory_format=torch.channels_last)
     student_net = StudentEncoder().to(dev).train().to(memory_format=torch.channels_last)
     nf = BATCH * FRAMES
 
     def step():
         with torch.no_grad():
             canvas = dbev.pillar_canvas(hp.d_points, hp.enc, hp.scat)
-            t_feat = teacher_net(canvas).contiguous()
+            t_feat = hp.secfpn(hp.second(canvas))[0].contiguous()       # ours (tcgen05), as in the headline step
         geom = hp.vt.get_geometry(*hp.d_calib)
         plan = hp.vt.make_plan(geom, nf)
         bev = dbev.lift_splat(hp.depth, hp.feat, plan)                    # [B*2, 64, 128, 128]
@@ -467,8 +474,8 @@ def full_path_probe(hp, steps=10):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / steps
-    return {"workload": "hot path + cuDNN conv stacks (teacher SECOND+SECONDFPN fwd, student ResNetForBEVDet+FPN_LSS "
-                        "fwd/bwd), one autograd chain, eager, TF32 convs, random weights", "ms_per_step": round(ms, 3),
+    return {"workload": "headline step + the student BEV encoder (ResNetForBEVDet + FPN_LSS fwd/bwd) through cuDNN, "
+                        "one autograd chain loss -> encoder -> lift+splat, eager, TF32 convs, random weights", "ms_per_step": round(ms, 3),
             "samples_per_sec": round(BATCH / (ms * 1e-3), 1), "loss_finite": bool(torch.isfinite(loss).item())}
 
 
@@ -590,7 +597,7 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "frames": FRAMES, "parallelism": "dp%d" % world,
-                   "l2": "inputs larger than L2 (student+teacher maps 335 MB, canvas 537 MB per step)",
+                   "l2": "inputs larger than L2 (student+teacher maps 335 MB, canvas 537 MB, teacher conv activations > 2 GB per step)",
                    "collective": "none in the hot path (per-sample ops; DDP all-reduce lives in the trainer)",
                    "cuda_graph": hp.captured is not None, "issue": graph_note},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(hp.h2d_bytes),
@@ -642,7 +649,8 @@ def _cpu_one_sample(seed):
     w = rng.randn(64, 10).astype(np.float32) * 0.1
     vf, vc = pillar_oracle.pillar_encode(pts, coors, w, np.ones(64), np.zeros(64), np.zeros(64), np.ones(64),
                                          1e-3, PILLAR_VS, PILLAR_RANGE)
-    pillar_oracle.pillar_scatter(vf, vc, 1, 512, 512)
+    canvas = pillar_oracle.pillar_scatter(vf, vc, 1, 512, 512)
+    _cpu_teacher_convs(canvas)
     # C: one sample at the head position
     teacher = np.maximum(rng.randn(1, C_TEACHER, BEV, BEV), 0).astype(np.float32)
     student = np.maximum(rng.randn(1, C_STUDENT, BEV, BEV), 0).astype(np.float32)
@@ -662,6 +670,40 @@ def _cpu_one_sample(seed):
                               fp=fp, fp_scale=fps, fp_count=cnt, want_grad=True)
     np.einsum("oc,bohw->bchw", wa, res["grad_student"].astype(np.float32), optimize=True)
     return time.perf_counter() - t0
+
+
+_CPU_TEACHER = None
+
+
+def _cpu_teacher_convs(canvas):
+    """SECOND + SECONDFPN forward of one sample on the host: the reference's own implementation of
+    these rows is torch.nn (Conv2d / BatchNorm2d / ReLU / ConvTranspose2d built by mmcv's
+    build_conv_layer), so the CPU arm runs exactly that, one thread per worker process."""
+    global _CPU_TEACHER
+    import torch
+    torch.set_num_threads(1)
+    if _CPU_TEACHER is None:
+        nn = torch.nn
+        torch.manual_seed(0)
+        blocks, cin = [], 64
+        for n, c in zip((3, 5, 5), (64, 128, 256)):
+            layers = [nn.Conv2d(cin, c, 3, 2, 1, bias=False), nn.BatchNorm2d(c, eps=1e-3), nn.ReLU(inplace=True)]
+            for _ in range(n):
+                layers += [nn.Conv2d(c, c, 3, 1, 1, bias=False), nn.BatchNorm2d(c, eps=1e-3), nn.ReLU(inplace=True)]
+            blocks.append(nn.Sequential(*layers))
+            cin = c
+        de = [nn.Sequential(nn.Conv2d(64, 128, 2, 2, bias=False), nn.BatchNorm2d(128, eps=1e-3), nn.ReLU(inplace=True)),
+              nn.Sequential(nn.ConvTranspose2d(128, 128, 1, 1, bias=False), nn.BatchNorm2d(128, eps=1e-3), nn.ReLU(inplace=True)),
+              nn.Sequential(nn.ConvTranspose2d(256, 128, 2, 2, bias=False), nn.BatchNorm2d(128, eps=1e-3), nn.ReLU(inplace=True))]
+        _CPU_TEACHER = (nn.ModuleList(blocks).eval(), nn.ModuleList(de).eval())
+    blocks, de = _CPU_TEACHER
+    with torch.no_grad():
+        x = torch.from_numpy(np.ascontiguousarray(canvas, dtype=np.float32)).reshape(1, 64, 512, 512)
+        outs = []
+        for b in blocks:
+            x = b(x)
+            outs.append(x)
+        return torch.cat([d(o) for d, o in zip(de, outs)], 1)
 
 
 def _load_synthetic():
@@ -685,8 +727,9 @@ def cpu_baseline(samples, procs, pool=None):
         pool.map(_cpu_one_sample, [7 + i for i in range(samples)])
     dt = time.perf_counter() - t0
     return {"value": round(samples / dt, 4), "unit": UNIT, "cores": procs, "kind": "port",
-            "sample": "%d sample(s): the same three stages (2 frames lift+splat fwd/bwd, one 30k-point cloud, "
-                      "one head-position loss fwd/bwd incl. the 1x1 adaptation) on oracle/ (numpy + C); "
+            "sample": "%d sample(s): the same stages (2 frames lift+splat fwd/bwd, one 30k-point cloud through "
+                      "pillar encoder + SECOND/SECONDFPN [torch CPU conv, 1 thread per process], one head-position "
+                      "loss fwd/bwd incl. the 1x1 adaptation) on oracle/ (numpy + C) + torch.nn; "
                       "host has %d cores" % (samples, os.cpu_count() or 1)}
 
 

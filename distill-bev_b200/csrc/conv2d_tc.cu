@@ -33,6 +33,7 @@ struct ConvShape {
   int tx, ty, tiles_x, tiles_y, n_tiles, cin_chunks;
   // output placement: pixel (oy*omul + oadd_y, ox*omul + oadd_x) of an [n, H_full, W_full, ld] tensor
   int omul, oadd_y, oadd_x, h_full, w_full, ld, c_off, relu;
+  int nchw;  // 1: out is [n, ld, H_full, W_full] (a lane = a pixel: stores of one channel coalesce along x)
 };
 
 template <int COUT, int STAGES>
@@ -141,8 +142,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const int n = tile / per_img, r = tile % per_img;
       const int oy = (r / s.tiles_x) * s.ty + py, ox = (r % s.tiles_x) * s.tx + px;
       const bool valid = oy < s.ho && ox < s.wo;
-      float* orow = out + (((long long)n * s.h_full + (oy * s.omul + s.oadd_y)) * s.w_full +
-                           (ox * s.omul + s.oadd_x)) * s.ld + s.c_off;
+      const int fy = oy * s.omul + s.oadd_y, fx = ox * s.omul + s.oadd_x;
+      float* orow = out + (((long long)n * s.h_full + fy) * s.w_full + fx) * s.ld + s.c_off;
+      const long long plane = (long long)s.h_full * s.w_full;
+      float* ocol = out + ((long long)n * s.ld + s.c_off) * plane + (long long)fy * s.w_full + fx;
       mbar_wait(&tmem_full_bar[buf], use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -164,7 +167,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               o.x += sh.x, o.y += sh.y, o.z += sh.z, o.w += sh.w;
             }
             if (s.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-            *reinterpret_cast<float4*>(orow + cc * 32 + j) = o;
+            if (s.nchw) {
+              float* oc = ocol + (long long)(cc * 32 + j) * plane;
+              oc[0] = o.x, oc[plane] = o.y, oc[2 * plane] = o.z, oc[3 * plane] = o.w;
+            } else {
+              *reinterpret_cast<float4*>(orow + cc * 32 + j) = o;
+            }
           }
         }
       }
@@ -187,7 +195,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, const float* w_packed,
                       int c_out, int kh, int kw, int stride, int pad, const float* scale,
                       const float* shift, int relu, float* out, int out_h, int out_w, int out_ld,
-                      int out_c_off, int out_mul, int out_add_y, int out_add_x, cudaStream_t stream) {
+                      int out_c_off, int out_mul, int out_add_y, int out_add_x, int out_nchw,
+                      cudaStream_t stream) {
   DBEV_CHECK_ARG(n_img > 0 && h > 0 && w > 0, "conv2d_tc: empty input");
   DBEV_CHECK_ARG(c_in % kKc == 0 && c_in >= kKc, "conv2d_tc: C_in must be a multiple of 32 (got %d)", c_in);
   DBEV_CHECK_ARG(c_out == 64 || c_out == 128 || c_out == 256,
@@ -215,7 +224,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   s.n_tiles = s.tiles_x * s.tiles_y * n_img;
   s.cin_chunks = c_in / kKc;
   s.omul = out_mul, s.oadd_y = out_add_y, s.oadd_x = out_add_x, s.h_full = out_h, s.w_full = out_w;
-  s.ld = out_ld, s.c_off = out_c_off, s.relu = relu;
+  s.ld = out_ld, s.c_off = out_c_off, s.relu = relu, s.nchw = out_nchw ? 1 : 0;
   DBEV_CHECK_ARG(s.tx * stride <= 256 && s.ty * stride <= 256, "conv2d_tc: tile too large for a TMA box");
 
   EncodeTiledFn encode = get_encode_fn();

@@ -41,8 +41,9 @@ def _packed(mod, fn):
 
 
 def conv_nhwc(x, w_packed, c_out, kh, kw, stride, pad, scale=None, shift=None, relu=False, out=None,
-              c_off=0, out_mul=1, out_add=(0, 0)):
-    """x [N, H, W, C_in] contiguous fp32 -> out [N, Ho*out_mul, Wo*out_mul, ld] (channel slice c_off)."""
+              c_off=0, out_mul=1, out_add=(0, 0), out_nchw=False):
+    """x [N, H, W, C_in] contiguous fp32 -> out [N, Ho*out_mul, Wo*out_mul, ld] (channel slice c_off),
+    or, with out_nchw, out [N, ld, Ho*out_mul, Wo*out_mul]."""
     lib = _lib.load()
     _lib.require_cuda(x, "x", torch.float32)
     if not x.is_contiguous():
@@ -53,10 +54,12 @@ def conv_nhwc(x, w_packed, c_out, kh, kw, stride, pad, scale=None, shift=None, r
     if out is None:
         out = torch.empty((n, ho * out_mul, wo * out_mul, c_out), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
+        oh, ow, ld = (out.shape[2], out.shape[3], out.shape[1]) if out_nchw else \
+            (out.shape[1], out.shape[2], out.shape[3])
         rc = lib.dbev_conv2d_tc_forward(_lib.ptr(x), n, h, w, c_in, _lib.ptr(w_packed), c_out, kh, kw, stride,
                                         pad, _lib.ptr(scale), _lib.ptr(shift), 1 if relu else 0, _lib.ptr(out),
-                                        out.shape[1], out.shape[2], out.shape[3], c_off, out_mul,
-                                        out_add[0], out_add[1], _lib.stream_ptr(x.device))
+                                        oh, ow, ld, c_off, out_mul, out_add[0], out_add[1],
+                                        1 if out_nchw else 0, _lib.stream_ptr(x.device))
     _lib.check(rc, "dbev_conv2d_tc_forward")
     return out
 
@@ -156,17 +159,17 @@ class SECONDFPN(nn.Module):
             else:
                 k = up.kernel_size[0]
                 ho, wo, mul = hh, ww, k
-            if out is None:
-                out = torch.empty((n, ho * mul, wo * mul, ld), dtype=torch.float32, device=h.device)
+            if out is None:   # NCHW-contiguous concat buffer: what the distillation-loss kernels read
+                out = torch.empty((n, ld, ho * mul, wo * mul), dtype=torch.float32, device=h.device)
             if isinstance(up, nn.Conv2d):
                 wp = _packed(up, lambda w: w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous())
-                conv_nhwc(h, wp, co, k, k, k, 0, scale, shift, True, out=out, c_off=c_off)
+                conv_nhwc(h, wp, co, k, k, k, 0, scale, shift, True, out=out, c_off=c_off, out_nchw=True)
             else:
                 # ConvTranspose2d(k, stride k): out[2y+dy, 2x+dx] = W[:, :, dy, dx]^T . in[y, x] -> k*k 1x1 convs
                 wps = _packed(up, lambda w: [w[:, :, dy, dx].t().contiguous() for dy in range(k) for dx in range(k)])
                 for dy in range(k):
                     for dx in range(k):
                         conv_nhwc(h, wps[dy * k + dx], co, 1, 1, 1, 0, scale, shift, True, out=out, c_off=c_off,
-                                  out_mul=k, out_add=(dy, dx))
+                                  out_mul=k, out_add=(dy, dx), out_nchw=True)
             c_off += co
-        return [out.permute(0, 3, 1, 2)]
+        return [out]

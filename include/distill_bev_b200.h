@@ -304,12 +304,14 @@ int dbev_adapt_conv1x1_forward(const float* x_cl, const float* w, const float* b
  *   out[((n*out_h + oy*out_mul + out_add_y)*out_w + ox*out_mul + out_add_x)*out_ld + out_c_off + c]
  * so a layer can write a channel slice of the FPN concat (out_c_off, out_ld) and a k2/s2
  * transposed conv is four 1x1 launches with out_mul = 2 and (out_add_y, out_add_x) = (dy, dx).
+ * out_nchw != 0 stores the same element at out[((n*out_ld + out_c_off + c)*out_h + y)*out_w + x]
+ * instead (NCHW; what the distillation-loss kernels read), saving a layout-conversion pass.
  * ------------------------------------------------------------------------ */
 int dbev_conv2d_tc_forward(const float* x_nhwc, int n, int h, int w, int c_in, const float* w_packed,
                            int c_out, int kh, int kw, int stride, int pad, const float* scale,
                            const float* shift, int relu, float* out, int out_h, int out_w,
                            int out_ld, int out_c_off, int out_mul, int out_add_y, int out_add_x,
-                           void* stream);
+                           int out_nchw, void* stream);
 
 /* ------------------------------------------------------------------------ *
  * Cross-modal feature distillation loss (FGD-style), BEVDetDistill
