@@ -208,12 +208,15 @@ class HotPath(object):
         with torch.cuda.stream(self.side[0]), torch.no_grad():
             canvas = dbev.pillar_canvas(points, self.enc, self.scat)
             teacher = self.secfpn(self.second(canvas))[0].contiguous()      # NCHW for the loss kernels
+            teacher_ready = torch.cuda.Event()
+            teacher_ready.record(self.side[0])
         # C: head-position distillation loss against that teacher feature (1x1 channel adaptation
-        # inside, as in the reference); depends on B
-        self.side[1].wait_stream(self.side[0])
+        # inside, as in the reference). Masks and the adaptation conv do not read the teacher and
+        # overlap B; the loss waits for B's event right before its first teacher read.
         with torch.cuda.stream(self.side[1]):
             losses = dbev.fgd.fgd_distill_loss(
                 teacher, self.student, boxes, DISTILL_PARAMS, TRAIN_CFG, channel_adaptation=self.adapt,
+                teacher_ready=teacher_ready,
                 spatial_adaptation=self.spatial, heatmaps=gt_hm, teacher_heatmaps=self.teacher_logit, epoch=1)
             total = losses["kd_fg_feat_loss"] + losses["kd_bg_feat_loss"] + losses["kd_spatial_loss"] \
                 + losses["kd_fp_bg_feat_loss"]

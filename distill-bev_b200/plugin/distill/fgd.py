@@ -218,7 +218,10 @@ def _loss_backward(cfg, state, student, teacher, cw, cb, grad_losses, conv_shape
 class _FGDLoss(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, student, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count):
+    def forward(ctx, student, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count,
+                teacher_ready=None):
+        if teacher_ready is not None:
+            torch.cuda.current_stream(student.device).wait_event(teacher_ready)
         losses, state, student, teacher, cw, cb, shp = _loss_forward(
             student, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count)
         ctx.cfg, ctx.state, ctx.conv_shape = cfg, state, shp
@@ -230,7 +233,7 @@ class _FGDLoss(torch.autograd.Function):
         student, teacher, cw, cb = ctx.saved_tensors
         gs, gw, gb, _ = _loss_backward(ctx.cfg, ctx.state, student, teacher, cw, cb, grad_losses,
                                        ctx.conv_shape)
-        return (gs, None, gw, gb, None, None, None, None, None, None)
+        return (gs, None, gw, gb, None, None, None, None, None, None, None)
 
 
 class _AdaptFGDLoss(torch.autograd.Function):
@@ -239,9 +242,12 @@ class _AdaptFGDLoss(torch.autograd.Function):
     backward kernel (per-channel sums of d loss / d adapted student)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count):
+    def forward(ctx, x, weight, bias, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count,
+                teacher_ready=None):
         from .adaptation import conv1x1_forward
         adapted, x = conv1x1_forward(x, weight, bias)
+        if teacher_ready is not None:   # the adaptation conv above does not read the teacher
+            torch.cuda.current_stream(x.device).wait_event(teacher_ready)
         losses, state, adapted, teacher, cw, cb, shp = _loss_forward(
             adapted, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count)
         ctx.cfg, ctx.state, ctx.conv_shape, ctx.has_bias = cfg, state, shp, bias is not None
@@ -256,24 +262,24 @@ class _AdaptFGDLoss(torch.autograd.Function):
                                           ctx.conv_shape, channel_sum=want_bias)
         gx = torch.nn.grad.conv2d_input(x.shape, weight, gs) if ctx.needs_input_grad[0] else None
         gwt = torch.nn.grad.conv2d_weight(x, weight.shape, gs) if ctx.needs_input_grad[1] else None
-        return (gx, gwt, gsum, None, gw, gb, None, None, None, None, None, None)
+        return (gx, gwt, gsum, None, gw, gb, None, None, None, None, None, None, None)
 
 
 def fgd_loss_terms(student_feat, teacher_feat, cfg, fg, fg_scale, fg_count, fp=None, fp_count=None,
-                   conv_weight=None, conv_bias=None, adapt_weight=None, adapt_bias=None):
+                   conv_weight=None, conv_bias=None, adapt_weight=None, adapt_bias=None, teacher_ready=None):
     """losses[5] tensor (order LOSS_KEYS), differentiable w.r.t. student_feat / conv. With
     ``adapt_weight`` [Ct, Cs, 1, 1] (+ ``adapt_bias``) the 1x1 adaptation conv is applied to
     ``student_feat`` [B, Cs, H, W] inside the same autograd node."""
     if adapt_weight is not None:
         return _AdaptFGDLoss.apply(student_feat, adapt_weight, adapt_bias, teacher_feat, conv_weight,
-                                   conv_bias, cfg, fg, fg_scale, fg_count, fp, fp_count)
+                                   conv_bias, cfg, fg, fg_scale, fg_count, fp, fp_count, teacher_ready)
     return _FGDLoss.apply(student_feat, teacher_feat, conv_weight, conv_bias, cfg, fg, fg_scale,
-                          fg_count, fp, fp_count)
+                          fg_count, fp, fp_count, teacher_ready)
 
 
 def fgd_distill_loss(teacher_feat, student_feat, gt_bboxes_3d, distill_params, train_cfg,
                      spatial_adaptation=None, heatmaps=None, teacher_heatmaps=None,
-                     student_heatmaps=None, index=0, epoch=0, channel_adaptation=None):
+                     student_heatmaps=None, index=0, epoch=0, channel_adaptation=None, teacher_ready=None):
     """Drop-in for the body of ``BEVDetDistill.fgd_distill_loss`` after the adaptation layers
     (:1006-1293): returns the same loss dict. ``train_cfg`` = pts_bbox_head.train_cfg
     (grid_size, point_cloud_range, voxel_size); ``spatial_adaptation`` = the
@@ -282,7 +288,11 @@ def fgd_distill_loss(teacher_feat, student_feat, gt_bboxes_3d, distill_params, t
     tensors or per-task lists, needed only when fp_as_foreground is active.
     ``channel_adaptation`` = ``channel_wise_adaptations[index]`` (:1004), applied to ``student_feat``
     here as the reference does; a 1x1 conv is fused with the loss (tcgen05 forward, bias gradient
-    from the loss backward), any other module is simply called."""
+    from the loss backward), any other module is simply called.
+    ``teacher_ready`` (optional torch.cuda.Event): recorded by the stream that produces
+    ``teacher_feat``; the current stream waits for it only right before the first kernel that reads
+    the teacher, so the masks and the student's adaptation conv overlap the frozen teacher's forward
+    (the reference runs teacher and student serially on one stream)."""
     adapt_w = adapt_b = None
     if channel_adaptation is not None:
         conv = channel_adaptation
@@ -313,7 +323,7 @@ def fgd_distill_loss(teacher_feat, student_feat, gt_bboxes_3d, distill_params, t
     cw = spatial_adaptation.weight if spatial_adaptation is not None else None
     cb = spatial_adaptation.bias if spatial_adaptation is not None else None
     losses = fgd_loss_terms(student_feat, teacher_feat, cfg, fg, fg_scale, fg_count, fp, fp_count, cw, cb,
-                            adapt_w, adapt_b)
+                            adapt_w, adapt_b, teacher_ready=teacher_ready)
     out = {"kd_fg_feat_loss": losses[0], "kd_bg_feat_loss": losses[1]}
     if cfg.channel_mask:
         out["kd_channel_loss"] = losses[3]
