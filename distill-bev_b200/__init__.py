@@ -19,6 +19,7 @@ from .plugin.distill.adaptation import Conv1x1Adaptation, conv1x1  # noqa: F401
 from .plugin.ops import spconv  # noqa: F401
 from .plugin.sparse_teacher import DynamicVoxelEncoder, HardSimpleVFE, SparseEncoder  # noqa: F401
 from .plugin.dense_teacher import SECOND, SECONDFPN  # noqa: F401
+from .plugin.bevdepth import get_depth_loss, shift_feature  # noqa: F401
 from .graph import CapturedStep  # noqa: F401
 
 __version__ = "0.1.0"

@@ -7,6 +7,7 @@
 #include "adapt_gemm.cuh"
 #include "affinity.cuh"
 #include "bev_pool.cuh"
+#include "bevdepth_aux.cuh"
 #include "conv2d_tc.cuh"
 #include "distill_loss.cuh"
 #include "pillar.cuh"
@@ -322,6 +323,32 @@ int dbev_spconv_forward(const float* in_feats, int c_in, const float* weight, in
                         void* stream) {
   return spconv_forward(in_feats, c_in, weight, c_out, nbr, kvol, n_out, scale, shift, residual,
                         relu, out, (cudaStream_t)stream);
+}
+
+int dbev_shift_feature_forward(const float* in, const float* tf, int n, int C, int h, int w, float* out,
+                               void* stream) {
+  return shift_feature_forward(in, tf, n, C, h, w, out, (cudaStream_t)stream);
+}
+
+int dbev_shift_feature_backward(const float* grad_out, const float* tf, int n, int C, int h, int w,
+                                float* grad_in, void* stream) {
+  return shift_feature_backward(grad_out, tf, n, C, h, w, grad_in, (cudaStream_t)stream);
+}
+
+size_t dbev_depth_loss_workspace_bytes(void) { return depth_loss_ws_bytes(); }
+
+int dbev_depth_loss_forward(const float* logits, const float* depth_gt, int BN, int D, int HW, float dmin,
+                            float dstep, float loss_weight, float* loss, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  return depth_loss_forward(logits, depth_gt, BN, D, HW, dmin, dstep, loss_weight, loss, workspace,
+                            workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_depth_loss_backward(const float* logits, const float* depth_gt, int BN, int D, int HW, float dmin,
+                             float dstep, float loss_weight, const float* grad_loss, float* grad_logits,
+                             void* stream) {
+  return depth_loss_backward(logits, depth_gt, BN, D, HW, dmin, dstep, loss_weight, grad_loss, grad_logits,
+                             (cudaStream_t)stream);
 }
 
 int dbev_conv2d_tc_forward(const float* x_nhwc, int n, int h, int w, int c_in, const float* w_packed,

@@ -292,6 +292,33 @@ int dbev_adapt_conv1x1_forward(const float* x_cl, const float* w, const float* b
                                int c_in, int c_out, int hw, float* y, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * BEVDepth4D steps around the view transform.
+ * ------------------------------------------------------------------------ */
+
+/* shift_feature (mmdet3d/models/detectors/bevdet.py:267-321): out[n,c,y,x] = bilinear sample
+ * (zeros padding, align_corners=True) of in[n,c] at tf[n] . (x, y, 1), tf[n] a 3x3 row-major affine
+ * map in feature-pixel units (= inv(feat2bev) . l02l1 . feat2bev, :313); the reference's
+ * [n,h,w,3,1] grid tensor, per-pixel matmul and normalisation pass are not materialised.
+ * Backward = gradient w.r.t. `in` (bilinear scatter with float atomics; grad_in fully written). */
+int dbev_shift_feature_forward(const float* in, const float* tf, int n, int C, int h, int w, float* out,
+                               void* stream);
+int dbev_shift_feature_backward(const float* grad_out, const float* tf, int n, int C, int h, int w,
+                                float* grad_in, void* stream);
+
+/* get_depth_loss (bevdet.py:397-417): loss_weight * mean over [BN, D, HW] of
+ * (depth_gt != 0) * BCE(sigmoid(logits), one_hot(clip(floor((depth_gt - dmin) / dstep), 0, D))),
+ * logits [BN, D, HW], depth_gt [BN, HW]; the one-hot tensor is never built. A ground-truth bin
+ * equal to D (F.one_hot raises in the reference) counts as "no positive class". loss / grad_loss:
+ * DEVICE float[1]; backward writes grad_logits completely. */
+size_t dbev_depth_loss_workspace_bytes(void);
+int dbev_depth_loss_forward(const float* logits, const float* depth_gt, int BN, int D, int HW, float dmin,
+                            float dstep, float loss_weight, float* loss, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int dbev_depth_loss_backward(const float* logits, const float* depth_gt, int BN, int D, int HW, float dmin,
+                             float dstep, float loss_weight, const float* grad_loss, float* grad_logits,
+                             void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Dense conv + eval BatchNorm + ReLU of the FROZEN LiDAR teacher's BEV backbone / neck on
  * tcgen05 tensor cores (TF32 inputs, fp32 accumulate): replaces the cuDNN conv + BatchNorm2d +
  * ReLU kernel triples of SECOND.forward (mmdet3d/models/backbones/second.py:80-93) and
