@@ -20,6 +20,7 @@ from .plugin.ops import spconv  # noqa: F401
 from .plugin.sparse_teacher import DynamicVoxelEncoder, HardSimpleVFE, SparseEncoder  # noqa: F401
 from .plugin.dense_teacher import SECOND, SECONDFPN  # noqa: F401
 from .plugin.bevdepth import get_depth_loss, shift_feature  # noqa: F401
+from .plugin.center_targets import CenterHeadTargets  # noqa: F401
 from .graph import CapturedStep  # noqa: F401
 
 __version__ = "0.1.0"

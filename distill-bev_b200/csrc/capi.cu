@@ -8,6 +8,7 @@
 #include "affinity.cuh"
 #include "bev_pool.cuh"
 #include "bevdepth_aux.cuh"
+#include "center_targets.cuh"
 #include "conv2d_tc.cuh"
 #include "distill_loss.cuh"
 #include "pillar.cuh"
@@ -349,6 +350,18 @@ int dbev_depth_loss_backward(const float* logits, const float* depth_gt, int BN,
                              void* stream) {
   return depth_loss_backward(logits, depth_gt, BN, D, HW, dmin, dstep, loss_weight, grad_loss, grad_logits,
                              (cudaStream_t)stream);
+}
+
+int dbev_center_targets(const float* boxes, int box_dim, const int* labels, const int* offsets, int batch,
+                        const int* class_task_host, const int* class_in_task_host, int num_classes,
+                        int num_tasks, int max_objs, int H, int W, float voxel_x, float voxel_y,
+                        float out_size_factor, float pc_min_x, float pc_min_y, float gaussian_overlap,
+                        int min_radius, int norm_bbox, float* heatmap, float* anno_box,
+                        long long* ind, unsigned char* mask, void* stream) {
+  return center_targets(boxes, box_dim, labels, offsets, batch, class_task_host, class_in_task_host,
+                        num_classes, num_tasks, max_objs, H, W, voxel_x, voxel_y, out_size_factor, pc_min_x,
+                        pc_min_y, gaussian_overlap, min_radius, norm_bbox, heatmap, anno_box, ind, mask,
+                        (cudaStream_t)stream);
 }
 
 int dbev_conv2d_tc_forward(const float* x_nhwc, int n, int h, int w, int c_in, const float* w_packed,

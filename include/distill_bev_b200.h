@@ -319,6 +319,23 @@ int dbev_depth_loss_backward(const float* logits, const float* depth_gt, int BN,
                              void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * CenterHead.get_targets on the device (SURVEY.md §8f rank 3;
+ * mmdet3d/models/dense_heads/centerpoint_head.py:400-445, 447-611, core/utils/gaussian.py:6-87):
+ * boxes[total, box_dim] = (gravity-centre-less) LiDAR boxes (x, y, z_bottom, dx, dy, dz, yaw, vx, vy)
+ * of all samples back to back, labels[total] int32, offsets[batch+1] (device ints);
+ * class_task_host / class_in_task_host[num_classes]: task of every class and its position inside
+ * the task (HOST ints, <= 32 classes). Outputs (fully written): heatmap[batch, num_classes, H, W]
+ * (the tasks' heat maps are its channel slices), anno_box[batch, num_tasks, max_objs, 10],
+ * ind[batch, num_tasks, max_objs] int64, mask[batch, num_tasks, max_objs] uint8.
+ * ------------------------------------------------------------------------ */
+int dbev_center_targets(const float* boxes, int box_dim, const int* labels, const int* offsets, int batch,
+                        const int* class_task_host, const int* class_in_task_host, int num_classes,
+                        int num_tasks, int max_objs, int H, int W, float voxel_x, float voxel_y,
+                        float out_size_factor, float pc_min_x, float pc_min_y, float gaussian_overlap,
+                        int min_radius, int norm_bbox, float* heatmap, float* anno_box,
+                        long long* ind, unsigned char* mask, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Dense conv + eval BatchNorm + ReLU of the FROZEN LiDAR teacher's BEV backbone / neck on
  * tcgen05 tensor cores (TF32 inputs, fp32 accumulate): replaces the cuDNN conv + BatchNorm2d +
  * ReLU kernel triples of SECOND.forward (mmdet3d/models/backbones/second.py:80-93) and

@@ -217,7 +217,7 @@ def _build_loss(cfg):
 
 def load_fgd_methods(names=("foreground_scale_mask", "add_fp_as_fg", "fgd_distill_loss",
                             "affinity_distill_loss"), cls_name="BEVDetDistill",
-                     relpath="mmdet3d/models/detectors/bevdet_distill.py"):
+                     relpath="mmdet3d/models/detectors/bevdet_distill.py", extra_ns=None):
     """dict name -> python function(self, ...) compiled from the reference source."""
     import ast
     import copy
@@ -237,6 +237,8 @@ def load_fgd_methods(names=("foreground_scale_mask", "add_fp_as_fg", "fgd_distil
     ns = dict(torch=torch, nn=nn, F=F, np=np, deepcopy=copy.deepcopy, partial=functools.partial,
               box_np_ops=box_np_ops, LiDARPoints=lidar_points.LiDARPoints,
               clip_sigmoid=clip.clip_sigmoid, build_loss=_build_loss, os=os)
+    if extra_ns:
+        ns.update(extra_ns)
     out = {}
     for node in cls.body:
         if isinstance(node, ast.FunctionDef) and node.name in names:
