@@ -33,16 +33,21 @@ class CenterHeadTargets(object):
         lib = _lib.load()
         cfg = self.train_cfg
         if device is None:
-            device = gt_labels_3d[0].device
+            device = gt_labels_3d.device if isinstance(gt_labels_3d, torch.Tensor) else gt_labels_3d[0].device
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("get_targets: device must be CUDA (no CPU path)")
         boxes, offs, _ = _fgd.pack_boxes(gt_bboxes_3d, device)
-        labels = torch.cat([torch.as_tensor(l).reshape(-1) for l in gt_labels_3d]).to(torch.int32)
-        if labels.numel() == 0:
-            labels = torch.zeros((1,), dtype=torch.int32)
-        labels = labels.contiguous().to(device) if labels.is_cuda else _lib.h2d_async(labels, device)
-        B = len(gt_labels_3d)
+        if isinstance(gt_labels_3d, torch.Tensor):
+            # already packed on the device (same order as the packed boxes): CUDA-graph friendly
+            labels = _lib.require_cuda(gt_labels_3d, "gt_labels_3d", torch.int32).contiguous()
+            B = len(gt_bboxes_3d)
+        else:
+            labels = torch.cat([torch.as_tensor(l).reshape(-1) for l in gt_labels_3d]).to(torch.int32)
+            if labels.numel() == 0:
+                labels = torch.zeros((1,), dtype=torch.int32)
+            labels = labels.contiguous().to(device) if labels.is_cuda else _lib.h2d_async(labels, device)
+            B = len(gt_labels_3d)
         nc, nt = len(self.class_task), len(self.class_names)
         max_objs = int(cfg["max_objs"] * cfg["dense_reg"])
         osf = cfg["out_size_factor"]
