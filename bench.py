@@ -497,6 +497,43 @@ def full_path_probe(hp, steps=10):
             "samples_per_sec": round(BATCH / (ms * 1e-3), 1), "loss_finite": bool(torch.isfinite(loss).item())}
 
 
+def teacher_conv_roofline(hp):
+    """Tensor-bound companion of `roofline`: the teacher's SECOND + SECONDFPN stack (the kernels with the
+    largest share of the v2 step, conv2d_tc_kernel<64|128|256>) timed alone with CUDA events on its
+    stream. peak = half of the measured bf16 rate (TF32 issues at half the bf16 rate on tcgen05)."""
+    import torch
+    dbev, dev = hp.dbev, hp.dev
+    with torch.no_grad():
+        canvas = dbev.pillar_canvas(hp.d_points, hp.enc, hp.scat)
+        for _ in range(3):
+            hp.secfpn(hp.second(canvas))
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        torch.cuda.synchronize()
+        iters = 10
+        a.record()
+        for _ in range(iters):
+            hp.secfpn(hp.second(canvas))
+        b.record()
+        torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    flops, hw, cin = 0.0, 512, 64
+    for n, c in zip((3, 5, 5), (64, 128, 256)):
+        hw //= 2
+        flops += 2.0 * BATCH * hw * hw * 9 * cin * c + n * 2.0 * BATCH * hw * hw * 9 * c * c
+        cin = c
+    flops += 2.0 * BATCH * 128 * 128 * (4 * 64 * 128 + 128 * 128 + 256 * 128)
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        peak, how = float(json.load(open(path))["bf16_tflops"]) / 2.0, "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 rate)"
+    else:
+        peak, how = 1100.0, "fallback: nominal dense TF32 1.1 PFLOP/s"
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"kernel": "dbev::conv2d_tc_kernel<64|128|256> x 22 launches (SECOND + SECONDFPN forward)", "bound": "tensor",
+            "achieved": round(ach, 1), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+            "traffic": None, "peak_source": how, "flops_per_stack": flops, "stack_ms": round(ms, 4),
+            "ncu": "profiles/r01_conv2d_tc.json (sm__pipe_tensor_cycles_active 27 / 50 / 67.5 % on the 64 / 128 / 256-channel layers)"}
+
+
 def bev_pool_roofline(device):
     """Live roofline of the dominant bev_pool kernel: gather-forward over materialised frustum
     features at the configs[1] shape (16 sample-frames, C=64): kernel timed alone with CUDA events
@@ -627,6 +664,10 @@ def run_ours(args):
     }
     if world == 1:
         line["roofline"] = bev_pool_roofline(device)
+        try:
+            line["roofline_tensor"] = teacher_conv_roofline(hp)
+        except Exception as exc:
+            line["roofline_tensor"] = {"error": str(exc)[:200]}
         line["cpu_baseline"] = cpu_baseline(samples=3, procs=1)
         for key, probe in (("sparse_teacher", lambda: sparse_teacher_probe(device)),
                            ("with_conv_stacks", lambda: full_path_probe(hp))):

@@ -14,7 +14,8 @@
 // Accumulators live in TMEM (two buffers: the epilogue of tile t overlaps the MMAs of tile t+1);
 // the epilogue applies scale/shift (eval BN folded) + ReLU and writes NHWC rows, optionally into
 // a channel slice / strided pixel lattice of a larger tensor (FPN concat, transposed conv).
-// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-5 = epilogue; persistent CTAs.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-5 = epilogue; persistent CTAs,
+// two per SM for C_out <= 128.
 #include "conv2d_tc.cuh"
 
 #include "umma.cuh"
@@ -36,8 +37,8 @@ struct ConvShape {
   int nchw;  // 1: out is [n, ld, H_full, W_full] (a lane = a pixel: stores of one channel coalesce along x)
 };
 
-template <int COUT, int STAGES>
-__global__ void __launch_bounds__(kConvThreads, 1)
+template <int COUT, int STAGES, int MINB>
+__global__ void __launch_bounds__(kConvThreads, MINB)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const float* __restrict__ scale, const float* __restrict__ shift,
                  float* __restrict__ out, ConvShape s) {
@@ -265,17 +266,20 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   int dev = 0, sms = 0;
   DBEV_CUDA(cudaGetDevice(&dev));
   DBEV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = s.n_tiles < sms ? s.n_tiles : sms;
-#define DBEV_CONV_LAUNCH(CO, STG)                                                                \
+#define DBEV_CONV_LAUNCH(CO, STG, MB)                                                            \
   do {                                                                                           \
     const size_t smem = (size_t)STG * (kATile + CO * kKc * 4) + 1024;                            \
-    DBEV_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel<CO, STG>,                                    \
+    const int grid = s.n_tiles < sms * MB ? s.n_tiles : sms * MB;                                \
+    DBEV_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel<CO, STG, MB>,                                \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    conv2d_tc_kernel<CO, STG><<<grid, kConvThreads, smem, stream>>>(tmap_x, tmap_w, scale, shift, out, s); \
+    conv2d_tc_kernel<CO, STG, MB><<<grid, kConvThreads, smem, stream>>>(tmap_x, tmap_w, scale, shift, out, s); \
   } while (0)
-  if (c_out == 64) DBEV_CONV_LAUNCH(64, 6);
-  else if (c_out == 128) DBEV_CONV_LAUNCH(128, 6);
-  else DBEV_CONV_LAUNCH(256, 4);
+  // two CTAs per SM where shared memory and TMEM allow it: one CTA's epilogue / TMA latency hides
+  // behind the other's MMAs (1.68 -> 1.56 ms for the whole SECOND + SECONDFPN stack); three CTAs of
+  // the 64-channel kernel or deeper stage rings gave nothing
+  if (c_out == 64) DBEV_CONV_LAUNCH(64, 4, 2);
+  else if (c_out == 128) DBEV_CONV_LAUNCH(128, 3, 2);
+  else DBEV_CONV_LAUNCH(256, 4, 1);
 #undef DBEV_CONV_LAUNCH
   DBEV_CHECK_LAUNCH("conv2d_tc_kernel");
   return DBEV_OK;
