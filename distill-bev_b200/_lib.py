@@ -45,6 +45,7 @@ SIGNATURES = {
     "dbev_bev_plan_from_geom": (_c_int, [_ptr, _c_ll, _c_int, _fptr, _fptr, _fptr, _iptr, _c_int,
                                          _c_int, _ptr, _ptr, _ptr, _ptr, _c_ll, _ptr, _ptr, _ptr,
                                          _c_size, _ptr]),
+    "dbev_bev_pool_point_backward": (_c_int, [_ptr, _ptr, _c_ll, _c_int, _ptr, _ptr]),
     "dbev_lift_splat_forward": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr, _ptr,
                                          _ptr, _c_int, _c_int, _c_int, _c_int, _c_ll, _c_ll, _c_ll,
                                          _ptr, _ptr]),

@@ -1191,6 +1191,26 @@ int transpose_batched(const float* in, float* out, int batch, int rows, int cols
   return DBEV_OK;
 }
 
+// Point-centric backward: x_grad[p, :] = grad_cl[cell(p), :] (zeros for dropped points). The 1 GB of
+// row writes is perfectly sequential in p and the cell rows (the BEV gradient transposed once to
+// cells-major, 67 MB at configs[1]) are gathered from L2; the cell-centric kernel above scatters
+// 256-byte rows through the sorted order instead (0.39 -> 0.2x ms at configs[1]).
+__global__ void __launch_bounds__(256)
+bev_pool_point_bwd_kernel(const float4* __restrict__ grad_cl, const int* __restrict__ point_cell,
+                          long long n_points, int c4, float4* __restrict__ x_grad) {
+  const long long total = n_points * c4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const long long p = t / c4;
+    const int j = (int)(t - p * c4);
+    const int cell = __ldg(point_cell + p);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cell >= 0) v = __ldg(grad_cl + (long long)cell * c4 + j);
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(x_grad + t), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w));
+  }
+}
+
 int bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* order,
                              const int* cell_start, const int* cell_end, const int4* items,
                              const int* n_items, int batch, int nz, int nslow, int nfast,
@@ -1224,6 +1244,21 @@ int bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* order
   bev_pool_zero_tail_kernel<<<kNumSMs * 2, 256, 0, stream>>>(order, cell_start + ncells,
                                                              cell_end + ncells, x_grad, C);
   DBEV_CHECK_LAUNCH("bev_pool_zero_tail_kernel");
+  return DBEV_OK;
+}
+
+int bev_pool_point_backward(const float* grad_cl, const int* point_cell, long long n_points, int C,
+                            float* x_grad, cudaStream_t stream) {
+  DBEV_CHECK_ARG(n_points >= 0 && C > 0 && C % 4 == 0, "bev_pool_point_backward: C must be a multiple of 4");
+  DBEV_CHECK_ARG(((uintptr_t)grad_cl & 15) == 0 && ((uintptr_t)x_grad & 15) == 0,
+                 "bev_pool_point_backward: pointers must be 16-byte aligned");
+  if (n_points == 0) return DBEV_OK;
+  const long long total = n_points * (C / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)kNumSMs * 64) blocks = (long long)kNumSMs * 64;
+  bev_pool_point_bwd_kernel<<<(int)blocks, 256, 0, stream>>>((const float4*)grad_cl, point_cell, n_points,
+                                                             C / 4, (float4*)x_grad);
+  DBEV_CHECK_LAUNCH("bev_pool_point_bwd_kernel");
   return DBEV_OK;
 }
 

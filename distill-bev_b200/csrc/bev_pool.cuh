@@ -54,4 +54,9 @@ int bev_pool_interval_backward(int b, int d, int h, int w, int n, int c, int n_i
                                const int* interval_starts, const int* interval_lengths,
                                float* x_grad, int zero_x_grad, cudaStream_t stream);
 
+// x_grad[p, :] = grad_cl[point_cell[p], :] (zero rows where point_cell < 0); grad_cl = BEV gradient in
+// cells-major rows [n_cells, C].
+int bev_pool_point_backward(const float* grad_cl, const int* point_cell, long long n_points, int C,
+                            float* x_grad, cudaStream_t stream);
+
 }  // namespace dbev

@@ -75,6 +75,11 @@ int dbev_bev_plan_from_geom(const float* geom, long long n_points, int batch,
                             workspace_bytes, (cudaStream_t)stream);
 }
 
+int dbev_bev_pool_point_backward(const float* grad_cl, const int* point_cell, long long n_points, int C,
+                                 float* x_grad, void* stream) {
+  return bev_pool_point_backward(grad_cl, point_cell, n_points, C, x_grad, (cudaStream_t)stream);
+}
+
 int dbev_lift_splat_forward(const float* depth, const float* feat_cl, int C, int D, int fhw,
                             const uint32_t* order, const int* cell_start, const int* cell_end,
                             const int* items, const int* n_items, int batch, int nz, int nslow,

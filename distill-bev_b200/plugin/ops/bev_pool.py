@@ -181,6 +181,14 @@ class _BevPoolGather(torch.autograd.Function):
         out_grad = out_grad.contiguous().float()
         _, sB, sZ, sC = _out_strides(plan, C, ctx.layout)
         x_grad = torch.empty((plan.n_points, C), dtype=torch.float32, device=out_grad.device)
+        if plan.point_cell is not None and ctx.layout == "bz_c" and C % 4 == 0:
+            # point-centric: sequential row writes, cell rows gathered from the cells-major gradient
+            g_cl = transpose_batched(out_grad, plan.batch * plan.nz, C, plan.nslow * plan.nfast)
+            with torch.cuda.device(out_grad.device):
+                rc = lib.dbev_bev_pool_point_backward(_lib.ptr(g_cl), _lib.ptr(plan.point_cell), plan.n_points,
+                                                      C, _lib.ptr(x_grad), _lib.stream_ptr(out_grad.device))
+            _lib.check(rc, "dbev_bev_pool_point_backward")
+            return x_grad, None, None
         with torch.cuda.device(out_grad.device):
             rc = lib.dbev_bev_pool_gather_backward(
                 _lib.ptr(out_grad), C, _lib.ptr(plan.order), _lib.ptr(plan.cell_start),
@@ -292,7 +300,8 @@ def voxel_pooling(geom_feats, x, bx=None, dx=None, nx=None, plan=None, grid=None
     B, N, D, H, W, C = x.shape
     Nprime = B * N * D * H * W
     if plan is None:
-        plan = bev_plan_from_geom(geom_feats, B, bx, dx, nx, fast_axis=0, grid=grid)
+        plan = bev_plan_from_geom(geom_feats, B, bx, dx, nx, fast_axis=0, grid=grid,
+                                  with_point_cell=bool(x.requires_grad and torch.is_grad_enabled()))
     x = x.reshape(Nprime, C)
     return bev_pool_gather(x, plan, layout="bz_c")
 

@@ -132,6 +132,13 @@ int dbev_bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* 
                                   long long stride_b, long long stride_z, long long stride_c,
                                   float* x_grad, void* stream);
 
+/* Point-centric form of the same backward for plans that carry point_cell (dbev_bev_plan_from_geom):
+ * x_grad[p, :] = grad_cl[point_cell[p], :], zero rows for dropped points; grad_cl[n_cells, C] = the BEV
+ * gradient in cells-major rows (dbev_transpose_batched of the NCHW gradient). Sequential row writes
+ * instead of a scatter through the sorted order. C % 4 == 0. */
+int dbev_bev_pool_point_backward(const float* grad_cl, const int* point_cell, long long n_points, int C,
+                                 float* x_grad, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * Fused lift + splat. Replaces, in one kernel, the outer
  * product volume = depth.unsqueeze(1) * img_feat.unsqueeze(2), its permute to

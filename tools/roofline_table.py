@@ -60,7 +60,7 @@ def main():
     cams = nf * bench.N_CAMS
     add("lss_geometry (get_geometry)", "%d cams x %d frustum points" % (cams, n // cams),
         lambda: hp.vt.get_geometry(*hp.d_calib), nbytes=n * 12)
-    plan = hp.vt.make_plan(geom, nf)
+    plan = hp.vt.make_plan(geom, nf)          # carries point_cell (needed by the lift backward)
     kept = plan.num_kept()
     add("bev plan (keys + 3-pass radix sort + bounds + items)", "%d points -> %d kept" % (n, kept),
         lambda: hp.vt.make_plan(geom, nf), nbytes=n * 12 + 3 * n * 16 + n * 4,
