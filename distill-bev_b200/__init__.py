@@ -17,6 +17,8 @@ from .plugin.distill import fgd  # noqa: F401
 from .plugin.distill import affinity, bevformer, detector  # noqa: F401
 from .plugin.distill.adaptation import Conv1x1Adaptation, conv1x1  # noqa: F401
 from .plugin.ops import spconv  # noqa: F401
+from .plugin.ops.ms_deform_attn import (MultiScaleDeformableAttnFunction,  # noqa: F401
+                                        MultiScaleDeformableAttnFunction_fp32, multi_scale_deformable_attn)
 from .plugin.sparse_teacher import DynamicVoxelEncoder, HardSimpleVFE, SparseEncoder  # noqa: F401
 from .plugin.dense_teacher import SECOND, SECONDFPN  # noqa: F401
 from .plugin.bevdepth import get_depth_loss, shift_feature  # noqa: F401

@@ -113,6 +113,8 @@ SIGNATURES = {
                                          _ptr, _c_size, _ptr]),
     "dbev_depth_loss_backward": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _c_float, _c_float, _c_float, _ptr,
                                           _ptr, _ptr]),
+    "dbev_ms_deform_attn_forward": (_c_int, [_ptr] * 5 + [_c_int] * 7 + [_ptr, _ptr]),
+    "dbev_ms_deform_attn_backward": (_c_int, [_ptr] * 6 + [_c_int] * 7 + [_ptr, _ptr, _ptr, _ptr]),
     "dbev_center_targets": (_c_int, [_ptr, _c_int, _ptr, _ptr, _c_int, _iptr, _iptr] + [_c_int] * 5
                             + [_c_float] * 6 + [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "dbev_conv2d_tc_forward": (_c_int, [_ptr] + [_c_int] * 4 + [_ptr] + [_c_int] * 5 + [_ptr, _ptr, _c_int, _ptr]

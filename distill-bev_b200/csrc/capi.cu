@@ -11,6 +11,7 @@
 #include "center_targets.cuh"
 #include "conv2d_tc.cuh"
 #include "distill_loss.cuh"
+#include "ms_deform_attn.cuh"
 #include "pillar.cuh"
 #include "sort.cuh"
 #include "spconv.cuh"
@@ -355,6 +356,24 @@ int dbev_depth_loss_backward(const float* logits, const float* depth_gt, int BN,
                              void* stream) {
   return depth_loss_backward(logits, depth_gt, BN, D, HW, dmin, dstep, loss_weight, grad_loss, grad_logits,
                              (cudaStream_t)stream);
+}
+
+int dbev_ms_deform_attn_forward(const float* value, const long long* spatial_shapes,
+                                const long long* level_start, const float* sampling_loc,
+                                const float* attn_weight, int bs, int num_keys, int heads, int dim,
+                                int num_queries, int levels, int points, float* out, void* stream) {
+  return ms_deform_attn_forward(value, spatial_shapes, level_start, sampling_loc, attn_weight, bs, num_keys,
+                                heads, dim, num_queries, levels, points, out, (cudaStream_t)stream);
+}
+
+int dbev_ms_deform_attn_backward(const float* value, const long long* spatial_shapes,
+                                 const long long* level_start, const float* sampling_loc,
+                                 const float* attn_weight, const float* grad_out, int bs, int num_keys,
+                                 int heads, int dim, int num_queries, int levels, int points,
+                                 float* grad_value, float* grad_loc, float* grad_attn, void* stream) {
+  return ms_deform_attn_backward(value, spatial_shapes, level_start, sampling_loc, attn_weight, grad_out, bs,
+                                 num_keys, heads, dim, num_queries, levels, points, grad_value, grad_loc,
+                                 grad_attn, (cudaStream_t)stream);
 }
 
 int dbev_center_targets(const float* boxes, int box_dim, const int* labels, const int* offsets, int batch,

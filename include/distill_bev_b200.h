@@ -326,6 +326,27 @@ int dbev_depth_loss_backward(const float* logits, const float* depth_gt, int BN,
                              void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * Multi-scale deformable attention of the BEVFormer student. Replaces mmcv
+ * 1.6.0 `_ext.ms_deform_attn_forward / ms_deform_attn_backward` as called by
+ * MultiScaleDeformableAttnFunction_fp32
+ * (mmdet3d/models/transformer_modules/multi_scale_deformable_attn_function.py:90-165); semantics =
+ * mmcv's multi_scale_deformable_attn_pytorch (third party: parity unpinned). value [bs, num_keys,
+ * heads, dim]; spatial_shapes [levels, 2] (h, w) and level_start [levels] int64 DEVICE tensors;
+ * sampling_loc [bs, nq, heads, levels, points, 2] in [0,1]; attn_weight [bs, nq, heads, levels,
+ * points]; out [bs, nq, heads*dim]. Backward writes all three gradients completely (grad_value by
+ * float atomics, like mmcv).
+ * ------------------------------------------------------------------------ */
+int dbev_ms_deform_attn_forward(const float* value, const long long* spatial_shapes,
+                                const long long* level_start, const float* sampling_loc,
+                                const float* attn_weight, int bs, int num_keys, int heads, int dim,
+                                int num_queries, int levels, int points, float* out, void* stream);
+int dbev_ms_deform_attn_backward(const float* value, const long long* spatial_shapes,
+                                 const long long* level_start, const float* sampling_loc,
+                                 const float* attn_weight, const float* grad_out, int bs, int num_keys,
+                                 int heads, int dim, int num_queries, int levels, int points,
+                                 float* grad_value, float* grad_loc, float* grad_attn, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * CenterHead.get_targets on the device (SURVEY.md §8f rank 3;
  * mmdet3d/models/dense_heads/centerpoint_head.py:400-445, 447-611, core/utils/gaussian.py:6-87):
  * boxes[total, box_dim] = (gravity-centre-less) LiDAR boxes (x, y, z_bottom, dx, dy, dz, yaw, vx, vy)
