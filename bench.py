@@ -46,7 +46,8 @@ FRAMES = 2           # BEVDepth4D: current + adjacent frame
 N_CAMS, D, FH, FW, C_TRANS, BEV = 6, 59, 16, 44, 64, 128
 N_POINTS = 30000
 C_STUDENT, C_TEACHER = 256, 384
-WORKLOAD = ("hotpath-ops-v2: lift+splat fwd/bwd (B=8 x 2 frames, 6 cams, D=59, 16x44, C=64 -> 128x128) "
+WORKLOAD = ("hotpath-ops-v2: lift+splat fwd/bwd (B=8 x 2 frames, 6 cams, D=59, 16x44, C=64 -> 128x128; sort-free splat: "
+            "vector float reductions into the L2-resident BEV map, summation order not fixed, --sorted-splat for the plan-based one) "
             "+ frozen LiDAR teacher end to end: voxelize/pillar-encode/scatter (8 x 30k pts -> 512x512x64) -> "
             "SECOND + SECONDFPN (tcgen05 conv+BN+ReLU, 601 GFLOP) -> teacher BEV feature [8,384,128,128] "
             "+ CenterHead GT heat maps rasterised on the device + 1x1 adaptation conv (tcgen05 fwd, cuDNN bwd) + fgd distill loss fwd/bwd at head against that "
@@ -172,6 +173,7 @@ class HotPath(object):
         self.depth = torch.randn(nf * N_CAMS, D, FH, FW, generator=g).softmax(1).to(device).requires_grad_(True)
         self.feat = torch.randn(nf * N_CAMS, C_TRANS, FH, FW, generator=g).to(device).requires_grad_(True)
         self.bev_grad = torch.rand(nf, C_TRANS, BEV, BEV, generator=g).to(device)
+        self.sorted_splat = False
         self.student = torch.relu(torch.randn(BATCH, C_STUDENT, BEV, BEV, generator=g)).to(device).requires_grad_(True)
         self.teacher = torch.relu(torch.randn(BATCH, C_TEACHER, BEV, BEV, generator=g)).to(device)
         self.teacher_logit = (torch.randn(BATCH, 10, BEV, BEV, generator=g) * 1.5 - 3.0).to(device)
@@ -239,7 +241,7 @@ class HotPath(object):
             loss_vec = torch.stack([losses[k] for k in sorted(losses)])
         # A: student view transform (geometry changes every step: augmentation)
         geom = self.vt.get_geometry(*calib)
-        plan = self.vt.make_plan(geom, BATCH * FRAMES)
+        plan = (self.vt.make_plan if self.sorted_splat else self.vt.make_cells)(geom, BATCH * FRAMES)
         bev = dbev.lift_splat(self.depth, self.feat, plan)
         bev.backward(self.bev_grad)
         for st in self.side:
@@ -602,6 +604,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     hp = HotPath(device, seed=rank_seed(rank))
+    hp.sorted_splat = args.sorted_splat
     graph_note = "eager (--no-graph)"
     if not args.no_graph:
         try:
@@ -832,6 +835,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly (no CUDA graph replay)")
+    ap.add_argument("--sorted-splat", action="store_true",
+                    help="lift+splat through the sorted plan (fixed summation order) instead of the sort-free splat")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

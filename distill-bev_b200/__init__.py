@@ -4,7 +4,8 @@ reference's mmdet3d operator names. See DESIGN.md and INTEGRATION.md.
 Import as ``distill_bev_b200`` (alias module at the repository root).
 """
 from . import _lib  # noqa: F401
-from .plugin.ops.bev_pool import (BevPlan, GridSpec, QuickCumsumCuda, bev_plan_from_coords,  # noqa: F401
+from .plugin.ops.bev_pool import (BevPlan, GridSpec, PointCells, QuickCumsumCuda, bev_plan_from_coords,  # noqa: F401
+                                  bev_point_cells,
                                   bev_plan_from_geom, bev_pool, bev_pool_ext, bev_pool_gather,
                                   lift_splat, transpose_batched, voxel_pooling)
 

@@ -70,7 +70,7 @@ bev_keys_from_geom_kernel(const float* __restrict__ geom, long long n, long long
     const int nfast = fast_axis == 0 ? n0 : n1;
     key = (uint32_t)((((long long)b * nz + i2) * nslow + islow) * nfast + ifast);
   }
-  keys[p] = key;
+  if (keys) keys[p] = key;
   if (point_cell) point_cell[p] = ok ? (int)key : -1;
 }
 
@@ -1211,6 +1211,52 @@ bev_pool_point_bwd_kernel(const float4* __restrict__ grad_cl, const int* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Sort-free lift + splat (opt-in, `deterministic = false`): one LPR-lane group per image pixel keeps
+// the pixel's feature row in registers (read ONCE: 17 MB instead of 0.9 GB of row reads from L2) and
+// walks its D depth bins; every kept (pixel, bin) adds depth * feat into the BEV cell's channels-last
+// row with 16-byte vector reductions (red.global.add.v4.f32) that resolve in L2, where the 67 MB BEV
+// map lives. No plan, no sort, no work list: the cell of a frustum point comes straight from the
+// geometry (point_cell). The price is the fp32 summation order (run-to-run differences ~1e-7
+// relative; the plan-based kernel above stays the bit-reproducible default).
+// ---------------------------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256)
+lift_splat_atomic_fwd_kernel(const float* __restrict__ depth, const float4* __restrict__ feat_cl,
+                             const int* __restrict__ point_cell, long long n_pixels, int D, int fhw,
+                             int c4, float4* __restrict__ out_cl) {
+  const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int sub = threadIdx.x % LPR;
+  const unsigned wmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << ((threadIdx.x & 31) / LPR * LPR));
+  const bool pix_ok = gid < n_pixels;
+  const long long pix = pix_ok ? gid : 0;
+  const long long bn = pix / fhw;
+  const long long p0 = bn * D * fhw + (pix - bn * fhw);   // point id of depth bin 0
+  const bool lane_ok = sub < c4;
+  float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pix_ok && lane_ok) f = __ldg(feat_cl + pix * c4 + sub);
+  for (int d0 = 0; d0 < D; d0 += LPR) {
+    // cooperative addressing: lane `sub` resolves bin d0 + sub, the group exchanges by shuffle
+    const int dm = d0 + sub;
+    int cell = -1;
+    float w = 0.f;
+    if (pix_ok && dm < D) {
+      cell = __ldg(point_cell + p0 + (long long)dm * fhw);
+      w = __ldg(depth + p0 + (long long)dm * fhw);
+    }
+    const int cnt = min(LPR, D - d0);
+    for (int j = 0; j < cnt; ++j) {
+      const int cj = __shfl_sync(wmask, cell, j, LPR);
+      const float wj = __shfl_sync(wmask, w, j, LPR);
+      if (cj >= 0 && lane_ok) {
+        // rounded product first, like the reference's materialised volume
+        const float4 v = make_float4(__fmul_rn(wj, f.x), __fmul_rn(wj, f.y), __fmul_rn(wj, f.z), __fmul_rn(wj, f.w));
+        atomicAdd(out_cl + (long long)cj * c4 + sub, v);
+      }
+    }
+  }
+}
+
 int bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* order,
                              const int* cell_start, const int* cell_end, const int4* items,
                              const int* n_items, int batch, int nz, int nslow, int nfast,
@@ -1259,6 +1305,50 @@ int bev_pool_point_backward(const float* grad_cl, const int* point_cell, long lo
   bev_pool_point_bwd_kernel<<<(int)blocks, 256, 0, stream>>>((const float4*)grad_cl, point_cell, n_points,
                                                              C / 4, (float4*)x_grad);
   DBEV_CHECK_LAUNCH("bev_pool_point_bwd_kernel");
+  return DBEV_OK;
+}
+
+int bev_point_cells(const float* geom, long long n_points, int batch, const float* off, const float* dx,
+                    const float* nx_f, const int* nx_i, int fast_axis, int* point_cell,
+                    cudaStream_t stream) {
+  DBEV_CHECK_ARG(fast_axis == 0 || fast_axis == 1, "bev_point_cells: fast_axis must be 0 or 1");
+  DBEV_CHECK_ARG(batch > 0 && n_points >= 0 && n_points % batch == 0, "bev_point_cells: bad sizes");
+  const long long ncells = (long long)batch * nx_i[0] * nx_i[1] * nx_i[2];
+  DBEV_CHECK_ARG(ncells > 0 && ncells < 0x7fffffffLL, "bev_point_cells: bad grid");
+  if (n_points == 0) return DBEV_OK;
+  bev_keys_from_geom_kernel<<<ceil_div(n_points, 256), 256, 0, stream>>>(
+      geom, n_points, n_points / batch, off[0], off[1], off[2], dx[0], dx[1], dx[2], nx_f[0], nx_f[1],
+      nx_f[2], nx_i[0], nx_i[1], nx_i[2], fast_axis, (uint32_t)ncells, nullptr, point_cell);
+  DBEV_CHECK_LAUNCH("bev_keys_from_geom_kernel");
+  return DBEV_OK;
+}
+
+int lift_splat_atomic_forward(const float* depth, const float* feat_cl, const int* point_cell,
+                              long long n_pixels, int C, int D, int fhw, long long n_cells, float* out_cl,
+                              cudaStream_t stream) {
+  DBEV_CHECK_ARG(n_pixels >= 0 && C > 0 && C % 4 == 0 && C <= 128 && D > 0 && fhw > 0 && n_cells > 0,
+                 "lift_splat_atomic: C must be a multiple of 4, at most 128");
+  DBEV_CHECK_ARG(((uintptr_t)feat_cl & 15) == 0 && ((uintptr_t)out_cl & 15) == 0,
+                 "lift_splat_atomic: pointers must be 16-byte aligned");
+  DBEV_CUDA(cudaMemsetAsync(out_cl, 0, (size_t)n_cells * C * sizeof(float), stream));
+  if (n_pixels == 0) return DBEV_OK;
+  const int c4 = C / 4;
+  int lpr = 1;
+  while (lpr < c4) lpr <<= 1;
+  const long long threads = n_pixels * lpr;
+#define DBEV_LSA(L)                                                                                  \
+  lift_splat_atomic_fwd_kernel<L><<<ceil_div(threads, 256), 256, 0, stream>>>(                       \
+      depth, (const float4*)feat_cl, point_cell, n_pixels, D, fhw, c4, (float4*)out_cl)
+  switch (lpr) {
+    case 1: DBEV_LSA(1); break;
+    case 2: DBEV_LSA(2); break;
+    case 4: DBEV_LSA(4); break;
+    case 8: DBEV_LSA(8); break;
+    case 16: DBEV_LSA(16); break;
+    default: DBEV_LSA(32); break;
+  }
+#undef DBEV_LSA
+  DBEV_CHECK_LAUNCH("lift_splat_atomic_fwd_kernel");
   return DBEV_OK;
 }
 

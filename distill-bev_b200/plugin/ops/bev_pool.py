@@ -267,12 +267,98 @@ class _LiftSplat(torch.autograd.Function):
         return d_depth, d_feat, None
 
 
+class PointCells(object):
+    """Geometry-only companion of BevPlan for the sort-free lift+splat: ``point_cell`` [n_points]
+    int32 = output cell of every frustum point (-1 = dropped), no sort / bounds / work list."""
+
+    def __init__(self, point_cell, n_points, batch, nz, nslow, nfast):
+        self.point_cell, self.n_points, self.batch = point_cell, n_points, batch
+        self.nz, self.nslow, self.nfast = nz, nslow, nfast
+        self.n_cells = batch * nz * nslow * nfast
+
+
+def bev_point_cells(geom, batch, bx=None, dx=None, nx=None, fast_axis=0, grid=None):
+    """Index math + bounds test of voxel_pooling (:150-161) only: PointCells for ``lift_splat``."""
+    lib = _lib.load()
+    _lib.require_cuda(geom, "geom", torch.float32)
+    geom = geom.contiguous()
+    n_points = geom.numel() // 3
+    if grid is None:
+        grid = GridSpec(bx, dx, nx)
+    n0, n1, nz = int(grid.nx_i[0]), int(grid.nx_i[1]), int(grid.nx_i[2])
+    pc = torch.empty(max(n_points, 1), dtype=torch.int32, device=geom.device)
+    with torch.cuda.device(geom.device):
+        rc = lib.dbev_bev_point_cells(_lib.ptr(geom), n_points, batch, _lib.host_f3(grid.off), _lib.host_f3(grid.dx),
+                                      _lib.host_f3(grid.nx_f), _lib.host_i3(grid.nx_i), fast_axis, _lib.ptr(pc),
+                                      _lib.stream_ptr(geom.device))
+    _lib.check(rc, "dbev_bev_point_cells")
+    nslow, nfast = (n1, n0) if fast_axis == 0 else (n0, n1)
+    return PointCells(pc, n_points, batch, nz, nslow, nfast)
+
+
+class _LiftSplatAtomic(torch.autograd.Function):
+    """Sort-free lift+splat (vector float reductions into the channels-last BEV map)."""
+
+    @staticmethod
+    def forward(ctx, depth, feat, cells):
+        lib = _lib.load()
+        _lib.require_cuda(depth, "depth", torch.float32)
+        _lib.require_cuda(feat, "feat", torch.float32)
+        BN, D, fH, fW = depth.shape
+        C = feat.shape[1]
+        if tuple(feat.shape) != (BN, C, fH, fW):
+            raise RuntimeError("feat must be [%d, C, %d, %d], got %s" % (BN, fH, fW, tuple(feat.shape)))
+        if cells.n_points != BN * D * fH * fW:
+            raise RuntimeError("cells were built for %d points, frustum has %d" % (cells.n_points, BN * D * fH * fW))
+        if cells.nz != 1:
+            raise NotImplementedError("sort-free lift_splat needs a single z bin (BEV)")
+        depth = depth.contiguous()
+        fhw = fH * fW
+        feat_cl = transpose_batched(feat, BN, C, fhw)
+        out_cl = torch.empty((cells.batch, cells.nslow, cells.nfast, C), dtype=torch.float32, device=depth.device)
+        with torch.cuda.device(depth.device):
+            rc = lib.dbev_lift_splat_atomic_forward(_lib.ptr(depth), _lib.ptr(feat_cl), _lib.ptr(cells.point_cell),
+                                                    BN * fhw, C, D, fhw, cells.n_cells, _lib.ptr(out_cl),
+                                                    _lib.stream_ptr(depth.device))
+        _lib.check(rc, "dbev_lift_splat_atomic_forward")
+        ctx.cells = cells
+        ctx.dims = (BN, C, D, fH, fW)
+        ctx.save_for_backward(depth, feat_cl)
+        return out_cl.permute(0, 3, 1, 2)          # [B, C, ny, nx] in channels_last memory
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        lib = _lib.load()
+        cells = ctx.cells
+        depth, feat_cl = ctx.saved_tensors
+        BN, C, D, fH, fW = ctx.dims
+        fhw = fH * fW
+        g_nhwc = out_grad.float().permute(0, 2, 3, 1)
+        if g_nhwc.is_contiguous():
+            g_cl = g_nhwc                             # channels_last upstream gradient: free
+        else:
+            g_cl = transpose_batched(out_grad.contiguous().float(), cells.batch, C, cells.nslow * cells.nfast)
+        d_depth = torch.empty_like(depth)
+        d_feat_cl = torch.empty_like(feat_cl)
+        with torch.cuda.device(depth.device):
+            rc = lib.dbev_lift_splat_backward(_lib.ptr(g_cl), _lib.ptr(depth), _lib.ptr(feat_cl),
+                                              _lib.ptr(cells.point_cell), BN * fhw, C, D, fhw, _lib.ptr(d_depth),
+                                              _lib.ptr(d_feat_cl), _lib.stream_ptr(depth.device))
+        _lib.check(rc, "dbev_lift_splat_backward")
+        d_feat = transpose_batched(d_feat_cl, BN, fhw, C).view(BN, C, fH, fW)
+        return d_depth, d_feat, None
+
+
 def lift_splat(depth_prob, img_feat, plan):
     """Fused lift + splat: depth_prob [B*N, D, fH, fW] (softmax depth), img_feat
     [B*N, C, fH, fW] -> BEV [B, C*nz, ny, nx], identical to
     ``voxel_pooling(geom, (depth.unsqueeze(1) * feat.unsqueeze(2)).view(B,N,C,D,fH,fW)
     .permute(0,1,3,4,5,2))`` (bevdet_distill_more.py:413-421) without materialising the
-    volume. ``plan`` = bev_plan_from_geom(geom, B, ..., with_point_cell=True)."""
+    volume. ``plan`` = bev_plan_from_geom(geom, B, ..., with_point_cell=True) (sorted plan: fixed
+    summation order, bit-reproducible) or bev_point_cells(geom, B, ...) (sort-free: the splat uses
+    vector float reductions, no plan is built; result in channels_last memory, sums in arbitrary order)."""
+    if isinstance(plan, PointCells):
+        return _LiftSplatAtomic.apply(depth_prob, img_feat, plan)
     return _LiftSplat.apply(depth_prob, img_feat, plan)
 
 

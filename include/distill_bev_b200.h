@@ -161,6 +161,19 @@ int dbev_lift_splat_backward(const float* grad_cl, const float* depth, const flo
                              const int* point_cell, long long n_pixels, int C, int D, int fhw,
                              float* d_depth, float* d_feat_cl, void* stream);
 
+/* Sort-free variant (opt-in; fp32 summation order not fixed, everything else identical).
+ * dbev_bev_point_cells: point_cell[n_points] = output cell of every frustum point, -1 when dropped —
+ * the index math of voxel_pooling (view_transformer_mine.py:150-161) without the argsort.
+ * dbev_lift_splat_atomic_forward: out_cl[n_cells, C] (channels-last BEV rows, zero-filled here) +=
+ * depth[p] * feat_cl[pixel(p), :] with 16-byte vector reductions that resolve in L2; the feature row
+ * of a pixel is read once for all its D depth bins. Backward = dbev_lift_splat_backward. */
+int dbev_bev_point_cells(const float* geom, long long n_points, int batch, const float* off_host3,
+                         const float* dx_host3, const float* nx_float_host3, const int* nx_int_host3,
+                         int fast_axis, int* point_cell, void* stream);
+int dbev_lift_splat_atomic_forward(const float* depth, const float* feat_cl, const int* point_cell,
+                                   long long n_pixels, int C, int D, int fhw, long long n_cells,
+                                   float* out_cl, void* stream);
+
 /* out[b][c][r] = in[b][r][c] for b < batch: NCHW <-> channels-last helper. */
 int dbev_transpose_batched(const float* in, float* out, int batch, int rows, int cols,
                            void* stream);

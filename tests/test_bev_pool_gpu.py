@@ -266,3 +266,27 @@ def test_lift_splat_full_size_equals_materialised_path(cuda, C, frames):
 def test_transpose_batched(cuda):
     x = torch.rand(3, 70, 45, device=cuda)
     assert torch.equal(dbev.transpose_batched(x, 3, 70, 45), x.transpose(1, 2).contiguous())
+
+
+def test_sort_free_lift_splat_matches_sorted(cuda):
+    """Opt-in sort-free lift+splat (vector float reductions, no plan) == the plan-based kernel up to
+    fp32 summation order, forward and gradients; output is channels_last."""
+    vt = dbev.ViewTransformerLiftSplatShoot(grid_config=synthetic.NUSC_GRID, numC_input=8).to(cuda)
+    nf = 4
+    calib = [torch.from_numpy(a).to(cuda) for a in synthetic.make_calibration(nf, 6, seed=5)]
+    geom = vt.get_geometry(*calib)
+    torch.manual_seed(0)
+    depth = torch.randn(nf * 6, 59, 16, 44, device=cuda).softmax(1)
+    feat = torch.randn(nf * 6, 64, 16, 44, device=cuda)
+    og = torch.rand(nf, 64, 128, 128, device=cuda)
+    outs = []
+    for mk in (lambda: vt.make_plan(geom, nf), lambda: vt.make_cells(geom, nf)):
+        d, f = depth.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+        out = dbev.lift_splat(d, f, mk())
+        out.backward(og)
+        outs.append((out.detach(), d.grad, f.grad))
+    assert outs[1][0].is_contiguous(memory_format=torch.channels_last)
+    for a, b in zip(outs[0], outs[1]):
+        torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-5 * float(a.abs().max()))
+    pc = vt.make_cells(geom, nf).point_cell
+    assert torch.equal(pc, vt.make_plan(geom, nf).point_cell)
