@@ -20,6 +20,9 @@
 
 #include "umma.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace dbev {
 
 namespace {
@@ -35,12 +38,13 @@ struct ConvShape {
   // output placement: pixel (oy*omul + oadd_y, ox*omul + oadd_x) of an [n, H_full, W_full, ld] tensor
   int omul, oadd_y, oadd_x, h_full, w_full, ld, c_off, relu;
   int nchw;  // 1: out is [n, ld, H_full, W_full] (a lane = a pixel: stores of one channel coalesce along x)
+  int tma_store;  // 1: NHWC output on the plain lattice, written by TMA from a shared-memory staging tile
 };
 
 template <int COUT, int STAGES, int MINB>
 __global__ void __launch_bounds__(kConvThreads, MINB)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                 const float* __restrict__ scale, const float* __restrict__ shift,
+                 const __grid_constant__ CUtensorMap tmap_o, const float* __restrict__ scale, const float* __restrict__ shift,
                  float* __restrict__ out, ConvShape s) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kWTile = COUT * kKc * 4;
@@ -49,7 +53,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // uniform for the compiler
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -106,46 +110,57 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(kPix, COUT);
-      const int steps = taps * s.cin_chunks;
-      uint32_t stage = 0, phase = 0, it = 0;
-      for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it & 1u, use = it >> 1;
-        mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);
+    // whole warp in the loop, one elected lane issues (see conv3x3_halo_kernel)
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_tf32(kPix, COUT);
+    const uint64_t desc0 = umma_desc(0, 16, 1024);
+    const int steps = taps * s.cin_chunks;
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u, use = it >> 1;
+      mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_tmem = tmem_base + buf * COUT;
+#pragma unroll 1
+      for (int step = 0; step < steps; ++step) {
+        mbar_wait(&full_bar[stage], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + buf * COUT;
-        for (int step = 0; step < steps; ++step) {
-          mbar_wait(&full_bar[stage], phase);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a0 = smem_addr(base + (size_t)stage * kStage);
-          const uint32_t b0 = a0 + kATile;
+        const uint32_t a0 = smem_addr(base + (size_t)stage * kStage);
+        const uint64_t ad = desc0 + (uint64_t)(a0 >> 4), bd = desc0 + (uint64_t)((a0 + kATile) >> 4);
+        const uint32_t acc0 = step != 0 ? 1u : 0u;
+        if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < kKc / 8; ++kk) {
-            const uint64_t adesc = umma_desc(a0 + kk * 32, 16, 1024);
-            const uint64_t bdesc = umma_desc(b0 + kk * 32, 16, 1024);
-            umma_tf32(d_tmem, adesc, bdesc, idesc, (step | kk) != 0 ? 1u : 0u);
-          }
+          for (int kk = 0; kk < kKc / 8; ++kk)
+            umma_tf32(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, kk != 0 ? 1u : acc0);
           umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tmem_full_bar[buf]);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (leader) umma_commit(&tmem_full_bar[buf]);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
+    // NHWC outputs on the plain pixel lattice leave through shared memory + TMA store (see
+    // conv3x3_halo_kernel); NCHW / strided-lattice outputs (FPN) are written directly, a lane = a pixel.
     const int q = warp & 3;
     const int row = q * 32 + lane;           // pixel of the tile = TMEM lane
     const int py = row / s.tx, px = row % s.tx;
-    uint32_t it = 0;
+    const int by0 = (q * 32) / s.tx, bx0 = (q * 32) % s.tx;   // this warp's store box inside the tile
+    uint8_t* stg = base + (size_t)STAGES * kStage + (size_t)q * 8192;
+    const uint32_t stg_row = smem_addr(stg) + (uint32_t)lane * 128u;
+    const uint32_t sw_xor = (uint32_t)(lane & 7);
+    uint32_t it = 0, sbuf = 0;
     for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, use = it >> 1;
       const int n = tile / per_img, r = tile % per_img;
-      const int oy = (r / s.tiles_x) * s.ty + py, ox = (r % s.tiles_x) * s.tx + px;
+      const int ty0 = (r / s.tiles_x) * s.ty, tx0 = (r % s.tiles_x) * s.tx;
+      const int oy = ty0 + py, ox = tx0 + px;
       const bool valid = oy < s.ho && ox < s.wo;
       const int fy = oy * s.omul + s.oadd_y, fx = ox * s.omul + s.oadd_x;
-      float* orow = out + (((long long)n * s.h_full + fy) * s.w_full + fx) * s.ld + s.c_off;
       const long long plane = (long long)s.h_full * s.w_full;
+      float* orow = out + (((long long)n * s.h_full + fy) * s.w_full + fx) * s.ld + s.c_off;
       float* ocol = out + ((long long)n * s.ld + s.c_off) * plane + (long long)fy * s.w_full + fx;
       mbar_wait(&tmem_full_bar[buf], use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -153,8 +168,13 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       for (int cc = 0; cc < COUT / 32; ++cc) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * COUT + (uint32_t)(cc * 32), v);
+        if (s.tma_store) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (valid) {
+        const uint32_t dst = stg_row + sbuf * 4096u;
+        if (valid || s.tma_store) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
@@ -168,7 +188,11 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               o.x += sh.x, o.y += sh.y, o.z += sh.z, o.w += sh.w;
             }
             if (s.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-            if (s.nchw) {
+            if (s.tma_store) {
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((((uint32_t)j >> 2) ^ sw_xor) << 4)),
+                           "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                           : "memory");
+            } else if (s.nchw) {
               float* oc = ocol + (long long)(cc * 32 + j) * plane;
               oc[0] = o.x, oc[plane] = o.y, oc[2 * plane] = o.z, oc[3 * plane] = o.w;
             } else {
@@ -176,10 +200,28 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
           }
         }
+        if (s.tma_store) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (ty0 + by0 < s.ho && tx0 + bx0 < s.wo) {
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmap_o),
+                  "r"(smem_addr(stg) + sbuf * 4096u), "r"(s.c_off + cc * 32), "r"(tx0 + bx0), "r"(ty0 + by0), "r"(n)
+                  : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          sbuf ^= 1u;
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    }
+    if (s.tma_store) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __syncwarp();
     }
   }
 
@@ -189,6 +231,255 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
                  : "memory");
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1 layers (13 of SECOND's 16 convs): HALO-REUSE variant.
+// The per-tap kernel above re-reads the input window from L2 once per filter tap and the weights
+// once per 128-pixel tile; at ~60 B/clk/SM of TMA fill the whole chip sits on the L2 slice
+// throughput cap (~6300 B/clk), the tensor pipe idles (27 / 50 / 67 % busy at 64 / 128 / 256 ch).
+// Here one TMA box brings the (32+2) x (8+2)-pixel halo of a 32 x 8-pixel output tile for a 32-channel
+// chunk ONCE, and the nine taps are nine shifted WINDOWS of it: the A descriptor of tap (ky, kx) starts
+// at pixel row (ky*HX + kx) of the halo and strides HX*128 B between 8-pixel groups (the SWIZZLE_128B
+// XOR is a function of the shared-memory address bits, so a window that starts mid-pattern reads what
+// TMA wrote). The tile is two M=128 halves (16 image rows each) that share every weight tile, so the
+// weight traffic per pixel halves as well. L2->SMEM bytes per 128 pixels (C_in = C_out):
+//   64 ch: 435 KB -> 117 KB, 128 ch: 1166 KB -> 387 KB, 256 ch: 3.5 MB -> 1.36 MB.
+// Warp roles as above; one CTA per SM; accumulators 2 halves x 2 buffers (x 1 at C_out = 256).
+constexpr int kHaloTx = 8, kHaloTy = 32;         // output pixels of a tile (two M=128 halves of 16 rows)
+constexpr int kHaloRows = kHaloTy + 2;
+
+struct HaloShape {
+  int n_img, c_in, ho, wo, tiles_x, tiles_y, n_tiles, cin_chunks;
+  int hx;            // halo pitch in pixels (box width), >= kHaloTx + 2
+  int a_stage;       // bytes of one halo stage (multiple of 1024)
+  int w_stages;      // weight ring depth
+  int c_off, relu;
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_o, const float* __restrict__ scale, const float* __restrict__ shift,
+                    float* __restrict__ out, HaloShape s, long long* __restrict__ prof) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int kWTile = COUT * kKc * 4;
+  constexpr int kNBuf = COUT <= 128 ? 2 : 1;
+  constexpr uint32_t kTmemCols = COUT <= 64 ? 256 : 512;     // 2 halves x kNBuf x COUT
+  constexpr int kMaxW = 8;
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* wbase = base + 2 * (size_t)s.a_stage;
+  __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[kMaxW], w_empty[kMaxW], tmem_full_bar[2],
+      tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // uniform for the compiler
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);
+    }
+    for (int i = 0; i < kMaxW; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_addr(&tmem_base_s)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const int per_img = s.tiles_x * s.tiles_y;
+  const uint32_t a_bytes = (uint32_t)(kHaloRows * s.hx * kKc * 4);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t sa = 0, pa = 0, sw = 0, pw = 0;
+      long long pw_a = 0, pw_w = 0;
+      const long long pt0 = prof ? clock64() : 0;
+      // the halo of chunk i+1 is requested while the weights of chunk i stream: at tap `ahead` the MMA
+      // warp (w_stages taps behind) has left chunk i-1, so its halo stage is free without waiting
+      int t_n = blockIdx.x, c_n = 0;
+      auto issue_halo = [&]() {
+        if (t_n >= s.n_tiles) return;
+        const int n = t_n / per_img, r = t_n % per_img;
+        const int y0 = (r / s.tiles_x) * kHaloTy, x0 = (r % s.tiles_x) * kHaloTx;
+        { const long long t = prof ? clock64() : 0; mbar_wait(&a_empty[sa], pa ^ 1u); if (prof) pw_a += clock64() - t; }
+        mbar_expect_tx(&a_full[sa], a_bytes);
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_addr(base + (size_t)sa * s.a_stage)),
+            "l"(&tmap_x), "r"(smem_addr(&a_full[sa])), "r"(c_n * kKc), "r"(x0 - 1), "r"(y0 - 1), "r"(n)
+            : "memory");
+        if (++sa == 2) { sa = 0; pa ^= 1u; }
+        if (++c_n == s.cin_chunks) { c_n = 0; t_n += gridDim.x; }
+      };
+      const int ahead = s.w_stages < 8 ? s.w_stages : 8;
+      issue_halo();
+      for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x) {
+        for (int cc = 0; cc < s.cin_chunks; ++cc) {
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            if (tap == ahead) issue_halo();
+            { const long long t = prof ? clock64() : 0; mbar_wait(&w_empty[sw], pw ^ 1u); if (prof) pw_w += clock64() - t; }
+            mbar_expect_tx(&w_full[sw], (uint32_t)kWTile);
+            tma_load_2d(wbase + (size_t)sw * kWTile, &tmap_w, tap * s.c_in + cc * kKc, 0, &w_full[sw]);
+            if (++sw == (uint32_t)s.w_stages) { sw = 0; pw ^= 1u; }
+          }
+        }
+      }
+      if (prof) { prof[blockIdx.x * 16 + 0] = clock64() - pt0; prof[blockIdx.x * 16 + 1] = pw_a; prof[blockIdx.x * 16 + 2] = pw_w; }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    // The whole warp walks the loop (warp-uniform control flow keeps the descriptors in uniform
+    // registers: a tcgen05.mma is issued every few instructions instead of every ~25); one elected
+    // lane issues the MMAs and commits. At N = 64 an MMA lasts ~45 clk, so issue cost is what bounds it.
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_tf32(kPix, COUT);
+    const uint64_t desc_a = umma_desc(0, 16, (uint32_t)s.hx * 128u), desc_b = umma_desc(0, 16, 1024);
+    const uint32_t half_units = (uint32_t)(16 * s.hx * 8);   // 16 halo rows, in 16-byte units
+    uint32_t sa = 0, pa = 0, sw = 0, pw = 0, it = 0;
+    long long mw_t = 0, mw_a = 0, mw_w = 0;
+    const long long mt0 = prof ? clock64() : 0;
+    for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = kNBuf == 2 ? (it & 1u) : 0u, use = kNBuf == 2 ? (it >> 1) : it;
+      { const long long t = prof ? clock64() : 0; mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u); if (prof) mw_t += clock64() - t; }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_tmem = tmem_base + buf * 2 * COUT;
+      for (int cc = 0; cc < s.cin_chunks; ++cc) {
+        { const long long t = prof ? clock64() : 0; mbar_wait(&a_full[sa], pa); if (prof) mw_a += clock64() - t; }
+        const uint32_t a_units = smem_addr(base + (size_t)sa * s.a_stage) >> 4;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - ky * 3;
+          { const long long t = prof ? clock64() : 0; mbar_wait(&w_full[sw], pw); if (prof) mw_w += clock64() - t; }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t ad = desc_a + (uint64_t)(a_units + (uint32_t)((ky * s.hx + kx) * 8));
+          const uint64_t bd = desc_b + (uint64_t)(smem_addr(wbase + (size_t)sw * kWTile) >> 4);
+          const uint32_t acc0 = (cc | tap) != 0 ? 1u : 0u;
+          if (leader) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+              for (int kk = 0; kk < kKc / 8; ++kk)
+                umma_tf32(d_tmem + h * COUT, ad + (uint64_t)(h * half_units + kk * 2), bd + (uint64_t)(kk * 2), idesc,
+                          kk != 0 ? 1u : acc0);
+            }
+            umma_commit(&w_empty[sw]);
+          }
+          __syncwarp();
+          if (++sw == (uint32_t)s.w_stages) { sw = 0; pw ^= 1u; }
+        }
+        if (leader) umma_commit(&a_empty[sa]);
+        __syncwarp();
+        if (++sa == 2) { sa = 0; pa ^= 1u; }
+      }
+      if (leader) umma_commit(&tmem_full_bar[buf]);
+      __syncwarp();
+    }
+    if (prof && leader) { prof[blockIdx.x * 16 + 4] = clock64() - mt0; prof[blockIdx.x * 16 + 5] = mw_t; prof[blockIdx.x * 16 + 6] = mw_a; prof[blockIdx.x * 16 + 7] = mw_w; }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // A lane owns one pixel (TMEM lane) and 32 channels per pass. Writing those straight to NHWC
+    // global memory is a 16-byte store per lane at pixel stride: 32 partial sectors per instruction,
+    // measured 25k clk per 128 KB tile (the MMAs of that tile: 18k) - the whole kernel ran at the
+    // speed of its epilogue. Instead each warp stages its 32 pixels x 32 channels in shared memory
+    // (128-byte swizzle, conflict-free) and one lane hands the box {32 ch, 8 px, 4 rows} to TMA.
+    const int q = warp & 3;                  // TMEM lane q*32 + lane = pixel (lane / 8, lane % 8) of the warp's box
+    uint8_t* stg = base + 2 * (size_t)s.a_stage + (size_t)s.w_stages * kWTile + (size_t)q * 8192;
+    const uint32_t stg_row = smem_addr(stg) + (uint32_t)lane * 128u;
+    const uint32_t sw_xor = (uint32_t)(lane & 7);
+    uint32_t it = 0, sbuf = 0;
+    long long ew_f = 0;
+    const long long et0 = prof ? clock64() : 0;
+    for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = kNBuf == 2 ? (it & 1u) : 0u, use = kNBuf == 2 ? (it >> 1) : it;
+      const int n = tile / per_img, r = tile % per_img;
+      const int ty0 = (r / s.tiles_x) * kHaloTy, tx0 = (r % s.tiles_x) * kHaloTx;
+      { const long long t = prof ? clock64() : 0; mbar_wait(&tmem_full_bar[buf], use & 1u); if (prof) ew_f += clock64() - t; }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int oy0 = ty0 + h * 16 + q * 4;      // first image row of this warp's 4 x 8 pixel box
+#pragma unroll 1
+        for (int cc = 0; cc < COUT / 32; ++cc) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + h) * COUT + (uint32_t)(cc * 32), v);
+          // the staging buffer written two passes ago must have been read by its TMA store
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const uint32_t dst = stg_row + sbuf * 4096u;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (scale) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cc * 32 + j));
+              o.x *= sc.x, o.y *= sc.y, o.z *= sc.z, o.w *= sc.w;
+            }
+            if (shift) {
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cc * 32 + j));
+              o.x += sh.x, o.y += sh.y, o.z += sh.z, o.w += sh.w;
+            }
+            if (s.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((((uint32_t)j >> 2) ^ sw_xor) << 4)),
+                         "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                         : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && oy0 < s.ho) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmap_o),
+                "r"(smem_addr(stg) + sbuf * 4096u), "r"(s.c_off + cc * 32), "r"(tx0), "r"(oy0), "r"(n)
+                : "memory");
+          }
+          if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          sbuf ^= 1u;
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (prof && threadIdx.x == 64) { prof[blockIdx.x * 16 + 8] = clock64() - et0; prof[blockIdx.x * 16 + 9] = ew_f; }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// A/B switch: DBEV_CONV_HALO = 0 (per-tap kernel for every layer), 1 (default: halo kernel, pitch 10),
+// 2 (pitch 16). Measured: both pitches are bit-identical to the per-tap kernel (descriptor base-offset 0);
+// setting the descriptor's base-offset field to (start >> 7) & 7 gives wrong results.
+int conv_halo_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("DBEV_CONV_HALO");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode;
 }
 
 }  // namespace
@@ -209,6 +500,107 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
                  "conv2d_tc: pointers must be 16-byte aligned");
   DBEV_CHECK_ARG(out_ld % 4 == 0 && out_c_off % 4 == 0 && out_c_off + c_out <= out_ld && out_mul >= 1,
                  "conv2d_tc: bad output placement");
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) {
+    set_last_error("conv2d_tc: cuTensorMapEncodeTiled not available from the driver");
+    return DBEV_ERR_CUDA;
+  }
+  int dev = 0, sms = 0;
+  DBEV_CUDA(cudaGetDevice(&dev));
+  DBEV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int halo_mode = conv_halo_mode();
+  if (halo_mode > 0 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && h >= 16 && w >= kHaloTx && out_mul == 1 &&
+      out_add_y == 0 && out_add_x == 0 && !out_nchw && out_h == h && out_w == w) {
+    HaloShape hs;
+    hs.n_img = n_img, hs.c_in = c_in, hs.ho = h, hs.wo = w;
+    hs.tiles_x = ceil_div(w, kHaloTx), hs.tiles_y = ceil_div(h, kHaloTy);
+    hs.n_tiles = hs.tiles_x * hs.tiles_y * n_img;
+    hs.cin_chunks = c_in / kKc;
+    hs.hx = halo_mode == 1 ? kHaloTx + 2 : 16;
+    hs.a_stage = (kHaloRows * hs.hx * kKc * 4 + 1023) / 1024 * 1024;
+    const int w_tile = c_out * kKc * 4;
+    const int stage_out = 4 * 2 * 4096;       // 4 epilogue warps x 2 staging buffers x (32 px x 128 B)
+    int w_stages = (227 * 1024 - 2048 - 2 * hs.a_stage - stage_out) / w_tile;
+    if (w_stages > 6) w_stages = 6;
+    DBEV_CHECK_ARG(w_stages >= 2, "conv2d_tc: halo tile does not fit shared memory");
+    hs.w_stages = w_stages;
+    hs.c_off = out_c_off, hs.relu = relu;
+    CUtensorMap tmap_x, tmap_w, tmap_o;
+    {
+      // NHWC output [n, H, W, ld] as (C, W, H, N); a store box = 32 channels x 8 px x 4 rows, clipped at the borders
+      cuuint64_t dims[4] = {(cuuint64_t)out_ld, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n_img};
+      cuuint64_t strides[3] = {(cuuint64_t)out_ld * 4, (cuuint64_t)w * out_ld * 4, (cuuint64_t)h * w * out_ld * 4};
+      cuuint32_t box[4] = {(cuuint32_t)kKc, (cuuint32_t)kHaloTx, 4, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = encode(&tmap_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)out, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_last_error("conv2d_tc: cuTensorMapEncodeTiled(out) failed (%d)", (int)r);
+        return DBEV_ERR_CUDA;
+      }
+    }
+    {
+      cuuint64_t dims[4] = {(cuuint64_t)c_in, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n_img};
+      cuuint64_t strides[3] = {(cuuint64_t)c_in * 4, (cuuint64_t)w * c_in * 4, (cuuint64_t)h * w * c_in * 4};
+      cuuint32_t box[4] = {(cuuint32_t)kKc, (cuuint32_t)hs.hx, (cuuint32_t)kHaloRows, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = encode(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x_nhwc, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_last_error("conv2d_tc: cuTensorMapEncodeTiled(x halo) failed (%d)", (int)r);
+        return DBEV_ERR_CUDA;
+      }
+    }
+    {
+      const int k_total = 9 * c_in;
+      cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)c_out};
+      cuuint64_t strides[1] = {(cuuint64_t)k_total * 4};
+      cuuint32_t box[2] = {(cuuint32_t)kKc, (cuuint32_t)c_out};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = encode(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w_packed, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_last_error("conv2d_tc: cuTensorMapEncodeTiled(w) failed (%d)", (int)r);
+        return DBEV_ERR_CUDA;
+      }
+    }
+    const size_t smem = 2 * (size_t)hs.a_stage + (size_t)w_stages * w_tile + stage_out + 1024;
+    const int grid = hs.n_tiles < sms ? hs.n_tiles : sms;
+    // DBEV_CONV_PROF=1: per-role wait cycles (debug only: synchronises and prints after every launch)
+    static long long* prof_buf = nullptr;
+    long long* prof = nullptr;
+    if (getenv("DBEV_CONV_PROF")) {
+      if (!prof_buf) DBEV_CUDA(cudaMalloc(&prof_buf, sizeof(long long) * 16 * 1024));
+      DBEV_CUDA(cudaMemsetAsync(prof_buf, 0, sizeof(long long) * 16 * 1024, stream));
+      prof = prof_buf;
+    }
+#define DBEV_HALO_LAUNCH(CO)                                                                                 \
+  do {                                                                                                       \
+    DBEV_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                   (int)smem));                                                              \
+    conv3x3_halo_kernel<CO><<<grid, kConvThreads, smem, stream>>>(tmap_x, tmap_w, tmap_o, scale, shift, out, hs, prof); \
+  } while (0)
+    if (c_out == 64) DBEV_HALO_LAUNCH(64);
+    else if (c_out == 128) DBEV_HALO_LAUNCH(128);
+    else DBEV_HALO_LAUNCH(256);
+#undef DBEV_HALO_LAUNCH
+    DBEV_CHECK_LAUNCH("conv3x3_halo_kernel");
+    if (prof) {
+      static long long hbuf[16 * 1024];
+      DBEV_CUDA(cudaStreamSynchronize(stream));
+      DBEV_CUDA(cudaMemcpy(hbuf, prof, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost));
+      double a[16] = {0};
+      for (int b = 0; b < grid; ++b)
+        for (int j = 0; j < 16; ++j) a[j] += (double)hbuf[b * 16 + j] / grid;
+      fprintf(stderr, "halo prof c=%d->%d %dx%d grid=%d tiles=%d | producer total %.0f wait_a %.0f wait_w %.0f | mma total %.0f "
+                      "wait_tmem %.0f wait_a %.0f wait_w %.0f | epi total %.0f wait_full %.0f\n",
+              c_in, c_out, h, w, grid, hs.n_tiles, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[8], a[9]);
+    }
+    return DBEV_OK;
+  }
   ConvShape s;
   s.n_img = n_img, s.c_in = c_in, s.c_out = c_out, s.kh = kh, s.kw = kw, s.stride = stride, s.pad = pad;
   s.ho = (h + 2 * pad - kh) / stride + 1;
@@ -228,12 +620,25 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   s.ld = out_ld, s.c_off = out_c_off, s.relu = relu, s.nchw = out_nchw ? 1 : 0;
   DBEV_CHECK_ARG(s.tx * stride <= 256 && s.ty * stride <= 256, "conv2d_tc: tile too large for a TMA box");
 
-  EncodeTiledFn encode = get_encode_fn();
-  if (!encode) {
-    set_last_error("conv2d_tc: cuTensorMapEncodeTiled not available from the driver");
-    return DBEV_ERR_CUDA;
+  s.tma_store = (!out_nchw && out_mul == 1 && out_add_y == 0 && out_add_x == 0 && out_h == s.ho && out_w == s.wo) ? 1 : 0;
+  CUtensorMap tmap_x, tmap_w, tmap_o;
+  tmap_o = CUtensorMap();
+  if (s.tma_store) {
+    // a warp's 32 pixels of the tile: min(TX, 32) px x 32 / min(TX, 32) rows
+    const int bx = s.tx < 32 ? s.tx : 32;
+    cuuint64_t dims[4] = {(cuuint64_t)out_ld, (cuuint64_t)out_w, (cuuint64_t)out_h, (cuuint64_t)n_img};
+    cuuint64_t strides[3] = {(cuuint64_t)out_ld * 4, (cuuint64_t)out_w * out_ld * 4,
+                             (cuuint64_t)out_h * out_w * out_ld * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kKc, (cuuint32_t)bx, (cuuint32_t)(32 / bx), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&tmap_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)out, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_last_error("conv2d_tc: cuTensorMapEncodeTiled(out) failed (%d)", (int)r);
+      return DBEV_ERR_CUDA;
+    }
   }
-  CUtensorMap tmap_x, tmap_w;
   {
     // NHWC input as a 4-D tensor (C, W, H, N); box {32, TX*s, TY*s, 1} traversed with element strides
     // {1, s, s, 1} loads TX x TY pixels; out-of-bounds coordinates (the padding) are zero-filled
@@ -263,22 +668,20 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
       return DBEV_ERR_CUDA;
     }
   }
-  int dev = 0, sms = 0;
-  DBEV_CUDA(cudaGetDevice(&dev));
-  DBEV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 #define DBEV_CONV_LAUNCH(CO, STG, MB)                                                            \
   do {                                                                                           \
-    const size_t smem = (size_t)STG * (kATile + CO * kKc * 4) + 1024;                            \
+    const size_t smem = (size_t)STG * (kATile + CO * kKc * 4) + 4 * 8192 + 1024;                 \
     const int grid = s.n_tiles < sms * MB ? s.n_tiles : sms * MB;                                \
     DBEV_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel<CO, STG, MB>,                                \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    conv2d_tc_kernel<CO, STG, MB><<<grid, kConvThreads, smem, stream>>>(tmap_x, tmap_w, scale, shift, out, s); \
+    conv2d_tc_kernel<CO, STG, MB><<<grid, kConvThreads, smem, stream>>>(tmap_x, tmap_w, tmap_o, scale, shift, out, s); \
   } while (0)
   // two CTAs per SM where shared memory and TMEM allow it: one CTA's epilogue / TMA latency hides
   // behind the other's MMAs (1.68 -> 1.56 ms for the whole SECOND + SECONDFPN stack); three CTAs of
   // the 64-channel kernel or deeper stage rings gave nothing
-  if (c_out == 64) DBEV_CONV_LAUNCH(64, 4, 2);
-  else if (c_out == 128) DBEV_CONV_LAUNCH(128, 3, 2);
+  // (+ 32 KB of output staging per CTA: 3 x 24 KB / 2 x 32 KB stage rings keep two CTAs resident)
+  if (c_out == 64) DBEV_CONV_LAUNCH(64, 3, 2);
+  else if (c_out == 128) DBEV_CONV_LAUNCH(128, 2, 2);
   else DBEV_CONV_LAUNCH(256, 4, 1);
 #undef DBEV_CONV_LAUNCH
   DBEV_CHECK_LAUNCH("conv2d_tc_kernel");
