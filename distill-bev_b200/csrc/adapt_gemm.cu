@@ -55,7 +55,7 @@ adapt_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_w,
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar, tmem_empty_bar;
   __shared__ uint32_t tmem_base_s;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // uniform for the compiler
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -103,35 +103,39 @@ adapt_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_w,
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(kBM, kBN);
-      uint32_t stage = 0, phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty_bar, acc_phase ^ 1u);  // epilogue has drained the accumulators
+    // The whole warp walks the loop and one elected lane issues: with warp-uniform control flow the
+    // descriptors live in uniform registers and the tcgen05.mma go out back to back (a lane-0-only
+    // loop rebuilt them through R2UR, ~25 instructions per MMA).
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_tf32(kBM, kBN);
+    const uint64_t desc0 = umma_desc(0, 16, 1024);   // K-major, 8-row groups 1024 B apart; a K step of 8 fp32 = 32 B
+    uint32_t stage = 0, phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar, acc_phase ^ 1u);  // epilogue has drained the accumulators
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int kc = 0; kc < s.k_chunks; ++kc) {
+        mbar_wait(&full_bar[stage], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int kc = 0; kc < s.k_chunks; ++kc) {
-          mbar_wait(&full_bar[stage], phase);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a0 = smem_addr(base + (size_t)stage * kStageBytes);
-          const uint32_t b0 = a0 + MT * kATileBytes;
+        const uint32_t a0 = smem_addr(base + (size_t)stage * kStageBytes);
+        const uint64_t ad = desc0 + (uint64_t)(a0 >> 4), bd = desc0 + (uint64_t)((a0 + MT * kATileBytes) >> 4);
+        const uint32_t acc0 = kc != 0 ? 1u : 0u;
+        if (leader) {
 #pragma unroll
           for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
-            // B (MN-major): one 8-row K group = 1024 B; MN atoms 4096 B apart
-            // both operands K-major: 8-row groups 1024 B apart; a K step of 8 fp32 = 32 B in the row
-            const uint64_t bdesc = umma_desc(b0 + kk * (kUmmaK * 4), 16, 1024);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              // A (K-major): 8-row groups 1024 B apart; a K step of 8 fp32 = 32 B inside the row
-              const uint64_t adesc = umma_desc(a0 + mt * kATileBytes + kk * (kUmmaK * 4), 16, 1024);
-              umma_tf32(tmem_base + mt * kBN, adesc, bdesc, idesc, (kc | kk) != 0 ? 1u : 0u);
-            }
+            for (int mt = 0; mt < MT; ++mt)
+              umma_tf32(tmem_base + mt * kBN, ad + (uint64_t)((mt * kATileBytes + kk * (kUmmaK * 4)) >> 4),
+                        bd + (uint64_t)((kk * (kUmmaK * 4)) >> 4), idesc, kk != 0 ? 1u : acc0);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tmem_full_bar);       // accumulators complete -> epilogue
-        acc_phase ^= 1u;
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (leader) umma_commit(&tmem_full_bar);       // accumulators complete -> epilogue
+      __syncwarp();
+      acc_phase ^= 1u;
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)

@@ -246,16 +246,31 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 // weight traffic per pixel halves as well. L2->SMEM bytes per 128 pixels (C_in = C_out):
 //   64 ch: 435 KB -> 117 KB, 128 ch: 1166 KB -> 387 KB, 256 ch: 3.5 MB -> 1.36 MB.
 // Warp roles as above; one CTA per SM; accumulators 2 halves x 2 buffers (x 1 at C_out = 256).
-constexpr int kHaloTx = 8, kHaloTy = 32;         // output pixels of a tile (two M=128 halves of 16 rows)
-constexpr int kHaloRows = kHaloTy + 2;
+constexpr int kHaloTx = 8;                        // tile width; a tile is one or two M=128 halves of 16 image rows
 
 struct HaloShape {
-  int n_img, c_in, ho, wo, tiles_x, tiles_y, n_tiles, cin_chunks;
+  int n_img, c_in, ho, wo, tiles_x, tiles_y, cin_chunks;
+  // work items: the first n_full items are whole tiles (item_halves halves of 16 rows each); the tiles of
+  // the last, partial round are split into single halves so that the round lasts half as long
+  int n_full, n_items, item_halves, tile_rows;
   int hx;            // halo pitch in pixels (box width), >= kHaloTx + 2
   int a_stage;       // bytes of one halo stage (multiple of 1024)
   int w_stages;      // weight ring depth
   int c_off, relu;
 };
+
+__device__ __forceinline__ void halo_item(const HaloShape& s, int i, int& n, int& y0, int& x0, int& halves) {
+  int t = i, yoff = 0;
+  halves = s.item_halves;
+  if (i >= s.n_full) {
+    const int j = i - s.n_full;
+    t = s.n_full + (j >> 1), yoff = (j & 1) * 16, halves = 1;
+  }
+  const int per_img = s.tiles_x * s.tiles_y;
+  n = t / per_img;
+  const int r = t - n * per_img;
+  y0 = (r / s.tiles_x) * s.tile_rows + yoff, x0 = (r % s.tiles_x) * kHaloTx;
+}
 
 template <int COUT>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -301,8 +316,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
-  const int per_img = s.tiles_x * s.tiles_y;
-  const uint32_t a_bytes = (uint32_t)(kHaloRows * s.hx * kKc * 4);
+  const uint32_t a_bytes = (uint32_t)((s.tile_rows + 2) * s.hx * kKc * 4);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -314,9 +328,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       // warp (w_stages taps behind) has left chunk i-1, so its halo stage is free without waiting
       int t_n = blockIdx.x, c_n = 0;
       auto issue_halo = [&]() {
-        if (t_n >= s.n_tiles) return;
-        const int n = t_n / per_img, r = t_n % per_img;
-        const int y0 = (r / s.tiles_x) * kHaloTy, x0 = (r % s.tiles_x) * kHaloTx;
+        if (t_n >= s.n_items) return;
+        int n, y0, x0, halves;
+        halo_item(s, t_n, n, y0, x0, halves);
         { const long long t = prof ? clock64() : 0; mbar_wait(&a_empty[sa], pa ^ 1u); if (prof) pw_a += clock64() - t; }
         mbar_expect_tx(&a_full[sa], a_bytes);
         asm volatile(
@@ -329,7 +343,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       };
       const int ahead = s.w_stages < 8 ? s.w_stages : 8;
       issue_halo();
-      for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < s.n_items; tile += gridDim.x) {
         for (int cc = 0; cc < s.cin_chunks; ++cc) {
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
@@ -355,8 +369,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     uint32_t sa = 0, pa = 0, sw = 0, pw = 0, it = 0;
     long long mw_t = 0, mw_a = 0, mw_w = 0;
     const long long mt0 = prof ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < s.n_items; tile += gridDim.x, ++it) {
       const uint32_t buf = kNBuf == 2 ? (it & 1u) : 0u, use = kNBuf == 2 ? (it >> 1) : it;
+      const int halves = tile < s.n_full ? s.item_halves : 1;
       { const long long t = prof ? clock64() : 0; mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u); if (prof) mw_t += clock64() - t; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + buf * 2 * COUT;
@@ -373,10 +388,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           const uint32_t acc0 = (cc | tap) != 0 ? 1u : 0u;
           if (leader) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int kk = 0; kk < kKc / 8; ++kk)
+              umma_tf32(d_tmem, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, kk != 0 ? 1u : acc0);
+            if (halves == 2) {
 #pragma unroll
               for (int kk = 0; kk < kKc / 8; ++kk)
-                umma_tf32(d_tmem + h * COUT, ad + (uint64_t)(h * half_units + kk * 2), bd + (uint64_t)(kk * 2), idesc,
+                umma_tf32(d_tmem + COUT, ad + (uint64_t)(half_units + kk * 2), bd + (uint64_t)(kk * 2), idesc,
                           kk != 0 ? 1u : acc0);
             }
             umma_commit(&w_empty[sw]);
@@ -406,14 +423,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     uint32_t it = 0, sbuf = 0;
     long long ew_f = 0;
     const long long et0 = prof ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < s.n_items; tile += gridDim.x, ++it) {
       const uint32_t buf = kNBuf == 2 ? (it & 1u) : 0u, use = kNBuf == 2 ? (it >> 1) : it;
-      const int n = tile / per_img, r = tile % per_img;
-      const int ty0 = (r / s.tiles_x) * kHaloTy, tx0 = (r % s.tiles_x) * kHaloTx;
+      int n, ty0, tx0, halves;
+      halo_item(s, tile, n, ty0, tx0, halves);
       { const long long t = prof ? clock64() : 0; mbar_wait(&tmem_full_bar[buf], use & 1u); if (prof) ew_f += clock64() - t; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < halves; ++h) {
         const int oy0 = ty0 + h * 16 + q * 4;      // first image row of this warp's 4 x 8 pixel box
 #pragma unroll 1
         for (int cc = 0; cc < COUT / 32; ++cc) {
@@ -471,7 +488,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 }
 
 // A/B switch: DBEV_CONV_HALO = 0 (per-tap kernel for every layer), 1 (default: halo kernel, pitch 10),
-// 2 (pitch 16). Measured: both pitches are bit-identical to the per-tap kernel (descriptor base-offset 0);
+// 2 (pitch 16), 4 (no split of the last round). Measured: both pitches are bit-identical to the per-tap kernel (descriptor base-offset 0);
 // setting the descriptor's base-offset field to (start >> 7) & 7 gives wrong results.
 int conv_halo_mode() {
   static int mode = -1;
@@ -513,14 +530,24 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
       out_add_y == 0 && out_add_x == 0 && !out_nchw && out_h == h && out_w == w) {
     HaloShape hs;
     hs.n_img = n_img, hs.c_in = c_in, hs.ho = h, hs.wo = w;
-    hs.tiles_x = ceil_div(w, kHaloTx), hs.tiles_y = ceil_div(h, kHaloTy);
-    hs.n_tiles = hs.tiles_x * hs.tiles_y * n_img;
     hs.cin_chunks = c_in / kKc;
-    hs.hx = halo_mode == 1 ? kHaloTx + 2 : 16;
-    hs.a_stage = (kHaloRows * hs.hx * kKc * 4 + 1023) / 1024 * 1024;
+    hs.hx = halo_mode == 2 ? 16 : kHaloTx + 2;
     const int w_tile = c_out * kKc * 4;
     const int stage_out = 4 * 2 * 4096;       // 4 epilogue warps x 2 staging buffers x (32 px x 128 B)
-    int w_stages = (227 * 1024 - 2048 - 2 * hs.a_stage - stage_out) / w_tile;
+    const int smem_max = 227 * 1024 - 2048;
+    // (keeping all 9 * C_in/32 weight tiles of a 64 -> 64 layer resident in shared memory was tried: only
+    // single-half tiles fit beside them, whose halo prefetch distance is too short - 0.132 vs 0.110 ms)
+    hs.item_halves = 2;
+    hs.tile_rows = 16 * hs.item_halves;
+    hs.tiles_x = ceil_div(w, kHaloTx), hs.tiles_y = ceil_div(h, hs.tile_rows);
+    const int n_tiles = hs.tiles_x * hs.tiles_y * n_img;
+    hs.n_full = n_tiles, hs.n_items = n_tiles;
+    if (halo_mode != 4) {
+      const int rem = n_tiles % sms;
+      if (rem > 0 && 2 * rem <= sms) hs.n_full = n_tiles - rem, hs.n_items = hs.n_full + 2 * rem;
+    }
+    hs.a_stage = ((hs.tile_rows + 2) * hs.hx * kKc * 4 + 1023) / 1024 * 1024;
+    int w_stages = (smem_max - 2 * hs.a_stage - stage_out) / w_tile;
     if (w_stages > 6) w_stages = 6;
     DBEV_CHECK_ARG(w_stages >= 2, "conv2d_tc: halo tile does not fit shared memory");
     hs.w_stages = w_stages;
@@ -543,7 +570,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
     {
       cuuint64_t dims[4] = {(cuuint64_t)c_in, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n_img};
       cuuint64_t strides[3] = {(cuuint64_t)c_in * 4, (cuuint64_t)w * c_in * 4, (cuuint64_t)h * w * c_in * 4};
-      cuuint32_t box[4] = {(cuuint32_t)kKc, (cuuint32_t)hs.hx, (cuuint32_t)kHaloRows, 1};
+      cuuint32_t box[4] = {(cuuint32_t)kKc, (cuuint32_t)hs.hx, (cuuint32_t)(hs.tile_rows + 2), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = encode(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x_nhwc, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -568,7 +595,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
       }
     }
     const size_t smem = 2 * (size_t)hs.a_stage + (size_t)w_stages * w_tile + stage_out + 1024;
-    const int grid = hs.n_tiles < sms ? hs.n_tiles : sms;
+    const int grid = hs.n_items < sms ? hs.n_items : sms;
     // DBEV_CONV_PROF=1: per-role wait cycles (debug only: synchronises and prints after every launch)
     static long long* prof_buf = nullptr;
     long long* prof = nullptr;
@@ -597,7 +624,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
         for (int j = 0; j < 16; ++j) a[j] += (double)hbuf[b * 16 + j] / grid;
       fprintf(stderr, "halo prof c=%d->%d %dx%d grid=%d tiles=%d | producer total %.0f wait_a %.0f wait_w %.0f | mma total %.0f "
                       "wait_tmem %.0f wait_a %.0f wait_w %.0f | epi total %.0f wait_full %.0f\n",
-              c_in, c_out, h, w, grid, hs.n_tiles, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[8], a[9]);
+              c_in, c_out, h, w, grid, hs.n_items, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[8], a[9]);
     }
     return DBEV_OK;
   }

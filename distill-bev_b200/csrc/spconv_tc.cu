@@ -80,7 +80,7 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
   __shared__ int idx_s[KVOL * kTileM];  // neighbour rows of the current tile, [k][row]
   __shared__ uint32_t tmem_base_s;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // uniform for the compiler
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -223,46 +223,49 @@ sp_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_whi,
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(kTileM, COUT);
-      uint32_t stage = 0, phase = 0;
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t buf = it % NBUF, use = it / NBUF;
-        mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);  // epilogue has drained this buffer
+    // whole warp in the loop (warp-uniform control flow -> descriptors in uniform registers, MMAs
+    // issued back to back), one elected lane issues and commits
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_tf32(kTileM, COUT);
+    const uint64_t desc0 = umma_desc(0, 16, 1024);
+    uint32_t stage = 0, phase = 0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it % NBUF, use = it / NBUF;
+      mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);  // epilogue has drained this buffer
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d0 = tmem_base + buf * (NACC * COUT);
+      const uint32_t d1 = d0 + (NACC > 1 ? COUT : 0);
+      const uint32_t d2 = d0 + (NACC > 2 ? 2 * COUT : (NACC > 1 ? COUT : 0));
+      uint32_t first = 1;                      // no accumulator of this tile has been written yet
+      while (true) {
+        mbar_wait(&full_bar[stage], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d0 = tmem_base + buf * (NACC * COUT);
-        const uint32_t d1 = d0 + (NACC > 1 ? COUT : 0);
-        const uint32_t d2 = d0 + (NACC > 2 ? 2 * COUT : (NACC > 1 ? COUT : 0));
-        uint32_t acc0 = 0, acc1 = 0, acc2 = 0;   // 0 until the accumulator has been written
-        while (true) {
-          mbar_wait(&full_bar[stage], phase);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t flags = stage_flags[stage];
-          const uint32_t w_hi = smem_addr(base + (size_t)stage * kStageBytes);
-          const uint32_t w_lo = w_hi + kWBytes;
-          const uint32_t a_hi = tmem_base + kAccCols + stage * kAStageCols;  // lane 0, A columns
-          const uint32_t a_lo = a_hi + 32;
+        const uint32_t flags = __shfl_sync(0xffffffffu, stage_flags[stage], 0);
+        const uint32_t w_hi = smem_addr(base + (size_t)stage * kStageBytes);
+        const uint64_t d_whi = desc0 + (uint64_t)(w_hi >> 4), d_wlo = desc0 + (uint64_t)((w_hi + kWBytes) >> 4);
+        const uint32_t a_hi = tmem_base + kAccCols + stage * kAStageCols;  // lane 0, A columns
+        const uint32_t a_lo = a_hi + 32;
+        if (leader && !(s.debug & 16)) {
 #pragma unroll
           for (int kk = 0; kk < kChunk / 8; ++kk) {
-            if (s.debug & 16) break;
-            const uint64_t d_whi = umma_desc(w_hi + kk * 32, 16, 1024);
-            const uint64_t d_wlo = umma_desc(w_lo + kk * 32, 16, 1024);
-            umma_tf32_ts(d0, a_hi + kk * 8, d_whi, idesc, acc0);
-            acc0 = 1;
-            if (NACC == 1) acc1 = acc2 = 1;
-            umma_tf32_ts(d1, a_lo + kk * 8, d_whi, idesc, acc1);
-            acc1 = 1;
-            if (NACC == 2) acc2 = 1;
-            umma_tf32_ts(d2, a_hi + kk * 8, d_wlo, idesc, acc2);
-            acc2 = 1;
+            // accumulate flags: with NACC < 3 several products share an accumulator, only the first write clears it
+            const uint32_t c0 = (kk == 0 && first) ? 0u : 1u;
+            const uint32_t c1 = (NACC > 1) ? c0 : 1u;
+            const uint32_t c2 = (NACC > 2) ? c0 : 1u;
+            umma_tf32_ts(d0, a_hi + kk * 8, d_whi + (uint64_t)(kk * 2), idesc, c0);
+            umma_tf32_ts(d1, a_lo + kk * 8, d_whi + (uint64_t)(kk * 2), idesc, c1);
+            umma_tf32_ts(d2, a_hi + kk * 8, d_wlo + (uint64_t)(kk * 2), idesc, c2);
           }
           umma_commit(&empty_bar[stage]);  // frees the stage when these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          if (flags & 2u) break;
         }
-        umma_commit(&tmem_full_bar[buf]);
+        __syncwarp();
+        first = 0;
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (flags & 2u) break;
       }
+      if (leader) umma_commit(&tmem_full_bar[buf]);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue (4 warps after the producers)
