@@ -47,7 +47,7 @@ N_CAMS, D, FH, FW, C_TRANS, BEV = 6, 59, 16, 44, 64, 128
 N_POINTS = 30000
 C_STUDENT, C_TEACHER = 256, 384
 WORKLOAD = ("hotpath-ops-v2: lift+splat fwd/bwd (B=8 x 2 frames, 6 cams, D=59, 16x44, C=64 -> 128x128; sort-free splat: "
-            "vector float reductions into the L2-resident BEV map, summation order not fixed, --sorted-splat for the plan-based one) "
+            "vector float reductions into the L2-resident channels-last BEV map, summation order not fixed, upstream gradient in the same layout; --sorted-splat for the plan-based one) "
             "+ frozen LiDAR teacher end to end: voxelize/pillar-encode/scatter (8 x 30k pts -> 512x512x64) -> "
             "SECOND + SECONDFPN (tcgen05 conv+BN+ReLU, 601 GFLOP) -> teacher BEV feature [8,384,128,128] "
             "+ CenterHead GT heat maps rasterised on the device + 1x1 adaptation conv (tcgen05 fwd, cuDNN bwd) + fgd distill loss fwd/bwd at head against that "
@@ -173,6 +173,9 @@ class HotPath(object):
         self.depth = torch.randn(nf * N_CAMS, D, FH, FW, generator=g).softmax(1).to(device).requires_grad_(True)
         self.feat = torch.randn(nf * N_CAMS, C_TRANS, FH, FW, generator=g).to(device).requires_grad_(True)
         self.bev_grad = torch.rand(nf, C_TRANS, BEV, BEV, generator=g).to(device)
+        # the sort-free splat returns channels_last memory; its upstream gradient (a cuDNN / tcgen05 conv backward on
+        # that tensor) arrives in the same layout
+        self.bev_grad_cl = self.bev_grad.contiguous(memory_format=torch.channels_last)
         self.sorted_splat = False
         self.student = torch.relu(torch.randn(BATCH, C_STUDENT, BEV, BEV, generator=g)).to(device).requires_grad_(True)
         self.teacher = torch.relu(torch.randn(BATCH, C_TEACHER, BEV, BEV, generator=g)).to(device)
@@ -243,7 +246,7 @@ class HotPath(object):
         geom = self.vt.get_geometry(*calib)
         plan = (self.vt.make_plan if self.sorted_splat else self.vt.make_cells)(geom, BATCH * FRAMES)
         bev = dbev.lift_splat(self.depth, self.feat, plan)
-        bev.backward(self.bev_grad)
+        bev.backward(self.bev_grad if self.sorted_splat else self.bev_grad_cl)
         for st in self.side:
             main.wait_stream(st)
         grads = [self.depth.grad, self.feat.grad, self.student.grad, self.adapt.weight.grad,

@@ -41,6 +41,46 @@ def test_conv_bn_relu_matches_torch(cuda, cin, cout, k, stride, pad, hw):
     _check(got.permute(0, 3, 1, 2), want)
 
 
+@pytest.mark.parametrize("n,cin,cout,hw", [(2, 64, 64, (40, 24)), (1, 128, 128, (64, 64)), (1, 64, 256, (37, 19)),
+                                           (1, 32, 64, (32, 8)), (2, 64, 128, (16, 8)), (1, 96, 64, (33, 41)),
+                                           (5, 64, 64, (96, 104))])
+def test_halo_conv3x3_matches_torch(cuda, n, cin, cout, hw):
+    """3x3 / stride 1 layers run on the halo-reuse kernel (taps = shifted descriptor windows of one TMA halo
+    box, TMA-store epilogue): ragged widths / heights (TMA clipping on both sides), tiles whose second half is
+    entirely outside the image, a last partial round split into single halves ((5, 96, 104): 195 tile pairs)."""
+    torch.manual_seed(n * 1000 + cin + cout)
+    conv = torch.nn.Conv2d(cin, cout, 3, 1, 1, bias=False).to(cuda)
+    x = torch.randn(n, cin, *hw, device=cuda)
+    scale = torch.rand(cout, device=cuda) + 0.5
+    shift = torch.randn(cout, device=cuda)
+    with torch.no_grad():
+        want = torch.relu(conv(x) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+        wp = conv.weight.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+        got = dt.conv_nhwc(x.permute(0, 2, 3, 1).contiguous(), wp, cout, 3, 3, 1, 1, scale, shift, True)
+        _check(got.permute(0, 3, 1, 2), want)
+        # no scale / shift / relu, written into a channel slice of a wider NHWC tensor: the rest stays untouched
+        wide = torch.full((n, hw[0], hw[1], cout + 64), -7.0, device=cuda)
+        dt.conv_nhwc(x.permute(0, 2, 3, 1).contiguous(), wp, cout, 3, 3, 1, 1, out=wide, c_off=32)
+        _check(wide[..., 32:32 + cout].permute(0, 3, 1, 2), conv(x))
+        assert bool((wide[..., :32] == -7.0).all()) and bool((wide[..., 32 + cout:] == -7.0).all())
+
+
+def test_halo_conv3x3_full_size_round_split(cuda):
+    """B=8 128x128 128->128 (512 tile pairs on 148 SMs: three full rounds + 68 pairs split into 136 halves)
+    against cuDNN fp32; run twice: bit-identical (fixed accumulation order)."""
+    torch.manual_seed(3)
+    conv = torch.nn.Conv2d(128, 128, 3, 1, 1, bias=False).to(cuda)
+    x = torch.randn(8, 128, 128, 128, device=cuda)
+    with torch.no_grad():
+        want = conv(x)
+        wp = conv.weight.permute(0, 2, 3, 1).reshape(128, -1).contiguous()
+        xh = x.permute(0, 2, 3, 1).contiguous()
+        got = dt.conv_nhwc(xh, wp, 128, 3, 3, 1, 1)
+        again = dt.conv_nhwc(xh, wp, 128, 3, 3, 1, 1)
+    _check(got.permute(0, 3, 1, 2), want)
+    assert torch.equal(got, again)
+
+
 def test_second_and_fpn_match_torch(cuda):
     torch.manual_seed(0)
     net = dbev.SECOND(in_channels=64, out_channels=[64, 128, 256], layer_nums=[3, 5, 5], layer_strides=[2, 2, 2]).to(cuda)
