@@ -122,6 +122,8 @@ SIGNATURES = {
                             + [_c_float] * 6 + [_c_int, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "dbev_conv2d_tc_forward": (_c_int, [_ptr] + [_c_int] * 4 + [_ptr] + [_c_int] * 5 + [_ptr, _ptr, _c_int, _ptr]
                                + [_c_int] * 8 + [_ptr]),
+    "dbev_conv2d_tc_forward_grouped": (_c_int, [_ptr] + [_c_int] * 4 + [_ptr] + [_c_int] * 5 + [_ptr, _ptr, _c_int, _ptr]
+                                       + [_c_int] * 9 + [_ptr]),
     "dbev_spconv_tc_supported": (_c_int, [_c_int, _c_int, _c_int]),
     "dbev_spconv_pack_weights": (_c_int, [_ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr]),
     "dbev_spconv_forward_tc": (_c_int, [_ptr, _c_int, _ptr, _ptr, _c_int, _ptr, _c_int, _c_int, _ptr,

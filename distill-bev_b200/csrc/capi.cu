@@ -409,7 +409,17 @@ int dbev_conv2d_tc_forward(const float* x_nhwc, int n, int h, int w, int c_in, c
                            int out_nchw, void* stream) {
   return conv2d_tc_forward(x_nhwc, n, h, w, c_in, w_packed, c_out, kh, kw, stride, pad, scale, shift,
                            relu, out, out_h, out_w, out_ld, out_c_off, out_mul, out_add_y, out_add_x,
-                           out_nchw, (cudaStream_t)stream);
+                           out_nchw, 1, (cudaStream_t)stream);
+}
+
+int dbev_conv2d_tc_forward_grouped(const float* x_nhwc, int n, int h, int w, int c_in, const float* w_packed,
+                                   int c_out, int kh, int kw, int stride, int pad, const float* scale,
+                                   const float* shift, int relu, float* out, int out_h, int out_w,
+                                   int out_ld, int out_c_off, int out_mul, int out_add_y, int out_add_x,
+                                   int out_nchw, int out_groups, void* stream) {
+  return conv2d_tc_forward(x_nhwc, n, h, w, c_in, w_packed, c_out, kh, kw, stride, pad, scale, shift,
+                           relu, out, out_h, out_w, out_ld, out_c_off, out_mul, out_add_y, out_add_x,
+                           out_nchw, out_groups, (cudaStream_t)stream);
 }
 
 int dbev_spconv_tc_supported(int c_in, int c_out, int kvol) {

@@ -39,6 +39,8 @@ struct ConvShape {
   int omul, oadd_y, oadd_x, h_full, w_full, ld, c_off, relu;
   int nchw;  // 1: out is [n, ld, H_full, W_full] (a lane = a pixel: stores of one channel coalesce along x)
   int tma_store;  // 1: NHWC output on the plain lattice, written by TMA from a shared-memory staging tile
+  int group_cols; // > 0: column block g = col / group_cols goes to lattice x + g, channel col % group_cols
+                  // (both x taps of a stride-2 transposed conv in one launch)
 };
 
 template <int COUT, int STAGES, int MINB>
@@ -174,17 +176,19 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const uint32_t dst = stg_row + sbuf * 4096u;
+        int grp = 0, ch0 = cc * 32;          // lattice x offset and first output channel of this column chunk
+        if (s.group_cols > 0) grp = ch0 / s.group_cols, ch0 -= grp * s.group_cols;
         if (valid || s.tma_store) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             if (scale) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cc * 32 + j));
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + ch0 + j));
               o.x *= sc.x, o.y *= sc.y, o.z *= sc.z, o.w *= sc.w;
             }
             if (shift) {
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cc * 32 + j));
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + ch0 + j));
               o.x += sh.x, o.y += sh.y, o.z += sh.z, o.w += sh.w;
             }
             if (s.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
@@ -193,10 +197,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                            "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
                            : "memory");
             } else if (s.nchw) {
-              float* oc = ocol + (long long)(cc * 32 + j) * plane;
+              float* oc = ocol + grp + (long long)(ch0 + j) * plane;
               oc[0] = o.x, oc[plane] = o.y, oc[2 * plane] = o.z, oc[3 * plane] = o.w;
             } else {
-              *reinterpret_cast<float4*>(orow + cc * 32 + j) = o;
+              *reinterpret_cast<float4*>(orow + (long long)grp * s.ld + ch0 + j) = o;
             }
           }
         }
@@ -505,7 +509,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
                       int c_out, int kh, int kw, int stride, int pad, const float* scale,
                       const float* shift, int relu, float* out, int out_h, int out_w, int out_ld,
                       int out_c_off, int out_mul, int out_add_y, int out_add_x, int out_nchw,
-                      cudaStream_t stream) {
+                      int out_groups, cudaStream_t stream) {
   DBEV_CHECK_ARG(n_img > 0 && h > 0 && w > 0, "conv2d_tc: empty input");
   DBEV_CHECK_ARG(c_in % kKc == 0 && c_in >= kKc, "conv2d_tc: C_in must be a multiple of 32 (got %d)", c_in);
   DBEV_CHECK_ARG(c_out == 64 || c_out == 128 || c_out == 256,
@@ -515,7 +519,9 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   DBEV_CHECK_ARG(((uintptr_t)x_nhwc & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)out & 15) == 0 &&
                      ((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0,
                  "conv2d_tc: pointers must be 16-byte aligned");
-  DBEV_CHECK_ARG(out_ld % 4 == 0 && out_c_off % 4 == 0 && out_c_off + c_out <= out_ld && out_mul >= 1,
+  DBEV_CHECK_ARG(out_groups >= 1 && out_groups <= out_mul && c_out % out_groups == 0 && (c_out / out_groups) % 32 == 0,
+                 "conv2d_tc: out_groups must divide C_out into multiples of 32 columns and fit the lattice step");
+  DBEV_CHECK_ARG(out_ld % 4 == 0 && out_c_off % 4 == 0 && out_c_off + c_out / out_groups <= out_ld && out_mul >= 1,
                  "conv2d_tc: bad output placement");
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) {
@@ -526,7 +532,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   DBEV_CUDA(cudaGetDevice(&dev));
   DBEV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int halo_mode = conv_halo_mode();
-  if (halo_mode > 0 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && h >= 16 && w >= kHaloTx && out_mul == 1 &&
+  if (halo_mode > 0 && out_groups == 1 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && h >= 16 && w >= kHaloTx && out_mul == 1 &&
       out_add_y == 0 && out_add_x == 0 && !out_nchw && out_h == h && out_w == w) {
     HaloShape hs;
     hs.n_img = n_img, hs.c_in = c_in, hs.ho = h, hs.wo = w;
@@ -633,7 +639,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   s.ho = (h + 2 * pad - kh) / stride + 1;
   s.wo = (w + 2 * pad - kw) / stride + 1;
   DBEV_CHECK_ARG(s.ho >= 1 && s.wo >= 1, "conv2d_tc: empty output");
-  DBEV_CHECK_ARG((s.ho - 1) * out_mul + out_add_y < out_h && (s.wo - 1) * out_mul + out_add_x < out_w,
+  DBEV_CHECK_ARG((s.ho - 1) * out_mul + out_add_y < out_h && (s.wo - 1) * out_mul + out_add_x + out_groups - 1 < out_w,
                  "conv2d_tc: output lattice exceeds the output tensor");
   // tile = TX x TY output pixels with TX * TY = 128, TX a power of two <= W_out
   int tx = 128;
@@ -647,7 +653,8 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   s.ld = out_ld, s.c_off = out_c_off, s.relu = relu, s.nchw = out_nchw ? 1 : 0;
   DBEV_CHECK_ARG(s.tx * stride <= 256 && s.ty * stride <= 256, "conv2d_tc: tile too large for a TMA box");
 
-  s.tma_store = (!out_nchw && out_mul == 1 && out_add_y == 0 && out_add_x == 0 && out_h == s.ho && out_w == s.wo) ? 1 : 0;
+  s.group_cols = out_groups > 1 ? c_out / out_groups : 0;
+  s.tma_store = (out_groups == 1 && !out_nchw && out_mul == 1 && out_add_y == 0 && out_add_x == 0 && out_h == s.ho && out_w == s.wo) ? 1 : 0;
   CUtensorMap tmap_x, tmap_w, tmap_o;
   tmap_o = CUtensorMap();
   if (s.tma_store) {
@@ -697,7 +704,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   }
 #define DBEV_CONV_LAUNCH(CO, STG, MB)                                                            \
   do {                                                                                           \
-    const size_t smem = (size_t)STG * (kATile + CO * kKc * 4) + 4 * 8192 + 1024;                 \
+    const size_t smem = (size_t)STG * (kATile + CO * kKc * 4) + (s.tma_store ? 4 * 8192 : 0) + 1024; \
     const int grid = s.n_tiles < sms * MB ? s.n_tiles : sms * MB;                                \
     DBEV_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel<CO, STG, MB>,                                \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
@@ -707,8 +714,9 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   // behind the other's MMAs (1.68 -> 1.56 ms for the whole SECOND + SECONDFPN stack); three CTAs of
   // the 64-channel kernel or deeper stage rings gave nothing
   // (+ 32 KB of output staging per CTA: 3 x 24 KB / 2 x 32 KB stage rings keep two CTAs resident)
-  if (c_out == 64) DBEV_CONV_LAUNCH(64, 3, 2);
-  else if (c_out == 128) DBEV_CONV_LAUNCH(128, 2, 2);
+  // direct-store outputs (FPN branches) need no staging and keep the deeper rings
+  if (c_out == 64) { if (s.tma_store) DBEV_CONV_LAUNCH(64, 3, 2); else DBEV_CONV_LAUNCH(64, 4, 2); }
+  else if (c_out == 128) { if (s.tma_store) DBEV_CONV_LAUNCH(128, 2, 2); else DBEV_CONV_LAUNCH(128, 3, 2); }
   else DBEV_CONV_LAUNCH(256, 4, 1);
 #undef DBEV_CONV_LAUNCH
   DBEV_CHECK_LAUNCH("conv2d_tc_kernel");

@@ -9,6 +9,6 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
                       int c_out, int kh, int kw, int stride, int pad, const float* scale,
                       const float* shift, int relu, float* out, int out_h, int out_w, int out_ld,
                       int out_c_off, int out_mul, int out_add_y, int out_add_x, int out_nchw,
-                      cudaStream_t stream);
+                      int out_groups, cudaStream_t stream);
 
 }  // namespace dbev

@@ -41,9 +41,10 @@ def _packed(mod, fn):
 
 
 def conv_nhwc(x, w_packed, c_out, kh, kw, stride, pad, scale=None, shift=None, relu=False, out=None,
-              c_off=0, out_mul=1, out_add=(0, 0), out_nchw=False):
+              c_off=0, out_mul=1, out_add=(0, 0), out_nchw=False, out_groups=1):
     """x [N, H, W, C_in] contiguous fp32 -> out [N, Ho*out_mul, Wo*out_mul, ld] (channel slice c_off),
-    or, with out_nchw, out [N, ld, Ho*out_mul, Wo*out_mul]."""
+    or, with out_nchw, out [N, ld, Ho*out_mul, Wo*out_mul]. out_groups > 1: the c_out columns are out_groups
+    blocks of c_out / out_groups channels, block g lands at lattice x + g (x taps of a transposed conv)."""
     lib = _lib.load()
     _lib.require_cuda(x, "x", torch.float32)
     if not x.is_contiguous():
@@ -56,10 +57,10 @@ def conv_nhwc(x, w_packed, c_out, kh, kw, stride, pad, scale=None, shift=None, r
     with torch.cuda.device(x.device):
         oh, ow, ld = (out.shape[2], out.shape[3], out.shape[1]) if out_nchw else \
             (out.shape[1], out.shape[2], out.shape[3])
-        rc = lib.dbev_conv2d_tc_forward(_lib.ptr(x), n, h, w, c_in, _lib.ptr(w_packed), c_out, kh, kw, stride,
-                                        pad, _lib.ptr(scale), _lib.ptr(shift), 1 if relu else 0, _lib.ptr(out),
-                                        oh, ow, ld, c_off, out_mul, out_add[0], out_add[1],
-                                        1 if out_nchw else 0, _lib.stream_ptr(x.device))
+        rc = lib.dbev_conv2d_tc_forward_grouped(_lib.ptr(x), n, h, w, c_in, _lib.ptr(w_packed), c_out, kh, kw,
+                                                stride, pad, _lib.ptr(scale), _lib.ptr(shift), 1 if relu else 0,
+                                                _lib.ptr(out), oh, ow, ld, c_off, out_mul, out_add[0], out_add[1],
+                                                1 if out_nchw else 0, out_groups, _lib.stream_ptr(x.device))
     _lib.check(rc, "dbev_conv2d_tc_forward")
     return out
 
@@ -165,11 +166,19 @@ class SECONDFPN(nn.Module):
                 wp = _packed(up, lambda w: w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous())
                 conv_nhwc(h, wp, co, k, k, k, 0, scale, shift, True, out=out, c_off=c_off, out_nchw=True)
             else:
-                # ConvTranspose2d(k, stride k): out[2y+dy, 2x+dx] = W[:, :, dy, dx]^T . in[y, x] -> k*k 1x1 convs
-                wps = _packed(up, lambda w: [w[:, :, dy, dx].t().contiguous() for dy in range(k) for dx in range(k)])
-                for dy in range(k):
-                    for dx in range(k):
-                        conv_nhwc(h, wps[dy * k + dx], co, 1, 1, 1, 0, scale, shift, True, out=out, c_off=c_off,
-                                  out_mul=k, out_add=(dy, dx), out_nchw=True)
+                # ConvTranspose2d(k, stride k): out[2y+dy, 2x+dx] = W[:, :, dy, dx]^T . in[y, x] -> k*k 1x1 convs;
+                # the k x taps of a row share the input tile: one launch with k column groups when it fits N <= 256
+                if k * co <= 256 and co % 32 == 0:
+                    wps = _packed(up, lambda w: [torch.cat([w[:, :, dy, dx].t() for dx in range(k)], 0).contiguous()
+                                                 for dy in range(k)])
+                    for dy in range(k):
+                        conv_nhwc(h, wps[dy], k * co, 1, 1, 1, 0, scale, shift, True, out=out, c_off=c_off,
+                                  out_mul=k, out_add=(dy, 0), out_nchw=True, out_groups=k)
+                else:
+                    wps = _packed(up, lambda w: [w[:, :, dy, dx].t().contiguous() for dy in range(k) for dx in range(k)])
+                    for dy in range(k):
+                        for dx in range(k):
+                            conv_nhwc(h, wps[dy * k + dx], co, 1, 1, 1, 0, scale, shift, True, out=out, c_off=c_off,
+                                      out_mul=k, out_add=(dy, dx), out_nchw=True)
             c_off += co
         return [out]

@@ -398,6 +398,16 @@ int dbev_conv2d_tc_forward(const float* x_nhwc, int n, int h, int w, int c_in, c
                            int out_ld, int out_c_off, int out_mul, int out_add_y, int out_add_x,
                            int out_nchw, void* stream);
 
+/* Same, with the C_out columns split into out_groups blocks of C_out / out_groups real channels: block g is
+ * written at lattice x + g (channel = column % (C_out / out_groups); scale / shift are per real channel).
+ * With out_mul = 2, out_groups = 2 one launch computes both x taps of a k2/s2 ConvTranspose2d row
+ * (second_fpn.py:41-46: the deconv of the stride-4 branch) from ONE read of the input tile. */
+int dbev_conv2d_tc_forward_grouped(const float* x_nhwc, int n, int h, int w, int c_in, const float* w_packed,
+                                   int c_out, int kh, int kw, int stride, int pad, const float* scale,
+                                   const float* shift, int relu, float* out, int out_h, int out_w,
+                                   int out_ld, int out_c_off, int out_mul, int out_add_y, int out_add_x,
+                                   int out_nchw, int out_groups, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * Cross-modal feature distillation loss (FGD-style), BEVDetDistill
  * (mmdet3d/models/detectors/bevdet_distill.py). The reference has no native
