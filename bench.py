@@ -487,19 +487,30 @@ def full_path_probe(hp, steps=10):
         hp.spatial.zero_grad(set_to_none=True)
         return total
 
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(True), torch.cuda.Event(True)
-    a.record()
-    for _ in range(steps):
-        loss = step()
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / steps
-    return {"workload": "headline step + the student BEV encoder (ResNetForBEVDet + FPN_LSS fwd/bwd) through cuDNN, "
-                        "one autograd chain loss -> encoder -> lift+splat, eager, TF32 convs, random weights", "ms_per_step": round(ms, 3),
-            "samples_per_sec": round(BATCH / (ms * 1e-3), 1), "loss_finite": bool(torch.isfinite(loss).item())}
+    def timed():
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record()
+        for _ in range(steps):
+            loss = step()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / steps, loss
+
+    ms_cudnn, loss = timed()
+    # the same encoder with every conv's FORWARD on the tcgen05 kernels (plugin/student_convs.py); BatchNorm (batch
+    # statistics), ReLU, upsampling and the conv backward stay torch / cuDNN
+    dbev.convert_convs(student_net)
+    ms_tc, loss_tc = timed()
+    return {"workload": "headline step + the student BEV encoder (ResNetForBEVDet + FPN_LSS fwd/bwd) through cuDNN, one autograd "
+                        "chain loss -> encoder -> lift+splat, eager, TF32 convs, random weights; ms_per_step_tc_forward: the same "
+                        "with the encoder's conv forwards on tcgen05 (plugin/student_convs.py), backward still cuDNN",
+            "ms_per_step": round(ms_cudnn, 3), "ms_per_step_tc_forward": round(ms_tc, 3),
+            "samples_per_sec": round(BATCH / (ms_cudnn * 1e-3), 1),
+            "loss_finite": bool(torch.isfinite(loss).item() and torch.isfinite(loss_tc).item()),
+            "loss_rel_diff_tc_vs_cudnn": round(abs(float(loss_tc) - float(loss)) / max(abs(float(loss)), 1e-12), 6)}
 
 
 def teacher_conv_roofline(hp):
