@@ -605,7 +605,8 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
     // DBEV_CONV_PROF=1: per-role wait cycles (debug only: synchronises and prints after every launch)
     static long long* prof_buf = nullptr;
     long long* prof = nullptr;
-    if (getenv("DBEV_CONV_PROF")) {
+    static const bool prof_on = getenv("DBEV_CONV_PROF") != nullptr;
+    if (prof_on) {
       if (!prof_buf) DBEV_CUDA(cudaMalloc(&prof_buf, sizeof(long long) * 16 * 1024));
       DBEV_CUDA(cudaMemsetAsync(prof_buf, 0, sizeof(long long) * 16 * 1024, stream));
       prof = prof_buf;
