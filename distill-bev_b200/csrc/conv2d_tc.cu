@@ -22,6 +22,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <utility>
 
 namespace dbev {
 
@@ -48,6 +49,8 @@ __global__ void __launch_bounds__(kConvThreads, MINB)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_o, const float* __restrict__ scale, const float* __restrict__ shift,
                  float* __restrict__ out, ConvShape s) {
+  // programmatic dependent launch: let the next kernel of the stream start its prologue on SMs this grid has left
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kWTile = COUT * kKc * 4;
   constexpr int kStage = kATile + kWTile;
@@ -82,6 +85,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
+  // everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail; its results
+  // (this kernel's input) are complete and visible after this point, and nothing is written before it
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int taps = s.kh * s.kw;
   const int per_img = s.tiles_x * s.tiles_y;
 
@@ -281,6 +287,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_o, const float* __restrict__ scale, const float* __restrict__ shift,
                     float* __restrict__ out, HaloShape s, long long* __restrict__ prof) {
+  // programmatic dependent launch: let the next kernel of the stream start its prologue on SMs this grid has left
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kWTile = COUT * kKc * 4;
   constexpr int kNBuf = COUT <= 128 ? 2 : 1;
@@ -320,6 +328,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
+  // everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail; its results
+  // (this kernel's input) are complete and visible after this point, and nothing is written before it
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t a_bytes = (uint32_t)((s.tile_rows + 2) * s.hx * kKc * 4);
 
   if (warp == 0) {
@@ -491,6 +502,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   }
 }
 
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may become resident while
+// its predecessor in the stream drains; it blocks in griddepcontrol.wait before touching memory.
+// DBEV_CONV_PDL=0 falls back to plain launches.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_conv(void (*kernel)(KArgs...), int grid, size_t smem, cudaStream_t stream, Args&&... args) {
+  static const bool pdl = !(getenv("DBEV_CONV_PDL") && atoi(getenv("DBEV_CONV_PDL")) == 0);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(kConvThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // A/B switch: DBEV_CONV_HALO = 0 (per-tap kernel for every layer), 1 (default: halo kernel, pitch 10),
 // 2 (pitch 16), 4 (no split of the last round). Measured: both pitches are bit-identical to the per-tap kernel (descriptor base-offset 0);
 // setting the descriptor's base-offset field to (start >> 7) & 7 gives wrong results.
@@ -615,7 +641,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   do {                                                                                                       \
     DBEV_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                    (int)smem));                                                              \
-    conv3x3_halo_kernel<CO><<<grid, kConvThreads, smem, stream>>>(tmap_x, tmap_w, tmap_o, scale, shift, out, hs, prof); \
+    DBEV_CUDA(launch_conv(conv3x3_halo_kernel<CO>, grid, smem, stream, tmap_x, tmap_w, tmap_o, scale, shift, out, hs, prof)); \
   } while (0)
     if (c_out == 64) DBEV_HALO_LAUNCH(64);
     else if (c_out == 128) DBEV_HALO_LAUNCH(128);
@@ -709,7 +735,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
     const int grid = s.n_tiles < sms * MB ? s.n_tiles : sms * MB;                                \
     DBEV_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel<CO, STG, MB>,                                \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    conv2d_tc_kernel<CO, STG, MB><<<grid, kConvThreads, smem, stream>>>(tmap_x, tmap_w, tmap_o, scale, shift, out, s); \
+    DBEV_CUDA(launch_conv(conv2d_tc_kernel<CO, STG, MB>, grid, smem, stream, tmap_x, tmap_w, tmap_o, scale, shift, out, s)); \
   } while (0)
   // two CTAs per SM where shared memory and TMEM allow it: one CTA's epilogue / TMA latency hides
   // behind the other's MMAs (1.68 -> 1.56 ms for the whole SECOND + SECONDFPN stack); three CTAs of
