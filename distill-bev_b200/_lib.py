@@ -78,6 +78,8 @@ SIGNATURES = {
                                           _c_float, _c_float, _c_float, _c_float, _c_int, _c_int,
                                           _ptr, _ptr, _ptr, _ptr]),
     "dbev_heatmap_class_max": (_c_int, [_ptr, _c_int, _c_int, _c_int, _c_int, _c_int, _ptr, _ptr]),
+    "dbev_fgd_fp_dfs_workspace_bytes": (_c_size, [_c_int, _c_int, _c_int]),
+    "dbev_fgd_fp_dfs_scale": (_c_int, [_ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _c_size, _ptr]),
     "dbev_fgd_fp_mask": (_c_int, [_ptr, _c_int, _ptr, _c_int, _ptr, _c_int, _ptr, _c_int, _c_int,
                                   _c_int, _c_float, _c_float, _ptr, _ptr, _ptr]),
     "dbev_fgd_state_bytes": (_c_size, [_cfgp]),

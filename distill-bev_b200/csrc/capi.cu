@@ -205,6 +205,13 @@ int dbev_heatmap_class_max(const float* heatmaps, int batch, int K, int H, int W
   return heatmap_class_max(heatmaps, batch, K, H, W, apply_clip_sigmoid, out, (cudaStream_t)stream);
 }
 
+size_t dbev_fgd_fp_dfs_workspace_bytes(int batch, int H, int W) { return fgd_fp_dfs_ws_bytes(batch, H, W); }
+
+int dbev_fgd_fp_dfs_scale(const float* fp, int batch, int H, int W, float* scale, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  return fgd_fp_dfs_scale(fp, batch, H, W, scale, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int dbev_fgd_fp_mask(const float* gt_max, int Sg, const float* teacher_max, int St,
                      const float* student_max, int Ss, const float* fg, int R, int batch,
                      int mode, float thres, float gt_thres, float* fp, int* fp_count,

@@ -814,6 +814,78 @@ int fgd_fp_mask(const float* gt_max, int Sg, const float* teacher_max, int St,
   return DBEV_OK;
 }
 
+// fp_scale_mode 'dfs' (bevdet_distill.py:926-966). The reference flood-fills every FP component with a
+// FIFO that marks a cell visited when it is POPPED, so a cell is queued once per pop of each neighbour of
+// the previous BFS layer and is counted that many times; the component's scale is 1 / (total pops). The
+// grid graph is bipartite (neighbours differ by exactly one layer, the FIFO drains a layer before the
+// next), hence pops(c) = sum of pops(n) over previous-layer neighbours and the total is a layered DP -
+// same numbers as the literal walk (oracle/fgd_oracle.py: fp_dfs_scale_literal) without its exponential
+// re-visits. One CTA per sample; the walk itself is serial (components are a handful of cells), mask and
+// layers live in shared memory, the queue and the pop counts in the workspace.
+__global__ void __launch_bounds__(128)
+fgd_fp_dfs_scale_kernel(const float* __restrict__ fp, int H, int W, float* __restrict__ scale,
+                        double* __restrict__ ws_pops, int* __restrict__ ws_queue) {
+  extern __shared__ __align__(16) uint8_t dfs_smem[];
+  const int b = blockIdx.x, HW = H * W;
+  uint16_t* layer = reinterpret_cast<uint16_t*>(dfs_smem);
+  uint8_t* m = dfs_smem + 2 * (size_t)HW;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    m[i] = fp[(size_t)b * HW + i] > 0.f ? 1 : 0;
+    layer[i] = 0xFFFFu;
+    scale[(size_t)b * HW + i] = 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double* pops = ws_pops + (size_t)b * HW;
+  int* q = ws_queue + (size_t)b * HW;
+  float* out = scale + (size_t)b * HW;
+  for (int s = 0; s < HW; ++s) {
+    if (!m[s] || layer[s] != 0xFFFFu) continue;
+    int head = 0, tail = 0;
+    double total = 0.0;
+    q[tail++] = s, layer[s] = 0, pops[s] = 1.0;
+    while (head < tail) {
+      const int c = q[head++];
+      const double pc = pops[c];
+      const uint16_t ln = (uint16_t)(layer[c] + 1);
+      const int y = c / W, x = c - y * W;
+      total += pc;
+#define DBEV_DFS_VISIT(cond, n)                                                    \
+  if ((cond) && m[n]) {                                                            \
+    if (layer[n] == 0xFFFFu) { layer[n] = ln; pops[n] = 0.0; q[tail++] = (n); }    \
+    if (layer[n] == ln) pops[n] += pc;                                             \
+  }
+      DBEV_DFS_VISIT(y + 1 < H, c + W)
+      DBEV_DFS_VISIT(y - 1 >= 0, c - W)
+      DBEV_DFS_VISIT(x + 1 < W, c + 1)
+      DBEV_DFS_VISIT(x - 1 >= 0, c - 1)
+#undef DBEV_DFS_VISIT
+    }
+    const float inv = (float)(1.0 / total);   // Python float (double) division stored into a float32 tensor
+    for (int i = 0; i < tail; ++i) out[q[i]] = inv;
+  }
+}
+
+size_t fgd_fp_dfs_ws_bytes(int batch, int H, int W) {
+  return (size_t)batch * H * W * (sizeof(double) + sizeof(int));
+}
+
+int fgd_fp_dfs_scale(const float* fp, int batch, int H, int W, float* scale, void* ws, size_t ws_bytes,
+                     cudaStream_t stream) {
+  DBEV_CHECK_ARG(batch > 0 && H > 0 && W > 0, "fgd_fp_dfs_scale: bad sizes");
+  DBEV_CHECK_ARG((long long)H * W <= 65534, "fgd_fp_dfs_scale: map too large (BFS layers are 16-bit)");
+  DBEV_CHECK_ARG(ws && ws_bytes >= fgd_fp_dfs_ws_bytes(batch, H, W) && ((uintptr_t)ws & 7) == 0,
+                 "fgd_fp_dfs_scale: workspace too small or misaligned");
+  const size_t smem = (size_t)H * W * 3;
+  DBEV_CHECK_ARG(smem <= 227 * 1024, "fgd_fp_dfs_scale: map does not fit shared memory (%d x %d)", H, W);
+  DBEV_CUDA(cudaFuncSetAttribute(fgd_fp_dfs_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  double* pops = reinterpret_cast<double*>(ws);
+  int* queue = reinterpret_cast<int*>(pops + (size_t)batch * H * W);
+  fgd_fp_dfs_scale_kernel<<<batch, 128, smem, stream>>>(fp, H, W, scale, pops, queue);
+  DBEV_CHECK_LAUNCH("fgd_fp_dfs_scale_kernel");
+  return DBEV_OK;
+}
+
 size_t fgd_state_bytes(const FgdConfig& c) {
   FgdDims d;
   if (make_dims(c, &d) != DBEV_OK) return 0;

@@ -16,6 +16,11 @@ int fgd_foreground_mask(const float* boxes, int box_dim, const int* box_offsets,
 int heatmap_class_max(const float* hm, int batch, int K, int H, int W, int apply_clip_sigmoid,
                       float* out, cudaStream_t stream);
 
+// fp_scale_mode 'dfs' (bevdet_distill.py:926-966): per-component scale 1 / (FIFO pops incl. re-queued cells)
+size_t fgd_fp_dfs_ws_bytes(int batch, int H, int W);
+int fgd_fp_dfs_scale(const float* fp, int batch, int H, int W, float* scale, void* ws, size_t ws_bytes,
+                     cudaStream_t stream);
+
 int fgd_fp_mask(const float* gt_max, int Sg, const float* teacher_max, int St,
                 const float* student_max, int Ss, const float* fg, int R, int batch, int mode,
                 float thres, float gt_thres, float* fp, int* fp_count, cudaStream_t stream);

@@ -115,9 +115,28 @@ def heatmap_class_max(heatmaps, apply_clip_sigmoid=False):
     return out
 
 
+def fp_dfs_scale(fp_mask):
+    """fp_scale_mode 'dfs' (bevdet_distill.py:926-966): [B,1,H,W] FP mask -> per-component scale map."""
+    lib = _lib.load()
+    _lib.require_cuda(fp_mask, "fp_mask", torch.float32)
+    fp_mask = fp_mask.contiguous()
+    B, _, H, W = fp_mask.shape
+    scale = torch.empty_like(fp_mask)
+    ws = torch.empty(int(lib.dbev_fgd_fp_dfs_workspace_bytes(B, H, W)) // 8 + 1, dtype=torch.float64,
+                     device=fp_mask.device)
+    with torch.cuda.device(fp_mask.device):
+        rc = lib.dbev_fgd_fp_dfs_scale(_lib.ptr(fp_mask), B, H, W, _lib.ptr(scale), _lib.ptr(ws), ws.numel() * 8,
+                                       _lib.stream_ptr(fp_mask.device))
+    _lib.check(rc, "dbev_fgd_fp_dfs_scale")
+    return scale
+
+
 def add_fp_as_fg(mode, fg_mask, gt_hm_max, teacher_hm_max, student_hm_max, thres, gt_thres=None,
-                 return_counts=False):
-    """Class-max maps [B,1,S,S] -> fp_mask, fp_scale_mask [B,1,H,W], fp count [B] (float)."""
+                 return_counts=False, scale_mode="average"):
+    """Class-max maps [B,1,S,S] -> fp_mask, fp_scale_mask [B,1,H,W], fp count [B] (float).
+    scale_mode = distill_params['fp_scale_mode']: 'average' (1 / #fp of the sample) or 'dfs'."""
+    if scale_mode not in ("average", "dfs"):
+        raise NotImplementedError("fp_scale_mode=%r" % (scale_mode,))
     lib = _lib.load()
     if mode not in _FP_MODE:
         raise NotImplementedError(mode)
@@ -136,7 +155,10 @@ def add_fp_as_fg(mode, fg_mask, gt_hm_max, teacher_hm_max, student_hm_max, thres
                                   _lib.ptr(cnt), _lib.stream_ptr(fg_mask.device))
     _lib.check(rc, "dbev_fgd_fp_mask")
     cntf = cnt.to(torch.float32)
-    scale = torch.where(cntf > 0, 1.0 / cntf.clamp(min=1.0), torch.zeros_like(cntf)).view(B, 1, 1, 1) * fp
+    if scale_mode == "dfs":
+        scale = fp_dfs_scale(fp)
+    else:
+        scale = torch.where(cntf > 0, 1.0 / cntf.clamp(min=1.0), torch.zeros_like(cntf)).view(B, 1, 1, 1) * fp
     if return_counts:
         return fp, scale, cntf, cnt
     return fp, scale, cntf
@@ -313,13 +335,17 @@ def fgd_distill_loss(teacher_feat, student_feat, gt_bboxes_3d, distill_params, t
         transpose_mask=distill_params.get("transpose_mask", False), return_counts=True)
     fp = fp_count = None
     if cfg.use_fp:
-        if distill_params.get("fp_scale_mode", "average") != "average":
-            raise NotImplementedError("fp_scale_mode=%r" % distill_params.get("fp_scale_mode"))
+        scale_mode = distill_params.get("fp_scale_mode", "average")
         g = heatmap_class_max(heatmaps)
         t = heatmap_class_max(teacher_heatmaps, apply_clip_sigmoid=True)
         s = heatmap_class_max(student_heatmaps) if student_heatmaps is not None else None
-        fp, _, _, fp_count = add_fp_as_fg(fp_mode, fg, g, t, s, distill_params["output_threshold"],
-                                          distill_params.get("groundtruth_threshold"), return_counts=True)
+        fp, fp_scale, cntf, fp_count = add_fp_as_fg(fp_mode, fg, g, t, s, distill_params["output_threshold"],
+                                                    distill_params.get("groundtruth_threshold"), return_counts=True,
+                                                    scale_mode=scale_mode)
+        if scale_mode == "dfs":
+            # the loss kernels weight FP cells by fp * (1 / fp_count): hand them scale * fp_count instead of the
+            # {0,1} mask (same non-zero pattern; the 'average' factor cancels)
+            fp = fp_scale * cntf.view(-1, 1, 1, 1)
     cw = spatial_adaptation.weight if spatial_adaptation is not None else None
     cb = spatial_adaptation.bias if spatial_adaptation is not None else None
     losses = fgd_loss_terms(student_feat, teacher_feat, cfg, fg, fg_scale, fg_count, fp, fp_count, cw, cb,

@@ -447,6 +447,15 @@ int dbev_fgd_fp_mask(const float* gt_max, int Sg, const float* teacher_max, int 
                      int mode, float thres, float gt_thres, float* fp, int* fp_count,
                      void* stream);
 
+/* fp_scale_mode 'dfs' of add_fp_as_fg (bevdet_distill.py:926-966): fp[batch,H,W] in {0,1} -> scale[batch,H,W],
+ * every 4-connected FP component gets 1 / n where n = the number of FIFO pops of the reference's flood fill
+ * (cells re-queued before they are visited count again: a 2x3 block gives 1/9). workspace: device memory,
+ * 8-byte aligned, dbev_fgd_fp_dfs_workspace_bytes(). The loss entry points take the map as
+ * fp = scale * fp_count (their 'average' factor 1 / fp_count cancels). */
+size_t dbev_fgd_fp_dfs_workspace_bytes(int batch, int H, int W);
+int dbev_fgd_fp_dfs_scale(const float* fp, int batch, int H, int W, float* scale, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 typedef struct dbev_fgd_config {
   int B, C, H, W;
   float spatial_t;             /* distill_params['spatial_t'] */

@@ -106,7 +106,77 @@ def _to_res(a, target):
     return a
 
 
-def add_fp_as_fg(mode, fg_mask, gt_hm, teacher_hm, student_hm, thres, gt_thres=None):
+def fp_dfs_scale_literal(fp, max_pops=2_000_000):
+    """fp_scale_mode 'dfs' exactly as written (bevdet_distill.py:926-966): FIFO flood fill from every unvisited
+    FP cell in row-major order, neighbours pushed in the order y+1, y-1, x+1, x-1, `visited` set when a cell is
+    POPPED - so a cell reachable from several already-queued neighbours is queued (and later counted) more than
+    once, and the component's scale is 1 / len(count) with those repeats included. fp: [B,1,H,W] -> scale."""
+    B, _, H, W = fp.shape
+    scale = np.zeros_like(fp, dtype=F32)
+    for b in range(B):
+        m = fp[b, 0] > 0
+        visited = np.zeros((H, W), bool)
+        for y0, x0 in zip(*np.nonzero(m)):
+            if visited[y0, x0]:
+                continue
+            queue, count, head = [(int(y0), int(x0))], [], 0
+            while head < len(queue):
+                y, x = queue[head]
+                head += 1
+                if head > max_pops:
+                    raise RuntimeError("fp_dfs_scale_literal: component too large for the literal walk")
+                visited[y, x] = True
+                count.append((y, x))
+                if y + 1 < H and not visited[y + 1, x] and m[y + 1, x]:
+                    queue.append((y + 1, x))
+                if y - 1 >= 0 and not visited[y - 1, x] and m[y - 1, x]:
+                    queue.append((y - 1, x))
+                if x + 1 < W and not visited[y, x + 1] and m[y, x + 1]:
+                    queue.append((y, x + 1))
+                if x - 1 >= 0 and not visited[y, x - 1] and m[y, x - 1]:
+                    queue.append((y, x - 1))
+            val = F32(1.0 / len(count))
+            for y, x in count:
+                scale[b, 0, y, x] = val
+    return scale
+
+
+def fp_dfs_scale(fp):
+    """Same result without the repeated work. The grid graph is bipartite, so neighbours differ by exactly one
+    BFS layer and the FIFO pops a whole layer (repeats included) before the next one: a cell is queued once per
+    pop of each previous-layer neighbour, pops(c) = sum of pops(n) over those neighbours, pops(seed) = 1, and
+    len(count) = sum of pops over the component (exact in Python ints; the literal walk is exponential in the
+    component's diameter)."""
+    B, _, H, W = fp.shape
+    scale = np.zeros_like(fp, dtype=F32)
+    for b in range(B):
+        m = fp[b, 0] > 0
+        layer = -np.ones((H, W), np.int64)
+        for y0, x0 in zip(*np.nonzero(m)):
+            if layer[y0, x0] >= 0:
+                continue
+            pops = {(int(y0), int(x0)): 1}
+            layer[y0, x0] = 0
+            order, head = [(int(y0), int(x0))], 0
+            while head < len(order):
+                y, x = order[head]
+                head += 1
+                for yy, xx in ((y + 1, x), (y - 1, x), (y, x + 1), (y, x - 1)):
+                    if 0 <= yy < H and 0 <= xx < W and m[yy, xx]:
+                        if layer[yy, xx] < 0:
+                            layer[yy, xx] = layer[y, x] + 1
+                            pops[(yy, xx)] = 0
+                            order.append((yy, xx))
+                        if layer[yy, xx] == layer[y, x] + 1:
+                            pops[(yy, xx)] += pops[(y, x)]
+            total = sum(pops.values())
+            val = F32(1.0 / total)
+            for y, x in order:
+                scale[b, 0, y, x] = val
+    return scale
+
+
+def add_fp_as_fg(mode, fg_mask, gt_hm, teacher_hm, student_hm, thres, gt_thres=None, scale_mode="average"):
     """gt_hm / teacher_hm / student_hm: [B, K, h, w] class heatmaps (teacher already
     through clip_sigmoid). -> fp_mask, fp_scale_mask [B,1,H,W] float32, fp_count [B]."""
     if gt_thres is None:
@@ -129,6 +199,10 @@ def add_fp_as_fg(mode, fg_mask, gt_hm, teacher_hm, student_hm, thres, gt_thres=N
     fp = _to_res(fp.astype(F32), fg_mask.shape[2]) > 0
     fp = (fp & (fg_mask == 0)).astype(F32)
     cnt = fp.sum(axis=(1, 2, 3))
+    if scale_mode == "dfs":
+        return fp, fp_dfs_scale(fp), cnt.astype(F32)
+    if scale_mode != "average":
+        raise NotImplementedError(scale_mode)
     scale = np.zeros_like(fp)
     for b in range(fp.shape[0]):
         if cnt[b] > 0:

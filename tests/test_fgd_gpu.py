@@ -248,3 +248,50 @@ def test_forward_distill_positions_and_affinity_branch(cuda):
     torch.testing.assert_close(early["kd_affinity_loss_head_head"], alone)
     sum(early.values()).backward()
     assert torch.isfinite(s_head.grad).all() and s_head.grad.abs().sum() > 0
+
+
+# ---------------------------------------------------------------- fp_scale_mode 'dfs' (bevdet_distill.py:926-966)
+@pytest.fixture(scope="module")
+def gd(golden_dir):
+    return np.load(os.path.join(golden_dir, "fp_dfs.npz"))      # tools/make_golden_fp_dfs.py (reference methods)
+
+
+def test_fp_dfs_scale_golden(cuda, gd):
+    p = json.loads(str(gd["params"]))
+    gm = fgd.heatmap_class_max(_t(gd["gt_hm"], cuda))
+    tm = fgd.heatmap_class_max(_t(gd["teacher_logit"], cuda), apply_clip_sigmoid=True)
+    sm = fgd.heatmap_class_max(_t(gd["student_prob"], cuda))
+    fp, fps, cnt = fgd.add_fp_as_fg("teacher", _t(gd["fg"], cuda), gm, tm, sm, p["output_threshold"],
+                                    p["groundtruth_threshold"], scale_mode="dfs")
+    np.testing.assert_array_equal(fp.cpu().numpy(), gd["fp"])
+    np.testing.assert_array_equal(cnt.cpu().numpy(), gd["fp_count"])
+    np.testing.assert_array_equal(fps.cpu().numpy(), gd["fp_scale"])          # bit-exact, repeats included
+
+
+def test_fp_dfs_scale_vs_oracle_random_maps(cuda):
+    rng = np.random.RandomState(8)
+    for (B, H, dens) in [(3, 16, 0.3), (2, 128, 0.02), (1, 200, 0.05), (2, 64, 0.0)]:
+        fp = (rng.rand(B, 1, H, H) < dens).astype(np.float32)
+        fp[0, 0, :2, :3] = 1 if dens > 0 else 0                                # a 2x3 block: 1/9
+        got = fgd.fp_dfs_scale(_t(fp, cuda)).cpu().numpy()
+        np.testing.assert_array_equal(got, fo.fp_dfs_scale(fp))
+
+
+def test_fgd_loss_dfs_golden(cuda, gd):
+    p = json.loads(str(gd["params"]))
+    conv = torch.nn.Conv2d(1, 1, 3, padding=1).to(cuda)
+    with torch.no_grad():
+        conv.weight.copy_(_t(gd["conv_w"], cuda).view(1, 1, 3, 3))
+        conv.bias.copy_(_t(gd["conv_b"], cuda))
+    student = _t(gd["student"], cuda).requires_grad_(True)
+    losses = fgd.fgd_distill_loss(_t(gd["teacher"], cuda), student, _boxes(gd), p, _train_cfg(gd),
+                                  spatial_adaptation=conv, heatmaps=_t(gd["gt_hm"], cuda),
+                                  teacher_heatmaps=_t(gd["teacher_logit"], cuda),
+                                  student_heatmaps=_t(gd["student_prob"], cuda), index=0, epoch=5)
+    keys = json.loads(str(gd["loss_keys"]))
+    assert sorted(losses) == keys
+    for k, v in zip(keys, gd["loss_vals"]):
+        assert abs(float(losses[k]) - v) <= 1e-4 * max(abs(v), 1e-3), (k, float(losses[k]), v)
+    sum(losses.values()).backward()
+    gs = gd["grad_student"]
+    np.testing.assert_allclose(student.grad.cpu().numpy(), gs, rtol=1e-4, atol=1e-4 * np.abs(gs).max())

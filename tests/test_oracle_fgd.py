@@ -71,3 +71,55 @@ def test_masks_losses_and_grads(g, name):
 def test_affinity(g):
     v = fo.affinity_loss([g["aff_t0"], g["aff_t1"]], [g["aff_s0"], g["aff_s1"]], 0.5)
     assert abs(v - float(g["aff_loss"])) < 1e-5 * abs(v)
+
+
+# ---------------------------------------------------------------- fp_scale_mode 'dfs' (bevdet_distill.py:926-966)
+@pytest.fixture(scope="module")
+def gd(golden_dir):
+    return np.load(os.path.join(golden_dir, "fp_dfs.npz"))      # tools/make_golden_fp_dfs.py
+
+
+def test_fp_dfs_scale_pinned_to_reference(gd):
+    """The literal FIFO walk and the layered-DP restatement both reproduce the reference's scale map bit for bit,
+    including its repeated counting of re-queued cells (a 2x3 block scales by 1/9, not 1/6)."""
+    p = json.loads(str(gd["params"]))
+    fp, fps, cnt = fo.add_fp_as_fg("teacher", gd["fg"], gd["gt_hm"], _sigmoid_clip(gd["teacher_logit"]),
+                                   gd["student_prob"], p["output_threshold"], p["groundtruth_threshold"],
+                                   scale_mode="dfs")
+    np.testing.assert_array_equal(fp, gd["fp"])
+    np.testing.assert_array_equal(cnt, gd["fp_count"])
+    np.testing.assert_array_equal(fps, gd["fp_scale"])
+    np.testing.assert_array_equal(fo.fp_dfs_scale_literal(gd["fp"]), gd["fp_scale"])
+    assert np.float32(1.0 / 9.0) in np.unique(gd["fp_scale"])
+
+
+def test_fp_dfs_dp_equals_literal_on_random_blobs():
+    rng = np.random.RandomState(4)
+    for density in (0.15, 0.3, 0.45):
+        fp = (rng.rand(3, 1, 12, 12) < density).astype(np.float32)
+        np.testing.assert_array_equal(fo.fp_dfs_scale(fp), fo.fp_dfs_scale_literal(fp))
+    # a 5 x 5 block: 1 / sum of binomial path counts; the literal walk needs 4421 pops for 25 cells
+    fp = np.zeros((1, 1, 9, 9), np.float32)
+    fp[0, 0, 2:7, 2:7] = 1
+    lit, dp = fo.fp_dfs_scale_literal(fp), fo.fp_dfs_scale(fp)
+    np.testing.assert_array_equal(dp, lit)
+    assert dp.max() < 1.0 / 25
+
+
+def test_fgd_loss_with_dfs_scale_pinned_to_reference(gd):
+    p = json.loads(str(gd["params"]))
+    H = gd["teacher"].shape[2]
+    boxes, o = [], 0
+    for n in gd["n_boxes"]:
+        boxes.append(gd["boxes"][o:o + n])
+        o += n
+    fg, fgs, bgs = fo.foreground_scale_mask(H, H, boxes, gd["grid"], gd["pc_range"], gd["voxel"])
+    np.testing.assert_array_equal(fg, gd["fg"])
+    fp, fps, cnt = fo.add_fp_as_fg("teacher", fg, gd["gt_hm"], _sigmoid_clip(gd["teacher_logit"]), gd["student_prob"],
+                                   p["output_threshold"], p["groundtruth_threshold"], scale_mode="dfs")
+    res = fo.fgd_loss(gd["teacher"], gd["student"], fg, fgs, bgs, oracle_params(p), conv_w=gd["conv_w"],
+                      conv_b=float(gd["conv_b"][0]), want_grad=True, fp=fp, fp_scale=fps, fp_count=cnt)
+    for k, v in zip(json.loads(str(gd["loss_keys"])), gd["loss_vals"]):
+        assert abs(res[k] - v) <= 2e-5 * max(abs(v), 1e-3), (k, res[k], v)
+    gs = gd["grad_student"]
+    np.testing.assert_allclose(res["grad_student"], gs, rtol=2e-4, atol=2e-6 * np.abs(gs).max())
