@@ -363,8 +363,8 @@ def fgd_distill_loss(teacher_feat, student_feat, gt_bboxes_3d, distill_params, t
         mode = mode[index] if len(mode) > 1 else mode[0]
     if mode != "none":
         from . import affinity as _aff
-        if mode not in ("foreground", "foreground+fp"):
-            raise NotImplementedError("affinity_mode=%r" % mode)   # 'attention' needs the top-k of the attention map
+        if mode not in ("foreground", "foreground+fp", "attention"):
+            raise NotImplementedError("affinity_mode=%r" % mode)
         if mode == "foreground+fp":
             assert fp_mode != "none"                                # :1297
         aw = distill_params["affinity_weights"]
@@ -373,8 +373,26 @@ def fgd_distill_loss(teacher_feat, student_feat, gt_bboxes_3d, distill_params, t
         if adapt_w is not None:
             from .adaptation import conv1x1
             adapted = conv1x1(student_feat, adapt_w, adapt_b)
+        if mode == "attention":
+            # :1302-1308 - cells whose (detached) spatial attention passes a threshold, or is above the k-th largest
+            # of its sample. Non-default mode: the attention map is rebuilt here with torch ops (:1084-1108).
+            with torch.no_grad():
+                n_cell = float(H * W)
+                att = torch.softmax(teacher_feat.abs().mean(1).view(B, -1) / cfg.spatial_t, 1) * n_cell
+                if cfg.spatial_att == 1:
+                    s_att = torch.softmax(adapted.abs().mean(1).view(B, -1) / cfg.spatial_t, 1) * n_cell
+                    att = (att + s_att * cfg.spatial_student_ratio) / (1 + cfg.spatial_student_ratio)
+                if "affinity_attention_threshold" in distill_params:
+                    sel = (att / n_cell) > distill_params["affinity_attention_threshold"]
+                else:
+                    kth = torch.topk(att, k=int(distill_params["affinity_attention_topk"]), dim=1)[0][:, -1:]
+                    sel = att > kth
+                sel = sel.view(B, 1, H, W).float()
+            mask_a, mask_b = sel, None
+        else:
+            mask_a, mask_b = fg, (fp if (mode == "foreground+fp" and cfg.use_fp) else None)
         out.update(_aff.affinity_distill_loss(
-            teacher_feat, adapted, fg, fp if (mode == "foreground+fp" and cfg.use_fp) else None, weight=aw,
+            teacher_feat, adapted, mask_a, mask_b, weight=aw,
             criterion=distill_params.get("affinity_criterion", dict(type="SmoothL1Loss")),
             split=int(distill_params.get("affinity_split", 1))))
     return out

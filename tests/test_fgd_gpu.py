@@ -295,3 +295,25 @@ def test_fgd_loss_dfs_golden(cuda, gd):
     sum(losses.values()).backward()
     gs = gd["grad_student"]
     np.testing.assert_allclose(student.grad.cpu().numpy(), gs, rtol=1e-4, atol=1e-4 * np.abs(gs).max())
+
+
+def test_attention_affinity_mode_golden(cuda, gd):
+    """affinity_mode 'attention' (top-k of the spatial attention, :1302-1308) through fgd_distill_loss: every loss
+    and the student gradient against the unmodified reference run."""
+    p = json.loads(str(gd["att_params"]))
+    conv = torch.nn.Conv2d(1, 1, 3, padding=1).to(cuda)
+    with torch.no_grad():
+        conv.weight.copy_(_t(gd["conv_w"], cuda).view(1, 1, 3, 3))
+        conv.bias.copy_(_t(gd["conv_b"], cuda))
+    student = _t(gd["student"], cuda).requires_grad_(True)
+    losses = fgd.fgd_distill_loss(_t(gd["teacher"], cuda), student, _boxes(gd), p, _train_cfg(gd),
+                                  spatial_adaptation=conv, heatmaps=_t(gd["gt_hm"], cuda),
+                                  teacher_heatmaps=_t(gd["teacher_logit"], cuda),
+                                  student_heatmaps=_t(gd["student_prob"], cuda), index=0, epoch=5)
+    keys = json.loads(str(gd["att_loss_keys"]))
+    assert sorted(losses) == keys
+    for k, v in zip(keys, gd["att_loss_vals"]):
+        assert abs(float(losses[k]) - v) <= 1e-4 * max(abs(v), 1e-3), (k, float(losses[k]), v)
+    sum(losses.values()).backward()
+    gs = gd["att_grad_student"]
+    np.testing.assert_allclose(student.grad.cpu().numpy(), gs, rtol=1e-4, atol=1e-4 * np.abs(gs).max())

@@ -123,3 +123,26 @@ def test_fgd_loss_with_dfs_scale_pinned_to_reference(gd):
         assert abs(res[k] - v) <= 2e-5 * max(abs(v), 1e-3), (k, res[k], v)
     gs = gd["grad_student"]
     np.testing.assert_allclose(res["grad_student"], gs, rtol=2e-4, atol=2e-6 * np.abs(gs).max())
+
+
+def test_attention_affinity_pinned_to_reference(gd):
+    """affinity_mode 'attention' (:1302-1308): rows = cells whose spatial attention is above the k-th largest of the
+    sample; oracle restatement (attention :1084-1108 + affinity_loss) against the reference's own loss value."""
+    p = json.loads(str(gd["att_params"]))
+    t, s = gd["teacher"].astype(np.float64), gd["student"].astype(np.float64)
+    B, C, H, W = t.shape
+
+    def att(f):
+        a = np.abs(f).mean(axis=1).reshape(B, -1) / p["spatial_t"]
+        e = np.exp(a - a.max(axis=1, keepdims=True))
+        return e / e.sum(axis=1, keepdims=True) * H * W
+    r = p["spatial_student_ratio"]
+    sa = (att(t) + att(s) * r) / (1 + r)
+    kth = np.sort(sa, axis=1)[:, -p["affinity_attention_topk"]][:, None]
+    sel = sa > kth
+    assert (sel.sum(axis=1) == p["affinity_attention_topk"] - 1).all()
+    t_rows = [t[b].reshape(C, -1).T[sel[b]] for b in range(B)]
+    s_rows = [s[b].reshape(C, -1).T[sel[b]] for b in range(B)]
+    got = fo.affinity_loss(t_rows, s_rows, p["affinity_weights"][0])
+    want = dict(zip(json.loads(str(gd["att_loss_keys"])), gd["att_loss_vals"]))["kd_affinity_loss"]
+    assert abs(got - want) <= 2e-5 * abs(want), (got, want)

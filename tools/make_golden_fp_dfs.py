@@ -1,6 +1,7 @@
 """Golden vectors for fp_scale_mode='dfs' (bevdet_distill.py:926-966) from the UNMODIFIED reference methods
 (ast-extracted by tools/ref_import.py, run here on CPU): add_fp_as_fg on small maps with a few FP blobs (the
-reference's flood fill counts re-queued cells, so blob shapes matter) and one fgd_distill_loss with the mode on.
+reference's flood fill counts re-queued cells, so blob shapes matter), one fgd_distill_loss with the mode on, and
+one fgd_distill_loss with affinity_mode='attention' (top-k of the spatial attention, :1302-1308).
 
     python tools/make_golden_fp_dfs.py      ->  tests/golden/fp_dfs.npz
 """
@@ -77,6 +78,19 @@ def main():
                loss_vals=np.array([float(losses[k]) for k in sorted(losses)], np.float64),
                grad_student=st.grad.numpy(), conv_w=conv.weight.detach().numpy().reshape(3, 3),
                conv_b=conv.bias.detach().numpy())
+    # affinity_mode 'attention' (:1302-1308): cells above the k-th largest spatial attention of their sample
+    p2 = dict(params, fp_as_foreground=["none"], fp_scale_mode="average", affinity_mode=["attention"],
+              affinity_attention_topk=40, affinity_weights=[0.5], affinity_split=1,
+              affinity_criterion=dict(type="SmoothL1Loss"))
+    me2 = mg._fgd_self(methods, AttrDict, p2, C, grid, pc_range, voxel)
+    st2 = student.clone().requires_grad_(True)
+    losses2 = me2.fgd_distill_loss(teacher.clone(), st2, bx, None, canvas, [gt_hm.clone()],
+                                   [[dict(heatmap=t_logit.clone())]], [[dict(heatmap=s_prob.clone())]], 0)
+    sum(losses2.values()).backward()
+    out.update(att_params=json.dumps(p2), att_loss_keys=json.dumps(sorted(losses2)),
+               att_loss_vals=np.array([float(losses2[k]) for k in sorted(losses2)], np.float64),
+               att_grad_student=st2.grad.numpy())
+    print("attention affinity", {k: float(v) for k, v in losses2.items()})
     np.savez_compressed(os.path.join(mg.GOLDEN, "fp_dfs.npz"), **out)
     print("fp cells", cnt.numpy(), "distinct scales", np.unique(fps.numpy()).tolist(), {k: float(v) for k, v in losses.items()})
 
