@@ -126,11 +126,16 @@ class _GatherRows(Function):
 
 
 def affinity_distill_loss(teacher_feat, student_feat, affinity_mask, affinity_mask_2=None,
-                          weight=1.0, criterion=dict(type="SmoothL1Loss"), split=1):
+                          weight=1.0, criterion=dict(type="SmoothL1Loss"), split=1, perms=None):
     """teacher_feat / student_feat [B, C, H, W], affinity_mask [B, 1, H, W] (non-zero = selected;
-    affinity_mask_2 is OR-ed in: the 'foreground+fp' mode, :1296-1299) -> dict(kd_affinity_loss)."""
-    if split != 1:
-        raise NotImplementedError("affinity_split > 1 (random partition) is not implemented")
+    affinity_mask_2 is OR-ed in: the 'foreground+fp' mode, :1296-1299) -> dict(kd_affinity_loss).
+    split > 1 (:738-747): the K rows of a sample are partitioned by a random permutation into
+    perm[j::split], one gram pair per part, loss averaged over the parts. perms (one index tensor per
+    sample) fixes the permutation; by default it is torch.randperm(K) drawn per sample from torch's CPU
+    generator in sample order - the reference's own call, so equal seeds give equal partitions."""
+    split = int(split)
+    if split < 1:
+        raise ValueError("affinity_split must be >= 1")
     cfg = dict(criterion)
     kind = _KIND[cfg.get("type", "SmoothL1Loss")]
     beta = float(cfg.get("beta", 1.0))
@@ -144,5 +149,20 @@ def affinity_distill_loss(teacher_feat, student_feat, affinity_mask, affinity_ma
     k_total = offs[-1]
     t_rows = gather_rows(teacher_feat.detach(), row_cell, row_offsets, k_total)
     s_rows = _GatherRows.apply(student_feat, row_cell, row_offsets, k_total)
+    if split > 1:
+        # every (sample, part) becomes one segment of the row list; mean per segment, weight / split
+        order, seg = [], [0]
+        for b in range(len(offs) - 1):
+            k = offs[b + 1] - offs[b]
+            perm = torch.randperm(k) if perms is None else torch.as_tensor(perms[b], dtype=torch.long).cpu()
+            if perm.numel() != k:
+                raise RuntimeError("perms[%d] has %d entries, sample has %d rows" % (b, perm.numel(), k))
+            for j in range(split):
+                part = perm[j::split] + offs[b]
+                order.append(part)
+                seg.append(seg[-1] + int(part.numel()))
+        index = torch.cat(order).to(t_rows.device) if order else torch.zeros(0, dtype=torch.long, device=t_rows.device)
+        t_rows, s_rows = t_rows.index_select(0, index).contiguous(), s_rows.index_select(0, index).contiguous()
+        offs, weight = seg, weight / split
     loss = _AffinityRows.apply(t_rows, s_rows, offs, kind, beta, weight)
     return dict(kd_affinity_loss=loss)

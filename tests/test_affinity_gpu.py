@@ -118,3 +118,34 @@ def test_large_k_deterministic(cuda):
     b = dbev.affinity.affinity_distill_loss(tt, ss, mm)["kd_affinity_loss"]
     assert torch.equal(a, b)
     np.testing.assert_allclose(float(a), want, rtol=1e-4)
+
+
+@pytest.mark.parametrize("split", [2, 3])
+def test_affinity_split_partitions(cuda, split):
+    """affinity_split > 1 (:738-747): rows of a sample partitioned by a permutation into perm[j::split], one gram pair
+    per part, averaged. Explicit permutations vs the oracle; default permutation = torch.randperm per sample from the
+    CPU generator (the reference's own draw), checked by re-seeding."""
+    rng = np.random.RandomState(split)
+    B, C, H = 3, 16, 12
+    t = rng.randn(B, C, H, H).astype(np.float32)
+    s = rng.randn(B, C, H, H).astype(np.float32)
+    mask = (rng.rand(B, 1, H, H) < 0.2).astype(np.float32)
+    mask[2] = 0
+    mask[2, 0, 0, :2] = 1                                     # 2 rows: with split 3 one part is empty
+    ks = [int(mask[b].sum()) for b in range(B)]
+    perms = [rng.permutation(k) for k in ks]
+    t_rows = [_rows(t[b], mask[b, 0] > 0) for b in range(B)]
+    s_rows = [_rows(s[b], mask[b, 0] > 0) for b in range(B)]
+    want = fo.affinity_loss(t_rows, s_rows, 0.7, perm=perms, split=split)
+    st = _t(s, cuda).requires_grad_(True)
+    got = dbev.affinity.affinity_distill_loss(_t(t, cuda), st, _t(mask, cuda), weight=0.7, split=split, perms=perms)["kd_affinity_loss"]
+    assert abs(float(got) - want) <= 1e-4 * abs(want), (float(got), want)
+    got.backward()
+    assert torch.isfinite(st.grad).all() and float(st.grad.abs().sum()) > 0
+    # default permutation: the same torch.randperm draws as the reference, in sample order
+    torch.manual_seed(123)
+    a = dbev.affinity.affinity_distill_loss(_t(t, cuda), _t(s, cuda), _t(mask, cuda), weight=0.7, split=split)["kd_affinity_loss"]
+    torch.manual_seed(123)
+    ref_perms = [torch.randperm(k).numpy() for k in ks]
+    want2 = fo.affinity_loss(t_rows, s_rows, 0.7, perm=ref_perms, split=split)
+    assert abs(float(a) - want2) <= 1e-4 * abs(want2), (float(a), want2)
