@@ -82,6 +82,26 @@ def main():
         lambda: dbev.lift_splat(hp.depth, hp.feat, plan), nbytes=(bench.D + C) * pix * 4 + kept * 4 + out.numel() * 4,
         note="algorithmic bytes exclude the never-materialised %d MB volume; the kernel is L2-bound (rows re-read from L2)"
              % (n * C * 4 // 1000000))
+    cells = hp.vt.make_cells(geom, nf)
+    add("bev_point_cells (geometry -> cell of every frustum point, no sort)", "%d points" % n,
+        lambda: hp.vt.make_cells(geom, nf), nbytes=n * 16)
+    add("sort-free lift+splat forward (float4 reductions into the L2-resident map, incl. its memset)", "same",
+        lambda: dbev.lift_splat(hp.depth, hp.feat, cells), nbytes=(bench.D + C) * pix * 4 + n * 4 + 2 * out.numel() * 4,
+        note="L2-bound: %d MB of 16-byte reductions stay in L2; HBM sees inputs + one write-back of the map" % (kept * C * 4 // 1000000))
+    # teacher dense convs (tcgen05 TF32): one layer of each width at the B=8 sizes, and the whole stack
+    from distill_bev_b200.plugin import dense_teacher as dt
+    for hh, cc in ((256, 64), (128, 128), (64, 256)):
+        xx = torch.randn(8, hh, hh, cc, device=dev)
+        wp = torch.randn(cc, 9 * cc, device=dev) * 0.05
+        sc, sh = torch.rand(cc, device=dev), torch.randn(cc, device=dev)
+        oo = torch.empty_like(xx)
+        add("conv3x3 + BN + ReLU (halo kernel, tcgen05 TF32)", "B=8, %d->%d, %dx%d" % (cc, cc, hh, hh),
+            lambda xx=xx, wp=wp, sc=sc, sh=sh, oo=oo, cc=cc: dt.conv_nhwc(xx, wp, cc, 3, 3, 1, 1, sc, sh, relu=True, out=oo),
+            nbytes=2 * xx.numel() * 4, flops=2.0 * xx.numel() * 9 * cc)
+    with torch.no_grad():
+        canvas = dbev.pillar_canvas(hp.d_points, hp.enc, hp.scat)
+        add("SECOND + SECONDFPN (22 launches, PDL)", "canvas [8,64,512,512] -> [8,384,128,128]",
+            lambda: hp.secfpn(hp.second(canvas)), flops=601.3e9)
     bev = dbev.lift_splat(hp.depth, hp.feat, plan)
 
     def lift_bwd():
