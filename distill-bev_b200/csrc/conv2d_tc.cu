@@ -6,16 +6,19 @@
 // The reference runs these through cuDNN (TF32 math under torch's default cudnn.allow_tf32) as
 // separate conv, BatchNorm and ReLU kernels. Here one implicit-GEMM kernel per layer, NHWC fp32:
 //   D[128 output pixels, C_out] += A[128 pixels, 32 ch] * B[C_out, 32 ch]^T  over (ky, kx, 32-ch chunk)
-//   A = the input window of the tile for filter tap (ky, kx): ONE 4-D TMA box {32 ch, TX, TY, 1}
-//       of the NHWC tensor at coordinates (c0, x0*s + kx - pad, y0*s + ky - pad, n); the borders
-//       are TMA out-of-bounds zero fill, stride-2 layers use the tensor map's element strides -
-//       no im2col buffer, no index arithmetic in the kernel;
+// Two kernels share the structure (warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5
+// epilogue; persistent; accumulators double-buffered in TMEM; programmatic dependent launch):
+//   * conv2d_tc_kernel    - any 1..3 x 1..3 filter, stride 1 or 2: the A operand of tap (ky, kx) is ONE
+//       4-D TMA box {32 ch, TX, TY, 1} of the NHWC tensor at (c0, x0*s + kx - pad, y0*s + ky - pad, n);
+//       borders are TMA out-of-bounds zero fill, stride 2 uses the tensor map's element strides - no
+//       im2col buffer, no index arithmetic. Used by the three stride-2 layers and the FPN branches
+//       (NCHW / strided-lattice stores, optional column groups for the transposed conv's x taps).
+//   * conv3x3_halo_kernel - 3x3 / stride 1 / pad 1 (13 of SECOND's 16 convs): the halo of a 32 x 8 pixel
+//       tile is loaded once per 32-channel chunk and the nine taps are shifted descriptor windows of it.
 //   B = weights pre-packed [C_out][(ky*KW + kx)*C_in + ci] (K-major), 2-D TMA box {32, C_out}.
-// Accumulators live in TMEM (two buffers: the epilogue of tile t overlaps the MMAs of tile t+1);
-// the epilogue applies scale/shift (eval BN folded) + ReLU and writes NHWC rows, optionally into
-// a channel slice / strided pixel lattice of a larger tensor (FPN concat, transposed conv).
-// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2-5 = epilogue; persistent CTAs,
-// two per SM for C_out <= 128.
+// The epilogue applies scale/shift (eval BN folded) + ReLU; NHWC outputs leave through a swizzled
+// shared-memory staging tile and a TMA store. Measurements and the order in which the bottlenecks
+// were found (MMA issue -> L2 fill -> epilogue): DESIGN.md §2.10, profiles/r01_conv3x3_halo.json.
 #include "conv2d_tc.cuh"
 
 #include "umma.cuh"

@@ -36,9 +36,7 @@ namespace {
 
 constexpr int kTileM = 128;                   // output voxels per tile (UMMA M, TMEM lanes)
 constexpr int kChunk = 32;                    // input channels per stage (one 128 B swizzle row)
-constexpr int kABytes = kTileM * kChunk * 4;  // 16 KB: one A operand tile (hi or lo)
 constexpr int kProdWarps = 4;                  // one warp per TMEM lane quarter (8 warps measured slower)
-constexpr int kEpiWarp0 = kProdWarps;          // warps 8..11: epilogue (warp % 4 = lane quarter)
 constexpr int kMmaWarp = kProdWarps + 4;       // warp 12: MMA issuer + TMEM owner
 constexpr int kTcThreads = (kMmaWarp + 1) * 32;  // 416
 
