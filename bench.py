@@ -544,7 +544,7 @@ def teacher_conv_roofline(hp):
     else:
         peak, how = 1100.0, "fallback: nominal dense TF32 1.1 PFLOP/s"
     ach = flops / (ms * 1e-3) / 1e12
-    return {"kernel": "dbev::conv3x3_halo_kernel<64|128|256> x 13 + dbev::conv2d_tc_kernel x 9 launches (SECOND + SECONDFPN forward)", "bound": "tensor",
+    return {"kernel": "dbev::conv3x3_halo_kernel<64|128|256> x 13 + dbev::conv2d_tc_kernel x 7 launches (SECOND + SECONDFPN forward)", "bound": "tensor",
             "achieved": round(ach, 1), "peak": round(peak, 1), "unit": "TFLOP/s", "frac": round(ach / peak, 4),
             "traffic": None, "peak_source": how, "flops_per_stack": flops, "stack_ms": round(ms, 4),
             "ncu": "profiles/r01_conv3x3_halo.json (sm__pipe_tensor_cycles_active 42 / 68 / 75 % of active cycles on the 64 / 128 / 256-channel 3x3 layers)"}

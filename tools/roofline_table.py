@@ -100,7 +100,7 @@ def main():
             nbytes=2 * xx.numel() * 4, flops=2.0 * xx.numel() * 9 * cc)
     with torch.no_grad():
         canvas = dbev.pillar_canvas(hp.d_points, hp.enc, hp.scat)
-        add("SECOND + SECONDFPN (22 launches, PDL)", "canvas [8,64,512,512] -> [8,384,128,128]",
+        add("SECOND + SECONDFPN (20 launches, PDL)", "canvas [8,64,512,512] -> [8,384,128,128]",
             lambda: hp.secfpn(hp.second(canvas)), flops=601.3e9)
     bev = dbev.lift_splat(hp.depth, hp.feat, plan)
 
