@@ -126,6 +126,22 @@ SIGNATURES = {
                                + [_c_int] * 8 + [_ptr]),
     "dbev_conv2d_tc_forward_grouped": (_c_int, [_ptr] + [_c_int] * 4 + [_ptr] + [_c_int] * 5 + [_ptr, _ptr, _c_int, _ptr]
                                        + [_c_int] * 9 + [_ptr]),
+    "dbev_conv2d_tc_forward_ex": (_c_int, [_ptr] + [_c_int] * 5 + [_ptr] + [_c_int] * 6 + [_ptr, _ptr, _c_int, _ptr]
+                                  + [_c_int] * 12 + [_ptr]),
+    "dbev_conv_wgrad_tc_workspace_bytes": (_c_size, [_c_int] * 8),
+    "dbev_conv_wgrad_tc": (_c_int, [_ptr] + [_c_int] * 5 + [_ptr] + [_c_int] * 8 + [_ptr, _c_int, _ptr, _c_size, _ptr]),
+    "dbev_pack_conv_weights": (_c_int, [_ptr] + [_c_int] * 5 + [_ptr, _ptr]),
+    "dbev_pack_conv_weights_train": (_c_int, [_ptr] + [_c_int] * 5 + [_ptr, _ptr, _ptr]),
+    "dbev_channel_stats_workspace_bytes": (_c_size, [_c_ll, _c_int]),
+    "dbev_bn_batch_stats": (_c_int, [_ptr, _c_int, _c_ll, _c_int, _ptr, _ptr, _c_float, _c_float, _ptr, _ptr, _ptr, _ptr,
+                                     _c_size, _ptr]),
+    "dbev_channel_sums": (_c_int, [_ptr, _c_int, _c_ll, _c_int, _ptr, _c_int, _ptr, _c_size, _ptr]),
+    "dbev_bn_act_forward": (_c_int, [_ptr, _c_int, _ptr, _ptr, _c_int, _c_ll, _c_int, _c_int, _ptr, _c_int, _ptr]),
+    "dbev_bn_backward": (_c_int, [_ptr, _c_int, _ptr, _c_int, _ptr, _c_int, _ptr, _c_ll, _c_int, _ptr, _ptr, _c_int, _ptr,
+                                  _c_int, _c_int, _ptr, _c_size, _ptr]),
+    "dbev_relu_mask_backward": (_c_int, [_ptr, _c_int, _ptr, _c_int, _c_ll, _c_int, _ptr, _c_int, _c_int, _ptr]),
+    "dbev_upsample_bilinear_forward": (_c_int, [_ptr] + [_c_int] * 7 + [_ptr, _c_int, _ptr]),
+    "dbev_upsample_bilinear_backward": (_c_int, [_ptr] + [_c_int] * 7 + [_ptr, _c_int, _c_int, _ptr]),
     "dbev_spconv_tc_supported": (_c_int, [_c_int, _c_int, _c_int]),
     "dbev_spconv_pack_weights": (_c_int, [_ptr, _c_int, _c_int, _c_int, _ptr, _ptr, _ptr]),
     "dbev_spconv_forward_tc": (_c_int, [_ptr, _c_int, _ptr, _ptr, _c_int, _ptr, _c_int, _c_int, _ptr,

@@ -6,10 +6,12 @@
 
 #include "adapt_gemm.cuh"
 #include "affinity.cuh"
+#include "bev_encoder_ops.cuh"
 #include "bev_pool.cuh"
 #include "bevdepth_aux.cuh"
 #include "center_targets.cuh"
 #include "conv2d_tc.cuh"
+#include "conv_wgrad_tc.cuh"
 #include "distill_loss.cuh"
 #include "ms_deform_attn.cuh"
 #include "pillar.cuh"
@@ -427,6 +429,79 @@ int dbev_conv2d_tc_forward_grouped(const float* x_nhwc, int n, int h, int w, int
   return conv2d_tc_forward(x_nhwc, n, h, w, c_in, w_packed, c_out, kh, kw, stride, pad, scale, shift,
                            relu, out, out_h, out_w, out_ld, out_c_off, out_mul, out_add_y, out_add_x,
                            out_nchw, out_groups, (cudaStream_t)stream);
+}
+
+int dbev_conv2d_tc_forward_ex(const float* x_nhwc, int n, int h, int w, int c_in, int x_ld, const float* w_packed,
+                              int c_out, int n_col_blocks, int kh, int kw, int stride, int pad, const float* scale,
+                              const float* shift, int relu, float* out, int out_h, int out_w,
+                              int out_ld, int out_c_off, int out_mul, int out_add_y, int out_add_x,
+                              int out_nchw, int out_groups, int force_ho, int force_wo, int accumulate,
+                              void* stream) {
+  return conv2d_tc_forward_ex(x_nhwc, n, h, w, c_in, x_ld, w_packed, c_out, n_col_blocks, kh, kw, stride, pad, scale, shift,
+                              relu, out, out_h, out_w, out_ld, out_c_off, out_mul, out_add_y, out_add_x,
+                              out_nchw, out_groups, force_ho, force_wo, accumulate, (cudaStream_t)stream);
+}
+
+size_t dbev_conv_wgrad_tc_workspace_bytes(int n, int ho, int wo, int c_in, int c_out, int kh, int kw, int stride) {
+  return conv_wgrad_tc_workspace_bytes(n, ho, wo, c_in, c_out, kh, kw, stride);
+}
+
+int dbev_conv_wgrad_tc(const float* x_nhwc, int n, int h, int w, int c_in, int x_ld, const float* dy_nhwc,
+                       int ho, int wo, int c_out, int dy_ld, int kh, int kw, int stride, int pad, float* dw,
+                       int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  return conv_wgrad_tc(x_nhwc, n, h, w, c_in, x_ld, dy_nhwc, ho, wo, c_out, dy_ld, kh, kw, stride, pad, dw,
+                       accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_pack_conv_weights(const float* w, int c_out, int c_in, int kh, int kw, int mode, float* out, void* stream) {
+  return pack_conv_weights(w, c_out, c_in, kh, kw, mode, out, (cudaStream_t)stream);
+}
+
+int dbev_pack_conv_weights_train(const float* w, int c_out, int c_in, int kh, int kw, int dgrad_mode, float* out_fwd,
+                                 float* out_dgrad, void* stream) {
+  return pack_conv_weights_train(w, c_out, c_in, kh, kw, dgrad_mode, out_fwd, out_dgrad, (cudaStream_t)stream);
+}
+
+size_t dbev_channel_stats_workspace_bytes(long long rows, int C) { return channel_stats_workspace_bytes(rows, C); }
+
+int dbev_bn_batch_stats(const float* y, int y_ld, long long rows, int C, const float* gamma, const float* beta,
+                        float eps, float momentum, float* running_mean, float* running_var, float* out4c,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  return bn_batch_stats(y, y_ld, rows, C, gamma, beta, eps, momentum, running_mean, running_var, out4c, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_channel_sums(const float* y, int y_ld, long long rows, int C, float* out, int accumulate,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  return channel_sums(y, y_ld, rows, C, out, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_bn_act_forward(const float* y, int y_ld, const float* ab, const float* residual, int res_ld,
+                        long long rows, int C, int relu, float* out, int out_ld, void* stream) {
+  return bn_act_forward(y, y_ld, ab, residual, res_ld, rows, C, relu, out, out_ld, (cudaStream_t)stream);
+}
+
+int dbev_bn_backward(const float* dz, int dz_ld, const float* z, int z_ld, const float* y, int y_ld,
+                     const float* fwd4c, long long rows, int C, float* bwd4c, float* dy, int dy_ld,
+                     float* g_out, int g_ld, int g_accumulate, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  return bn_backward(dz, dz_ld, z, z_ld, y, y_ld, fwd4c, rows, C, bwd4c, dy, dy_ld, g_out, g_ld, g_accumulate,
+                     workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int dbev_relu_mask_backward(const float* dz, int dz_ld, const float* z, int z_ld, long long rows, int C,
+                            float* g_out, int g_ld, int accumulate, void* stream) {
+  return relu_mask_backward(dz, dz_ld, z, z_ld, rows, C, g_out, g_ld, accumulate, (cudaStream_t)stream);
+}
+
+int dbev_upsample_bilinear_forward(const float* in, int in_ld, int n, int h, int w, int C, int H, int W,
+                                   float* out, int out_ld, void* stream) {
+  return upsample_bilinear_forward(in, in_ld, n, h, w, C, H, W, out, out_ld, (cudaStream_t)stream);
+}
+
+int dbev_upsample_bilinear_backward(const float* dout, int dout_ld, int n, int h, int w, int C, int H, int W,
+                                    float* din, int din_ld, int accumulate, void* stream) {
+  return upsample_bilinear_backward(dout, dout_ld, n, h, w, C, H, W, din, din_ld, accumulate, (cudaStream_t)stream);
 }
 
 int dbev_spconv_tc_supported(int c_in, int c_out, int kvol) {

@@ -45,6 +45,9 @@ struct ConvShape {
   int tma_store;  // 1: NHWC output on the plain lattice, written by TMA from a shared-memory staging tile
   int group_cols; // > 0: column block g = col / group_cols goes to lattice x + g, channel col % group_cols
                   // (both x taps of a stride-2 transposed conv in one launch)
+  int ncb;        // column blocks: C_out total = ncb * COUT; a work item = (pixel tile, column block), block fastest
+  int accumulate; // 1: out += result (TMA reduce-add store / read-modify-write) - gradient accumulation of the
+                  // training path (residual branches of BasicBlock, res_block.py:70-99)
 };
 
 template <int COUT, int STAGES, int MINB>
@@ -98,7 +101,8 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < s.n_tiles * s.ncb; item += gridDim.x) {
+        const int tile = item / s.ncb, cb = item - tile * s.ncb;
         const int n = tile / per_img, r = tile % per_img;
         const int y0 = (r / s.tiles_x) * s.ty, x0 = (r % s.tiles_x) * s.tx;
         for (int tap = 0; tap < taps; ++tap) {
@@ -113,7 +117,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_addr(st)),
                 "l"(&tmap_x), "r"(smem_addr(&full_bar[stage])), "r"(cc * kKc), "r"(ix), "r"(iy), "r"(n)
                 : "memory");
-            tma_load_2d(st + kATile, &tmap_w, tap * s.c_in + cc * kKc, 0, &full_bar[stage]);
+            tma_load_2d(st + kATile, &tmap_w, tap * s.c_in + cc * kKc, cb * COUT, &full_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -127,7 +131,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const uint64_t desc0 = umma_desc(0, 16, 1024);
     const int steps = taps * s.cin_chunks;
     uint32_t stage = 0, phase = 0, it = 0;
-    for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < s.n_tiles * s.ncb; item += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, use = it >> 1;
       mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -163,8 +167,9 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const uint32_t stg_row = smem_addr(stg) + (uint32_t)lane * 128u;
     const uint32_t sw_xor = (uint32_t)(lane & 7);
     uint32_t it = 0, sbuf = 0;
-    for (int tile = blockIdx.x; tile < s.n_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < s.n_tiles * s.ncb; item += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, use = it >> 1;
+      const int tile = item / s.ncb, cb = item - tile * s.ncb;
       const int n = tile / per_img, r = tile % per_img;
       const int ty0 = (r / s.tiles_x) * s.ty, tx0 = (r % s.tiles_x) * s.tx;
       const int oy = ty0 + py, ox = tx0 + px;
@@ -185,7 +190,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const uint32_t dst = stg_row + sbuf * 4096u;
-        int grp = 0, ch0 = cc * 32;          // lattice x offset and first output channel of this column chunk
+        int grp = 0, ch0 = cb * COUT + cc * 32;   // lattice x offset and first output channel of this column chunk
         if (s.group_cols > 0) grp = ch0 / s.group_cols, ch0 -= grp * s.group_cols;
         if (valid || s.tma_store) {
 #pragma unroll
@@ -207,9 +212,15 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                            : "memory");
             } else if (s.nchw) {
               float* oc = ocol + grp + (long long)(ch0 + j) * plane;
+              if (s.accumulate) o.x += oc[0], o.y += oc[plane], o.z += oc[2 * plane], o.w += oc[3 * plane];
               oc[0] = o.x, oc[plane] = o.y, oc[2 * plane] = o.z, oc[3 * plane] = o.w;
             } else {
-              *reinterpret_cast<float4*>(orow + (long long)grp * s.ld + ch0 + j) = o;
+              float4* op = reinterpret_cast<float4*>(orow + (long long)grp * s.ld + ch0 + j);
+              if (s.accumulate) {
+                const float4 prev = *op;
+                o.x += prev.x, o.y += prev.y, o.z += prev.z, o.w += prev.w;
+              }
+              *op = o;
             }
           }
         }
@@ -218,10 +229,16 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           __syncwarp();
           if (lane == 0) {
             if (ty0 + by0 < s.ho && tx0 + bx0 < s.wo) {
-              asm volatile(
-                  "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmap_o),
-                  "r"(smem_addr(stg) + sbuf * 4096u), "r"(s.c_off + cc * 32), "r"(tx0 + bx0), "r"(ty0 + by0), "r"(n)
-                  : "memory");
+              if (s.accumulate)
+                asm volatile(
+                    "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmap_o),
+                    "r"(smem_addr(stg) + sbuf * 4096u), "r"(s.c_off + ch0), "r"(tx0 + bx0), "r"(ty0 + by0), "r"(n)
+                    : "memory");
+              else
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmap_o),
+                    "r"(smem_addr(stg) + sbuf * 4096u), "r"(s.c_off + ch0), "r"(tx0 + bx0), "r"(ty0 + by0), "r"(n)
+                    : "memory");
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -269,7 +286,8 @@ struct HaloShape {
   int hx;            // halo pitch in pixels (box width), >= kHaloTx + 2
   int a_stage;       // bytes of one halo stage (multiple of 1024)
   int w_stages;      // weight ring depth
-  int c_off, relu;
+  int c_off, relu, accumulate;
+  int ncb;           // column blocks (see ConvShape)
 };
 
 __device__ __forceinline__ void halo_item(const HaloShape& s, int i, int& n, int& y0, int& x0, int& halves) {
@@ -346,9 +364,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       // warp (w_stages taps behind) has left chunk i-1, so its halo stage is free without waiting
       int t_n = blockIdx.x, c_n = 0;
       auto issue_halo = [&]() {
-        if (t_n >= s.n_items) return;
+        if (t_n >= s.n_items * s.ncb) return;
         int n, y0, x0, halves;
-        halo_item(s, t_n, n, y0, x0, halves);
+        halo_item(s, t_n / s.ncb, n, y0, x0, halves);
         { const long long t = prof ? clock64() : 0; mbar_wait(&a_empty[sa], pa ^ 1u); if (prof) pw_a += clock64() - t; }
         mbar_expect_tx(&a_full[sa], a_bytes);
         asm volatile(
@@ -361,14 +379,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       };
       const int ahead = s.w_stages < 8 ? s.w_stages : 8;
       issue_halo();
-      for (int tile = blockIdx.x; tile < s.n_items; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < s.n_items * s.ncb; item += gridDim.x) {
+        const int cb = item % s.ncb;
         for (int cc = 0; cc < s.cin_chunks; ++cc) {
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             if (tap == ahead) issue_halo();
             { const long long t = prof ? clock64() : 0; mbar_wait(&w_empty[sw], pw ^ 1u); if (prof) pw_w += clock64() - t; }
             mbar_expect_tx(&w_full[sw], (uint32_t)kWTile);
-            tma_load_2d(wbase + (size_t)sw * kWTile, &tmap_w, tap * s.c_in + cc * kKc, 0, &w_full[sw]);
+            tma_load_2d(wbase + (size_t)sw * kWTile, &tmap_w, tap * s.c_in + cc * kKc, cb * COUT, &w_full[sw]);
             if (++sw == (uint32_t)s.w_stages) { sw = 0; pw ^= 1u; }
           }
         }
@@ -387,9 +406,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     uint32_t sa = 0, pa = 0, sw = 0, pw = 0, it = 0;
     long long mw_t = 0, mw_a = 0, mw_w = 0;
     const long long mt0 = prof ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < s.n_items; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < s.n_items * s.ncb; item += gridDim.x, ++it) {
       const uint32_t buf = kNBuf == 2 ? (it & 1u) : 0u, use = kNBuf == 2 ? (it >> 1) : it;
-      const int halves = tile < s.n_full ? s.item_halves : 1;
+      const int halves = item / s.ncb < s.n_full ? s.item_halves : 1;
       { const long long t = prof ? clock64() : 0; mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u); if (prof) mw_t += clock64() - t; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + buf * 2 * COUT;
@@ -441,10 +460,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     uint32_t it = 0, sbuf = 0;
     long long ew_f = 0;
     const long long et0 = prof ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < s.n_items; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < s.n_items * s.ncb; item += gridDim.x, ++it) {
       const uint32_t buf = kNBuf == 2 ? (it & 1u) : 0u, use = kNBuf == 2 ? (it >> 1) : it;
       int n, ty0, tx0, halves;
-      halo_item(s, tile, n, ty0, tx0, halves);
+      const int cb = item % s.ncb;
+      halo_item(s, item / s.ncb, n, ty0, tx0, halves);
       { const long long t = prof ? clock64() : 0; mbar_wait(&tmem_full_bar[buf], use & 1u); if (prof) ew_f += clock64() - t; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -464,11 +484,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             if (scale) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cc * 32 + j));
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cb * COUT + cc * 32 + j));
               o.x *= sc.x, o.y *= sc.y, o.z *= sc.z, o.w *= sc.w;
             }
             if (shift) {
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cc * 32 + j));
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cb * COUT + cc * 32 + j));
               o.x += sh.x, o.y += sh.y, o.z += sh.z, o.w += sh.w;
             }
             if (s.relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
@@ -479,10 +499,16 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0 && oy0 < s.ho) {
-            asm volatile(
-                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmap_o),
-                "r"(smem_addr(stg) + sbuf * 4096u), "r"(s.c_off + cc * 32), "r"(tx0), "r"(oy0), "r"(n)
-                : "memory");
+            if (s.accumulate)
+              asm volatile(
+                  "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmap_o),
+                  "r"(smem_addr(stg) + sbuf * 4096u), "r"(s.c_off + cb * COUT + cc * 32), "r"(tx0), "r"(oy0), "r"(n)
+                  : "memory");
+            else
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmap_o),
+                  "r"(smem_addr(stg) + sbuf * 4096u), "r"(s.c_off + cb * COUT + cc * 32), "r"(tx0), "r"(oy0), "r"(n)
+                  : "memory");
           }
           if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           sbuf ^= 1u;
@@ -539,6 +565,26 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
                       const float* shift, int relu, float* out, int out_h, int out_w, int out_ld,
                       int out_c_off, int out_mul, int out_add_y, int out_add_x, int out_nchw,
                       int out_groups, cudaStream_t stream) {
+  return conv2d_tc_forward_ex(x_nhwc, n_img, h, w, c_in, c_in, w_packed, c_out, 1, kh, kw, stride, pad, scale, shift, relu, out,
+                              out_h, out_w, out_ld, out_c_off, out_mul, out_add_y, out_add_x, out_nchw, out_groups, 0, 0,
+                              0, stream);
+}
+
+// x_ld: channel stride of the input rows (>= c_in: the input may be a channel slice of a wider NHWC tensor);
+// force_ho / force_wo > 0 override the output size (taps that fall outside the input read zeros: the four
+// output-parity classes of a stride-2 input gradient are stride-1 convolutions of dy padded on ONE side);
+// accumulate != 0 adds to the output instead of overwriting it; n_col_blocks > 1: the layer has
+// n_col_blocks * c_out output channels (w_packed / scale / shift / the output slice cover all of them) and a work
+// item is (pixel tile, block of c_out columns) - layers with few pixel tiles (16 x 16 .. 64 x 64 BEV maps) fill
+// the SMs with column blocks instead of running one under-filled launch per block.
+int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in, int x_ld, const float* w_packed,
+                         int c_out, int n_col_blocks, int kh, int kw, int stride, int pad, const float* scale,
+                         const float* shift, int relu, float* out, int out_h, int out_w, int out_ld,
+                         int out_c_off, int out_mul, int out_add_y, int out_add_x, int out_nchw,
+                         int out_groups, int force_ho, int force_wo, int accumulate, cudaStream_t stream) {
+  DBEV_CHECK_ARG(x_ld >= c_in && x_ld % 4 == 0, "conv2d_tc: bad input channel stride");
+  DBEV_CHECK_ARG(n_col_blocks >= 1 && (n_col_blocks == 1 || out_groups == 1), "conv2d_tc: column blocks need out_groups == 1");
+  const int ncb = n_col_blocks;
   DBEV_CHECK_ARG(n_img > 0 && h > 0 && w > 0, "conv2d_tc: empty input");
   DBEV_CHECK_ARG(c_in % kKc == 0 && c_in >= kKc, "conv2d_tc: C_in must be a multiple of 32 (got %d)", c_in);
   DBEV_CHECK_ARG(c_out == 64 || c_out == 128 || c_out == 256,
@@ -550,7 +596,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
                  "conv2d_tc: pointers must be 16-byte aligned");
   DBEV_CHECK_ARG(out_groups >= 1 && out_groups <= out_mul && c_out % out_groups == 0 && (c_out / out_groups) % 32 == 0,
                  "conv2d_tc: out_groups must divide C_out into multiples of 32 columns and fit the lattice step");
-  DBEV_CHECK_ARG(out_ld % 4 == 0 && out_c_off % 4 == 0 && out_c_off + c_out / out_groups <= out_ld && out_mul >= 1,
+  DBEV_CHECK_ARG(out_ld % 4 == 0 && out_c_off % 4 == 0 && out_c_off + c_out * ncb / out_groups <= out_ld && out_mul >= 1,
                  "conv2d_tc: bad output placement");
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) {
@@ -562,7 +608,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   DBEV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int halo_mode = conv_halo_mode();
   if (halo_mode > 0 && out_groups == 1 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && h >= 16 && w >= kHaloTx && out_mul == 1 &&
-      out_add_y == 0 && out_add_x == 0 && !out_nchw && out_h == h && out_w == w) {
+      out_add_y == 0 && out_add_x == 0 && !out_nchw && out_h == h && out_w == w && force_ho == 0 && force_wo == 0) {
     HaloShape hs;
     hs.n_img = n_img, hs.c_in = c_in, hs.ho = h, hs.wo = w;
     hs.cin_chunks = c_in / kKc;
@@ -572,12 +618,13 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
     const int smem_max = 227 * 1024 - 2048;
     // (keeping all 9 * C_in/32 weight tiles of a 64 -> 64 layer resident in shared memory was tried: only
     // single-half tiles fit beside them, whose halo prefetch distance is too short - 0.132 vs 0.110 ms)
-    hs.item_halves = 2;
+    hs.item_halves = h > 16 ? 2 : 1;      // 16-row images (the student's 512-channel stage): one M=128 half per item
     hs.tile_rows = 16 * hs.item_halves;
     hs.tiles_x = ceil_div(w, kHaloTx), hs.tiles_y = ceil_div(h, hs.tile_rows);
     const int n_tiles = hs.tiles_x * hs.tiles_y * n_img;
     hs.n_full = n_tiles, hs.n_items = n_tiles;
-    if (halo_mode != 4) {
+    hs.ncb = ncb;
+    if (halo_mode != 4 && hs.item_halves == 2 && ncb == 1) {
       const int rem = n_tiles % sms;
       if (rem > 0 && 2 * rem <= sms) hs.n_full = n_tiles - rem, hs.n_items = hs.n_full + 2 * rem;
     }
@@ -586,7 +633,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
     if (w_stages > 6) w_stages = 6;
     DBEV_CHECK_ARG(w_stages >= 2, "conv2d_tc: halo tile does not fit shared memory");
     hs.w_stages = w_stages;
-    hs.c_off = out_c_off, hs.relu = relu;
+    hs.c_off = out_c_off, hs.relu = relu, hs.accumulate = accumulate ? 1 : 0;
     CUtensorMap tmap_x, tmap_w, tmap_o;
     {
       // NHWC output [n, H, W, ld] as (C, W, H, N); a store box = 32 channels x 8 px x 4 rows, clipped at the borders
@@ -604,7 +651,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
     }
     {
       cuuint64_t dims[4] = {(cuuint64_t)c_in, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n_img};
-      cuuint64_t strides[3] = {(cuuint64_t)c_in * 4, (cuuint64_t)w * c_in * 4, (cuuint64_t)h * w * c_in * 4};
+      cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)w * x_ld * 4, (cuuint64_t)h * w * x_ld * 4};
       cuuint32_t box[4] = {(cuuint32_t)kKc, (cuuint32_t)hs.hx, (cuuint32_t)(hs.tile_rows + 2), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = encode(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x_nhwc, dims, strides, box, estr,
@@ -617,7 +664,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
     }
     {
       const int k_total = 9 * c_in;
-      cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)c_out};
+      cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)c_out * ncb};
       cuuint64_t strides[1] = {(cuuint64_t)k_total * 4};
       cuuint32_t box[2] = {(cuuint32_t)kKc, (cuuint32_t)c_out};
       cuuint32_t estr[2] = {1, 1};
@@ -630,7 +677,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
       }
     }
     const size_t smem = 2 * (size_t)hs.a_stage + (size_t)w_stages * w_tile + stage_out + 1024;
-    const int grid = hs.n_items < sms ? hs.n_items : sms;
+    const int grid = hs.n_items * ncb < sms ? hs.n_items * ncb : sms;
     // DBEV_CONV_PROF=1: per-role wait cycles (debug only: synchronises and prints after every launch)
     static long long* prof_buf = nullptr;
     long long* prof = nullptr;
@@ -666,8 +713,9 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   }
   ConvShape s;
   s.n_img = n_img, s.c_in = c_in, s.c_out = c_out, s.kh = kh, s.kw = kw, s.stride = stride, s.pad = pad;
-  s.ho = (h + 2 * pad - kh) / stride + 1;
-  s.wo = (w + 2 * pad - kw) / stride + 1;
+  s.ho = force_ho > 0 ? force_ho : (h + 2 * pad - kh) / stride + 1;
+  s.wo = force_wo > 0 ? force_wo : (w + 2 * pad - kw) / stride + 1;
+  s.accumulate = accumulate ? 1 : 0;
   DBEV_CHECK_ARG(s.ho >= 1 && s.wo >= 1, "conv2d_tc: empty output");
   DBEV_CHECK_ARG((s.ho - 1) * out_mul + out_add_y < out_h && (s.wo - 1) * out_mul + out_add_x + out_groups - 1 < out_w,
                  "conv2d_tc: output lattice exceeds the output tensor");
@@ -678,6 +726,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   s.tx = tx, s.ty = kPix / tx;
   s.tiles_x = ceil_div(s.wo, s.tx), s.tiles_y = ceil_div(s.ho, s.ty);
   s.n_tiles = s.tiles_x * s.tiles_y * n_img;
+  s.ncb = ncb;
   s.cin_chunks = c_in / kKc;
   s.omul = out_mul, s.oadd_y = out_add_y, s.oadd_x = out_add_x, s.h_full = out_h, s.w_full = out_w;
   s.ld = out_ld, s.c_off = out_c_off, s.relu = relu, s.nchw = out_nchw ? 1 : 0;
@@ -707,7 +756,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
     // NHWC input as a 4-D tensor (C, W, H, N); box {32, TX*s, TY*s, 1} traversed with element strides
     // {1, s, s, 1} loads TX x TY pixels; out-of-bounds coordinates (the padding) are zero-filled
     cuuint64_t dims[4] = {(cuuint64_t)c_in, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n_img};
-    cuuint64_t strides[3] = {(cuuint64_t)c_in * 4, (cuuint64_t)w * c_in * 4, (cuuint64_t)h * w * c_in * 4};
+    cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)w * x_ld * 4, (cuuint64_t)h * w * x_ld * 4};
     cuuint32_t box[4] = {(cuuint32_t)kKc, (cuuint32_t)(s.tx * stride), (cuuint32_t)(s.ty * stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = encode(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x_nhwc, dims, strides, box, estr,
@@ -720,7 +769,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
   }
   {
     const int k_total = kh * kw * c_in;
-    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)c_out};
+    cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)c_out * ncb};
     cuuint64_t strides[1] = {(cuuint64_t)k_total * 4};
     cuuint32_t box[2] = {(cuuint32_t)kKc, (cuuint32_t)c_out};
     cuuint32_t estr[2] = {1, 1};
@@ -735,7 +784,7 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
 #define DBEV_CONV_LAUNCH(CO, STG, MB)                                                            \
   do {                                                                                           \
     const size_t smem = (size_t)STG * (kATile + CO * kKc * 4) + (s.tma_store ? 4 * 8192 : 0) + 1024; \
-    const int grid = s.n_tiles < sms * MB ? s.n_tiles : sms * MB;                                \
+    const int grid = s.n_tiles * ncb < sms * MB ? s.n_tiles * ncb : sms * MB;                    \
     DBEV_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel<CO, STG, MB>,                                \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
     DBEV_CUDA(launch_conv(conv2d_tc_kernel<CO, STG, MB>, grid, smem, stream, tmap_x, tmap_w, tmap_o, scale, shift, out, s)); \

@@ -408,6 +408,80 @@ int dbev_conv2d_tc_forward_grouped(const float* x_nhwc, int n, int h, int w, int
                                    int out_ld, int out_c_off, int out_mul, int out_add_y, int out_add_x,
                                    int out_nchw, int out_groups, void* stream);
 
+/* Extended form used by the TRAINING path (input gradients are convolutions of dy with re-packed weights):
+ * x_ld = channel stride of the input rows (>= c_in; the input may be a channel slice of a wider NHWC
+ * tensor); force_ho / force_wo > 0 override the output size (taps outside the input read zeros: the four
+ * output-parity classes of a stride-2 input gradient are stride-1 convolutions padded on one side);
+ * accumulate != 0 adds to `out` (TMA reduce-add store) - the residual branches of BasicBlock
+ * (mmdet3d/models/bricks/res_block.py:70-99) sum their input gradients this way; n_col_blocks > 1: the layer has
+ * n_col_blocks * c_out output channels (c_out in {64, 128, 256} is the tile width) and a work item is
+ * (pixel tile, column block), so small BEV maps (16 x 16 .. 64 x 64) still fill the 148 SMs in one launch. */
+int dbev_conv2d_tc_forward_ex(const float* x_nhwc, int n, int h, int w, int c_in, int x_ld, const float* w_packed,
+                              int c_out, int n_col_blocks, int kh, int kw, int stride, int pad, const float* scale,
+                              const float* shift, int relu, float* out, int out_h, int out_w,
+                              int out_ld, int out_c_off, int out_mul, int out_add_y, int out_add_x,
+                              int out_nchw, int out_groups, int force_ho, int force_wo, int accumulate,
+                              void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Training of the student's BEV encoder: ResNetForBEVDet.forward
+ * (mmdet3d/models/backbones/resnet.py:51-62), BasicBlock (bricks/res_block.py:70-99), FPN_LSS.forward
+ * (necks/lss_fpn.py:62-72) and the adaptation convs (detectors/bevdet_distill.py:261-345). The reference
+ * runs these as nn.Conv2d / nn.BatchNorm2d (training mode) / nn.ReLU / nn.Upsample through cuDNN + ATen
+ * with autograd; these entry points are what replaces aten::convolution_backward, native_batch_norm
+ * (+ backward), upsample_bilinear2d (+ backward). NHWC fp32, row strides (`*_ld`, in floats) so that an
+ * operand can be a channel slice of a wider tensor (torch.cat is never materialised separately).
+ * ------------------------------------------------------------------------ */
+
+/* dW[c_out][c_in][kh][kw] (torch layout) (+)= sum_pixels dy (x) x on tcgen05 (TF32, MN-major operands,
+ * split-K over pixel strips, partial sums combined in fixed order). c_in, c_out % 128 == 0; 3x3 / pad 1 /
+ * stride 1|2 or 1x1 / stride 1. workspace: dbev_conv_wgrad_tc_workspace_bytes, 256-byte aligned. */
+size_t dbev_conv_wgrad_tc_workspace_bytes(int n, int ho, int wo, int c_in, int c_out, int kh, int kw, int stride);
+int dbev_conv_wgrad_tc(const float* x_nhwc, int n, int h, int w, int c_in, int x_ld, const float* dy_nhwc,
+                       int ho, int wo, int c_out, int dy_ld, int kh, int kw, int stride, int pad, float* dw,
+                       int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* torch weight [c_out][c_in][kh][kw] -> K-major matrices for the conv kernels' TMA loads. mode 0: forward
+ * [c_out][(ky*kw+kx)*c_in + ci]; mode 1: stride-1 input gradient [c_in][flipped tap * c_out + co];
+ * mode 2 (3x3): the four parity-class matrices of a stride-2 input gradient at float offsets
+ * {0, 1, 3, 5} * c_in*c_out, class (a, b): [c_in][(ty*(1+b) + tx)*c_out + co], ky = a+1-2ty, kx = b+1-2tx. */
+int dbev_pack_conv_weights(const float* w, int c_out, int c_in, int kh, int kw, int mode, float* out, void* stream);
+/* Forward matrix (mode 0 layout) and input-gradient matrix (dgrad_mode 1 or 2 layout) of one layer in ONE pass over
+ * the weights (shared-memory tiles: every global access is a 128-byte run); either output may be NULL. */
+int dbev_pack_conv_weights_train(const float* w, int c_out, int c_in, int kh, int kw, int dgrad_mode, float* out_fwd,
+                                 float* out_dgrad, void* stream);
+
+/* Workspace of the per-channel reductions below (per-block partial sums, combined in block order). */
+size_t dbev_channel_stats_workspace_bytes(long long rows, int C);
+/* nn.BatchNorm2d training forward, statistics part: out4c[4][C] = (a, b, mean, invstd) with
+ * a = gamma*invstd, b = beta - mean*a over the `rows` pixels; running_mean / running_var (nullable pair)
+ * are updated like torch (momentum, unbiased variance). */
+int dbev_bn_batch_stats(const float* y, int y_ld, long long rows, int C, const float* gamma, const float* beta,
+                        float eps, float momentum, float* running_mean, float* running_var, float* out4c,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* out[C] (+)= column sums of y[rows, C] (conv bias gradient). */
+int dbev_channel_sums(const float* y, int y_ld, long long rows, int C, float* out, int accumulate,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* out = relu?(a*y + b (+ residual)); ab[2][C] nullable (identity affine). */
+int dbev_bn_act_forward(const float* y, int y_ld, const float* ab, const float* residual, int res_ld,
+                        long long rows, int C, int relu, float* out, int out_ld, void* stream);
+/* Backward of z = relu?(BN(y) (+ identity)): g = dz * (z > 0) (z nullable: no ReLU);
+ * bwd4c[4][C] = (dgamma, dbeta, mean g, mean g*yhat); dy = a*(g - mean g - yhat*mean(g*yhat));
+ * g_out (nullable) receives g (the identity-branch gradient), added when g_accumulate. */
+int dbev_bn_backward(const float* dz, int dz_ld, const float* z, int z_ld, const float* y, int y_ld,
+                     const float* fwd4c, long long rows, int C, float* bwd4c, float* dy, int dy_ld,
+                     float* g_out, int g_ld, int g_accumulate, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* g_out (+)= dz * (z > 0) without a BatchNorm. */
+int dbev_relu_mask_backward(const float* dz, int dz_ld, const float* z, int z_ld, long long rows, int C,
+                            float* g_out, int g_ld, int accumulate, void* stream);
+/* nn.Upsample(mode='bilinear', align_corners=True) on NHWC, ATen's index arithmetic; the backward is a
+ * gather (no atomics, deterministic). */
+int dbev_upsample_bilinear_forward(const float* in, int in_ld, int n, int h, int w, int C, int H, int W,
+                                   float* out, int out_ld, void* stream);
+int dbev_upsample_bilinear_backward(const float* dout, int dout_ld, int n, int h, int w, int C, int H, int W,
+                                    float* din, int din_ld, int accumulate, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * Cross-modal feature distillation loss (FGD-style), BEVDetDistill
  * (mmdet3d/models/detectors/bevdet_distill.py). The reference has no native
