@@ -1,29 +1,29 @@
-"""bench.py — DistillBEV hot-path throughput on B200 (contract: see DESIGN.md §Measurement).
+"""bench.py — DistillBEV hot-path training step on B200 (contract: see DESIGN.md §Measurement).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-One "step" = one pass of the hot path over one synthetic nuScenes-shaped batch per GPU
-(BASELINE.json configs[1]: CenterPoint -> BEVDepth-R50 distillation, per-GPU batch 8, 2 frames,
-6 cams, D=59, 16x44 frustum, C=64 -> 128x128 BEV; 30k-point LiDAR; head position 256 -> 384 ch):
-  A  student view transform: get_geometry -> frustum sort plan -> fused lift+splat, forward
-     and backward, for 16 sample-frames
-  B  frozen teacher LiDAR path: voxelize -> fused DynamicPillarFeatureNet -> PointPillarsScatter
-     (512x512x64 pseudo image), 8 clouds
-  C  head-position distillation loss: fg / fp masks from GT boxes and heat maps, 1x1 adaptation
-     conv (tcgen05 TF32 forward; its backward GEMMs still go through cuDNN), fused fgd loss
-     forward and backward
-The dense conv stacks around these stages (image backbone, SECOND/SECONDFPN, BEV encoder) are
-library code (cuDNN) that this repository does not replace yet; they are NOT in the step and
-`config.workload` says so.
+One "step" = one TRAINING pass of the hot path over one synthetic nuScenes-shaped batch per GPU
+(BASELINE.json configs[1]: CenterPoint -> BEVDepth-R50 distillation, per-GPU batch 8, 2 frames, 6 cams, D=59,
+16x44 frustum, C=64 -> 128x128 BEV; 30k-point LiDAR; head position 256 -> 384 ch), one autograd chain:
+  A  student view transform: get_geometry -> point cells -> fused lift+splat (16 sample-frames), frames concatenated
+  S  student BEV encoder, TRAINING mode: ResNetForBEVDet (3 x 2 BasicBlocks, 128 -> 128/256/512) + FPN_LSS
+     (-> 256 ch @ 128x128) on the tcgen05 conv kernels (forward, input gradient, weight gradient), batch-stat BatchNorm
+  B  frozen teacher LiDAR path (side stream): voxelize -> DynamicPillarFeatureNet -> PointPillarsScatter ->
+     SECOND + SECONDFPN (tcgen05 conv+BN+ReLU) -> teacher BEV feature [8,384,128,128]
+  C  head-position distillation loss: fg / fp masks from GT boxes and device-rasterised heat maps, 1x1 adaptation
+     conv, fused fgd loss
+  backward of C -> S -> A, then (N > 1) the data-parallel gradient all-reduce (NCCL, flat bf16 buckets), then a fused
+  AdamW step on the student encoder + adaptation parameters.
+The image backbone / depth net / CenterHead (mmdet / mmcv third-party modules outside SURVEY §8) are not in the step.
 
-`value` times the step with every input resident in HBM; `e2e` times the same step when the
-host-originated inputs (calibration, LiDAR points, GT boxes, GT heat maps) start in pinned host
-memory and the loss scalars are read back, every step. `roofline` is measured live for the
-bev_pool gather kernel (BASELINE.json's "bev_pool HBM GB/s vs roofline") on the same shape.
-`--impl reference` / `cpu_baseline` time the CPU oracle port of the same stages (oracle/, numpy +
-C; the voxelization leg is bit-identical to the reference's own CPU build in oracle/_ref).
+`value` times the step with every input resident in HBM; `e2e` times the same step when the host-originated inputs
+(calibration, LiDAR points, GT boxes, labels) start in pinned host memory and the loss scalars are read back, every
+step. `roofline` is measured live for the kernel class that dominates the step (conv3x3_halo_kernel<256>, tensor
+bound); `roofline_bev_pool` is BASELINE.json's "bev_pool HBM GB/s vs roofline". `--impl reference` / `cpu_baseline`
+time the CPU implementation of the same stages (oracle/ numpy + C; the conv stacks through torch.nn on the CPU, which
+IS the reference's implementation of those rows).
 """
 import argparse
 import json
@@ -46,12 +46,14 @@ FRAMES = 2           # BEVDepth4D: current + adjacent frame
 N_CAMS, D, FH, FW, C_TRANS, BEV = 6, 59, 16, 44, 64, 128
 N_POINTS = 30000
 C_STUDENT, C_TEACHER = 256, 384
-WORKLOAD = ("hotpath-ops-v2: lift+splat fwd/bwd (B=8 x 2 frames, 6 cams, D=59, 16x44, C=64 -> 128x128; sort-free splat: "
-            "vector float reductions into the L2-resident channels-last BEV map, summation order not fixed, upstream gradient in the same layout; --sorted-splat for the plan-based one) "
-            "+ frozen LiDAR teacher end to end: voxelize/pillar-encode/scatter (8 x 30k pts -> 512x512x64) -> "
-            "SECOND + SECONDFPN (tcgen05 conv+BN+ReLU, 601 GFLOP) -> teacher BEV feature [8,384,128,128] "
-            "+ CenterHead GT heat maps rasterised on the device + 1x1 adaptation conv (tcgen05 fwd, cuDNN bwd) + fgd distill loss fwd/bwd at head against that "
-            "teacher feature (256->384 ch, 128x128, fg+fp masks); student image/BEV conv stacks (cuDNN) not in step")
+WORKLOAD = ("distill-train-hotpath-v3 (configs[1], B=8/GPU): lift+splat (2 frames x 6 cams, D=59, 16x44, C=64 -> 128x128, "
+            "sort-free splat) -> student BEV encoder in TRAINING mode (ResNetForBEVDet 128->128/256/512 + FPN_LSS -> 256 ch, "
+            "tcgen05 TF32 fwd / dgrad / wgrad, batch-stat BN) -> 1x1 adaptation + fgd distill loss at head "
+            "(256->384 ch, fg+fp masks) against the frozen LiDAR teacher run end to end in the step (voxelize/pillar-encode/"
+            "scatter 8 x 30k pts -> SECOND + SECONDFPN on tcgen05 -> [8,384,128,128]); backward through loss, encoder and "
+            "lift+splat; gradient all-reduce when N > 1; fused AdamW step. Image backbone / depth net / CenterHead "
+            "(third-party mmdet modules, outside SURVEY 8) not in the step")
+ENC_CHANNELS, ENC_OUT = [128, 256, 512], 256
 PILLAR_VS, PILLAR_RANGE = [0.2, 0.2, 8.0], [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0]
 CENTER_TASKS = [dict(num_class=1, class_names=['car']), dict(num_class=2, class_names=['truck', 'construction_vehicle']),
                 dict(num_class=2, class_names=['bus', 'trailer']), dict(num_class=1, class_names=['barrier']),
@@ -147,14 +149,73 @@ def measured_peaks():
 
 # ----------------------------------------------------------------------------- our arm
 
-class HotPath(object):
-    """Synthetic batch + the step, built on the public plugin API (distill_bev_b200)."""
+def encoder_flops(batch):
+    """Forward FLOPs of the student BEV encoder (2 per multiply-add); training = 3x (fwd + dgrad + wgrad)."""
+    f, cin, hw = 0.0, 2 * C_TRANS, BEV
+    for c in ENC_CHANNELS:
+        hw //= 2
+        f += 2.0 * batch * hw * hw * 9 * (2 * cin * c + 3 * c * c)      # conv1 + downsample (stride 2), 3 more 3x3
+        cin = c
+    h1 = BEV // 2
+    f += 2.0 * batch * h1 * h1 * 9 * ((ENC_CHANNELS[0] + ENC_CHANNELS[2]) * 2 * ENC_OUT + 4 * ENC_OUT * ENC_OUT)
+    f += 2.0 * batch * BEV * BEV * (9 * 2 * ENC_OUT * ENC_OUT + ENC_OUT * ENC_OUT)
+    return f
 
-    def __init__(self, device, seed):
+
+class CudnnEncoder(object):
+    """The same encoder from plain torch modules (what the reference runs: cuDNN TF32 + ATen), for the side-by-side key."""
+
+    @staticmethod
+    def build(device):
+        import torch
+        import torch.nn as nn
+
+        def cbr(cin, cout, k=3, s=1, p=1):
+            return nn.Sequential(nn.Conv2d(cin, cout, k, s, p, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+        class Basic(nn.Module):
+            def __init__(self, cin, cout, stride=1):
+                super().__init__()
+                self.c1 = cbr(cin, cout, 3, stride, 1)
+                self.c2 = nn.Sequential(nn.Conv2d(cout, cout, 3, 1, 1, bias=False), nn.BatchNorm2d(cout))
+                self.down = nn.Conv2d(cin, cout, 3, stride, 1) if stride != 1 else None
+
+            def forward(self, x):
+                idt = x if self.down is None else self.down(x)
+                return torch.relu(self.c2(self.c1(x)) + idt)
+
+        class Encoder(nn.Module):
+            def __init__(self):
+                super().__init__()
+                layers, cin = [], 2 * C_TRANS
+                for cout in ENC_CHANNELS:
+                    layers.append(nn.Sequential(Basic(cin, cout, 2), Basic(cout, cout)))
+                    cin = cout
+                self.layers = nn.ModuleList(layers)
+                self.up = nn.Upsample(scale_factor=4, mode="bilinear", align_corners=True)
+                self.conv = nn.Sequential(cbr(ENC_CHANNELS[0] + ENC_CHANNELS[2], 2 * ENC_OUT), cbr(2 * ENC_OUT, 2 * ENC_OUT))
+                self.up2 = nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True),
+                                         cbr(2 * ENC_OUT, ENC_OUT), nn.Conv2d(ENC_OUT, ENC_OUT, 1))
+
+            def forward(self, x):
+                feats = []
+                for l in self.layers:
+                    x = l(x)
+                    feats.append(x)
+                return self.up2(self.conv(torch.cat([feats[0], self.up(feats[2])], 1)))
+
+        torch.manual_seed(0)
+        return Encoder().to(device).train().to(memory_format=torch.channels_last)
+
+
+class HotPath(object):
+    """Synthetic batch + the training step, built on the public plugin API (distill_bev_b200)."""
+
+    def __init__(self, device, seed, world=1, allreduce="after", comm_dtype="bf16", encoder="tcgen05"):
         import torch
         import distill_bev_b200 as dbev
         from distill_bev_b200 import synthetic
-        self.torch, self.dbev, self.dev = torch, dbev, device
+        self.torch, self.dbev, self.dev, self.world = torch, dbev, device, world
         g = torch.Generator().manual_seed(seed)
         nf = BATCH * FRAMES
         # --- host-originated inputs (pinned) -------------------------------------------------
@@ -169,19 +230,13 @@ class HotPath(object):
         # CenterHead targets (GT heat maps of add_fp_as_fg) are rasterised on the device from the boxes
         self.targets = dbev.CenterHeadTargets(CENTER_TASKS, dict(TRAIN_CFG, out_size_factor=8, dense_reg=1,
                                                                   gaussian_overlap=0.1, max_objs=500, min_radius=2))
-        # --- device-resident activations (produced by the conv stacks in the real model) -----
+        # --- device-resident activations produced by the image branch (outside SURVEY 8) ------
         self.depth = torch.randn(nf * N_CAMS, D, FH, FW, generator=g).softmax(1).to(device).requires_grad_(True)
         self.feat = torch.randn(nf * N_CAMS, C_TRANS, FH, FW, generator=g).to(device).requires_grad_(True)
-        self.bev_grad = torch.rand(nf, C_TRANS, BEV, BEV, generator=g).to(device)
-        # the sort-free splat returns channels_last memory; its upstream gradient (a cuDNN / tcgen05 conv backward on
-        # that tensor) arrives in the same layout
-        self.bev_grad_cl = self.bev_grad.contiguous(memory_format=torch.channels_last)
         self.sorted_splat = False
-        self.student = torch.relu(torch.randn(BATCH, C_STUDENT, BEV, BEV, generator=g)).to(device).requires_grad_(True)
-        self.teacher = torch.relu(torch.randn(BATCH, C_TEACHER, BEV, BEV, generator=g)).to(device)
         self.teacher_logit = (torch.randn(BATCH, 10, BEV, BEV, generator=g) * 1.5 - 3.0).to(device)
         # --- modules ---------------------------------------------------------------------------
-        torch.manual_seed(seed)
+        torch.manual_seed(0)          # identical initial weights on every rank, like DDP's broadcast at construction
         self.vt = dbev.ViewTransformerLiftSplatShoot(grid_config=synthetic.NUSC_GRID, numC_input=32,
                                                      numC_Trans=C_TRANS).to(device)
         self.enc = dbev.DynamicPillarFeatureNet(in_channels=5, feat_channels=(64,), voxel_size=PILLAR_VS,
@@ -192,9 +247,25 @@ class HotPath(object):
                                   layer_strides=[2, 2, 2]).to(device).eval()
         self.secfpn = dbev.SECONDFPN(in_channels=[64, 128, 256], out_channels=[128, 128, 128],
                                      upsample_strides=[0.5, 1, 2]).to(device).eval()
+        # student BEV encoder (img_bev_encoder_backbone / img_bev_encoder_neck of ...bevdepth4d_r50.py:122-126)
+        self.encoder_kind = encoder
+        if encoder == "cudnn":
+            self.student_net = CudnnEncoder.build(device)
+        else:
+            self.backbone = dbev.ResNetForBEVDet(numC_input=2 * C_TRANS, num_channels=ENC_CHANNELS).to(device).train()
+            self.neck = dbev.FPN_LSS(in_channels=ENC_CHANNELS[0] + ENC_CHANNELS[2], out_channels=ENC_OUT).to(device).train()
+            self.student_net = torch.nn.ModuleList([self.backbone, self.neck])
         from distill_bev_b200.plugin.distill.adaptation import Conv1x1Adaptation
-        self.adapt = Conv1x1Adaptation(C_STUDENT, C_TEACHER).to(device)            # '1x1conv' adaptation, tcgen05 fwd
+        self.adapt = Conv1x1Adaptation(C_STUDENT, C_TEACHER).to(device)            # '1x1conv' adaptation
         self.spatial = torch.nn.Conv2d(1, 1, 3, padding=1).to(device)            # spatial_wise_adaptations
+        self.trainable = [p for m in (self.student_net, self.adapt, self.spatial) for p in m.parameters()]
+        self.n_params = sum(p.numel() for p in self.trainable)
+        self.optim = torch.optim.AdamW(self.trainable, lr=2e-4, weight_decay=0.01, fused=True, capturable=True)
+        self.reducer, self.allreduce = None, allreduce
+        if world > 1 and allreduce != "none":
+            from distill_bev_b200.plugin.data_parallel import GradientAllReduce
+            self.reducer = GradientAllReduce(self.trainable, world, comm_dtype=torch.bfloat16 if comm_dtype == "bf16" else None,
+                                             overlap=(allreduce == "overlap"))
         self.d_calib = [t.to(device) for t in self.h_calib]
         self.d_points = [t.to(device) for t in self.h_points]
         counts = [int(b.shape[0]) for b in self.boxes]
@@ -203,64 +274,75 @@ class HotPath(object):
         self.h_box_offs = torch.tensor(np.concatenate([[0], np.cumsum(counts)]), dtype=torch.int32).pin_memory()
         self.d_boxes, self.d_box_offs = self.h_boxes.to(device), self.h_box_offs.to(device)
         self.d_labels = self.h_labels.to(device)
-        self.targets.get_targets(dbev.fgd.PackedBoxes(self.d_boxes, self.d_box_offs, self.max_boxes), self.d_labels)
-        self.d_gt_hm = self.targets.last_heatmap.clone()     # for the per-stage tools
-        self.captured = None
-        self.side = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
+        self.captured, self.split = None, False
+        self.side = [torch.cuda.Stream(device)]
         self.h2d_bytes = (sum(t.numel() * 4 for t in self.h_calib) + sum(t.numel() * 4 for t in self.h_points)
                           + self.h_labels.numel() * 4 + self.h_box_offs.numel() * 4
                           + sum(b.numel() * 4 for b in self.boxes))
         self.d2h_bytes = 5 * 4
 
-    def _compute(self, calib, points, labels, boxes):
-        """One pass of the hot path over one batch (public plugin API only). The three stages are
-        independent (student view transform / frozen teacher / distillation head), so they are
-        issued on three streams and joined: the latency-bound sort passes of A and B overlap the
-        HBM-bound passes of C."""
+    def encode(self, bev):
+        if self.encoder_kind == "cudnn":
+            return self.student_net(bev)
+        return self.neck(self.backbone(bev))
+
+    def _forward_backward(self, calib, points, labels, boxes):
+        """Forward and backward of one batch (public plugin API only). The frozen teacher (B) is independent of the
+        student chain (A -> S) until the loss, so it runs on a side stream and the loss waits for its event."""
         torch, dbev = self.torch, self.dbev
         main = torch.cuda.current_stream(self.dev)
-        for st in self.side:
-            st.wait_stream(main)
-        # B: frozen teacher, points -> BEV feature (pillar path, then SECOND + SECONDFPN on tcgen05)
+        self.side[0].wait_stream(main)
         with torch.cuda.stream(self.side[0]), torch.no_grad():
             canvas = dbev.pillar_canvas(points, self.enc, self.scat)
             teacher = self.secfpn(self.second(canvas))[0].contiguous()      # NCHW for the loss kernels
             teacher_ready = torch.cuda.Event()
             teacher_ready.record(self.side[0])
-        # C: head-position distillation loss against that teacher feature (1x1 channel adaptation
-        # inside, as in the reference). Masks and the adaptation conv do not read the teacher and
-        # overlap B; the loss waits for B's event right before its first teacher read.
-        with torch.cuda.stream(self.side[1]):
-            # CenterHead targets: the GT heat maps add_fp_as_fg needs, rasterised from the boxes on the device
-            self.targets.get_targets(boxes, labels, device=self.dev)
-            gt_hm = self.targets.last_heatmap
-            losses = dbev.fgd.fgd_distill_loss(
-                teacher, self.student, boxes, DISTILL_PARAMS, TRAIN_CFG, channel_adaptation=self.adapt,
-                teacher_ready=teacher_ready,
-                spatial_adaptation=self.spatial, heatmaps=gt_hm, teacher_heatmaps=self.teacher_logit, epoch=1)
-            total = losses["kd_fg_feat_loss"] + losses["kd_bg_feat_loss"] + losses["kd_spatial_loss"] \
-                + losses["kd_fp_bg_feat_loss"]
-            total.backward()
-            loss_vec = torch.stack([losses[k] for k in sorted(losses)])
         # A: student view transform (geometry changes every step: augmentation)
         geom = self.vt.get_geometry(*calib)
-        plan = (self.vt.make_plan if self.sorted_splat else self.vt.make_cells)(geom, BATCH * FRAMES)
-        bev = dbev.lift_splat(self.depth, self.feat, plan)
-        bev.backward(self.bev_grad if self.sorted_splat else self.bev_grad_cl)
-        for st in self.side:
-            main.wait_stream(st)
-        grads = [self.depth.grad, self.feat.grad, self.student.grad, self.adapt.weight.grad,
-                 self.adapt.bias.grad, self.spatial.weight.grad]
-        for t in [canvas, teacher, loss_vec] + grads:
+        if self.sorted_splat:
+            bev = dbev.lift_splat(self.depth, self.feat, self.vt.make_plan(geom, BATCH * FRAMES))     # [B*2, 64, 128, 128]
+            # the two frames of a sample concatenated along the channels (bevdet.py:300-320), channels-last memory
+            bev = bev.permute(0, 2, 3, 1).reshape(BATCH, FRAMES, BEV, BEV, C_TRANS).permute(0, 2, 3, 1, 4) \
+                     .reshape(BATCH, BEV, BEV, FRAMES * C_TRANS).permute(0, 3, 1, 2)
+        else:
+            # sort-free splat with the frame index numbered last: the result IS the channel concat of the two frames
+            bev = dbev.lift_splat(self.depth, self.feat, self.vt.make_cells(geom, BATCH * FRAMES, frames=FRAMES))
+        # S: student BEV encoder (training mode)
+        s_feat = self.encode(bev)
+        # C: head-position distillation loss (1x1 channel adaptation inside, as in the reference)
+        self.targets.get_targets(boxes, labels, device=self.dev)
+        gt_hm = self.targets.last_heatmap
+        losses = dbev.fgd.fgd_distill_loss(
+            teacher, s_feat, boxes, DISTILL_PARAMS, TRAIN_CFG, channel_adaptation=self.adapt, teacher_ready=teacher_ready,
+            spatial_adaptation=self.spatial, heatmaps=gt_hm, teacher_heatmaps=self.teacher_logit, epoch=1)
+        total = losses["kd_fg_feat_loss"] + losses["kd_bg_feat_loss"] + losses["kd_spatial_loss"] \
+            + losses["kd_fp_bg_feat_loss"]
+        if self.reducer is not None:
+            self.reducer.begin()
+        total.backward()
+        loss_vec = torch.stack([losses[k] for k in sorted(losses)]).detach()
+        main.wait_stream(self.side[0])
+        for t in (canvas, teacher):
             t.record_stream(main)
-        for p in (self.depth, self.feat, self.student):
+        for p in (self.depth, self.feat):
             p.grad = None
-        self.adapt.zero_grad(set_to_none=True)
-        self.spatial.zero_grad(set_to_none=True)
-        return loss_vec, canvas, grads
+        return loss_vec, canvas
+
+    def _update(self):
+        self.optim.step()
+        if self.reducer is None:
+            self.optim.zero_grad(set_to_none=True)
+
+    def _compute(self, calib, points, labels, boxes):
+        """One whole training step issued in one go (used eagerly and as the single captured graph when the gradient
+        all-reduce is absent or captured with it)."""
+        out = self._forward_backward(calib, points, labels, boxes)
+        if self.reducer is not None:
+            self.reducer.finish()
+        self._update()
+        return out
 
     def _device_inputs(self):
-        torch = self.torch
         d = dict(calib=[t.to(self.dev) for t in self.h_calib], points=[t.to(self.dev) for t in self.h_points],
                  labels=self.h_labels.to(self.dev), boxes=self.h_boxes.to(self.dev),
                  box_offs=self.h_box_offs.to(self.dev))
@@ -278,28 +360,47 @@ class HotPath(object):
         d["box_offs"].copy_(self.h_box_offs, non_blocking=True)
 
     def enable_graph(self):
-        """Capture the step once per input set; afterwards step() copies the new batch into the
-        static input tensors (e2e) and replays. Two input sets + two graphs let the e2e path copy
-        batch i+1 on a side stream while step i runs (what a prefetching data loader does)."""
+        """Capture the step once per input set; afterwards step() copies the new batch into the static input tensors
+        (e2e) and replays. Two input sets + two graphs let the e2e path copy batch i+1 on a side stream while step i
+        runs (what a prefetching data loader does). With allreduce='after' the NCCL all-reduce is issued eagerly
+        between a captured forward+backward graph and a captured optimizer graph; with 'overlap' / 'none' or N = 1
+        the whole step is one graph (NCCL kernels recorded into it)."""
         torch, dbev = self.torch, self.dbev
         self.sets = [dict(calib=self.d_calib, points=self.d_points, labels=self.d_labels, boxes=self.d_boxes,
                           box_offs=self.d_box_offs,
                           packed=dbev.fgd.PackedBoxes(self.d_boxes, self.d_box_offs, self.max_boxes)),
                      self._device_inputs()]
-        self.graphs = [dbev.CapturedStep(
-            (lambda d=d: self._compute(d["calib"], d["points"], d["labels"], d["packed"])), warmup=3,
-            device=self.dev) for d in self.sets]
+        self.split = self.reducer is not None and self.allreduce == "after"
+        if self.split:
+            self.graphs = [dbev.CapturedStep(
+                (lambda d=d: self._forward_backward(d["calib"], d["points"], d["labels"], d["packed"])), warmup=3,
+                device=self.dev) for d in self.sets]
+            for _ in range(2):            # optimizer state must exist before its capture
+                self.reducer.finish()
+                self._update()
+            self.update_graph = dbev.CapturedStep(lambda: (self._update(), self.trainable[0])[1], warmup=1, device=self.dev)
+        else:
+            self.graphs = [dbev.CapturedStep(
+                (lambda d=d: self._compute(d["calib"], d["points"], d["labels"], d["packed"])), warmup=3,
+                device=self.dev) for d in self.sets]
         self.captured = self.graphs[0]
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.copied = [torch.cuda.Event(), torch.cuda.Event()]      # batch landed in set k
         self.consumed = [torch.cuda.Event(), torch.cuda.Event()]    # graph k finished reading set k
         self.e2e_idx, self.prefetched = 0, False
 
+    def _replay(self, k):
+        out = self.graphs[k].replay()
+        if self.split:
+            self.reducer.finish()
+            self.update_graph.replay()
+        return out
+
     def step(self, e2e):
         torch = self.torch
         if self.captured is not None:
             if not e2e:
-                loss_vec, canvas, _ = self.graphs[0].replay()
+                loss_vec, canvas = self._replay(0)
                 return loss_vec, canvas
             main = torch.cuda.current_stream(self.dev)
             cur, nxt = self.e2e_idx % 2, (self.e2e_idx + 1) % 2
@@ -308,7 +409,7 @@ class HotPath(object):
                     self._copy_batch(self.sets[cur])
                     self.copied[cur].record(self.copy_stream)
             main.wait_event(self.copied[cur])
-            loss_vec, canvas, _ = self.graphs[cur].replay()
+            loss_vec, canvas = self._replay(cur)
             self.consumed[cur].record(main)
             # the NEXT step's batch: H2D on the copy stream while this step computes
             with torch.cuda.stream(self.copy_stream):
@@ -324,7 +425,7 @@ class HotPath(object):
             labels = self.h_labels.to(self.dev, non_blocking=True)
         else:
             calib, points, labels = self.d_calib, self.d_points, self.d_labels
-        loss_vec, canvas, _ = self._compute(calib, points, labels, self.boxes)
+        loss_vec, canvas = self._compute(calib, points, labels, self.boxes)
         return (loss_vec.cpu() if e2e else loss_vec), canvas
 
 
@@ -393,124 +494,72 @@ def sparse_teacher_probe(device, batch=2, n_points=240000):
             "note": "includes the host read-backs of voxel / output counts the reference API implies"}
 
 
-def full_path_probe(hp, steps=10):
-    """Extra evidence, NOT the headline: the same step with the student BEV encoder that sits between
-    lift+splat and the loss put back as a plain torch / cuDNN library module with random weights
-    (ResNetForBEVDet + FPN_LSS, backbones/resnet.py:51-62, necks/lss_fpn.py:62-72); the teacher side
-    is the headline's own tcgen05 SECOND + SECONDFPN. Gradients flow from the
-    distillation loss through the encoder into lift+splat (one autograd chain through our custom
-    Functions and cuDNN). Eager, CUDA events."""
+def cudnn_encoder_probe(device, seed, steps=10):
+    """Side-by-side evidence, NOT the headline: the identical training step with the student BEV encoder built from
+    plain torch modules (nn.Conv2d / BatchNorm2d / ReLU / Upsample: cuDNN TF32 + ATen, channels_last) - what the
+    reference runs for row S1 - everything else unchanged (our lift+splat, teacher, loss, fused AdamW), same CUDA
+    graph capture."""
     import torch
-    import torch.nn as nn
-    dbev, dev = hp.dbev, hp.dev
+    hp2 = HotPath(device, seed=seed, encoder="cudnn")
+    note = "graph"
+    try:
+        hp2.enable_graph()
+    except Exception as exc:  # noqa: BLE001
+        hp2.captured, note = None, "eager (%s)" % str(exc).splitlines()[0][:80]
+    for _ in range(3):
+        hp2.step(False)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+    a.record()
+    for _ in range(steps):
+        loss_vec, _ = hp2.step(False)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    del hp2
+    torch.cuda.empty_cache()
+    return {"workload": "the same step with the student BEV encoder through torch modules (cuDNN TF32 channels_last + ATen "
+                        "BatchNorm / ReLU / Upsample + autograd), " + note,
+            "ms_per_step": round(ms, 3), "samples_per_sec": round(BATCH / (ms * 1e-3), 1),
+            "loss_finite": bool(torch.isfinite(loss_vec).all().item())}
 
-    def cbr(cin, cout, k=3, s=1, p=1):
-        return nn.Sequential(nn.Conv2d(cin, cout, k, s, p, bias=False), nn.BatchNorm2d(cout, eps=1e-3, momentum=0.01),
-                             nn.ReLU(inplace=True))
 
-    class Second(nn.Module):       # layer_nums (3,5,5), strides (2,2,2), 64 -> 64/128/256
-        def __init__(self):
-            super().__init__()
-            blocks, cin = [], 64
-            for n, cout in zip((3, 5, 5), (64, 128, 256)):
-                layers = [cbr(cin, cout, 3, 2, 1)] + [cbr(cout, cout) for _ in range(n)]
-                blocks.append(nn.Sequential(*layers))
-                cin = cout
-            self.blocks = nn.ModuleList(blocks)
-            # SECONDFPN: upsample_strides (0.5, 1, 2) -> 3 x 128 channels at 128 x 128
-            self.de = nn.ModuleList([
-                nn.Sequential(nn.Conv2d(64, 128, 2, 2, bias=False), nn.BatchNorm2d(128), nn.ReLU(inplace=True)),
-                nn.Sequential(nn.ConvTranspose2d(128, 128, 1, 1, bias=False), nn.BatchNorm2d(128), nn.ReLU(inplace=True)),
-                nn.Sequential(nn.ConvTranspose2d(256, 128, 2, 2, bias=False), nn.BatchNorm2d(128), nn.ReLU(inplace=True))])
-
-        def forward(self, x):
-            outs = []
-            for b in self.blocks:
-                x = b(x)
-                outs.append(x)
-            return torch.cat([d(o) for d, o in zip(self.de, outs)], 1)
-
-    class Basic(nn.Module):
-        def __init__(self, cin, cout, stride=1):
-            super().__init__()
-            self.c1, self.c2 = cbr(cin, cout, 3, stride, 1), nn.Sequential(nn.Conv2d(cout, cout, 3, 1, 1, bias=False),
-                                                                            nn.BatchNorm2d(cout))
-            self.down = nn.Conv2d(cin, cout, 3, stride, 1) if (stride != 1 or cin != cout) else None
-
-        def forward(self, x):
-            idt = x if self.down is None else self.down(x)
-            return torch.relu(self.c2(self.c1(x)) + idt)
-
-    class StudentEncoder(nn.Module):   # ResNetForBEVDet (2,2,2 basic blocks, 128 -> 128/256/512) + FPN_LSS
-        def __init__(self):
-            super().__init__()
-            layers, cin = [], 128
-            for cout in (128, 256, 512):
-                layers.append(nn.Sequential(Basic(cin, cout, 2), Basic(cout, cout)))
-                cin = cout
-            self.layers = nn.ModuleList(layers)
-            self.up = nn.Upsample(scale_factor=4, mode="bilinear", align_corners=True)
-            self.conv = nn.Sequential(cbr(640, 512), cbr(512, 512))
-            self.up2 = nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True), cbr(512, 256),
-                                     nn.Conv2d(256, 256, 1))
-
-        def forward(self, x):
-            feats = []
-            for l in self.layers:
-                x = l(x)
-                feats.append(x)
-            x = torch.cat([feats[0], self.up(feats[2])], 1)
-            return self.up2(self.conv(x))
-
-    torch.manual_seed(0)
-    student_net = StudentEncoder().to(dev).train().to(memory_format=torch.channels_last)
-    nf = BATCH * FRAMES
-
-    def step():
-        with torch.no_grad():
-            canvas = dbev.pillar_canvas(hp.d_points, hp.enc, hp.scat)
-            t_feat = hp.secfpn(hp.second(canvas))[0].contiguous()       # ours (tcgen05), as in the headline step
-        geom = hp.vt.get_geometry(*hp.d_calib)
-        plan = hp.vt.make_plan(geom, nf)
-        bev = dbev.lift_splat(hp.depth, hp.feat, plan)                    # [B*2, 64, 128, 128]
-        bev = bev.view(BATCH, FRAMES * C_TRANS, BEV, BEV)                 # frames concatenated (bevdet.py:300-320)
-        s_feat = student_net(bev.contiguous(memory_format=torch.channels_last)).contiguous()
-        losses = dbev.fgd.fgd_distill_loss(t_feat, s_feat, hp.boxes, DISTILL_PARAMS, TRAIN_CFG,
-                                           channel_adaptation=hp.adapt, spatial_adaptation=hp.spatial,
-                                           heatmaps=hp.d_gt_hm, teacher_heatmaps=hp.teacher_logit, epoch=1)
-        total = sum(losses.values())
-        total.backward()
-        for p in (hp.depth, hp.feat):
-            p.grad = None
-        student_net.zero_grad(set_to_none=True)
-        hp.adapt.zero_grad(set_to_none=True)
-        hp.spatial.zero_grad(set_to_none=True)
-        return total
-
-    def timed():
-        for _ in range(3):
-            step()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
-        a.record()
-        for _ in range(steps):
-            loss = step()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / steps, loss
-
-    ms_cudnn, loss = timed()
-    # the same encoder with every conv's FORWARD on the tcgen05 kernels (plugin/student_convs.py); BatchNorm (batch
-    # statistics), ReLU, upsampling and the conv backward stay torch / cuDNN
-    dbev.convert_convs(student_net)
-    ms_tc, loss_tc = timed()
-    return {"workload": "headline step + the student BEV encoder (ResNetForBEVDet + FPN_LSS fwd/bwd) through cuDNN, one autograd "
-                        "chain loss -> encoder -> lift+splat, eager, TF32 convs, random weights; ms_per_step_tc_forward: the same "
-                        "with the encoder's conv forwards on tcgen05 (plugin/student_convs.py), backward still cuDNN",
-            "ms_per_step": round(ms_cudnn, 3), "ms_per_step_tc_forward": round(ms_tc, 3),
-            "samples_per_sec": round(BATCH / (ms_cudnn * 1e-3), 1),
-            "loss_finite": bool(torch.isfinite(loss).item() and torch.isfinite(loss_tc).item()),
-            "loss_rel_diff_tc_vs_cudnn": round(abs(float(loss_tc) - float(loss)) / max(abs(float(loss)), 1e-12), 6)}
+def student_conv_roofline(hp):
+    """`roofline` of the kernel class with the largest share of the step (profiles/r02_launches_bench_step.json):
+    conv3x3_halo_kernel<256>, timed alone with CUDA events on its stream on the step's largest layer (FPN_LSS
+    512 -> 256 @ 128x128, B=8: forward; the input gradients of the 3x3 / stride-1 layers run the same kernel).
+    peak = half of the measured bf16 rate (kind::tf32 issues at half the bf16 rate on tcgen05). Activations
+    (268 MB in, 134 MB out) exceed L2."""
+    import torch
+    from distill_bev_b200 import conv_train as ct
+    dev = hp.dev
+    x = torch.randn(BATCH, BEV, BEV, 2 * ENC_OUT, device=dev)
+    w = torch.randn(ENC_OUT, 2 * ENC_OUT, 3, 3, device=dev) * 0.05
+    wf = ct.pack_weights(w, 0)
+    out = torch.empty(BATCH, BEV, BEV, ENC_OUT, device=dev)
+    for _ in range(3):
+        ct.conv_forward(x, wf, ENC_OUT, 3, 3, 1, 1, out=out)
+    iters = 20
+    a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        ct.conv_forward(x, wf, ENC_OUT, 3, 3, 1, 1, out=out)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    flops = 2.0 * BATCH * BEV * BEV * 9 * 2 * ENC_OUT * ENC_OUT
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        peak, how = float(json.load(open(path))["bf16_tflops"]) / 2.0, "MEASURED_PEAKS.json bf16_tflops (burst) / 2 = TF32 rate"
+    else:
+        peak, how = 1100.0, "fallback: nominal dense TF32 1.1 PFLOP/s (B200_PROFILING.md)"
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"kernel": "dbev::conv3x3_halo_kernel<256>", "bound": "tensor", "achieved": round(ach, 1), "peak": round(peak, 1),
+            "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None, "peak_source": how,
+            "algorithmic_flops_per_launch": flops, "launch_ms": round(ms, 5),
+            "shape": "FPN_LSS conv 512 -> 256, 3x3, [8,128,128] NHWC fp32 (TF32 multiply, fp32 accumulate)",
+            "ncu": "profiles/r02_conv_train.json (sm__pipe_tensor_cycles_active, per kernel)"}
 
 
 def teacher_conv_roofline(hp):
@@ -617,15 +666,16 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
-    hp = HotPath(device, seed=rank_seed(rank))
+    hp = HotPath(device, seed=rank_seed(rank), world=world, allreduce=args.allreduce, comm_dtype=args.comm_dtype)
     hp.sorted_splat = args.sorted_splat
     graph_note = "eager (--no-graph)"
     if not args.no_graph:
         try:
             hp.enable_graph()
-            graph_note = ("step captured once in a CUDA graph and replayed; e2e copies every batch from pinned host memory "
+            graph_note = ("step captured once in a CUDA graph and replayed%s; e2e copies every batch from pinned host memory "
                           "into one of two static input sets on a copy stream while the previous step runs (prefetch), "
-                          "and reads the losses back every step")
+                          "and reads the losses back every step"
+                          % (" (forward+backward graph, eager NCCL all-reduce, optimizer graph)" if hp.split else ""))
         except Exception as exc:  # keep measuring, eagerly, and say so
             hp.captured = None
             graph_note = "eager (graph capture failed: %s)" % str(exc).splitlines()[0][:120]
@@ -656,44 +706,59 @@ def run_ours(args):
     total_ms = timed(False)
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms = timed(True)
+    ours, all_k = count_our_kernels(hp)      # on every rank: the eager step contains the gradient all-reduce
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
-    ours, all_k = count_our_kernels(hp)
+    if world > 1:
+        dist.barrier()
     ms_per_step = total_ms / args.steps
     value = samples_per_sec(total_ms, args.steps, world)
     e2e_value = samples_per_sec(e2e_ms, args.steps, world)
+    flops = 3.0 * encoder_flops(BATCH)
+    coll = hp.reducer.describe() if hp.reducer is not None else {"collective": "none (N = 1)" if world == 1 else "none (--allreduce none)"}
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "frames": FRAMES, "parallelism": "dp%d" % world,
-                   "l2": "inputs larger than L2 (student+teacher maps 335 MB, canvas 537 MB, teacher conv activations > 2 GB per step)",
-                   "collective": "none in the hot path (per-sample ops; DDP all-reduce lives in the trainer)",
-                   "cuda_graph": hp.captured is not None, "issue": graph_note},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TF32 tensor-core multiply, fp32 accumulate: the reference's "
+                                                         "cuDNN arithmetic under torch defaults)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "frames": FRAMES, "parallelism": "dp%d" % world},
+        "step_detail": {"l2": "activations larger than L2 (encoder activations > 3 GB, teacher conv activations > 2 GB per step)",
+                        "collective": coll, "allreduce_mode": args.allreduce if world > 1 else "n/a",
+                        "trainable_parameters": int(hp.n_params), "optimizer": "torch.optim.AdamW(fused=True, capturable=True)",
+                        "student_encoder_train_flops_per_step": flops,
+                        "student_encoder_tflops_if_alone": None,
+                        "cuda_graph": hp.captured is not None, "issue": graph_note},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(hp.h2d_bytes),
                 "d2h_bytes_per_step": int(hp.d2h_bytes),
                 "note": "host-originated inputs (calibration, LiDAR, GT boxes + labels) copied from "
-                        "pinned memory every step, 5 loss scalars read back"},
+                        "pinned memory every step, loss scalars read back"},
         "gpu_launches": int(ours * args.steps), "gpu_launches_per_step": int(ours),
         "all_cuda_kernels_per_step": all_k, "clocks": clocks,
     }
+    del line["step_detail"]["student_encoder_tflops_if_alone"]
     if world == 1:
-        line["roofline"] = bev_pool_roofline(device)
         try:
-            line["roofline_tensor"] = teacher_conv_roofline(hp)
+            line["roofline"] = student_conv_roofline(hp)
+        except Exception as exc:  # noqa: BLE001
+            line["roofline"] = {"error": str(exc)[:200]}
+        line["roofline_bev_pool"] = bev_pool_roofline(device)
+        try:
+            line["roofline_teacher_convs"] = teacher_conv_roofline(hp)
         except Exception as exc:
-            line["roofline_tensor"] = {"error": str(exc)[:200]}
-        line["cpu_baseline"] = cpu_baseline(samples=3, procs=1)
-        for key, probe in (("sparse_teacher", lambda: sparse_teacher_probe(device)),
-                           ("with_conv_stacks", lambda: full_path_probe(hp))):
+            line["roofline_teacher_convs"] = {"error": str(exc)[:200]}
+        line["cpu_baseline"] = cpu_baseline(samples=1, procs=1)
+        for key, probe in (("cudnn_encoder_step", lambda: cudnn_encoder_probe(device, rank_seed(rank))),
+                           ("sparse_teacher", lambda: sparse_teacher_probe(device))):
             try:
                 line[key] = probe()
             except Exception as exc:  # extra evidence only: never lose the headline line over it
                 line[key] = {"error": str(exc)[:200]}
     else:
-        line["roofline"] = bev_pool_roofline(device)
+        line["roofline"] = student_conv_roofline(hp)
+        line["roofline_bev_pool"] = bev_pool_roofline(device)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -727,6 +792,8 @@ def _cpu_one_sample(seed):
                                          1e-3, PILLAR_VS, PILLAR_RANGE)
     canvas = pillar_oracle.pillar_scatter(vf, vc, 1, 512, 512)
     _cpu_teacher_convs(canvas)
+    # S: student BEV encoder, training mode, forward + backward (torch.nn on the CPU = the reference's implementation)
+    _cpu_student_encoder(np.concatenate([bev[0:1], bev[1:2]], 1))
     # C: one sample at the head position
     teacher = np.maximum(rng.randn(1, C_TEACHER, BEV, BEV), 0).astype(np.float32)
     student = np.maximum(rng.randn(1, C_STUDENT, BEV, BEV), 0).astype(np.float32)
@@ -757,7 +824,7 @@ def _cpu_teacher_convs(canvas):
     build_conv_layer), so the CPU arm runs exactly that, one thread per worker process."""
     global _CPU_TEACHER
     import torch
-    torch.set_num_threads(1)
+    torch.set_num_threads(int(os.environ.get("DBEV_CPU_THREADS", "1")))
     if _CPU_TEACHER is None:
         nn = torch.nn
         torch.manual_seed(0)
@@ -782,6 +849,24 @@ def _cpu_teacher_convs(canvas):
         return torch.cat([d(o) for d, o in zip(de, outs)], 1)
 
 
+_CPU_STUDENT = None
+
+
+def _cpu_student_encoder(bev):
+    """ResNetForBEVDet + FPN_LSS forward and backward of one sample on the host (nn.Conv2d / BatchNorm2d in
+    training mode / ReLU / Upsample - the modules the reference builds), one thread per worker process."""
+    global _CPU_STUDENT
+    import torch
+    torch.set_num_threads(int(os.environ.get("DBEV_CPU_THREADS", "1")))
+    if _CPU_STUDENT is None:
+        _CPU_STUDENT = CudnnEncoder.build(torch.device("cpu")).to(memory_format=torch.contiguous_format)
+    x = torch.from_numpy(np.ascontiguousarray(bev, dtype=np.float32)).reshape(1, 2 * C_TRANS, BEV, BEV).requires_grad_(True)
+    y = _CPU_STUDENT(x)
+    y.backward(torch.ones_like(y))
+    _CPU_STUDENT.zero_grad(set_to_none=True)
+    return y.detach()
+
+
 def _load_synthetic():
     """distill-bev_b200/synthetic.py as a standalone module (numpy only; keeps torch out of the
     CPU worker processes)."""
@@ -803,9 +888,9 @@ def cpu_baseline(samples, procs, pool=None):
         pool.map(_cpu_one_sample, [7 + i for i in range(samples)])
     dt = time.perf_counter() - t0
     return {"value": round(samples / dt, 4), "unit": UNIT, "cores": procs, "kind": "port",
-            "sample": "%d sample(s): the same stages (2 frames lift+splat fwd/bwd, one 30k-point cloud through "
-                      "pillar encoder + SECOND/SECONDFPN [torch CPU conv, 1 thread per process], one head-position "
-                      "loss fwd/bwd incl. the 1x1 adaptation) on oracle/ (numpy + C) + torch.nn; "
+            "sample": "%d sample(s): the same stages (2 frames lift+splat fwd/bwd, student BEV encoder fwd/bwd and one "
+                      "30k-point cloud through pillar encoder + SECOND/SECONDFPN [torch.nn on the CPU, 1 thread per process], "
+                      "one head-position loss fwd/bwd incl. the 1x1 adaptation) on oracle/ (numpy + C) + torch.nn; "
                       "host has %d cores" % (samples, os.cpu_count() or 1)}
 
 
@@ -815,13 +900,18 @@ def run_reference(args):
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     import multiprocessing as mp
-    procs = max(1, min(os.cpu_count() or 1, 16))
+    # one sample per process, 4 threads per process for the torch.nn conv stacks (no oversubscription): a step stays
+    # a few seconds long, so the driver's --steps 20 --warmup 5 run ends within a few minutes
+    cores = max(1, min(os.cpu_count() or 1, 16))
+    threads = 4 if cores >= 4 else 1
+    procs = max(1, cores // threads)
     per_step = procs
-    os.environ.setdefault("OMP_NUM_THREADS", "1")      # one sample per process, no oversubscription
+    os.environ["DBEV_CPU_THREADS"] = str(threads)
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    os.environ.setdefault("MKL_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", str(threads))
     with mp.get_context("spawn").Pool(procs) as pool:
-        for _ in range(min(args.warmup, 1)):
+        for _ in range(max(args.warmup, 0)):
             cpu_baseline(per_step, procs, pool)
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -829,14 +919,15 @@ def run_reference(args):
         dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
     res["value"] = round(value, 4)
+    res["cores"] = procs * threads
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt / args.steps * 1e3, 2),
+            "steps": args.steps, "warmup": max(args.warmup, 0), "ms_per_step": round(dt / args.steps * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "frames": FRAMES,
-                       "note": "CPU oracle port of the reference algorithm (the reference's Python files need "
-                               "/root/reference + mmcv and cannot travel to the GPU box); each step = %d samples "
-                               "in %d host processes" % (per_step, procs)},
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "frames": FRAMES, "parallelism": "dp%d" % world},
+            "step_detail": {"note": "CPU oracle port of the reference algorithm (the reference's Python files need "
+                                    "/root/reference + mmcv and cannot travel to the GPU box) + torch.nn conv stacks on the CPU; "
+                                    "each step = %d samples in %d host processes; no optimizer step" % (per_step, procs)},
             "cpu_baseline": res,
             "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -849,6 +940,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly (no CUDA graph replay)")
+    ap.add_argument("--allreduce", default="after", choices=["after", "overlap", "none"],
+                    help="N > 1: gradient all-reduce after the backward graph (default), recorded into the graph and "
+                         "overlapped with the backward ('overlap'), or skipped ('none': replicas, not training)")
+    ap.add_argument("--comm-dtype", default="bf16", choices=["bf16", "f32"], help="wire dtype of the gradient all-reduce")
     ap.add_argument("--sorted-splat", action="store_true",
                     help="lift+splat through the sorted plan (fixed summation order) instead of the sort-free splat")
     args = ap.parse_args()

@@ -52,6 +52,7 @@ SIGNATURES = {
     "dbev_lift_splat_backward": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_ll, _c_int, _c_int, _c_int,
                                           _ptr, _ptr, _ptr]),
     "dbev_bev_point_cells": (_c_int, [_ptr, _c_ll, _c_int, _fptr, _fptr, _fptr, _iptr, _c_int, _ptr, _ptr]),
+    "dbev_bev_point_cells_frames": (_c_int, [_ptr, _c_ll, _c_int, _c_int, _fptr, _fptr, _fptr, _iptr, _c_int, _ptr, _ptr]),
     "dbev_lift_splat_atomic_forward": (_c_int, [_ptr, _ptr, _ptr, _c_ll, _c_int, _c_int, _c_int, _c_ll, _ptr,
                                                 _ptr]),
     "dbev_transpose_batched": (_c_int, [_ptr, _ptr, _c_int, _c_int, _c_int, _ptr]),

@@ -81,13 +81,15 @@ def build(force=False, verbose=False):
         results = list(ex.map(lambda s: _compile_one(s, force, verbose), srcs))
     objs = [o for o, _ in results]
     if force or _stale(LIB_PATH, objs):
-        cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + [
+        tmp_path = LIB_PATH + ".tmp%d" % os.getpid()      # link aside, then rename: the library on disk is always whole
+        cmd = [_nvcc(), "-shared", "-o", tmp_path] + objs + [
             "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
             "-Xcompiler", "-fPIC",
         ]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (p.stdout, p.stderr))
+        os.replace(tmp_path, LIB_PATH)
     return LIB_PATH
 
 

@@ -102,33 +102,41 @@ __global__ void __launch_bounds__(kStatThreads) channel_stats_kernel(StatArgs a)
 }
 
 // Combines the per-block partial sums in block order with fp64 accumulation (deterministic) and finalises:
-// a block owns 32 channels; warps 0-3 / 4-7 sum the first / second statistic over a quarter of the blocks each
+// a block owns 16 channels; lanes 0-15 / 16-31 of every warp carry the first / second statistic, the eight warps
+// each sum an eighth of the blocks with eight loads in flight (the chain of dependent loads is what this kernel costs)
 template <int MODE>
 __global__ void __launch_bounds__(256) channel_stats_final_kernel(StatArgs a, int n_blocks) {
-  __shared__ double part[2][4][32];
+  __shared__ double part[8][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int stat = warp >> 2, quarter = warp & 3;
-  const int c = blockIdx.x * 32 + lane;
+  const int stat = lane >> 4;
+  const int c = blockIdx.x * 16 + (lane & 15);
   double t = 0.0;
   if (c < a.C) {
-    const int b0 = (int)((long long)n_blocks * quarter / 4), b1 = (int)((long long)n_blocks * (quarter + 1) / 4);
+    const int b0 = (int)((long long)n_blocks * warp / 8), b1 = (int)((long long)n_blocks * (warp + 1) / 8);
     const float* p = a.partial + stat * a.C + c;
+    const long long st = 2LL * a.C;
     int b = b0;
-    double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0;
-    for (; b + 3 < b1; b += 4) {
-      u0 += (double)p[(long long)b * 2 * a.C];
-      u1 += (double)p[(long long)(b + 1) * 2 * a.C];
-      u2 += (double)p[(long long)(b + 2) * 2 * a.C];
-      u3 += (double)p[(long long)(b + 3) * 2 * a.C];
+    double u[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (; b + 7 < b1; b += 8) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldcg(p + (long long)(b + k) * st);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] += (double)v[k];
     }
-    for (; b < b1; ++b) u0 += (double)p[(long long)b * 2 * a.C];
-    t = (u0 + u1) + (u2 + u3);
+    for (; b < b1; ++b) u[0] += (double)__ldcg(p + (long long)b * st);
+    t = ((u[0] + u[1]) + (u[2] + u[3])) + ((u[4] + u[5]) + (u[6] + u[7]));
   }
-  part[stat][quarter][lane] = t;
+  part[warp][lane] = t;
   __syncthreads();
-  if (warp != 0 || c >= a.C) return;
-  const double t1 = (part[0][0][lane] + part[0][1][lane]) + (part[0][2][lane] + part[0][3][lane]);
-  const double t2 = (part[1][0][lane] + part[1][1][lane]) + (part[1][2][lane] + part[1][3][lane]);
+  if (warp != 0) return;
+  double tot = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot += part[k][lane];
+  // lane l (< 16) needs the second statistic of its channel from lane l + 16
+  const double other = __shfl_down_sync(0xffffffffu, tot, 16);
+  if (lane >= 16 || c >= a.C) return;
+  const double t1 = tot, t2 = other;
   const double n = (double)a.rows;
   if (MODE == 0) {
     if (a.plain_sum) {
@@ -362,9 +370,28 @@ __global__ void __launch_bounds__(256) pack_conv_weights_tile_kernel(const float
   extern __shared__ float tile[];                     // [32 co][pitch]
   const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int co = warp; co < 32; co += 8) {
-    const float* src = w + ((long long)(co0 + co) * CI + ci0) * taps;
-    for (int j = lane; j < 32 * taps; j += 32) tile[co * pitch + j] = (co0 + co < CO && ci0 + j / taps < CI) ? src[j] : 0.f;
+  // flat, coalesced copy of the 32 rows (each 32 * taps contiguous floats); loads issued in batches of 12 so that
+  // the (cold) global latency is paid three times, not 36 times
+  const int row_len = 32 * taps, total = 32 * row_len;
+  for (int base_i = threadIdx.x; base_i < total; base_i += 256 * 12) {
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int i = base_i + k * 256;
+      v[k] = 0.f;
+      if (i < total) {
+        const int co = i / row_len, j = i - co * row_len;
+        if (co0 + co < CO && ci0 + j / taps < CI) v[k] = __ldg(w + ((long long)(co0 + co) * CI + ci0) * taps + j);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const int i = base_i + k * 256;
+      if (i < total) {
+        const int co = i / row_len, j = i - co * row_len;
+        tile[co * pitch + j] = v[k];
+      }
+    }
   }
   __syncthreads();
   if (out_f) {                                        // [co][tap][ci]: lane = ci
@@ -401,7 +428,7 @@ int grid_for(long long total, int threads) {
 }
 
 int stat_blocks(long long rows, int* rows_per_block) {
-  int blocks = kNumSMs * 4;     // 256-thread blocks, two row loads in flight per thread
+  int blocks = kNumSMs * 2;     // 256-thread blocks, two row loads in flight per thread
   if (blocks > rows) blocks = (int)rows;
   int rpb = (int)((rows + blocks - 1) / blocks);
   blocks = (int)((rows + rpb - 1) / rpb);
@@ -439,7 +466,7 @@ int bn_batch_stats(const float* y, int y_ld, long long rows, int C, const float*
   const int quads = C / 4, threads = quads * (kStatThreads / quads);
   channel_stats_kernel<0><<<blocks, threads, 0, stream>>>(a);
   DBEV_CHECK_LAUNCH("channel_stats_kernel<0>");
-  channel_stats_final_kernel<0><<<ceil_div(C, 32), 256, 0, stream>>>(a, blocks);
+  channel_stats_final_kernel<0><<<ceil_div(C, 16), 256, 0, stream>>>(a, blocks);
   DBEV_CHECK_LAUNCH("channel_stats_final_kernel<0>");
   return DBEV_OK;
 }
@@ -457,7 +484,7 @@ int channel_sums(const float* y, int y_ld, long long rows, int C, float* out, in
   const int quads = C / 4, threads = quads * (kStatThreads / quads);
   channel_stats_kernel<0><<<blocks, threads, 0, stream>>>(a);
   DBEV_CHECK_LAUNCH("channel_stats_kernel<0>");
-  channel_stats_final_kernel<0><<<ceil_div(C, 32), 256, 0, stream>>>(a, blocks);
+  channel_stats_final_kernel<0><<<ceil_div(C, 16), 256, 0, stream>>>(a, blocks);
   DBEV_CHECK_LAUNCH("channel_stats_final_kernel<0>");
   return DBEV_OK;
 }
@@ -486,7 +513,7 @@ int bn_backward(const float* dz, int dz_ld, const float* z, int z_ld, const floa
   const int quads = C / 4, threads = quads * (kStatThreads / quads);
   channel_stats_kernel<1><<<blocks, threads, 0, stream>>>(a);
   DBEV_CHECK_LAUNCH("channel_stats_kernel<1>");
-  channel_stats_final_kernel<1><<<ceil_div(C, 32), 256, 0, stream>>>(a, blocks);
+  channel_stats_final_kernel<1><<<ceil_div(C, 16), 256, 0, stream>>>(a, blocks);
   DBEV_CHECK_LAUNCH("channel_stats_final_kernel<1>");
   bn_bwd_apply_kernel<<<grid_for(rows * quads, 256), 256, 0, stream>>>(dz, dz_ld, z, z_ld, y, y_ld, fwd4c, bwd4c, rows, C, dy, dy_ld,
                                                                        g_out, g_ld, g_accumulate);

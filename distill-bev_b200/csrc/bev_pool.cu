@@ -50,7 +50,7 @@ bev_keys_from_geom_kernel(const float* __restrict__ geom, long long n, long long
                           float off0, float off1, float off2, float dx0, float dx1, float dx2,
                           float nxf0, float nxf1, float nxf2, int n0, int n1, int nz,
                           int fast_axis, uint32_t sentinel, uint32_t* __restrict__ keys,
-                          int* __restrict__ point_cell) {
+                          int* __restrict__ point_cell, int frames = 1) {
   long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const float g0 = geom[p * 3 + 0], g1 = geom[p * 3 + 1], g2 = geom[p * 3 + 2];
@@ -68,7 +68,11 @@ bev_keys_from_geom_kernel(const float* __restrict__ geom, long long n, long long
     const int ifast = fast_axis == 0 ? i0 : i1;
     const int nslow = fast_axis == 0 ? n1 : n0;
     const int nfast = fast_axis == 0 ? n0 : n1;
-    key = (uint32_t)((((long long)b * nz + i2) * nslow + islow) * nfast + ifast);
+    // frames > 1 (BEVDepth4D): sample-frame b = s * frames + f; the frame index becomes the FASTEST part of the cell
+    // number, so a channels-last BEV map indexed by it is [s][y][x][f][C] = the frames concatenated along the
+    // channels (torch.cat(bev_feat_list, dim=1), bevdet.py:300-320) with no concat pass
+    const int smp = b / frames, fr = b - smp * frames;
+    key = (uint32_t)((((((long long)smp * nz + i2) * nslow + islow) * nfast + ifast) * frames) + fr);
   }
   if (keys) keys[p] = key;
   if (point_cell) point_cell[p] = ok ? (int)key : -1;
@@ -214,7 +218,8 @@ struct LiftArgs {
 // device counter (items differ 100x in row count, a static round-robin leaves a long tail). Each
 // launch takes the next of kSchedSlots counter pairs {next item, warps done}; the last warp to
 // finish re-zeroes its pair, so a slot is clean again long before the host wraps around to it.
-constexpr int kSchedSlots = 256;
+constexpr int kEagerSlots = 256;      // round-robin for eager launches
+constexpr int kSchedSlots = 4096;     // the rest: one slot per launch recorded into a CUDA graph, never reused
 __device__ int g_sched[kSchedSlots * 2];
 
 struct WorkQueue {
@@ -1091,10 +1096,36 @@ static int pick_lpr(int C) {  // lanes per row of one channel block (<= 64 chann
     }                                    \
   } while (0)
 
-static int next_sched_slot() {
-  static std::atomic<unsigned> n{0};
-  return (int)(n.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
+// Work-queue counters are per-launch state. Eager launches take the next of kEagerSlots pairs round-robin; a
+// launch recorded into a CUDA graph gets a pair of its own that no other launch (eager or captured) ever uses,
+// because the graph replays with the slot baked into its arguments while the host counter moves on - two
+// kernels pulling from one counter would skip or split items. The pair is zeroed on the launching stream
+// right before the kernel (a memset node in a graph), so a slot left dirty by a faulted kernel heals itself.
+static int next_sched_slot(cudaStream_t stream) {
+  static std::atomic<unsigned> eager{0}, captured{0};
+  static int* base = nullptr;
+  if (!base && cudaGetSymbolAddress((void**)&base, g_sched) != cudaSuccess) return -1;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) return -1;
+  int slot;
+  if (st == cudaStreamCaptureStatusActive) {
+    const unsigned k = captured.fetch_add(1, std::memory_order_relaxed);
+    if (k >= (unsigned)(kSchedSlots - kEagerSlots)) return -1;
+    slot = kEagerSlots + (int)k;
+  } else {
+    slot = (int)(eager.fetch_add(1, std::memory_order_relaxed) % kEagerSlots);
+  }
+  if (cudaMemsetAsync(base + 2 * slot, 0, 2 * sizeof(int), stream) != cudaSuccess) return -1;
+  return slot;
 }
+
+#define DBEV_SCHED_SLOT(var)                                                                              \
+  const int var = next_sched_slot(stream);                                                                \
+  if (var < 0) {                                                                                          \
+    set_last_error("bev_pool: no work-queue slot (more than %d captured launches, or a CUDA error)",      \
+                   kSchedSlots - kEagerSlots);                                                            \
+    return DBEV_ERR_CUDA;                                                                                 \
+  }
 
 static int gather_forward_impl(const float* x, int C, const uint32_t* order, const int* cell_start,
                                const int* cell_end, const int4* items, const int* n_items,
@@ -1114,7 +1145,8 @@ static int gather_forward_impl(const float* x, int C, const uint32_t* order, con
   rc = persistent_grid(bev_pool_gather_fwd_kernel<L, true>, smem, &grid);                \
   if (rc != DBEV_OK) return rc;                                                          \
   bev_pool_gather_fwd_kernel<L, true><<<grid, kPoolBlock, smem, stream>>>(               \
-      x, order, cell_start, cell_end, items, n_items, out, g, *lift, next_sched_slot())
+      x, order, cell_start, cell_end, items, n_items, out, g, *lift, sched_slot)
+    DBEV_SCHED_SLOT(sched_slot);
     DBEV_DISPATCH_LPR(lpr, LAUNCH);
 #undef LAUNCH
     DBEV_CHECK_LAUNCH("lift_splat_fwd_kernel");
@@ -1129,7 +1161,8 @@ static int gather_forward_impl(const float* x, int C, const uint32_t* order, con
   rc = persistent_grid(bev_pool_gather_fwd_kernel<L, false, 6>, smem, &grid);            \
   if (rc != DBEV_OK) return rc;                                                          \
   bev_pool_gather_fwd_kernel<L, false, 6><<<grid, kPoolBlock, smem, stream>>>(           \
-      x, order, cell_start, cell_end, items, n_items, out, g, none, next_sched_slot())
+      x, order, cell_start, cell_end, items, n_items, out, g, none, sched_slot)
+    DBEV_SCHED_SLOT(sched_slot);
     DBEV_DISPATCH_LPR(lpr, LAUNCH);
 #undef LAUNCH
   } else {
@@ -1274,7 +1307,8 @@ int bev_pool_gather_backward(const float* out_grad, int C, const uint32_t* order
   rc = persistent_grid(bev_pool_gather_bwd_kernel<L>, smem, &grid);                      \
   if (rc != DBEV_OK) return rc;                                                          \
   bev_pool_gather_bwd_kernel<L><<<grid, kPoolBlock, smem, stream>>>(                     \
-      out_grad, order, cell_start, cell_end, items, n_items, x_grad, g, next_sched_slot())
+      out_grad, order, cell_start, cell_end, items, n_items, x_grad, g, sched_slot)
+    DBEV_SCHED_SLOT(sched_slot);
     DBEV_DISPATCH_LPR(lpr, LAUNCH);
 #undef LAUNCH
   } else {
@@ -1310,15 +1344,16 @@ int bev_pool_point_backward(const float* grad_cl, const int* point_cell, long lo
 
 int bev_point_cells(const float* geom, long long n_points, int batch, const float* off, const float* dx,
                     const float* nx_f, const int* nx_i, int fast_axis, int* point_cell,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, int frames) {
   DBEV_CHECK_ARG(fast_axis == 0 || fast_axis == 1, "bev_point_cells: fast_axis must be 0 or 1");
   DBEV_CHECK_ARG(batch > 0 && n_points >= 0 && n_points % batch == 0, "bev_point_cells: bad sizes");
+  DBEV_CHECK_ARG(frames >= 1 && batch % frames == 0, "bev_point_cells: batch must be a multiple of frames");
   const long long ncells = (long long)batch * nx_i[0] * nx_i[1] * nx_i[2];
   DBEV_CHECK_ARG(ncells > 0 && ncells < 0x7fffffffLL, "bev_point_cells: bad grid");
   if (n_points == 0) return DBEV_OK;
   bev_keys_from_geom_kernel<<<ceil_div(n_points, 256), 256, 0, stream>>>(
       geom, n_points, n_points / batch, off[0], off[1], off[2], dx[0], dx[1], dx[2], nx_f[0], nx_f[1],
-      nx_f[2], nx_i[0], nx_i[1], nx_i[2], fast_axis, (uint32_t)ncells, nullptr, point_cell);
+      nx_f[2], nx_i[0], nx_i[1], nx_i[2], fast_axis, (uint32_t)ncells, nullptr, point_cell, frames);
   DBEV_CHECK_LAUNCH("bev_keys_from_geom_kernel");
   return DBEV_OK;
 }

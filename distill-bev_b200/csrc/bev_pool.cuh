@@ -62,7 +62,7 @@ int bev_pool_point_backward(const float* grad_cl, const int* point_cell, long lo
 // point_cell[p] = output cell of frustum point p (or -1) straight from the geometry: no sort.
 int bev_point_cells(const float* geom, long long n_points, int batch, const float* off, const float* dx,
                     const float* nx_f, const int* nx_i, int fast_axis, int* point_cell,
-                    cudaStream_t stream);
+                    cudaStream_t stream, int frames = 1);
 // Sort-free lift + splat into a channels-last BEV map out_cl[n_cells, C] (zero-filled here) with
 // vector float reductions; summation order is not fixed.
 int lift_splat_atomic_forward(const float* depth, const float* feat_cl, const int* point_cell,

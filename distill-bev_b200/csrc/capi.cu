@@ -107,6 +107,13 @@ int dbev_bev_point_cells(const float* geom, long long n_points, int batch, const
                          point_cell, (cudaStream_t)stream);
 }
 
+int dbev_bev_point_cells_frames(const float* geom, long long n_points, int batch, int frames, const float* off_host3,
+                                const float* dx_host3, const float* nx_float_host3, const int* nx_int_host3,
+                                int fast_axis, int* point_cell, void* stream) {
+  return bev_point_cells(geom, n_points, batch, off_host3, dx_host3, nx_float_host3, nx_int_host3, fast_axis,
+                         point_cell, (cudaStream_t)stream, frames);
+}
+
 int dbev_lift_splat_atomic_forward(const float* depth, const float* feat_cl, const int* point_cell,
                                    long long n_pixels, int C, int D, int fhw, long long n_cells,
                                    float* out_cl, void* stream) {

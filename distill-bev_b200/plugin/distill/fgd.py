@@ -179,6 +179,19 @@ def make_config(B, C, H, W, distill_params, index=0, use_fp=None, epoch=0):
     att = pick("spatial_attentions")
     if att not in ("teacher", "teacher_student"):
         raise NotImplementedError(att)
+    # options that change the reference loss and are not implemented raise (they must never be ignored silently):
+    # the non-empty background term (bevdet_distill.py:1137-1165, :1287-1291), the enlarged-foreground context
+    # (:803-817), criteria other than the shipped MSE / L1 / L1 with reduction='none' (:997-999)
+    if float(p.get("non_empty_weight", 0) or 0) != 0:
+        raise NotImplementedError("distill_params['non_empty_weight'] != 0 (kd_non_empty_bg_feat_loss) is not implemented")
+    if float(p.get("context_length", 0) or 0) > 0 and float(p.get("context_weight", 0) or 0) > 0:
+        raise NotImplementedError("distill_params context_length / context_weight > 0 is not implemented")
+    for key, want in (("feat_criterion", "MSELoss"), ("spatial_criterion", "L1Loss"), ("channel_criterion", "L1Loss")):
+        crit = p.get(key)
+        if crit is not None and (crit.get("type") != want or crit.get("reduction", "none") != "none"
+                                 or float(crit.get("loss_weight", 1.0)) != 1.0):
+            raise NotImplementedError("distill_params[%r] = %r: only dict(type=%r, reduction='none') is implemented"
+                                      % (key, crit, want))
     if p.get("scale_mask") not in _SCALE:
         raise NotImplementedError(p.get("scale_mask"))
     if p.get("background_mask", "logical_not") not in ("logical_not", "1minus"):
@@ -200,6 +213,9 @@ def _loss_forward(student, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count,
     if student.shape != teacher.shape:
         raise RuntimeError("student %s and teacher %s must have the same shape after adaptation"
                            % (tuple(student.shape), tuple(teacher.shape)))
+    if cfg.spatial_mask and conv_w is None:
+        raise RuntimeError("distill_params['spatial_mask'] is set: the spatial loss needs spatial_adaptation "
+                           "(spatial_wise_adaptations[index], bevdet_distill.py:348-351, :1272-1278)")
     student, teacher = student.contiguous(), teacher.contiguous()
     dev = student.device
     if conv_w is None:
@@ -246,7 +262,7 @@ class _FGDLoss(torch.autograd.Function):
             torch.cuda.current_stream(student.device).wait_event(teacher_ready)
         losses, state, student, teacher, cw, cb, shp = _loss_forward(
             student, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count)
-        ctx.cfg, ctx.state, ctx.conv_shape = cfg, state, shp
+        ctx.cfg, ctx.state, ctx.conv_shape, ctx.has_conv = cfg, state, shp, conv_w is not None
         ctx.save_for_backward(student, teacher, cw, cb)
         return losses
 
@@ -255,6 +271,8 @@ class _FGDLoss(torch.autograd.Function):
         student, teacher, cw, cb = ctx.saved_tensors
         gs, gw, gb, _ = _loss_backward(ctx.cfg, ctx.state, student, teacher, cw, cb, grad_losses,
                                        ctx.conv_shape)
+        if not ctx.has_conv:      # no spatial_adaptation module: autograd accepts no gradient for a None input
+            gw = gb = None
         return (gs, None, gw, gb, None, None, None, None, None, None, None)
 
 
@@ -273,6 +291,7 @@ class _AdaptFGDLoss(torch.autograd.Function):
         losses, state, adapted, teacher, cw, cb, shp = _loss_forward(
             adapted, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count)
         ctx.cfg, ctx.state, ctx.conv_shape, ctx.has_bias = cfg, state, shp, bias is not None
+        ctx.has_conv = conv_w is not None
         ctx.save_for_backward(x, weight, adapted, teacher, cw, cb)
         return losses
 
@@ -282,8 +301,10 @@ class _AdaptFGDLoss(torch.autograd.Function):
         want_bias = ctx.has_bias and ctx.needs_input_grad[2]
         gs, gw, gb, gsum = _loss_backward(ctx.cfg, ctx.state, adapted, teacher, cw, cb, grad_losses,
                                           ctx.conv_shape, channel_sum=want_bias)
-        gx = torch.nn.grad.conv2d_input(x.shape, weight, gs) if ctx.needs_input_grad[0] else None
-        gwt = torch.nn.grad.conv2d_weight(x, weight.shape, gs) if ctx.needs_input_grad[1] else None
+        from .adaptation import conv1x1_backward
+        gx, gwt = conv1x1_backward(x, weight, gs, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        if not ctx.has_conv:
+            gw = gb = None
         return (gx, gwt, gsum, None, gw, gb, None, None, None, None, None, None, None)
 
 
@@ -320,7 +341,8 @@ def fgd_distill_loss(teacher_feat, student_feat, gt_bboxes_3d, distill_params, t
         conv = channel_adaptation
         if (isinstance(conv, torch.nn.Conv2d) and conv.kernel_size == (1, 1) and conv.stride == (1, 1)
                 and conv.padding == (0, 0) and conv.groups == 1 and conv.dilation == (1, 1)
-                and student_feat.is_cuda and student_feat.dtype == torch.float32):
+                and student_feat.is_cuda and student_feat.dtype == torch.float32 and conv.in_channels % 32 == 0
+                and conv.out_channels in (128, 256, 384, 512)):        # the shapes csrc/adapt_gemm.cu covers
             adapt_w, adapt_b = conv.weight, conv.bias
         else:
             student_feat = channel_adaptation(student_feat)

@@ -271,14 +271,18 @@ class PointCells(object):
     """Geometry-only companion of BevPlan for the sort-free lift+splat: ``point_cell`` [n_points]
     int32 = output cell of every frustum point (-1 = dropped), no sort / bounds / work list."""
 
-    def __init__(self, point_cell, n_points, batch, nz, nslow, nfast):
+    def __init__(self, point_cell, n_points, batch, nz, nslow, nfast, frames=1):
         self.point_cell, self.n_points, self.batch = point_cell, n_points, batch
         self.nz, self.nslow, self.nfast = nz, nslow, nfast
         self.n_cells = batch * nz * nslow * nfast
+        self.frames = frames      # > 1: cells numbered [sample][y][x][frame] (frames concatenated along the channels)
 
 
-def bev_point_cells(geom, batch, bx=None, dx=None, nx=None, fast_axis=0, grid=None):
-    """Index math + bounds test of voxel_pooling (:150-161) only: PointCells for ``lift_splat``."""
+def bev_point_cells(geom, batch, bx=None, dx=None, nx=None, fast_axis=0, grid=None, frames=1):
+    """Index math + bounds test of voxel_pooling (:150-161) only: PointCells for ``lift_splat``.
+    ``frames`` > 1 (BEVDepth4D, batch = samples * frames): the sort-free lift_splat then returns
+    [samples, frames * C, ny, nx] - ``torch.cat`` of the per-frame BEV maps along the channels (bevdet.py:300-320)
+    falls out of the cell numbering, no concat pass."""
     lib = _lib.load()
     _lib.require_cuda(geom, "geom", torch.float32)
     geom = geom.contiguous()
@@ -288,12 +292,12 @@ def bev_point_cells(geom, batch, bx=None, dx=None, nx=None, fast_axis=0, grid=No
     n0, n1, nz = int(grid.nx_i[0]), int(grid.nx_i[1]), int(grid.nx_i[2])
     pc = torch.empty(max(n_points, 1), dtype=torch.int32, device=geom.device)
     with torch.cuda.device(geom.device):
-        rc = lib.dbev_bev_point_cells(_lib.ptr(geom), n_points, batch, _lib.host_f3(grid.off), _lib.host_f3(grid.dx),
-                                      _lib.host_f3(grid.nx_f), _lib.host_i3(grid.nx_i), fast_axis, _lib.ptr(pc),
-                                      _lib.stream_ptr(geom.device))
-    _lib.check(rc, "dbev_bev_point_cells")
+        rc = lib.dbev_bev_point_cells_frames(_lib.ptr(geom), n_points, batch, int(frames), _lib.host_f3(grid.off),
+                                             _lib.host_f3(grid.dx), _lib.host_f3(grid.nx_f), _lib.host_i3(grid.nx_i),
+                                             fast_axis, _lib.ptr(pc), _lib.stream_ptr(geom.device))
+    _lib.check(rc, "dbev_bev_point_cells_frames")
     nslow, nfast = (n1, n0) if fast_axis == 0 else (n0, n1)
-    return PointCells(pc, n_points, batch, nz, nslow, nfast)
+    return PointCells(pc, n_points, batch, nz, nslow, nfast, frames=int(frames))
 
 
 class _LiftSplatAtomic(torch.autograd.Function):
@@ -324,6 +328,8 @@ class _LiftSplatAtomic(torch.autograd.Function):
         ctx.cells = cells
         ctx.dims = (BN, C, D, fH, fW)
         ctx.save_for_backward(depth, feat_cl)
+        if cells.frames > 1:                       # memory is [samples, ny, nx, frames, C]
+            out_cl = out_cl.view(cells.batch // cells.frames, cells.nslow, cells.nfast, cells.frames * C)
         return out_cl.permute(0, 3, 1, 2)          # [B, C, ny, nx] in channels_last memory
 
     @staticmethod
@@ -337,7 +343,8 @@ class _LiftSplatAtomic(torch.autograd.Function):
         if g_nhwc.is_contiguous():
             g_cl = g_nhwc                             # channels_last upstream gradient: free
         else:
-            g_cl = transpose_batched(out_grad.contiguous().float(), cells.batch, C, cells.nslow * cells.nfast)
+            g_cl = transpose_batched(out_grad.contiguous().float(), cells.batch // cells.frames, C * cells.frames,
+                                     cells.nslow * cells.nfast)
         d_depth = torch.empty_like(depth)
         d_feat_cl = torch.empty_like(feat_cl)
         with torch.cuda.device(depth.device):

@@ -91,9 +91,10 @@ class ViewTransformerLiftSplatShoot(nn.Module):
         return _bp.bev_plan_from_geom(geom, batch, fast_axis=0, with_point_cell=with_point_cell,
                                       grid=self._grid)
 
-    def make_cells(self, geom, batch):
-        """Geometry -> cell of every frustum point, no sort: input of the sort-free ``lift_splat``."""
-        return _bp.bev_point_cells(geom, batch, fast_axis=0, grid=self._grid)
+    def make_cells(self, geom, batch, frames=1):
+        """Geometry -> cell of every frustum point, no sort: input of the sort-free ``lift_splat``.
+        ``frames`` > 1: batch = samples * frames and the splat returns the frames concatenated along the channels."""
+        return _bp.bev_point_cells(geom, batch, fast_axis=0, grid=self._grid, frames=frames)
 
     def voxel_pooling(self, geom_feats, x, plan=None):
         return _bp.voxel_pooling(geom_feats, x, plan=plan, grid=self._grid)

@@ -170,6 +170,13 @@ int dbev_lift_splat_backward(const float* grad_cl, const float* depth, const flo
 int dbev_bev_point_cells(const float* geom, long long n_points, int batch, const float* off_host3,
                          const float* dx_host3, const float* nx_float_host3, const int* nx_int_host3,
                          int fast_axis, int* point_cell, void* stream);
+/* Same with the sample-frames of a sample numbered LAST: batch = samples * frames, sample-frame b = s*frames + f,
+ * cell = ((s*ny + y)*nx + x)*frames + f. A channels-last map out_cl[n_cells, C] indexed by these cells is
+ * [s][y][x][f][C], i.e. the frames concatenated along the channels (torch.cat(bev_feat_list, dim=1),
+ * bevdet.py:300-320) - the student BEV encoder reads it as [samples, ny, nx, frames*C] with no concat pass. */
+int dbev_bev_point_cells_frames(const float* geom, long long n_points, int batch, int frames, const float* off_host3,
+                                const float* dx_host3, const float* nx_float_host3, const int* nx_int_host3,
+                                int fast_axis, int* point_cell, void* stream);
 int dbev_lift_splat_atomic_forward(const float* depth, const float* feat_cl, const int* point_cell,
                                    long long n_pixels, int C, int D, int fhw, long long n_cells,
                                    float* out_cl, void* stream);

@@ -14,6 +14,10 @@
    live in one module, so nvcc compiles the .cu files for sm_100) into
    oracle/_ref/ref_sparse_conv_ext*.so. Its CPU path pins oracle/spconv_oracle.py.
    oracle/_ref/ is git-ignored but travels to the GPU box with the snapshot.
+4. The reference's CUDA extensions for bev_pool (bev_pool.cpp + bev_pool_cuda.cu) and voxelization
+   (voxelization*.cpp/.cu, scatter_points*.cpp/.cu, -DWITH_CUDA), unmodified, for sm_100:
+   oracle/_ref/ref_bev_pool_ext*.so, ref_voxel_layer_cuda*.so - the kernels BASELINE.md §4 says to beat, timed beside
+   ours by tools/microbench_reference_cuda.py.
    No reference source is copied into this repository.
 """
 import glob
@@ -86,11 +90,46 @@ def build_ref_spconv():
     return dst
 
 
+def _build_ref_cuda(name, srcs, extra=()):
+    """One of the reference's CUDA extensions, UNMODIFIED sources compiled where they lie for sm_100 (nvcc cross-compiles
+    without a GPU): the "kernels to beat" of BASELINE.md §4, timed on the GPU box by tools/microbench_reference_cuda.py.
+    Checker / evidence only - never imported by the product path."""
+    if not all(os.path.exists(f) for f in srcs):
+        return None
+    os.makedirs(REF_OUT, exist_ok=True)
+    existing = glob.glob(os.path.join(REF_OUT, name + "*.so"))
+    if existing:
+        return existing[0]
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
+    from torch.utils.cpp_extension import load
+    tmp = os.path.join(REF_OUT, "_jit_" + name)
+    os.makedirs(tmp, exist_ok=True)
+    load(name=name, sources=srcs, extra_cflags=["-O2", "-w", "-DWITH_CUDA"] + list(extra),
+         extra_cuda_cflags=["-w", "-DWITH_CUDA"] + list(extra), build_directory=tmp, verbose=False)
+    so = glob.glob(os.path.join(tmp, name + "*.so"))[0]
+    dst = os.path.join(REF_OUT, os.path.basename(so))
+    shutil.copy(so, dst)
+    shutil.rmtree(tmp, ignore_errors=True)
+    return dst
+
+
+def build_ref_bev_pool_cuda():
+    d = "/root/reference/mmdet3d/ops/bev_pool/src"
+    return _build_ref_cuda("ref_bev_pool_ext", [os.path.join(d, "bev_pool.cpp"), os.path.join(d, "bev_pool_cuda.cu")])
+
+
+def build_ref_voxel_cuda():
+    return _build_ref_cuda("ref_voxel_layer_cuda", [os.path.join(REF_SRC, f) for f in (
+        "voxelization.cpp", "voxelization_cpu.cpp", "scatter_points_cpu.cpp", "voxelization_cuda.cu", "scatter_points_cuda.cu")])
+
+
 if __name__ == "__main__":
     print(build_c())
     try:
         print(build_ref())
         print(build_ref_spconv())
+        print(build_ref_bev_pool_cuda())
+        print(build_ref_voxel_cuda())
     except Exception as e:  # the reference build is optional evidence, not a dependency
         print("reference CPU build unavailable: %s" % e)
         sys.exit(0)

@@ -331,3 +331,55 @@ def test_cpu_input_raises():
     ours = dbev.ResNetForBEVDet(numC_input=128, num_channels=[128, 256, 512])
     with pytest.raises(RuntimeError):
         ours(torch.zeros(1, 128, 32, 32))
+
+
+# ------------------------------------------------------------------------------------------------ adaptation layers (row D1)
+class _RefThreeLayer(nn.Module):       # bevdet_distill.py:99-130 with kernel_size = stride = 1 (the shipped recipe)
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv1, self.norm1 = nn.Conv2d(cin, cin, 1), nn.BatchNorm2d(cin)
+        self.conv2, self.norm2 = nn.Conv2d(cin, cin, 1), nn.BatchNorm2d(cin)
+        self.conv3, self.norm3 = nn.Conv2d(cin, cout, 1), nn.BatchNorm2d(cout)
+
+    def forward(self, x):
+        x = torch.relu(self.norm1(self.conv1(x)))
+        x = torch.relu(self.norm2(self.conv2(x)))
+        return torch.relu(self.norm3(self.conv3(x)))
+
+
+def test_upsample_3layer_adaptation_matches_torch_modules(cuda):
+    """'upsample_3layer' (bevdet_distill.py:275-301; the two backbone positions of scripts/.../centerpoint2bevdepth.sh:32-37):
+    bilinear x4 (align_corners) + 3 x (1x1 conv + BatchNorm2d + ReLU), training mode, fwd + bwd."""
+    from distill_bev_b200.plugin.distill import adaptation as A
+    torch.manual_seed(4)
+    p = dict(adaptation_type=["upsample_3layer", "1x1conv"], teacher_adaptation_type="identity",
+             student_adaptation_params=dict(kernel_size=1, stride=1, upsample_factor=4), student_channels=[256, 256],
+             teacher_channels=[128, 384], spatial_mask=True)
+    student_layers, teacher_layers, spatial = A.build_adaptation_layers(p)
+    student_layers = student_layers.to(cuda).train()
+    assert student_layers[0].stride == (0.25, 0.25) and teacher_layers[0].stride == (1, 1) and len(spatial) == 2
+    ref = nn.Sequential(nn.Upsample(scale_factor=4, mode="bilinear", align_corners=True), _RefThreeLayer(256, 128)).to(cuda).train()
+    ref.load_state_dict(student_layers[0].state_dict(), strict=True)       # identical key layout
+    tf = copy.deepcopy(ref)
+    x = torch.relu(torch.randn(2, 256, 16, 16, device=cuda))
+    with torch.no_grad():
+        g = torch.randn_like(copy.deepcopy(ref)(x))
+    y32, g32 = _grads(ref, x, g, False)
+    ytf, gtf = _grads(tf, x, g, True)            # cuDNN TF32: the reference's own GPU arithmetic
+    yo, go = _grads(student_layers[0], x, g, False)
+    assert _relerr(yo, y32) <= max(5e-3, 2 * _relerr(ytf, y32))
+    for k in g32:                                  # three BN + ReLU layers amplify TF32 rounding: bar = 2 x cuDNN-TF32's own error
+        assert _relerr(go[k], g32[k]) <= 2.0 * _relerr(gtf[k], g32[k]) + 2e-3, (k, _relerr(go[k], g32[k]), _relerr(gtf[k], g32[k]))
+
+
+def test_mlp_and_3x3_adaptations(cuda):
+    from distill_bev_b200.plugin.distill import adaptation as A
+    torch.manual_seed(5)
+    x = torch.relu(torch.randn(2, 256, 24, 24, device=cuda))
+    mlp = A.Mlp(256, out_features=384).to(cuda)
+    want = mlp.fc2(torch.relu(mlp.fc1(x)))
+    assert _relerr(mlp(x), want.detach()) <= 3e-3
+    c3 = A.Conv3x3Adaptation(256, 128).to(cuda)
+    assert _relerr(c3(x), F.conv2d(x, c3.weight, c3.bias, 1, 1).detach()) <= 3e-3
+    with pytest.raises(NotImplementedError):
+        A.TwoLayer(256, out_features=128, kernel_size=4, stride=4).to(cuda)(x)

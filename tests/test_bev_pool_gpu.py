@@ -290,3 +290,34 @@ def test_sort_free_lift_splat_matches_sorted(cuda):
         torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-5 * float(a.abs().max()))
     pc = vt.make_cells(geom, nf).point_cell
     assert torch.equal(pc, vt.make_plan(geom, nf).point_cell)
+
+
+def test_sort_free_lift_splat_frames_is_the_channel_concat(cuda):
+    """frames=2 (BEVDepth4D): with the frame index numbered last in the cell id the splat's channels-last map IS
+    torch.cat([frame 0, frame 1], dim=1) of the per-sample-frame result (bevdet.py:300-320); same for the gradients."""
+    vt = dbev.ViewTransformerLiftSplatShoot(grid_config=synthetic.NUSC_GRID, numC_input=8).to(cuda)
+    nf, frames = 6, 2
+    calib = [torch.from_numpy(a).to(cuda) for a in synthetic.make_calibration(nf, 6, seed=9)]
+    geom = vt.get_geometry(*calib)
+    torch.manual_seed(1)
+    depth = torch.randn(nf * 6, 59, 16, 44, device=cuda).softmax(1)
+    feat = torch.randn(nf * 6, 64, 16, 44, device=cuda)
+    og = torch.rand(nf // frames, frames * 64, 128, 128, device=cuda).contiguous(memory_format=torch.channels_last)
+    d0, f0 = depth.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    ref = dbev.lift_splat(d0, f0, vt.make_cells(geom, nf))                        # [nf, 64, 128, 128]
+    ref_cat = torch.cat([ref[0::2], ref[1::2]], 1)
+    ref_cat.backward(og)
+    d1, f1 = depth.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    out = dbev.lift_splat(d1, f1, vt.make_cells(geom, nf, frames=frames))
+    assert tuple(out.shape) == (nf // frames, frames * 64, 128, 128)
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    out.backward(og)
+    torch.testing.assert_close(out.detach(), ref_cat.detach(), rtol=1e-4, atol=1e-5 * float(ref_cat.abs().max()))
+    torch.testing.assert_close(d1.grad, d0.grad, rtol=1e-4, atol=1e-5 * float(d0.grad.abs().max()))
+    torch.testing.assert_close(f1.grad, f0.grad, rtol=1e-4, atol=1e-5 * float(f0.grad.abs().max()))
+    # a gradient that is not channels_last goes through the transpose path
+    d2, f2 = depth.clone().requires_grad_(True), feat.clone().requires_grad_(True)
+    dbev.lift_splat(d2, f2, vt.make_cells(geom, nf, frames=frames)).backward(og.contiguous())
+    torch.testing.assert_close(d2.grad, d1.grad, rtol=1e-5, atol=1e-6 * float(d1.grad.abs().max()))
+    with pytest.raises(RuntimeError):
+        vt.make_cells(geom, nf, frames=4)           # 6 sample-frames are not a multiple of 4

@@ -317,3 +317,32 @@ def test_attention_affinity_mode_golden(cuda, gd):
     sum(losses.values()).backward()
     gs = gd["att_grad_student"]
     np.testing.assert_allclose(student.grad.cpu().numpy(), gs, rtol=1e-4, atol=1e-4 * np.abs(gs).max())
+
+
+def test_backward_without_spatial_adaptation(cuda):
+    """spatial_mask=False and no spatial_wise_adaptations conv (the default of fgd_distill_loss / fgd_loss_terms and of
+    the BEVFormer variant): the autograd node must return None for the absent conv inputs (round-1 ADVICE: it
+    returned tensors, which makes .backward() raise), and spatial_mask=True without the conv raises up front."""
+    from distill_bev_b200.plugin.distill import fgd as F
+    torch.manual_seed(1)
+    B, C, H = 2, 32, 32
+    params = dict(spatial_t=0.5, spatial_student_ratio=1.0, channel_t=0.5, fg_feat_loss_weights=[6e-3],
+                  bg_feat_loss_weights=[4e-2], channel_loss_weights=[0.25], spatial_loss_weights=[2.5e-3],
+                  spatial_attentions=["teacher_student"], transpose_mask=False, foreground_mask="gt",
+                  background_mask="logical_not", scale_mask="combine_gt", spatial_mask=False, channel_mask=True,
+                  fp_as_foreground=["none"], fp_weight=0.0, fp_epoch=0)
+    cfg = dict(grid_size=[256, 256, 40], point_cloud_range=[-12.8, -12.8, -5.0, 12.8, 12.8, 3.0], voxel_size=[0.1, 0.1, 0.2])
+    boxes = [torch.tensor([[0.0, 0.0, -1.0, 4.0, 3.0, 1.5, 0.3, 0, 0]]), torch.tensor([[-3.0, 2.0, -1.0, 5.0, 4.0, 1.5, -0.7, 0, 0]])]
+    teacher = torch.relu(torch.randn(B, C, H, H, device=cuda))
+    s = torch.relu(torch.randn(B, C, H, H, device=cuda)).requires_grad_(True)
+    losses = F.fgd_distill_loss(teacher, s, boxes, params, cfg)
+    assert "kd_spatial_loss" not in losses
+    sum(losses.values()).backward()
+    assert torch.isfinite(s.grad).all() and float(s.grad.abs().sum()) > 0
+    # the same through the fused 1x1 adaptation node
+    conv = torch.nn.Conv2d(C, C, 1).to(cuda)
+    s2 = s.detach().clone().requires_grad_(True)
+    sum(F.fgd_distill_loss(teacher, s2, boxes, params, cfg, channel_adaptation=conv).values()).backward()
+    assert conv.weight.grad is not None and torch.isfinite(s2.grad).all()
+    with pytest.raises(RuntimeError):
+        F.fgd_distill_loss(teacher, s, boxes, dict(params, spatial_mask=True), cfg)

@@ -63,3 +63,26 @@ def test_cpu_tensors_are_rejected():
         dbev.HardSimpleVFE(4)(torch.zeros(3, 5, 4), torch.ones(3, dtype=torch.int32))
     with pytest.raises(RuntimeError):
         dbev.affinity.affinity_distill_loss(torch.zeros(1, 8, 4, 4), torch.zeros(1, 8, 4, 4), torch.ones(1, 1, 4, 4))
+
+
+def test_unimplemented_distill_options_raise():
+    """distill_params that change the reference loss and are not implemented must raise, never be ignored
+    (round-1 ADVICE): non_empty_weight (bevdet_distill.py:1137-1165), context_length x context_weight (:803-817),
+    criteria other than the shipped MSE / L1 / L1 'none' (:997-999)."""
+    import pytest
+    from distill_bev_b200.plugin.distill import fgd
+    base = dict(spatial_t=0.5, spatial_student_ratio=1.0, channel_t=0.5, fg_feat_loss_weights=[6e-3],
+                bg_feat_loss_weights=[4e-2], channel_loss_weights=[0.25], spatial_loss_weights=[2.5e-3],
+                spatial_attentions=["teacher_student"], background_mask="logical_not", scale_mask="combine_gt",
+                spatial_mask=True, channel_mask=False, fp_as_foreground=["none"], fp_weight=0.0, fp_epoch=0,
+                non_empty_weight=0, context_length=0, context_weight=0.5,
+                feat_criterion=dict(type="MSELoss", reduction="none"), spatial_criterion=dict(type="L1Loss", reduction="none"),
+                channel_criterion=dict(type="L1Loss", reduction="none"))
+    cfg, fp_mode = fgd.make_config(2, 32, 16, 16, base)
+    assert cfg.B == 2 and fp_mode == "none"
+    for bad in (dict(non_empty_weight=0.1), dict(context_length=2, context_weight=0.5),
+                dict(feat_criterion=dict(type="SmoothL1Loss", reduction="none")),
+                dict(spatial_criterion=dict(type="L1Loss", reduction="mean")),
+                dict(channel_criterion=dict(type="L1Loss", reduction="none", loss_weight=2.0))):
+        with pytest.raises(NotImplementedError):
+            fgd.make_config(2, 32, 16, 16, dict(base, **bad))
