@@ -211,7 +211,7 @@ class CudnnEncoder(object):
 class HotPath(object):
     """Synthetic batch + the training step, built on the public plugin API (distill_bev_b200)."""
 
-    def __init__(self, device, seed, world=1, allreduce="after", comm_dtype="bf16", encoder="tcgen05"):
+    def __init__(self, device, seed, world=1, allreduce="overlap", comm_dtype="bf16", encoder="tcgen05"):
         import torch
         import distill_bev_b200 as dbev
         from distill_bev_b200 import synthetic
@@ -261,11 +261,8 @@ class HotPath(object):
         self.trainable = [p for m in (self.student_net, self.adapt, self.spatial) for p in m.parameters()]
         self.n_params = sum(p.numel() for p in self.trainable)
         self.optim = torch.optim.AdamW(self.trainable, lr=2e-4, weight_decay=0.01, fused=True, capturable=True)
-        self.reducer, self.allreduce = None, allreduce
-        if world > 1 and allreduce != "none":
-            from distill_bev_b200.plugin.data_parallel import GradientAllReduce
-            self.reducer = GradientAllReduce(self.trainable, world, comm_dtype=torch.bfloat16 if comm_dtype == "bf16" else None,
-                                             overlap=(allreduce == "overlap"))
+        self.reducer, self.allreduce, self.comm_dtype = None, allreduce, comm_dtype
+        self.set_allreduce(allreduce)
         self.d_calib = [t.to(device) for t in self.h_calib]
         self.d_points = [t.to(device) for t in self.h_points]
         counts = [int(b.shape[0]) for b in self.boxes]
@@ -280,6 +277,21 @@ class HotPath(object):
                           + self.h_labels.numel() * 4 + self.h_box_offs.numel() * 4
                           + sum(b.numel() * 4 for b in self.boxes))
         self.d2h_bytes = 5 * 4
+
+    def set_allreduce(self, mode):
+        """(Re)build the gradient reducer: 'overlap' = per-bucket all-reduce launched from gradient hooks on a side
+        stream (recorded into the CUDA graph), 'after' = all buckets after the backward (eager NCCL between two graphs),
+        'none' = no collective (replicas; not data-parallel training)."""
+        torch = self.torch
+        if self.reducer is not None:
+            for h in self.reducer._hooks:
+                h.remove()
+        self.reducer, self.allreduce = None, mode
+        if self.world > 1 and mode != "none":
+            from distill_bev_b200.plugin.data_parallel import GradientAllReduce
+            self.reducer = GradientAllReduce(self.trainable, self.world,
+                                             comm_dtype=torch.bfloat16 if self.comm_dtype == "bf16" else None,
+                                             overlap=(mode == "overlap"))
 
     def encode(self, bev):
         if self.encoder_kind == "cudnn":
@@ -653,6 +665,16 @@ def bev_pool_roofline(device):
             "launch_ms": round(ms, 5), "shape": "16 sample-frames, n=%d rows kept of %d, C=64, 128x128" % (kept, n)}
 
 
+def _exit_multi_rank():
+    """Leave without tearing the NCCL communicator down: CUDA graphs that recorded NCCL kernels keep it busy and
+    destroy_process_group() can wait forever on them. All results are printed and flushed before this is called."""
+    import torch
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -670,16 +692,24 @@ def run_ours(args):
     hp.sorted_splat = args.sorted_splat
     graph_note = "eager (--no-graph)"
     if not args.no_graph:
-        try:
-            hp.enable_graph()
-            graph_note = ("step captured once in a CUDA graph and replayed%s; e2e copies every batch from pinned host memory "
-                          "into one of two static input sets on a copy stream while the previous step runs (prefetch), "
-                          "and reads the losses back every step"
-                          % (" (forward+backward graph, eager NCCL all-reduce, optimizer graph)" if hp.split else ""))
-        except Exception as exc:  # keep measuring, eagerly, and say so
-            hp.captured = None
-            graph_note = "eager (graph capture failed: %s)" % str(exc).splitlines()[0][:120]
-            sys.stderr.write("bench.py: CUDA graph capture failed, running eagerly: %s\n" % exc)
+        attempts = [args.allreduce] + (["after"] if (world > 1 and args.allreduce == "overlap") else [])
+        for mode in attempts:
+            try:
+                if mode != hp.allreduce:
+                    hp.set_allreduce(mode)
+                hp.enable_graph()
+                graph_note = ("step captured once in a CUDA graph and replayed%s; e2e copies every batch from pinned host memory "
+                              "into one of two static input sets on a copy stream while the previous step runs (prefetch), "
+                              "and reads the losses back every step"
+                              % (" (forward+backward graph, eager NCCL all-reduce, optimizer graph)" if hp.split else
+                                 (" (NCCL all-reduce kernels recorded in the graph, launched per bucket from gradient hooks)"
+                                  if hp.reducer is not None else "")))
+                break
+            except Exception as exc:  # keep measuring, eagerly, and say so
+                hp.captured = None
+                graph_note = "eager (graph capture failed: %s)" % str(exc).splitlines()[0][:120]
+                sys.stderr.write("bench.py: CUDA graph capture failed (allreduce=%s): %s\n" % (mode, exc))
+                torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -710,7 +740,7 @@ def run_ours(args):
     if rank != 0:
         if world > 1:
             dist.barrier()
-            dist.destroy_process_group()
+            _exit_multi_rank()
         return
     if world > 1:
         dist.barrier()
@@ -726,7 +756,7 @@ def run_ours(args):
                                                          "cuDNN arithmetic under torch defaults)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "frames": FRAMES, "parallelism": "dp%d" % world},
         "step_detail": {"l2": "activations larger than L2 (encoder activations > 3 GB, teacher conv activations > 2 GB per step)",
-                        "collective": coll, "allreduce_mode": args.allreduce if world > 1 else "n/a",
+                        "collective": coll, "allreduce_mode": hp.allreduce if world > 1 else "n/a",
                         "trainable_parameters": int(hp.n_params), "optimizer": "torch.optim.AdamW(fused=True, capturable=True)",
                         "student_encoder_train_flops_per_step": flops,
                         "student_encoder_tflops_if_alone": None,
@@ -760,8 +790,9 @@ def run_ours(args):
         line["roofline"] = student_conv_roofline(hp)
         line["roofline_bev_pool"] = bev_pool_roofline(device)
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        _exit_multi_rank()
 
 
 # ----------------------------------------------------------------------------- CPU oracle arm
@@ -940,9 +971,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly (no CUDA graph replay)")
-    ap.add_argument("--allreduce", default="after", choices=["after", "overlap", "none"],
-                    help="N > 1: gradient all-reduce after the backward graph (default), recorded into the graph and "
-                         "overlapped with the backward ('overlap'), or skipped ('none': replicas, not training)")
+    ap.add_argument("--allreduce", default="overlap", choices=["after", "overlap", "none"],
+                    help="N > 1: gradient all-reduce recorded into the step's CUDA graph and overlapped with the backward "
+                         "(default; falls back to 'after' if the capture fails), issued eagerly after the backward graph "
+                         "('after'), or skipped ('none': replicas, not training)")
     ap.add_argument("--comm-dtype", default="bf16", choices=["bf16", "f32"], help="wire dtype of the gradient all-reduce")
     ap.add_argument("--sorted-splat", action="store_true",
                     help="lift+splat through the sorted plan (fixed summation order) instead of the sort-free splat")

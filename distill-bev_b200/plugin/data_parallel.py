@@ -6,13 +6,18 @@ of every student parameter over the ranks with bucketed NCCL all-reduces that ov
 teacher is held outside ``parameters()`` (bevdet_distill.py:1599-1610) and is not reduced; BatchNorm statistics stay
 per-GPU (plain BN in the shipped configs).
 
-``GradientAllReduce`` is that reducer for a CUDA-graph-replayed step: DDP's Python hooks cannot be replayed, so the
-gradients live in flat per-bucket buffers (``p.grad`` are views; autograd accumulates into them in place) and each
-bucket is reduced with ONE collective - optionally compressed to bf16 like DDP's ``bf16_compress_hook``
-(divide by the world size, cast, all-reduce, cast back). Buckets follow the order in which gradients become ready
-(reverse registration order, as DDP does), so with ``overlap=True`` a bucket's all-reduce is issued on a side
-stream from the post-accumulate hook of its last parameter while the rest of the backward still runs - inside a
-CUDA graph capture the NCCL kernels are recorded like any other. Works with any torch.distributed backend (the
+``GradientAllReduce`` is that reducer for a CUDA-graph-replayed step (DDP's Python-side reducer cannot be replayed).
+Parameters are grouped into buckets in the order their gradients become ready (reverse registration order, as DDP
+does). Per bucket and step:
+
+    one multi-tensor copy  gradients -> flat wire buffer (cast to bf16 like DDP's bf16_compress_hook, or fp32)
+    ONE all-reduce of the flat buffer (AVG on NCCL; SUM + divide elsewhere)
+    one multi-tensor copy  flat wire buffer -> the same gradient tensors
+
+The gradients themselves stay where autograd put them (``p.grad`` is set to None before the backward so the
+accumulation step adopts the incoming tensor: no zero-fill, no add). With ``overlap=True`` a bucket is launched on a
+side stream from the post-accumulate hook of its last parameter while the rest of the backward still runs; inside a
+CUDA graph capture the NCCL kernel is recorded like any other kernel. Works with any torch.distributed backend (the
 CPU tests use gloo, world_size 2).
 """
 import torch
@@ -28,11 +33,12 @@ class GradientAllReduce(object):
         self.group = process_group
         self.world = int(world_size if world_size is not None else (dist.get_world_size(process_group)
                                                                     if dist.is_initialized() else 1))
-        self.comm_dtype = comm_dtype
-        self.overlap = bool(overlap) and self.world > 1
         dev, dt = self.params[0].device, self.params[0].dtype
         if any(p.device != dev or p.dtype != dt for p in self.params):
             raise ValueError("GradientAllReduce: parameters must share one device and dtype")
+        self.comm_dtype = comm_dtype if comm_dtype is not None else dt
+        self.overlap = bool(overlap) and self.world > 1
+        self.use_avg = self.world > 1 and dist.is_initialized() and dist.get_backend(process_group) == "nccl"
         # buckets in the order gradients become ready: last registered parameter first
         self.buckets, cur, cur_bytes = [], [], 0
         for p in reversed(self.params):
@@ -44,33 +50,30 @@ class GradientAllReduce(object):
             cur_bytes += nbytes
         if cur:
             self.buckets.append(cur)
-        self.flat, self.comm = [], []
+        self.flat, self.views = [], []
         for bucket in self.buckets:
-            n = sum((p.numel() + 3) // 4 * 4 for p in bucket)          # 16-byte aligned views
-            flat = torch.zeros(n, dtype=dt, device=dev)
-            off = 0
+            n = sum((p.numel() + 7) // 8 * 8 for p in bucket)          # 16-byte aligned views for bf16 and fp32
+            flat = torch.zeros(n, dtype=self.comm_dtype, device=dev)
+            views, off = [], 0
             for p in bucket:
-                p.grad = flat[off:off + p.numel()].view_as(p)
-                off += (p.numel() + 3) // 4 * 4
+                views.append(flat[off:off + p.numel()].view_as(p))
+                off += (p.numel() + 7) // 8 * 8
             self.flat.append(flat)
-            self.comm.append(torch.empty(n, dtype=comm_dtype, device=dev) if comm_dtype not in (None, dt) else None)
-        self.bytes_per_step = sum((c if c is not None else f).numel() * (c if c is not None else f).element_size()
-                                  for f, c in zip(self.flat, self.comm))
-        self._pending, self._left, self._hooks = [], [], []
+            self.views.append(views)
+        self.bytes_per_step = sum(f.numel() * f.element_size() for f in self.flat)
+        self._left, self._hooks = [len(b) for b in self.buckets], []
         self._stream = torch.cuda.Stream(dev) if (self.overlap and dev.type == "cuda") else None
         if self.overlap:
             for bi, bucket in enumerate(self.buckets):
                 for p in bucket:
                     self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
-            self.begin()
 
     # ------------------------------------------------------------------ per step
     def begin(self):
-        """Before the backward pass: gradients start from zero (autograd adds into the flat views)."""
-        for flat in self.flat:
-            flat.zero_()
+        """Before the backward pass: drop the old gradients so that autograd adopts the new tensors (no add)."""
+        for p in self.params:
+            p.grad = None
         self._left = [len(b) for b in self.buckets]
-        self._pending = []
 
     def _make_hook(self, bi):
         def hook(_param):
@@ -80,28 +83,27 @@ class GradientAllReduce(object):
         return hook
 
     def _reduce_bucket(self, bi):
-        flat, comm = self.flat[bi], self.comm[bi]
-        if self.world == 1:
-            return None
-        flat.div_(self.world)                      # average, pre-divided like DDP (keeps bf16 in range)
-        if comm is not None:
-            comm.copy_(flat)
-            work = dist.all_reduce(comm, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        grads = [p.grad for p in self.buckets[bi]]
+        if any(g is None for g in grads):
+            raise RuntimeError("GradientAllReduce: a parameter of bucket %d received no gradient this step" % bi)
+        flat, views = self.flat[bi], self.views[bi]
+        torch._foreach_copy_(views, grads)                               # gather + cast, one multi-tensor kernel
+        if self.use_avg:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
         else:
-            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        return work
+            flat.div_(self.world)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        torch._foreach_copy_(grads, views)                               # scatter + cast back, in place
 
     def _launch(self, bi):
+        if self.world == 1:
+            return
         if self._stream is not None:
             self._stream.wait_stream(torch.cuda.current_stream(self.flat[bi].device))
             with torch.cuda.stream(self._stream):
-                work = self._reduce_bucket(bi)
-                if work is not None:
-                    work.wait()                    # stream-level wait: orders the cast-back after the collective
-                if self.comm[bi] is not None:
-                    self.flat[bi].copy_(self.comm[bi])
+                self._reduce_bucket(bi)
         else:
-            self._pending.append((bi, self._reduce_bucket(bi)))
+            self._reduce_bucket(bi)
 
     def finish(self):
         """After the backward pass: every ``p.grad`` holds the rank-averaged gradient when this returns (stream-ordered)."""
@@ -113,24 +115,13 @@ class GradientAllReduce(object):
                                    % sum(1 for n in self._left if n != 0))
             if self._stream is not None:
                 torch.cuda.current_stream(self.flat[0].device).wait_stream(self._stream)
-            else:
-                self._drain()
             return
         for bi in range(len(self.buckets)):
-            self._pending.append((bi, self._reduce_bucket(bi)))
-        self._drain()
-
-    def _drain(self):
-        for bi, work in self._pending:
-            if work is not None:
-                work.wait()
-            if self.comm[bi] is not None:
-                self.flat[bi].copy_(self.comm[bi])
-        self._pending = []
+            self._reduce_bucket(bi)
 
     def describe(self):
-        return {"collective": "all_reduce(SUM) of %d flat gradient bucket(s), pre-divided by the world size"
-                              % len(self.buckets),
+        return {"collective": "%d x all_reduce(%s) of a flat gradient bucket, averaged over the ranks"
+                              % (len(self.buckets), "AVG" if self.use_avg else "SUM, pre-divided"),
                 "bytes_per_step": int(self.bytes_per_step), "buckets": [int(f.numel()) for f in self.flat],
-                "comm_dtype": str(self.comm_dtype or self.flat[0].dtype).replace("torch.", ""),
+                "comm_dtype": str(self.comm_dtype).replace("torch.", ""),
                 "overlap_with_backward": self.overlap, "parameters": len(self.params)}
