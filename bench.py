@@ -626,28 +626,34 @@ def bev_pool_roofline(device):
     plan = vt.make_plan(geom, nf, with_point_cell=False)
     n = geom.numel() // 3
     x = torch.rand(n, C_TRANS, device=device)
-    shape, sB, sZ, sC = bp._out_strides(plan, C_TRANS, "bz_c")
-    out = torch.empty(shape, device=device)
     lib = _lib.load()
     stream = torch.cuda.current_stream(device)
 
-    def launch():
-        rc = lib.dbev_bev_pool_gather_forward(
-            _lib.ptr(x), C_TRANS, _lib.ptr(plan.order), _lib.ptr(plan.cell_start), _lib.ptr(plan.cell_end),
-            _lib.ptr(plan.items), _lib.ptr(plan.n_items), plan.batch, plan.nz, plan.nslow, plan.nfast,
-            sB, sZ, sC, _lib.ptr(out), _lib.stream_ptr(device))
-        _lib.check(rc, "dbev_bev_pool_gather_forward")
-    for _ in range(5):
-        launch()
-    iters = 30
-    a, b = torch.cuda.Event(True), torch.cuda.Event(True)
-    torch.cuda.synchronize()
-    a.record(stream)
-    for _ in range(iters):
-        launch()
-    b.record(stream)
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / iters
+    def time_layout(layout):
+        shape, sB, sZ, sC = bp._out_strides(plan, C_TRANS, layout)
+        out = torch.empty(shape, device=device)
+
+        def launch():
+            rc = lib.dbev_bev_pool_gather_forward(
+                _lib.ptr(x), C_TRANS, _lib.ptr(plan.order), _lib.ptr(plan.cell_start), _lib.ptr(plan.cell_end),
+                _lib.ptr(plan.items), _lib.ptr(plan.n_items), plan.batch, plan.nz, plan.nslow, plan.nfast,
+                sB, sZ, sC, _lib.ptr(out), _lib.stream_ptr(device))
+            _lib.check(rc, "dbev_bev_pool_gather_forward")
+        for _ in range(5):
+            launch()
+        iters = 30
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        torch.cuda.synchronize()
+        a.record(stream)
+        for _ in range(iters):
+            launch()
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters, out
+
+    ms_nchw, out_nchw = time_layout("bz_c")
+    ms, out = time_layout("cl")
+    same = bool(torch.equal(out.view(plan.batch, plan.nslow, plan.nfast, C_TRANS).permute(0, 3, 1, 2), out_nchw))
     kept = plan.num_kept()
     alg_bytes = kept * C_TRANS * 4 + kept * 4 + out.numel() * 4
     peak, how = measured_peaks()
@@ -659,10 +665,14 @@ def bev_pool_roofline(device):
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    return {"kernel": "dbev::bev_pool_gather_fwd_kernel<16,false>", "bound": "hbm", "achieved": round(ach, 1),
-            "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
+    ach_nchw = alg_bytes / (ms_nchw * 1e-3) / 1e9
+    return {"kernel": "dbev::bev_pool_gather_fwd_kernel<16,false,6,true> (channels-last output rows)", "bound": "hbm",
+            "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
             "peak_source": how, "algorithmic_bytes_per_launch": int(alg_bytes),
-            "launch_ms": round(ms, 5), "shape": "16 sample-frames, n=%d rows kept of %d, C=64, 128x128" % (kept, n)}
+            "launch_ms": round(ms, 5), "shape": "16 sample-frames, n=%d rows kept of %d, C=64, 128x128" % (kept, n),
+            "nchw_output_variant": {"kernel": "dbev::bev_pool_gather_fwd_kernel<16,false,6,false> (transposing epilogue)",
+                                    "launch_ms": round(ms_nchw, 5), "achieved": round(ach_nchw, 1),
+                                    "frac": round(ach_nchw / peak, 4), "bit_identical_values": same}}
 
 
 def _exit_multi_rank():

@@ -241,7 +241,10 @@ struct WorkQueue {
 // MINB = CTAs per SM the register allocation must allow. The materialised-row variant (LIFT =
 // false) is latency-bound and gains from the 6th resident CTA (80 instead of 96 registers, a
 // 60-byte spill outside the row loop): 0.2355 -> 0.2295 ms on the configs[1] shape.
-template <int LPR, bool LIFT, int MINB = 1>
+// CL = channels-last output (out[cell][C], g.sC == 1): a finished cell is ONE 16-byte store per lane straight from the
+// accumulator (a coalesced row) - no shared-memory tile, no transposing epilogue; what the student BEV encoder's NHWC
+// conv kernels read, and the layout in which the gather reaches its best fraction of the HBM roofline.
+template <int LPR, bool LIFT, int MINB = 1, bool CL = false>
 __global__ void __launch_bounds__(kPoolBlock, MINB)
 bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restrict__ order,
                            const int* __restrict__ cell_start, const int* __restrict__ cell_end,
@@ -256,8 +259,8 @@ bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restri
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % LPR, worker = lane / LPR;
-  float* tile = smem + (size_t)warp * (CB * kTilePitch + NW * 2 * CB);  // [CB][kTilePitch]
-  float* side = tile + CB * kTilePitch;                                  // [NW*2][CB]
+  float* tile = smem + (size_t)warp * ((CL ? 0 : CB * kTilePitch) + NW * 2 * CB);  // [CB][kTilePitch] (not in CL mode)
+  float* side = tile + (CL ? 0 : CB * kTilePitch);                                  // [NW*2][CB]
   int* cs = cstart_s[warp];
   int* ce = cend_s[warp];
   int* side_cell = side_cell_s[warp];
@@ -299,6 +302,11 @@ bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restri
         const bool complete = cs[cell] >= ws && ce[cell] <= we;
         float* dst;
         int pitch;
+        if (CL && complete) {
+          if (lane_active)
+            *reinterpret_cast<float4*>(out + (ic.cell0 + cell) * g.C + cb + sub * 4) = acc;
+          return;
+        }
         if (complete) {
           dst = tile + cell;
           pitch = kTilePitch;
@@ -433,38 +441,71 @@ bev_pool_gather_fwd_kernel(const float* __restrict__ x, const uint32_t* __restri
       flush(cur);
     }
     __syncwarp();
-    // boundary partial sums: a cell shared by several workers has its partials in
-    // consecutive slots; first assigns, the rest add, in slot order (reproducible)
-    {
+    if constexpr (CL) {
+      // boundary partial sums (a cell shared by the workers has its partials in consecutive slots, added in slot
+      // order: reproducible), written as whole rows; then zero rows for the empty cells of the item
+      const int cmax = min(CB, g.C - cb);
+      float a0 = 0.f, a1 = 0.f;
       int prev = -1;
-      for (int w = 0; w < NW * 2; ++w) {
-        const int cell = side_cell[w];
+      for (int w = 0; w <= NW * 2; ++w) {
+        const int cell = w < NW * 2 ? side_cell[w] : -2;
+        if (cell == -1) continue;
+        if (cell != prev && prev >= 0) {
+          float* orow = out + (ic.cell0 + prev) * g.C + cb;
+          if (lane < cmax) orow[lane] = a0;
+          if (lane + 32 < cmax) orow[lane + 32] = a1;
+          if (CB > 64)
+            for (int c = lane + 64; c < cmax; c += 32) {
+              float t = 0.f;
+              for (int v = 0; v < NW * 2; ++v)
+                if (side_cell[v] == prev) t += side[v * CB + c];
+              orow[c] = t;
+            }
+          a0 = a1 = 0.f;
+        }
         if (cell >= 0) {
-          for (int c = lane; c < CB; c += 32) {
-            const float v = side[w * CB + c];
-            if (cell == prev) tile[c * kTilePitch + cell] += v;
-            else tile[c * kTilePitch + cell] = v;
+          if (lane < CB) a0 += side[w * CB + lane];
+          if (lane + 32 < CB) a1 += side[w * CB + lane + 32];
+        }
+        prev = cell;
+      }
+      for (int cell = ic.c0 + worker; cell < ic.c1; cell += NW)
+        if (ce[cell] <= cs[cell] && lane_active)
+          *reinterpret_cast<float4*>(out + (ic.cell0 + cell) * g.C + cb + sub * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      // boundary partial sums: a cell shared by several workers has its partials in
+      // consecutive slots; first assigns, the rest add, in slot order (reproducible)
+      {
+        int prev = -1;
+        for (int w = 0; w < NW * 2; ++w) {
+          const int cell = side_cell[w];
+          if (cell >= 0) {
+            for (int c = lane; c < CB; c += 32) {
+              const float v = side[w * CB + c];
+              if (cell == prev) tile[c * kTilePitch + cell] += v;
+              else tile[c * kTilePitch + cell] = v;
+            }
+            prev = cell;
           }
-          prev = cell;
         }
       }
+      __syncwarp();
+      // epilogue: lanes = (cell, channel group); empty cells are written as zero here
+      {
+        const int span = ic.c1 - ic.c0;
+        int npow = 1;
+        while (npow < span) npow <<= 1;
+        const int cpar = 32 / npow;
+        const int cell = ic.c0 + lane % npow;
+        const bool wr = cell < ic.c1;
+        const bool empty = wr ? (ce[cell] <= cs[cell]) : true;
+        float* ob = out + ic.obase + cell;
+        const int cmax = min(CB, g.C - cb);
+        for (int c = lane / npow; c < cmax; c += cpar)
+          if (wr) ob[(long long)(cb + c) * g.sC] = empty ? 0.f : tile[c * kTilePitch + cell];
+      }
     }
-    __syncwarp();
-    // epilogue: lanes = (cell, channel group); empty cells are written as zero here
-    {
-      const int span = ic.c1 - ic.c0;
-      int npow = 1;
-      while (npow < span) npow <<= 1;
-      const int cpar = 32 / npow;
-      const int cell = ic.c0 + lane % npow;
-      const bool wr = cell < ic.c1;
-      const bool empty = wr ? (ce[cell] <= cs[cell]) : true;
-      float* ob = out + ic.obase + cell;
-      const int cmax = min(CB, g.C - cb);
-      for (int c = lane / npow; c < cmax; c += cpar)
-        if (wr) ob[(long long)(cb + c) * g.sC] = empty ? 0.f : tile[c * kTilePitch + cell];
     }
-  }
   queue.finish(lane, gridDim.x * kPoolWarps);
 }
 
@@ -1153,6 +1194,24 @@ static int gather_forward_impl(const float* x, int C, const uint32_t* order, con
     return DBEV_OK;
   }
   const LiftArgs none{nullptr, FastDiv(1), FastDiv(1)};
+  if (lpr > 0 && sC == 1) {
+    // channels-last output: rows of the cells-major map [batch][nz][nslow][nfast][C]
+    DBEV_CHECK_ARG(sZ == (long long)nslow * nfast * C && sB == (long long)nz * nslow * nfast * C,
+                   "bev_pool: a channel stride of 1 needs the cells-major layout [B][nz][slow][fast][C]");
+    const int cb = lpr * 4, nw = 32 / lpr;
+    const size_t smem = (size_t)kPoolWarps * (nw * 2 * cb) * sizeof(float);
+    int grid = 0;
+#define LAUNCH(L)                                                                        \
+  rc = persistent_grid(bev_pool_gather_fwd_kernel<L, false, 6, true>, smem, &grid);      \
+  if (rc != DBEV_OK) return rc;                                                          \
+  bev_pool_gather_fwd_kernel<L, false, 6, true><<<grid, kPoolBlock, smem, stream>>>(     \
+      x, order, cell_start, cell_end, items, n_items, out, g, none, sched_slot)
+    DBEV_SCHED_SLOT(sched_slot);
+    DBEV_DISPATCH_LPR(lpr, LAUNCH);
+#undef LAUNCH
+    DBEV_CHECK_LAUNCH("bev_pool_gather_fwd_kernel (channels-last)");
+    return DBEV_OK;
+  }
   if (lpr > 0) {
     const int cb = lpr * 4, nw = 32 / lpr;
     const size_t smem = (size_t)kPoolWarps * (cb * kTilePitch + nw * 2 * cb) * sizeof(float);

@@ -147,6 +147,8 @@ def _out_strides(plan, C, layout):
         return (plan.batch, plan.nz * C, plan.nslow, plan.nfast), plan.nz * C * plane, C * plane, plane
     if layout == "b_c_z":     # [B, C, nz, slow, fast]  (bev_pool: permute(0,4,1,2,3))
         return (plan.batch, C, plan.nz, plan.nslow, plan.nfast), C * plan.nz * plane, plane, plan.nz * plane
+    if layout == "cl":        # [B, nz, slow, fast, C]  cells-major / channels-last rows (what the NHWC conv kernels read)
+        return (plan.batch, plan.nz, plan.nslow, plan.nfast, C), plan.nz * plane * C, plane * C, 1
     raise ValueError(layout)
 
 
@@ -181,9 +183,14 @@ class _BevPoolGather(torch.autograd.Function):
         out_grad = out_grad.contiguous().float()
         _, sB, sZ, sC = _out_strides(plan, C, ctx.layout)
         x_grad = torch.empty((plan.n_points, C), dtype=torch.float32, device=out_grad.device)
-        if plan.point_cell is not None and ctx.layout == "bz_c" and C % 4 == 0:
+        if ctx.layout == "cl" and not (plan.point_cell is not None and C % 4 == 0):
+            # no point -> cell map in the plan: back to the [B, nz*C, slow, fast] layout of the gather-backward kernel
+            out_grad = out_grad.permute(0, 1, 4, 2, 3).reshape(plan.batch, plan.nz * C, plan.nslow, plan.nfast).contiguous()
+            _, sB, sZ, sC = _out_strides(plan, C, "bz_c")
+        elif plan.point_cell is not None and ctx.layout in ("bz_c", "cl") and C % 4 == 0:
             # point-centric: sequential row writes, cell rows gathered from the cells-major gradient
-            g_cl = transpose_batched(out_grad, plan.batch * plan.nz, C, plan.nslow * plan.nfast)
+            g_cl = out_grad if ctx.layout == "cl" else transpose_batched(out_grad, plan.batch * plan.nz, C,
+                                                                        plan.nslow * plan.nfast)
             with torch.cuda.device(out_grad.device):
                 rc = lib.dbev_bev_pool_point_backward(_lib.ptr(g_cl), _lib.ptr(plan.point_cell), plan.n_points,
                                                       C, _lib.ptr(x_grad), _lib.stream_ptr(out_grad.device))
@@ -384,11 +391,14 @@ def bev_pool(feats, coords, B, D, H, W):
     return bev_pool_gather(feats, plan, layout="b_c_z")
 
 
-def voxel_pooling(geom_feats, x, bx=None, dx=None, nx=None, plan=None, grid=None):
+def voxel_pooling(geom_feats, x, bx=None, dx=None, nx=None, plan=None, grid=None, channels_last=False):
     """Drop-in for ``ViewTransformerLiftSplatShoot.voxel_pooling`` (:141-181).
 
     geom_feats [B, N, D, H, W, 3] fp32 ego-frame xyz, x [B, N, D, H, W, C] ->
     [B, C * nz, ny, nx]. ``plan`` may carry a cached BevPlan for this geometry.
+    ``channels_last=True`` (single z bin): the same values in ``torch.channels_last`` memory - every pooled cell is
+    one coalesced row store of the gather kernel (no transposing epilogue) and the BEV encoder's NHWC conv kernels
+    read it as is.
     """
     B, N, D, H, W, C = x.shape
     Nprime = B * N * D * H * W
@@ -396,6 +406,11 @@ def voxel_pooling(geom_feats, x, bx=None, dx=None, nx=None, plan=None, grid=None
         plan = bev_plan_from_geom(geom_feats, B, bx, dx, nx, fast_axis=0, grid=grid,
                                   with_point_cell=bool(x.requires_grad and torch.is_grad_enabled()))
     x = x.reshape(Nprime, C)
+    if channels_last:
+        if plan.nz != 1:
+            raise NotImplementedError("voxel_pooling(channels_last=True) needs a single z bin (BEV)")
+        out = bev_pool_gather(x, plan, layout="cl")                       # [B, 1, ny, nx, C]
+        return out.view(plan.batch, plan.nslow, plan.nfast, C).permute(0, 3, 1, 2)
     return bev_pool_gather(x, plan, layout="bz_c")
 
 

@@ -96,8 +96,8 @@ class ViewTransformerLiftSplatShoot(nn.Module):
         ``frames`` > 1: batch = samples * frames and the splat returns the frames concatenated along the channels."""
         return _bp.bev_point_cells(geom, batch, fast_axis=0, grid=self._grid, frames=frames)
 
-    def voxel_pooling(self, geom_feats, x, plan=None):
-        return _bp.voxel_pooling(geom_feats, x, plan=plan, grid=self._grid)
+    def voxel_pooling(self, geom_feats, x, plan=None, channels_last=False):
+        return _bp.voxel_pooling(geom_feats, x, plan=plan, grid=self._grid, channels_last=channels_last)
 
     voxel_pooling_accelerated = voxel_pooling   # same result as the scatter_sum path (:184-240)
 

@@ -321,3 +321,27 @@ def test_sort_free_lift_splat_frames_is_the_channel_concat(cuda):
     torch.testing.assert_close(d2.grad, d1.grad, rtol=1e-5, atol=1e-6 * float(d1.grad.abs().max()))
     with pytest.raises(RuntimeError):
         vt.make_cells(geom, nf, frames=4)           # 6 sample-frames are not a multiple of 4
+
+
+@pytest.mark.parametrize("C", [64, 32, 80, 128])
+def test_channels_last_gather_is_bit_identical_to_the_nchw_layout(cuda, C):
+    """layout 'cl' / voxel_pooling(channels_last=True): finished cells are stored as whole rows straight from the
+    accumulator (no transposing epilogue); same accumulation order -> bit-identical values, forward and backward,
+    including empty cells (zero rows) and cells split between the two workers of a warp."""
+    vt = dbev.ViewTransformerLiftSplatShoot(grid_config=synthetic.NUSC_GRID, numC_input=8).to(cuda)
+    nf = 3
+    calib = [torch.from_numpy(a).to(cuda) for a in synthetic.make_calibration(nf, 6, seed=11)]
+    geom = vt.get_geometry(*calib)
+    torch.manual_seed(C)
+    x = torch.rand(nf, 6, 59, 16, 44, C, device=cuda)
+    for with_pc in (True, False):
+        plan = vt.make_plan(geom, nf, with_point_cell=with_pc)
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        ref = vt.voxel_pooling(geom, xa, plan=plan)
+        got = vt.voxel_pooling(geom, xb, plan=plan, channels_last=True)
+        assert got.shape == ref.shape and got.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(got, ref)
+        g = torch.rand_like(ref)
+        ref.backward(g)
+        got.backward(g.contiguous(memory_format=torch.channels_last))
+        assert torch.equal(xb.grad, xa.grad)
