@@ -17,6 +17,8 @@
 // HBM traffic = n*C*4 (rows) + n*4 (ids) + cells*8 + out  ~ algorithmic bytes.
 #include "bev_pool.cuh"
 
+#include <cstdlib>
+
 #include <atomic>
 
 #include "sort.cuh"
@@ -1201,14 +1203,18 @@ static int gather_forward_impl(const float* x, int C, const uint32_t* order, con
     const int cb = lpr * 4, nw = 32 / lpr;
     const size_t smem = (size_t)kPoolWarps * (nw * 2 * cb) * sizeof(float);
     int grid = 0;
-#define LAUNCH(L)                                                                        \
-  rc = persistent_grid(bev_pool_gather_fwd_kernel<L, false, 6, true>, smem, &grid);      \
+    static const int minb = getenv("DBEV_POOL_MINB") ? atoi(getenv("DBEV_POOL_MINB")) : 6;   // experiment switch
+#define LAUNCH_MB(L, MB)                                                                  \
+  rc = persistent_grid(bev_pool_gather_fwd_kernel<L, false, MB, true>, smem, &grid);     \
   if (rc != DBEV_OK) return rc;                                                          \
-  bev_pool_gather_fwd_kernel<L, false, 6, true><<<grid, kPoolBlock, smem, stream>>>(     \
+  bev_pool_gather_fwd_kernel<L, false, MB, true><<<grid, kPoolBlock, smem, stream>>>(    \
       x, order, cell_start, cell_end, items, n_items, out, g, none, sched_slot)
+#define LAUNCH(L)                                                                        \
+  if (minb == 8) { LAUNCH_MB(L, 8); } else if (minb == 7) { LAUNCH_MB(L, 7); } else if (minb == 5) { LAUNCH_MB(L, 5); } else { LAUNCH_MB(L, 6); }
     DBEV_SCHED_SLOT(sched_slot);
     DBEV_DISPATCH_LPR(lpr, LAUNCH);
 #undef LAUNCH
+#undef LAUNCH_MB
     DBEV_CHECK_LAUNCH("bev_pool_gather_fwd_kernel (channels-last)");
     return DBEV_OK;
   }
