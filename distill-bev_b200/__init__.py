@@ -12,8 +12,9 @@ from .plugin.ops.bev_pool import (BevPlan, GridSpec, PointCells, QuickCumsumCuda
 from .plugin.ops.voxel import (DynamicScatter, Voxelization, dynamic_scatter, voxel_layer,  # noqa: F401
                                voxelization)
 
-from .plugin.pillars import DynamicPillarFeatureNet, PointPillarsScatter, pillar_canvas  # noqa: F401
-from .plugin.view_transformer import ViewTransformerLiftSplatShoot, lss_geometry  # noqa: F401
+from .plugin.pillars import DynamicPillarFeatureNet, PFNLayer, PillarFeatureNet, PointPillarsScatter, pillar_canvas  # noqa: F401
+from .plugin.view_transformer import (ModulatedDeformConv2dPack, SELikeModule, ViewTransformerLiftSplatShoot,  # noqa: F401
+                                      ViewTransformerLSSBEVDepth, lss_geometry)
 from .plugin.distill import fgd  # noqa: F401
 from .plugin.distill import affinity, bevformer, detector  # noqa: F401
 from .plugin.distill.adaptation import Conv1x1Adaptation, conv1x1  # noqa: F401

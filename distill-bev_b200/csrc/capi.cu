@@ -15,6 +15,7 @@
 #include "distill_loss.cuh"
 #include "ms_deform_attn.cuh"
 #include "pillar.cuh"
+#include "pillar_hard.cuh"
 #include "sort.cuh"
 #include "spconv.cuh"
 #include "voxel_encoders.cuh"
@@ -509,6 +510,14 @@ int dbev_upsample_bilinear_forward(const float* in, int in_ld, int n, int h, int
 int dbev_upsample_bilinear_backward(const float* dout, int dout_ld, int n, int h, int w, int C, int H, int W,
                                     float* din, int din_ld, int accumulate, void* stream) {
   return upsample_bilinear_backward(dout, dout_ld, n, h, w, C, H, W, din, din_ld, accumulate, (cudaStream_t)stream);
+}
+
+int dbev_hard_pillar_encode(const float* voxels, const int* num_points, const int* coors, const int* m_dev, int m_max,
+                            int max_points, int nfeat, const float* voxel_size_xy_host2, float x_offset, float y_offset,
+                            const float* weight, int nout, const float* bn_scale, const float* bn_shift, int legacy,
+                            float* out, void* stream) {
+  return hard_pillar_encode(voxels, num_points, coors, m_dev, m_max, max_points, nfeat, voxel_size_xy_host2, x_offset,
+                            y_offset, weight, nout, bn_scale, bn_shift, legacy, out, (cudaStream_t)stream);
 }
 
 int dbev_spconv_tc_supported(int c_in, int c_out, int kvol) {

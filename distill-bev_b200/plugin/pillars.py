@@ -88,6 +88,77 @@ def pillar_scatter(voxel_features, coors, batch_size, ny, nx, channels_last=Fals
     return canvas
 
 
+class PFNLayer(nn.Module):
+    """voxel_encoders/utils.py:107-181 (sub-module names ``norm`` / ``linear`` as in the reference)."""
+
+    def __init__(self, in_channels, out_channels, norm_cfg=dict(type='BN1d', eps=1e-3, momentum=0.01), last_layer=False,
+                 mode='max'):
+        super().__init__()
+        self.name = 'PFNLayer'
+        self.last_vfe = last_layer
+        if not self.last_vfe:
+            out_channels = out_channels // 2
+        self.units = out_channels
+        self.norm = nn.BatchNorm1d(self.units, eps=norm_cfg.get('eps', 1e-5), momentum=norm_cfg.get('momentum', 0.1))
+        self.linear = nn.Linear(in_channels, self.units, bias=False)
+        assert mode in ['max', 'avg']
+        self.mode = mode
+
+
+class PillarFeatureNet(nn.Module):
+    """pillar_encoder.py:14-162: the hard-voxel pillar encoder of the shipped CenterPoint teacher
+    (configs/_base_/models/centerpoint_02pillar_second_secfpn_nus.py:6-13). Same constructor arguments and
+    ``state_dict`` keys (``pfn_layers.0.linear.weight``, ``pfn_layers.0.norm.*``). Eval mode (the DistillBEV teacher is
+    frozen, bevdet_distill.py:1591-1597): one fused kernel (csrc/pillar_hard.cu). Training mode needs batch statistics
+    over all points of all pillars and raises (train the teacher with the reference; distillation never does)."""
+
+    def __init__(self, in_channels=4, feat_channels=(64,), with_distance=False, with_cluster_center=True,
+                 with_voxel_center=True, voxel_size=(0.2, 0.2, 4), point_cloud_range=(0, -40, -3, 70.4, 40, 1),
+                 norm_cfg=dict(type='BN1d', eps=1e-3, momentum=0.01), mode='max', legacy=True, virtual=False):
+        super(PillarFeatureNet, self).__init__()
+        assert len(feat_channels) > 0
+        if len(feat_channels) != 1 or with_distance or not with_cluster_center or not with_voxel_center or virtual \
+                or mode != 'max':
+            raise NotImplementedError("PillarFeatureNet: only the shipped teacher configuration is implemented: one PFN "
+                                      "layer, cluster + voxel centre decorations, max pooling, no virtual points")
+        self.legacy = legacy
+        self.in_channels = in_channels + 5
+        self._with_distance, self._with_cluster_center, self._with_voxel_center = False, True, True
+        self.pfn_layers = nn.ModuleList([PFNLayer(self.in_channels, feat_channels[0], norm_cfg=norm_cfg, last_layer=True,
+                                                  mode=mode)])
+        self.vx, self.vy = voxel_size[0], voxel_size[1]
+        self.x_offset = self.vx / 2 + point_cloud_range[0]
+        self.y_offset = self.vy / 2 + point_cloud_range[1]
+        self.point_cloud_range = point_cloud_range
+        self.virtual = virtual
+
+    def forward(self, features, num_points, coors, count=None):
+        """features [M, max_points, F], num_points [M], coors [M, 4] (b, z, y, x) -> [M, nout]
+        (``count``: optional device int = number of valid voxels when the buffers are over-allocated)."""
+        if self.training:
+            raise NotImplementedError("PillarFeatureNet: training mode (batch statistics) is not implemented; the "
+                                      "distillation teacher is always eval()")
+        lib = _lib.load()
+        _lib.require_cuda(features, "features", torch.float32)
+        features = features.contiguous()
+        m, t, f = features.shape
+        layer = self.pfn_layers[0]
+        if layer.linear.weight.shape[1] != f + 5:
+            raise RuntimeError("features have %d channels, the PFN layer expects %d" % (f, layer.linear.weight.shape[1] - 5))
+        scale, shift = fold_bn(layer.norm)
+        out = torch.empty((m, layer.units), dtype=torch.float32, device=features.device)
+        npts = num_points.to(torch.int32).contiguous()
+        co = coors.to(torch.int32).contiguous()
+        with torch.cuda.device(features.device):
+            rc = lib.dbev_hard_pillar_encode(_lib.ptr(features), _lib.ptr(npts), _lib.ptr(co), _lib.ptr(count), m, t, f,
+                                             _lib.host_floats([self.vx, self.vy]), float(self.x_offset), float(self.y_offset),
+                                             _lib.ptr(layer.linear.weight.detach().float().contiguous()), layer.units,
+                                             _lib.ptr(scale), _lib.ptr(shift), 1 if self.legacy else 0, _lib.ptr(out),
+                                             _lib.stream_ptr(features.device))
+        _lib.check(rc, "dbev_hard_pillar_encode")
+        return out.squeeze()
+
+
 class DynamicPillarFeatureNet(nn.Module):
     """pillar_encoder.py:165-338 with one PFN layer (the only case the reference supports,
     ':219 TODO: currently only support one PFNLayer')."""

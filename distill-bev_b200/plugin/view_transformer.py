@@ -4,8 +4,9 @@ Mirrors ``ViewTransformerLiftSplatShoot`` (mmdet3d/models/necks/view_transformer
 same constructor arguments, same ``dx/bx/nx/frustum/D`` attributes and the methods the
 DistillBEV detectors call directly (bevdet_distill_more.py:398-421): ``get_geometry``,
 ``voxel_pooling``, ``voxel_pooling_accelerated`` — plus ``lift_splat`` (fused, no volume).
-The learned sub-modules of the BEVDepth variant (featnet / depthnet / SE / DCN, :283-344) are
-dense convolutions outside this package's kernels and are not re-implemented here.
+``ViewTransformerLSSBEVDepth`` (:283-344) adds the BEVDepth sub-modules the detectors call one by one
+(featnet / se / extra_depthnet / dcn / depthnet): small image-branch modules kept as torch modules, except
+``extra_depthnet`` which is this package's ResNetForBEVDet.
 """
 import torch
 from torch import nn
@@ -68,6 +69,13 @@ class ViewTransformerLiftSplatShoot(nn.Module):
         self.depthnet = nn.Conv2d(numC_input, self.D + numC_Trans, kernel_size=1, padding=0)
         self.accelerate = accelerate
         self._grid = _bp.GridSpec(bx, dx, nx)   # host copy: no device read-back per call
+        # dx / bx / nx are state_dict entries (as in the reference, which reads them on every call): a checkpoint
+        # with another grid must refresh the host copy too
+        self.register_load_state_dict_post_hook(ViewTransformerLiftSplatShoot._refresh_grid)
+
+    @staticmethod
+    def _refresh_grid(module, incompatible_keys):
+        module._grid = _bp.GridSpec(module.bx.detach().cpu(), module.dx.detach().cpu(), module.nx.detach().cpu())
 
     def get_depth_dist(self, x):
         return x.softmax(dim=1)
@@ -113,3 +121,85 @@ class ViewTransformerLiftSplatShoot(nn.Module):
         depth = self.get_depth_dist(x[:, :self.D])
         geom = self.get_geometry(rots, trans, intrins, post_rots, post_trans)
         return self.lift_splat(geom, depth, x[:, self.D:(self.D + self.numC_Trans)].contiguous(), B)
+
+
+class SELikeModule(nn.Module):
+    """view_transformer_mine.py:267-280 (camera-parameter gating of the depth branch): a 1x1 conv and a tiny MLP on
+    16 x 44 maps - plain torch modules, same sub-module names / state_dict keys."""
+
+    def __init__(self, in_channel=512, feat_channel=256, intrinsic_channel=33):
+        super(SELikeModule, self).__init__()
+        self.input_conv = nn.Conv2d(in_channel, feat_channel, kernel_size=1, padding=0)
+        self.fc = nn.Sequential(nn.BatchNorm1d(intrinsic_channel), nn.Linear(intrinsic_channel, feat_channel), nn.Sigmoid())
+
+    def forward(self, x, cam_params):
+        x = self.input_conv(x)
+        b, c, _, _ = x.shape
+        y = self.fc(cam_params).view(b, c, 1, 1)
+        return x * y.expand_as(x)
+
+
+class ModulatedDeformConv2dPack(nn.Module):
+    """mmcv 1.6.0 'DCNv2' (mmcv/ops/modulated_deform_conv.py; third party, parity unpinned): parameters ``weight``,
+    ``bias``, ``conv_offset.{weight,bias}`` (zero-initialised offsets), forward through
+    torchvision.ops.deform_conv2d with the sigmoid mask - same offset channel order (y, x interleaved per tap)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, deform_groups=1, bias=True):
+        super().__init__()
+        k = kernel_size
+        self.stride, self.padding, self.dilation, self.deform_groups = stride, padding, dilation, deform_groups
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, k, k))
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+        n = in_channels * k * k
+        nn.init.uniform_(self.weight, -1.0 / n ** 0.5, 1.0 / n ** 0.5)       # mmcv: uniform(-stdv, stdv), stdv = 1/sqrt(n)
+        self.conv_offset = nn.Conv2d(in_channels, deform_groups * 3 * k * k, kernel_size=k, stride=stride, padding=padding,
+                                     dilation=dilation, bias=True)
+        nn.init.zeros_(self.conv_offset.weight)
+        nn.init.zeros_(self.conv_offset.bias)
+
+    def forward(self, x):
+        from torchvision.ops import deform_conv2d
+        out = self.conv_offset(x)
+        o1, o2, mask = torch.chunk(out, 3, dim=1)
+        return deform_conv2d(x, torch.cat((o1, o2), dim=1), self.weight, self.bias, stride=self.stride,
+                             padding=self.padding, dilation=self.dilation, mask=torch.sigmoid(mask))
+
+
+class ViewTransformerLSSBEVDepth(ViewTransformerLiftSplatShoot):
+    """view_transformer_mine.py:283-344. Same constructor arguments, attributes (``featnet``, ``se``, ``extra_depthnet``,
+    ``dcn``, ``depthnet``, ``loss_depth_weight`` - the detectors call them one by one, bevdet_distill_more.py:398-421)
+    and state_dict keys. ``extra_depthnet`` is this package's ResNetForBEVDet (tcgen05 training kernels); the 1x1 convs,
+    the SE gate and the deformable conv act on 16 x 44 image-feature maps and stay torch modules (image branch, outside
+    SURVEY §8 (a)); geometry and lift+splat are the kernels of the base class - ``forward`` never builds the
+    [B, N, D, fH, fW, C] volume."""
+
+    def __init__(self, extra_depth_net, loss_depth_weight, se_config=dict(), dcn_config=dict(bias=True), **kwargs):
+        super(ViewTransformerLSSBEVDepth, self).__init__(**kwargs)
+        from .bev_encoder import ResNetForBEVDet
+        self.loss_depth_weight = loss_depth_weight
+        cfg = dict(extra_depth_net)
+        if cfg.pop("type", "ResNetForBEVDet") != "ResNetForBEVDet":
+            raise NotImplementedError("extra_depth_net type %r" % extra_depth_net.get("type"))
+        self.extra_depthnet = ResNetForBEVDet(**cfg)
+        ch = extra_depth_net['num_channels'][0]
+        self.featnet = nn.Conv2d(self.numC_input, self.numC_Trans, kernel_size=1, padding=0)
+        self.depthnet = nn.Conv2d(ch, self.D, kernel_size=1, padding=0)
+        self.dcn = nn.Sequential(ModulatedDeformConv2dPack(ch, ch, kernel_size=3, stride=1, padding=1, dilation=1,
+                                                           deform_groups=1, **dcn_config), nn.BatchNorm2d(ch))
+        self.se = SELikeModule(self.numC_input, feat_channel=ch, **se_config)
+
+    def forward(self, input):
+        x, rots, trans, intrins, post_rots, post_trans, depth_gt = input
+        B, N, C, H, W = x.shape
+        x = x.view(B * N, C, H, W)
+        img_feat = self.featnet(x)
+        cam_params = torch.cat([intrins.reshape(B * N, -1), post_rots.reshape(B * N, -1), post_trans.reshape(B * N, -1),
+                                rots.reshape(B * N, -1), trans.reshape(B * N, -1)], dim=1)
+        depth_feat = self.se(x, cam_params)
+        depth_feat = self.extra_depthnet(depth_feat)[0]
+        depth_feat = self.dcn(depth_feat)
+        depth_digit = self.depthnet(depth_feat)
+        depth_prob = self.get_depth_dist(depth_digit)
+        geom = self.get_geometry(rots, trans, intrins, post_rots, post_trans)
+        bev_feat = self.lift_splat(geom, depth_prob, img_feat.contiguous(), B)      # lift + splat fused
+        return bev_feat, depth_digit

@@ -490,6 +490,19 @@ int dbev_upsample_bilinear_backward(const float* dout, int dout_ld, int n, int h
                                     float* din, int din_ld, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * PillarFeatureNet.forward in eval mode (mmdet3d/models/voxel_encoders/pillar_encoder.py:95-162 + PFNLayer
+ * utils.py:107-181; one PFN layer, cluster + voxel-centre decorations, max pooling: the shipped pillar teacher,
+ * configs/_base_/models/centerpoint_02pillar_second_secfpn_nus.py:6-13). voxels[m_max, max_points, F] / num_points[m_max]
+ * / coors[m_max, 4] (b, z, y, x) as hard_voxelize + the batch padding produce them; m_dev (nullable) = device voxel count;
+ * weight[nout, F + 5] (nn.Linear), bn_scale / bn_shift = folded BatchNorm1d; legacy != 0 reproduces the in-place
+ * centre offset of legacy=True (:132-139). out[m_max, nout].
+ * ------------------------------------------------------------------------ */
+int dbev_hard_pillar_encode(const float* voxels, const int* num_points, const int* coors, const int* m_dev, int m_max,
+                            int max_points, int nfeat, const float* voxel_size_xy_host2, float x_offset, float y_offset,
+                            const float* weight, int nout, const float* bn_scale, const float* bn_shift, int legacy,
+                            float* out, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * Cross-modal feature distillation loss (FGD-style), BEVDetDistill
  * (mmdet3d/models/detectors/bevdet_distill.py). The reference has no native
  * interface for this path: it is ~20 torch kernels plus numpy/numba on the

@@ -57,3 +57,34 @@ def pillar_scatter(voxel_feats, coors, batch_size, ny, nx):
     canvas = np.zeros((batch_size, vf.shape[1], ny, nx), dtype=F32)
     canvas[co[:, 0], :, co[:, 2], co[:, 3]] = vf
     return canvas
+
+
+def hard_pillar_encode(voxels, num_points, coors, weight, bn_weight, bn_bias, bn_mean, bn_var, bn_eps, voxel_size,
+                       point_cloud_range, legacy=False):
+    """PillarFeatureNet.forward in eval mode (pillar_encoder.py:95-162; PFNLayer utils.py:107-181, one layer, max):
+    voxels [M, T, F] f32 (padded rows as hard_voxelize leaves them), num_points [M], coors [M, 4] (b, z, y, x)
+    -> [M, nout]. The mean divides the sum over ALL T rows by num_points (:121-124); padded rows are zeroed before
+    the linear layer (:149-153) and therefore enter the maximum as relu(BN(0)); legacy=True: f_center is a view of the
+    raw features, so x / y of the raw block hold the centre offsets too (:132-139)."""
+    v = np.asarray(voxels, dtype=F32).copy()
+    n = np.asarray(num_points).astype(np.int64)
+    co = np.asarray(coors).astype(np.int64)
+    M, T, F = v.shape
+    mean = (v[:, :, :3].sum(axis=1, keepdims=True, dtype=F32) / n.astype(F32).reshape(-1, 1, 1)).astype(F32)
+    f_cluster = (v[:, :, :3] - mean).astype(F32)
+    vx, vy = F32(voxel_size[0]), F32(voxel_size[1])
+    x_off = F32(float(voxel_size[0]) / 2 + float(point_cloud_range[0]))
+    y_off = F32(float(voxel_size[1]) / 2 + float(point_cloud_range[1]))
+    cxs = ((co[:, 3].astype(F32) * vx).astype(F32) + x_off).astype(F32).reshape(-1, 1)
+    cys = ((co[:, 2].astype(F32) * vy).astype(F32) + y_off).astype(F32).reshape(-1, 1)
+    f_center = np.stack([v[:, :, 0] - cxs, v[:, :, 1] - cys], 2).astype(F32)
+    raw = v.copy()
+    if legacy:
+        raw[:, :, :2] = f_center
+    feats = np.concatenate([raw, f_cluster, f_center], axis=2)
+    mask = (np.arange(T).reshape(1, T) < n.reshape(-1, 1)).astype(F32)[:, :, None]
+    feats = (feats * mask).astype(np.float64)
+    y = feats @ np.asarray(weight, dtype=np.float64).T
+    scale = np.asarray(bn_weight, np.float64) / np.sqrt(np.asarray(bn_var, np.float64) + float(bn_eps))
+    y = (y - np.asarray(bn_mean, np.float64)) * scale + np.asarray(bn_bias, np.float64)
+    return np.maximum(y, 0.0).max(axis=1).astype(F32)

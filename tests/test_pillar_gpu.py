@@ -133,3 +133,33 @@ def test_view_transformer_module_config1(cuda):
     feats = torch.rand(1, 6, 32, 16, 44, device=cuda)
     bev = vt((feats,) + tuple(_t(a, cuda) for a in calib))
     assert tuple(bev.shape) == (1, 64, 128, 128) and torch.isfinite(bev).all()
+
+
+def test_bevdepth_view_transformer_forward_backward(cuda):
+    """ViewTransformerLSSBEVDepth.forward == the same sub-modules composed like the reference's forward
+    (view_transformer_mine.py:312-344: lift volume + voxel_pooling), without building the volume; gradients reach the
+    depth branch (se / extra_depthnet / dcn / depthnet) and featnet."""
+    import distill_bev_b200 as dbev
+    from distill_bev_b200 import synthetic
+    torch.manual_seed(0)
+    vt = dbev.ViewTransformerLSSBEVDepth(
+        extra_depth_net=dict(type='ResNetForBEVDet', numC_input=256, num_layer=[1, ], num_channels=[256, ], stride=[1, ]),
+        loss_depth_weight=100.0, grid_config=synthetic.NUSC_GRID, numC_input=128, numC_Trans=64).to(cuda).train()
+    B, N = 1, 6
+    calib = [torch.from_numpy(a).to(cuda) for a in synthetic.make_calibration(B, N, seed=2)]
+    rots, trans, intrins, post_rots, post_trans = [c.view(B, N, *c.shape[2:]) for c in calib]
+    x = torch.randn(B, N, 128, 16, 44, device=cuda, requires_grad=True)
+    bev, depth_digit = vt((x, rots, trans, intrins, post_rots, post_trans, None))
+    assert tuple(bev.shape) == (B, 64, 128, 128) and tuple(depth_digit.shape) == (B * N, 59, 16, 44)
+    with torch.no_grad():
+        xf = x.view(B * N, 128, 16, 44)
+        img_feat = vt.featnet(xf)
+        depth = vt.get_depth_dist(depth_digit)
+        volume = (depth.unsqueeze(1) * img_feat.unsqueeze(2)).view(B, N, 64, 59, 16, 44).permute(0, 1, 3, 4, 5, 2)
+        want = vt.voxel_pooling(vt.get_geometry(rots, trans, intrins, post_rots, post_trans), volume.contiguous())
+    torch.testing.assert_close(bev.detach(), want, rtol=1e-4, atol=1e-5 * float(want.abs().max()))
+    (bev.sum() + depth_digit.sum()).backward()
+    for p in (vt.featnet.weight, vt.depthnet.weight, vt.se.input_conv.weight, vt.dcn[0].weight,
+              vt.extra_depthnet.layers[0][0].conv1.weight):
+        assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().sum()) > 0
+    assert torch.isfinite(x.grad).all()
