@@ -26,6 +26,7 @@ from .plugin.dense_teacher import SECOND, SECONDFPN  # noqa: F401
 from .plugin.student_convs import Conv2dTC, conv2d_tc, conv2d_tc_supported, convert_convs  # noqa: F401
 from .plugin.bev_encoder import BasicBlock, FPN_LSS, ResNetForBEVDet, conv_bn_act, upsample_cat  # noqa: F401
 from .plugin.ops import conv_train  # noqa: F401
+from .plugin import bev_encoder  # noqa: F401
 from .plugin.bevdepth import get_depth_loss, shift_feature  # noqa: F401
 from .plugin.center_targets import CenterHeadTargets  # noqa: F401
 from .graph import CapturedStep  # noqa: F401

@@ -37,7 +37,13 @@ class _ConvBNActFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gamma, beta, residual, bn, owner, stride, pad, relu):
         xh = ct.as_nhwc(x)
         co, ci, kh, kw = weight.shape
-        w_fwd, w_bwd = ct.pack_weights_train(weight, stride)      # the backward reads w_bwd (same step, same weights)
+        pre = getattr(owner, "_dbev_prepacked", None)
+        if pre is not None and pre[0] == (weight.data_ptr(), weight._version):
+            w_fwd, w_bwd, ready = pre[1]                           # packed ahead of time on the side stream (prepack())
+            if ready is not None:
+                torch.cuda.current_stream(x.device).wait_event(ready)
+        else:
+            w_fwd, w_bwd = ct.pack_weights_train(weight, stride)   # the backward reads w_bwd (same step, same weights)
         y = ct.conv_forward(xh, w_fwd, co, kh, kw, stride, pad, bias=bias.detach() if bias is not None else None)
         rh = ct.as_nhwc(residual) if residual is not None else None
         fwd = None
@@ -93,7 +99,21 @@ class _ConvBNActFn(torch.autograd.Function):
         dx = None
         if need[0]:
             dx = ct.as_nchw(ct.conv_input_grad(dy, w_bwd, ci, kh, kw, stride, pad, in_hw))
-        dw = ct.conv_weight_grad(xh, dy, kh, kw, stride, pad) if need[1] else None
+        dw = None
+        if need[1]:
+            side = ct.side_stream(dy.device)
+            if side is None:
+                dw = ct.conv_weight_grad(xh, dy, kh, kw, stride, pad)
+            else:
+                # nothing in the backward chain reads dW: run it beside the input-gradient chain (joined by
+                # ct.join_side_stream() before the optimizer / all-reduce)
+                cur = torch.cuda.current_stream(dy.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    dw = ct.conv_weight_grad(xh, dy, kh, kw, stride, pad)
+                for t in (xh, dy, dw):
+                    t.record_stream(side)
+                dw.record_stream(cur)
         if d_res is not None:
             d_res = ct.as_nchw(d_res) if need[5] else None
         return dx, dw, d_bias, d_gamma, d_beta, d_res, None, None, None, None, None
@@ -108,6 +128,31 @@ def _stats_ws(owner, y):
         cache = (key, ct.stats_workspace(rows, c, y.device))
         owner._dbev_stats_ws = cache
     return cache[1]
+
+
+def prepack(module):
+    """Pack the weights of every conv of ``module`` that conv_bn_act will run, now, on the side stream (or the current
+    stream when overlap is off): one pass per layer, off the critical path of the step that follows. Call it once per
+    step after the optimizer has updated the weights; a conv whose weight changed since falls back to packing in its
+    forward."""
+    convs = [m for m in module.modules() if isinstance(m, nn.Conv2d) and m.weight.is_cuda and m.groups == 1
+             and m.kernel_size[0] == m.kernel_size[1] and m.kernel_size[0] in (1, 3)]
+    if not convs:
+        return
+    dev = convs[0].weight.device
+    side = ct.side_stream(dev)
+    cur = torch.cuda.current_stream(dev)
+    if side is not None:
+        side.wait_stream(cur)
+    with torch.cuda.stream(side if side is not None else cur):
+        for m in convs:
+            w_fwd, w_bwd = ct.pack_weights_train(m.weight, m.stride[0])
+            ready = None
+            if side is not None:
+                ready = torch.cuda.Event()
+                ready.record(side)
+                w_fwd.record_stream(cur), w_bwd.record_stream(cur)
+            m._dbev_prepacked = ((m.weight.data_ptr(), m.weight._version), (w_fwd, w_bwd, ready))
 
 
 def conv_bn_act(x, conv, bn=None, residual=None, relu=True):

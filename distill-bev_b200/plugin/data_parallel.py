@@ -95,14 +95,26 @@ class GradientAllReduce(object):
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         torch._foreach_copy_(grads, views)                               # scatter + cast back, in place
 
+    def _join_producers(self, stream):
+        """Weight gradients may have been computed on the conv kernels' side stream (plugin/ops/conv_train.py)."""
+        try:
+            from .ops import conv_train as ct
+        except Exception:  # noqa: BLE001 - CPU-only installs (gloo tests) have no CUDA library
+            return
+        dev = self.flat[0].device
+        if dev.type == "cuda":
+            ct.join_side_stream(dev, stream)
+
     def _launch(self, bi):
         if self.world == 1:
             return
         if self._stream is not None:
             self._stream.wait_stream(torch.cuda.current_stream(self.flat[bi].device))
+            self._join_producers(self._stream)
             with torch.cuda.stream(self._stream):
                 self._reduce_bucket(bi)
         else:
+            self._join_producers(None)
             self._reduce_bucket(bi)
 
     def finish(self):
@@ -116,6 +128,7 @@ class GradientAllReduce(object):
             if self._stream is not None:
                 torch.cuda.current_stream(self.flat[0].device).wait_stream(self._stream)
             return
+        self._join_producers(None)
         for bi in range(len(self.buckets)):
             self._reduce_bucket(bi)
 

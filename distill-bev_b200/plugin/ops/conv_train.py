@@ -17,6 +17,38 @@ from ... import _lib
 
 _TILE_N = (256, 128, 64)
 
+# ---------------------------------------------------------------------------------------------------------------
+# Side stream for work that is off the critical path of a training step: weight gradients (nothing in the backward
+# chain depends on dW; only the optimizer / gradient all-reduce does) and the per-step weight packing (depends only on
+# the weights). The small-map layers of the BEV encoder (16 x 16 ... 64 x 64) do not fill 148 SMs, so these launches
+# overlap the input-gradient chain instead of queueing behind it. Off by default (plain single-stream semantics);
+# bench.py / a training loop turns it on and must call ``join_side_stream()`` before reading the weight gradients
+# (GradientAllReduce does it by itself).
+_side = {"enabled": False, "streams": {}}
+
+
+def set_side_stream(enabled):
+    _side["enabled"] = bool(enabled)
+
+
+def side_stream(device):
+    """The side stream of ``device`` if overlap is enabled, else None."""
+    if not _side["enabled"]:
+        return None
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _side["streams"].get(key)
+    if st is None:
+        st = _side["streams"][key] = torch.cuda.Stream(torch.device("cuda", key))
+    return st
+
+
+def join_side_stream(device, stream=None):
+    """Make ``stream`` (default: the current stream) wait for everything queued on the side stream."""
+    st = side_stream(device)
+    if st is not None:
+        (stream if stream is not None else torch.cuda.current_stream(st.device)).wait_stream(st)
+
 
 def nhwc_ld(t, name="tensor"):
     """Row stride (floats) of an NHWC tensor / channel slice; raises if the layout is anything else."""

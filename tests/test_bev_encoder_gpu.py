@@ -383,3 +383,31 @@ def test_mlp_and_3x3_adaptations(cuda):
     assert _relerr(c3(x), F.conv2d(x, c3.weight, c3.bias, 1, 1).detach()) <= 3e-3
     with pytest.raises(NotImplementedError):
         A.TwoLayer(256, out_features=128, kernel_size=4, stride=4).to(cuda)(x)
+
+
+def test_side_stream_overlap_gives_identical_gradients(cuda):
+    """conv_train.set_side_stream(True): weight gradients and prepack() run on a side stream beside the input-gradient
+    chain; after join_side_stream() every gradient is bit-identical to the single-stream run."""
+    from distill_bev_b200 import bev_encoder
+    torch.manual_seed(7)
+    net = _OurEncoder().to(cuda).train()
+    x = torch.relu(torch.randn(2, 128, 32, 32, device=cuda)).contiguous(memory_format=torch.channels_last)
+    g = torch.randn(2, 256, 32, 32, device=cuda).contiguous(memory_format=torch.channels_last)
+    state = copy.deepcopy(net.state_dict())
+    res = []
+    try:
+        for side in (False, True):
+            net.load_state_dict(state)
+            net.zero_grad(set_to_none=True)
+            ct.set_side_stream(side)
+            if side:
+                bev_encoder.prepack(net)
+            xin = x.clone().requires_grad_(True)
+            net(xin).backward(g)
+            ct.join_side_stream(cuda)
+            torch.cuda.synchronize()
+            res.append([p.grad.clone() for p in net.parameters()] + [xin.grad.clone()])
+    finally:
+        ct.set_side_stream(False)
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
