@@ -27,6 +27,7 @@ from .plugin.student_convs import Conv2dTC, conv2d_tc, conv2d_tc_supported, conv
 from .plugin.bev_encoder import BasicBlock, FPN_LSS, ResNetForBEVDet, conv_bn_act, upsample_cat  # noqa: F401
 from .plugin.ops import conv_train  # noqa: F401
 from .plugin import bev_encoder  # noqa: F401
+from .plugin.bevformer_attention import MSDeformableAttention3D, SpatialCrossAttention  # noqa: F401
 from .plugin.bevdepth import get_depth_loss, shift_feature  # noqa: F401
 from .plugin.center_targets import CenterHeadTargets  # noqa: F401
 from .graph import CapturedStep  # noqa: F401

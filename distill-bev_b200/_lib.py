@@ -143,6 +143,8 @@ SIGNATURES = {
     "dbev_relu_mask_backward": (_c_int, [_ptr, _c_int, _ptr, _c_int, _c_ll, _c_int, _ptr, _c_int, _c_int, _ptr]),
     "dbev_upsample_bilinear_forward": (_c_int, [_ptr] + [_c_int] * 7 + [_ptr, _c_int, _ptr]),
     "dbev_upsample_bilinear_backward": (_c_int, [_ptr] + [_c_int] * 7 + [_ptr, _c_int, _c_int, _ptr]),
+    "dbev_sca_gather_rows": (_c_int, [_ptr, _ptr, _ptr] + [_c_int] * 5 + [_c_ll, _c_ll, _c_ll, _ptr, _ptr]),
+    "dbev_sca_reduce_rows": (_c_int, [_ptr, _ptr, _ptr] + [_c_int] * 5 + [_ptr, _ptr]),
     "dbev_hard_pillar_encode": (_c_int, [_ptr, _ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _fptr, _c_float, _c_float, _ptr, _c_int,
                                          _ptr, _ptr, _c_int, _ptr, _ptr]),
     "dbev_spconv_tc_supported": (_c_int, [_c_int, _c_int, _c_int]),

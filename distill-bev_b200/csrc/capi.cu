@@ -16,6 +16,7 @@
 #include "ms_deform_attn.cuh"
 #include "pillar.cuh"
 #include "pillar_hard.cuh"
+#include "sca_rebatch.cuh"
 #include "sort.cuh"
 #include "spconv.cuh"
 #include "voxel_encoders.cuh"
@@ -510,6 +511,17 @@ int dbev_upsample_bilinear_forward(const float* in, int in_ld, int n, int h, int
 int dbev_upsample_bilinear_backward(const float* dout, int dout_ld, int n, int h, int w, int C, int H, int W,
                                     float* din, int din_ld, int accumulate, void* stream) {
   return upsample_bilinear_backward(dout, dout_ld, n, h, w, C, H, W, din, din_ld, accumulate, (cudaStream_t)stream);
+}
+
+int dbev_sca_gather_rows(const float* in, const int* idx, const float* scale, int bs, int cams, int max_len, int nq, int C,
+                         long long in_cam_stride, long long in_batch_stride, long long in_query_stride, float* out, void* stream) {
+  return sca_gather_rows(in, idx, scale, bs, cams, max_len, nq, C, in_cam_stride, in_batch_stride, in_query_stride, out,
+                         (cudaStream_t)stream);
+}
+
+int dbev_sca_reduce_rows(const float* in, const int* pos, const float* scale, int bs, int cams, int max_len, int nq, int C,
+                         float* out, void* stream) {
+  return sca_reduce_rows(in, pos, scale, bs, cams, max_len, nq, C, out, (cudaStream_t)stream);
 }
 
 int dbev_hard_pillar_encode(const float* voxels, const int* num_points, const int* coors, const int* m_dev, int m_max,

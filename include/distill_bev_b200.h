@@ -490,6 +490,23 @@ int dbev_upsample_bilinear_backward(const float* dout, int dout_ld, int n, int h
                                     float* din, int din_ld, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------ *
+ * Per-camera re-batching of BEV queries in BEVFormer's SpatialCrossAttention.forward
+ * (mmdet3d/models/transformer_modules/spatial_cross_attention.py:128-167; the reference uses Python double loops over
+ * batch x camera and nonzero() index lists). idx[cams, max_len] = k-th query seen by the camera or -1;
+ * pos[cams, nq] = rank of the query in the camera's list or -1; scale[bs, nq] nullable.
+ *   gather: out[bs, cams, max_len, C] = scale * in[b, idx, :] (0 for padding); `in` rows addressed by
+ *           cam*in_cam_stride + b*in_batch_stride + q*in_query_stride (floats): [bs, nq, C] (camera stride 0) and
+ *           [cams, bs, nq, C] sources both work
+ *   reduce: out[bs, nq, C] = scale * sum over cameras of in[b, cam, pos, :] (fixed camera order: deterministic)
+ * forward re-batch = gather (backward: reduce); forward slot accumulation / count = reduce with scale = 1 / count
+ * (backward: gather with the same scale).
+ * ------------------------------------------------------------------------ */
+int dbev_sca_gather_rows(const float* in, const int* idx, const float* scale, int bs, int cams, int max_len, int nq, int C,
+                         long long in_cam_stride, long long in_batch_stride, long long in_query_stride, float* out, void* stream);
+int dbev_sca_reduce_rows(const float* in, const int* pos, const float* scale, int bs, int cams, int max_len, int nq, int C,
+                         float* out, void* stream);
+
+/* ------------------------------------------------------------------------ *
  * PillarFeatureNet.forward in eval mode (mmdet3d/models/voxel_encoders/pillar_encoder.py:95-162 + PFNLayer
  * utils.py:107-181; one PFN layer, cluster + voxel-centre decorations, max pooling: the shipped pillar teacher,
  * configs/_base_/models/centerpoint_02pillar_second_secfpn_nus.py:6-13). voxels[m_max, max_points, F] / num_points[m_max]
