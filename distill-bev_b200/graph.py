@@ -1,11 +1,17 @@
 """CUDA-graph capture of a hot-path step.
 
-Every entry point of the library is stream-ordered and free of host synchronisation (outputs and
-workspaces come from torch's caching allocator, device-side counts stay on the device), so a whole
-training-step slice - geometry, plan, lift+splat forward/backward, pillar canvas, adaptation conv
-and distillation loss with its backward - can be captured ONCE and replayed: the ~100 launches
-of a step are then issued by the GPU front end instead of Python + ctypes (the step is otherwise
-bound by CPU issue time, see profiles/r01_step_timeline.txt).
+The entry points of the training step are stream-ordered and free of host synchronisation (outputs and
+workspaces come from torch's caching allocator, device-side counts stay on the device), so the whole step -
+geometry, point cells / plan, lift+splat forward/backward, the student BEV encoder (tcgen05 forward / input
+gradient / weight gradient, BatchNorm, upsampling), pillar canvas + teacher convs, adaptation conv, distillation
+loss with its backward, the NCCL gradient all-reduce and the fused optimizer step - is captured ONCE and replayed:
+its ~350 launches are then issued by the GPU front end instead of Python + ctypes (the step is otherwise bound by
+CPU issue time, see profiles/r01_step_timeline.txt).
+
+NOT capturable (they return host-side counts, as the reference's API implies): ``Voxelization`` / ``hard_voxelize``
+(voxel count as a Python int; ``voxel_layer.hard_voxelize_device`` keeps it on the device),
+``dynamic_point_to_voxel_forward`` (output row count), ``affinity.select_rows`` (row offsets), the spconv
+rulebook builders (output counts), ``SpatialCrossAttention`` (longest per-camera query list).
 
 Rules for the captured callable: read inputs only from tensors that live across replays (copy the
 new batch INTO them before each replay), no `.item()` / `.cpu()`, no pageable host-to-device

@@ -8,8 +8,8 @@ mmdet3d/models/detectors/bevdet_distill.py:735-748) together with the masked-cel
     kd_affinity_loss = sum_b weight * mean(criterion(T_b T_b^T, S_b S_b^T))
 
 with criterion = mmdet SmoothL1Loss (beta 1) / L1Loss / MSELoss, reduction 'mean'. The K x K
-gram matrices are never written. ``affinity_split`` > 1 draws a random partition
-(torch.randperm, :741-743) and is not implemented (the shipped configs use 1).
+gram matrices are never written. ``affinity_split`` > 1 partitions every sample's rows at random
+(torch.randperm drawn like the reference, :741-743, or caller-given permutations) and sums the per-part losses.
 """
 import torch
 from torch.autograd import Function

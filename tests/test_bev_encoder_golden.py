@@ -84,3 +84,63 @@ def test_forward_backward_match_the_reference_classes(cuda):
     xg = torch.from_numpy(ref["x_grad"]).to(cuda)
     cos = torch.nn.functional.cosine_similarity(xin.grad.flatten(), xg.flatten(), dim=0)
     assert float(cos) >= 0.98
+
+
+ADAPT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "adaptation_3layer.npz")
+
+
+def _adaptation_modules():
+    from distill_bev_b200.plugin.distill import adaptation as A
+    p = dict(adaptation_type=["upsample_3layer", "mlp"], teacher_adaptation_type="identity",
+             student_adaptation_params=dict(kernel_size=1, stride=1, upsample_factor=4), student_channels=[128, 128],
+             teacher_channels=[128, 128], spatial_mask=False)
+    return A.build_adaptation_layers(p)[0]
+
+
+def test_adaptation_state_dict_keys_match_the_reference_classes():
+    """'upsample_3layer' = nn.Sequential(nn.Upsample, ThreeLayer) and 'mlp' = Mlp as BEVDetDistill.__init__ builds them
+    (bevdet_distill.py:230-301): key-for-key the state_dict of the UNMODIFIED classes (tools/make_golden_bev_encoder.py)."""
+    ref = np.load(ADAPT)
+    layers = _adaptation_modules()
+    assert list(layers[0].state_dict().keys()) == [str(k) for k in ref["keys"]]
+    assert list(layers[1].state_dict().keys()) == [str(k) for k in ref["mlp_keys"]]
+    for k, v in layers[0].state_dict().items():
+        assert tuple(v.shape) == tuple(ref["sd/" + k].shape), k
+
+
+@pytest.mark.gpu
+def test_upsample_3layer_and_mlp_match_the_reference_classes(cuda):
+    ref = np.load(ADAPT)
+    layers = _adaptation_modules()
+    sd = {str(k): torch.from_numpy(ref["sd/" + str(k)]) for k in ref["keys"]}
+    for k in list(sd):                     # the fixture holds the state AFTER one training forward: reset the statistics
+        if k.endswith("running_mean"):
+            sd[k] = torch.zeros_like(sd[k])
+        elif k.endswith("running_var"):
+            sd[k] = torch.ones_like(sd[k])
+        elif k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros_like(sd[k])
+    up3 = layers[0]
+    up3.load_state_dict(sd, strict=True)
+    up3 = up3.to(cuda).train()
+    x = torch.from_numpy(ref["x"]).to(cuda).requires_grad_(True)
+    y = up3(x)
+    want = torch.from_numpy(ref["y"]).to(cuda)
+    assert float((y - want).abs().max()) <= 3e-3 * float(want.abs().max())          # three TF32 1x1 convs
+    g = torch.randn(tuple(want.shape), generator=torch.Generator().manual_seed(10)).to(cuda)
+    y.backward(g)
+    xg = torch.from_numpy(ref["x_grad"]).to(cuda)
+    assert float(torch.nn.functional.cosine_similarity(x.grad.flatten(), xg.flatten(), dim=0)) >= 0.999
+    assert float((x.grad - xg).abs().max()) <= 5e-2 * float(xg.abs().max())       # TF32 + 3 BN/ReLU layers (see test_bev_encoder_gpu)
+    for k, p in up3.named_parameters():
+        w = torch.from_numpy(ref["grad/" + k]).to(cuda)
+        assert float((p.grad - w).abs().max()) <= 5e-2 * float(w.abs().max()) + 1e-6, k
+    for k, v in up3.state_dict().items():  # running statistics after the forward, like torch
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            torch.testing.assert_close(v, torch.from_numpy(ref["sd/" + k]).to(cuda), rtol=5e-3, atol=5e-4)
+    mlp = layers[1]
+    mlp.load_state_dict({str(k): torch.from_numpy(ref["mlp_sd/" + str(k)]) for k in ref["mlp_keys"]}, strict=True)
+    mlp = mlp.to(cuda)
+    ym = mlp(torch.from_numpy(ref["mlp_x"]).to(cuda))
+    wm = torch.from_numpy(ref["mlp_y"]).to(cuda)
+    assert float((ym - wm).abs().max()) <= 3e-3 * float(wm.abs().max())

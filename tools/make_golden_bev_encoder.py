@@ -103,5 +103,47 @@ def main():
     print("wrote %s (%d state_dict entries, %.1f MB)" % (path, len(keys), os.path.getsize(path) / 1e6))
 
 
+def adaptation_golden():
+    """'upsample_3layer' adaptation (bevdet_distill.py:275-301) from the UNMODIFIED ThreeLayer class (:99-130), cut out of
+    bevdet_distill.py with `ast` (the module itself needs mmcv / mmdet / cv2): nn.Sequential(nn.Upsample(x4, bilinear,
+    align_corners), ThreeLayer(128 -> 128, kernel_size 1, stride 1)) in training mode on the CPU, and an Mlp (:48-68).
+    Writes tests/golden/adaptation_3layer.npz."""
+    import ast
+    from functools import partial
+    from torch import nn
+    from torch.nn.modules.utils import _pair
+    path = os.path.join(ref_import.REF_ROOT, "mmdet3d/models/detectors/bevdet_distill.py")
+    tree = ast.parse(open(path).read())
+    ns = dict(nn=nn, torch=torch, partial=partial, _pair=_pair, build_norm_layer=None)
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name in ("Mlp", "TwoLayer", "ThreeLayer"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Upsample(scale_factor=4, mode="bilinear", align_corners=True),
+                        ns["ThreeLayer"](in_features=128, out_features=128, kernel_size=1, stride=1)).train()
+    mlp = ns["Mlp"](in_features=128, out_features=128)
+    gen = torch.Generator().manual_seed(9)
+    x = torch.relu(torch.randn(2, 128, 5, 5, generator=gen)).requires_grad_(True)
+    y = net(x)
+    g = torch.randn(y.shape, generator=torch.Generator().manual_seed(10))      # the test re-draws it from the seed
+    y.backward(g)
+    xm = torch.relu(torch.randn(2, 128, 8, 8, generator=gen))
+    out = {"x": x.detach().numpy(), "y": y.detach().numpy(), "x_grad": x.grad.numpy(),
+           "keys": np.array(list(net.state_dict().keys())), "mlp_keys": np.array(list(mlp.state_dict().keys())),
+           "mlp_x": xm.numpy(), "mlp_y": mlp(xm).detach().numpy()}
+    for k, v in net.state_dict().items():
+        out["sd/" + k] = v.numpy()          # after the training forward: running stats included
+    for k, v in mlp.state_dict().items():
+        out["mlp_sd/" + k] = v.numpy()
+    for k, p in net.named_parameters():
+        out["grad/" + k] = p.grad.numpy()
+    p = os.path.join(ROOT, "tests", "golden", "adaptation_3layer.npz")
+    np.savez_compressed(p, **out)
+    print("wrote", p, "%.2f MB" % (os.path.getsize(p) / 1e6))
+
+
 if __name__ == "__main__":
-    main()
+    if "--adaptation" in sys.argv:
+        adaptation_golden()
+    else:
+        main()
