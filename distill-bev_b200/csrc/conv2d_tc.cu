@@ -286,6 +286,7 @@ struct HaloShape {
   int hx;            // halo pitch in pixels (box width), >= kHaloTx + 2
   int a_stage;       // bytes of one halo stage (multiple of 1024)
   int w_stages;      // weight ring depth
+  int a_stages;      // halo ring depth (2; 3 for the 64-column tiles whose chunks last only ~1700 clk)
   int c_off, relu, accumulate;
   int ncb;           // column blocks (see ConvShape)
 };
@@ -314,18 +315,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   constexpr int kWTile = COUT * kKc * 4;
   constexpr int kNBuf = COUT <= 128 ? 2 : 1;
   constexpr uint32_t kTmemCols = COUT <= 64 ? 256 : 512;     // 2 halves x kNBuf x COUT
-  constexpr int kMaxW = 8;
+  constexpr int kMaxW = 16;
+  constexpr int kMaxA = 3;
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* wbase = base + 2 * (size_t)s.a_stage;
-  __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[kMaxW], w_empty[kMaxW], tmem_full_bar[2],
+  uint8_t* wbase = base + (size_t)s.a_stages * s.a_stage;
+  __shared__ __align__(8) uint64_t a_full[kMaxA], a_empty[kMaxA], w_full[kMaxW], w_empty[kMaxW], tmem_full_bar[2],
       tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_s;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // uniform for the compiler
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxA; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], 4);
     }
@@ -374,11 +378,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_addr(base + (size_t)sa * s.a_stage)),
             "l"(&tmap_x), "r"(smem_addr(&a_full[sa])), "r"(c_n * kKc), "r"(x0 - 1), "r"(y0 - 1), "r"(n)
             : "memory");
-        if (++sa == 2) { sa = 0; pa ^= 1u; }
+        if (++sa == (uint32_t)s.a_stages) { sa = 0; pa ^= 1u; }
         if (++c_n == s.cin_chunks) { c_n = 0; t_n += gridDim.x; }
       };
       const int ahead = s.w_stages < 8 ? s.w_stages : 8;
-      issue_halo();
+      for (int i = 0; i < s.a_stages - 1; ++i) issue_halo();
       for (int item = blockIdx.x; item < s.n_items * s.ncb; item += gridDim.x) {
         const int cb = item % s.ncb;
         for (int cc = 0; cc < s.cin_chunks; ++cc) {
@@ -440,7 +444,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         }
         if (leader) umma_commit(&a_empty[sa]);
         __syncwarp();
-        if (++sa == 2) { sa = 0; pa ^= 1u; }
+        if (++sa == (uint32_t)s.a_stages) { sa = 0; pa ^= 1u; }
       }
       if (leader) umma_commit(&tmem_full_bar[buf]);
       __syncwarp();
@@ -454,7 +458,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // speed of its epilogue. Instead each warp stages its 32 pixels x 32 channels in shared memory
     // (128-byte swizzle, conflict-free) and one lane hands the box {32 ch, 8 px, 4 rows} to TMA.
     const int q = warp & 3;                  // TMEM lane q*32 + lane = pixel (lane / 8, lane % 8) of the warp's box
-    uint8_t* stg = base + 2 * (size_t)s.a_stage + (size_t)s.w_stages * kWTile + (size_t)q * 8192;
+    uint8_t* stg = base + (size_t)s.a_stages * s.a_stage + (size_t)s.w_stages * kWTile + (size_t)q * 8192;
     const uint32_t stg_row = smem_addr(stg) + (uint32_t)lane * 128u;
     const uint32_t sw_xor = (uint32_t)(lane & 7);
     uint32_t it = 0, sbuf = 0;
@@ -629,8 +633,12 @@ int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in,
       if (rem > 0 && 2 * rem <= sms) hs.n_full = n_tiles - rem, hs.n_items = hs.n_full + 2 * rem;
     }
     hs.a_stage = ((hs.tile_rows + 2) * hs.hx * kKc * 4 + 1023) / 1024 * 1024;
-    int w_stages = (smem_max - 2 * hs.a_stage - stage_out) / w_tile;
-    if (w_stages > 6) w_stages = 6;
+    // 64-column tiles: a weight tile lasts ~190 clk and a halo chunk ~1700 clk against ~2000 clk of TMA latency -> three
+    // halo stages and a deep weight ring (small-map layers of the student encoder were latency-bound with 2 + 6)
+    hs.a_stages = c_out == 64 ? 3 : 2;
+    int w_stages = (smem_max - hs.a_stages * hs.a_stage - stage_out) / w_tile;
+    const int w_cap = c_out == 64 ? 14 : 6;
+    if (w_stages > w_cap) w_stages = w_cap;
     DBEV_CHECK_ARG(w_stages >= 2, "conv2d_tc: halo tile does not fit shared memory");
     hs.w_stages = w_stages;
     hs.c_off = out_c_off, hs.relu = relu, hs.accumulate = accumulate ? 1 : 0;
@@ -676,7 +684,7 @@ int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in,
         return DBEV_ERR_CUDA;
       }
     }
-    const size_t smem = 2 * (size_t)hs.a_stage + (size_t)w_stages * w_tile + stage_out + 1024;
+    const size_t smem = (size_t)hs.a_stages * hs.a_stage + (size_t)w_stages * w_tile + stage_out + 1024;
     const int grid = hs.n_items * ncb < sms ? hs.n_items * ncb : sms;
     // DBEV_CONV_PROF=1: per-role wait cycles (debug only: synchronises and prints after every launch)
     static long long* prof_buf = nullptr;
@@ -794,9 +802,18 @@ int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in,
   // the 64-channel kernel or deeper stage rings gave nothing
   // (+ 32 KB of output staging per CTA: 3 x 24 KB / 2 x 32 KB stage rings keep two CTAs resident)
   // direct-store outputs (FPN branches) need no staging and keep the deeper rings
-  if (c_out == 64) { if (s.tma_store) DBEV_CONV_LAUNCH(64, 3, 2); else DBEV_CONV_LAUNCH(64, 4, 2); }
-  else if (c_out == 128) { if (s.tma_store) DBEV_CONV_LAUNCH(128, 2, 2); else DBEV_CONV_LAUNCH(128, 3, 2); }
-  else DBEV_CONV_LAUNCH(256, 4, 1);
+  // grids that do not fill the SMs twice (small BEV maps of the student encoder): one CTA per SM with a ring deep
+  // enough to cover the TMA latency (a 64-column stage lasts ~190 clk, a 128-column stage ~260 clk)
+  const bool small_grid = (long long)s.n_tiles * ncb <= (long long)sms;
+  if (c_out == 64) {
+    if (small_grid) DBEV_CONV_LAUNCH(64, 7, 1);
+    else if (s.tma_store) DBEV_CONV_LAUNCH(64, 3, 2);
+    else DBEV_CONV_LAUNCH(64, 4, 2);
+  } else if (c_out == 128) {
+    if (small_grid) DBEV_CONV_LAUNCH(128, 5, 1);
+    else if (s.tma_store) DBEV_CONV_LAUNCH(128, 2, 2);
+    else DBEV_CONV_LAUNCH(128, 3, 2);
+  } else DBEV_CONV_LAUNCH(256, 4, 1);
 #undef DBEV_CONV_LAUNCH
   DBEV_CHECK_LAUNCH("conv2d_tc_kernel");
   return DBEV_OK;
