@@ -134,8 +134,15 @@ def test_upsample_3layer_and_mlp_match_the_reference_classes(cuda):
     # TF32 rounding flips ReLU masks and three small-batch BatchNorms (800 pixels per channel) amplify it: single entries
     # move by up to ~1e-1 of the max (cuDNN TF32 does the same, test_bev_encoder_gpu.py), the direction is preserved
     assert float((x.grad - xg).abs().max()) <= 1.5e-1 * float(xg.abs().max())
-    for k, p in up3.named_parameters():
+    grads = dict(up3.named_parameters())
+    for k, p in grads.items():
         w = torch.from_numpy(ref["grad/" + k]).to(cuda)
+        if k.endswith(".bias") and ".conv" in k:
+            # a conv bias in front of a BatchNorm has a mathematically ZERO gradient (BN subtracts the mean): both the
+            # reference's value and ours are rounding noise - bound it against the weight gradient's scale instead
+            scale = float(grads[k.replace(".bias", ".weight")].grad.abs().max())
+            assert float(p.grad.abs().max()) <= 1e-3 * scale and float(w.abs().max()) <= 1e-3 * scale, k
+            continue
         assert float((p.grad - w).abs().max()) <= 1.5e-1 * float(w.abs().max()) + 1e-6, k
         if w.numel() > 1000:
             assert float(torch.nn.functional.cosine_similarity(p.grad.flatten(), w.flatten(), dim=0)) >= 0.999, k
