@@ -110,6 +110,8 @@ class _ConvBNActFn(torch.autograd.Function):
                 cur = torch.cuda.current_stream(dy.device)
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
+                    if ct._side["test_delay_cycles"]:          # tests: hold the side stream back to expose any consumer racing ahead
+                        torch.cuda._sleep(ct._side["test_delay_cycles"])
                     dw = ct.conv_weight_grad(xh, dy, kh, kw, stride, pad)
                 for t in (xh, dy, dw):
                     t.record_stream(side)

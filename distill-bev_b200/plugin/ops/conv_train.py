@@ -24,7 +24,7 @@ _TILE_N = (256, 128, 64)
 # overlap the input-gradient chain instead of queueing behind it. Off by default (plain single-stream semantics);
 # bench.py / a training loop turns it on and must call ``join_side_stream()`` before reading the weight gradients
 # (GradientAllReduce does it by itself).
-_side = {"enabled": False, "streams": {}}
+_side = {"enabled": False, "streams": {}, "test_delay_cycles": 0}
 
 
 def set_side_stream(enabled):

@@ -385,9 +385,13 @@ def test_mlp_and_3x3_adaptations(cuda):
         A.TwoLayer(256, out_features=128, kernel_size=4, stride=4).to(cuda)(x)
 
 
-def test_side_stream_overlap_gives_identical_gradients(cuda):
+@pytest.mark.parametrize("delay_cycles", [0, 2000000])
+def test_side_stream_overlap_gives_identical_gradients(cuda, delay_cycles):
     """conv_train.set_side_stream(True): weight gradients and prepack() run on a side stream beside the input-gradient
-    chain; after join_side_stream() every gradient is bit-identical to the single-stream run."""
+    chain; after join_side_stream() every gradient is bit-identical to the single-stream run - also when every weight
+    gradient is held back by ~1 ms on the side stream (a consumer that did not wait for the join would read garbage).
+    (Under compute-sanitizer this comparison reports all-zero weight gradients for the side-stream run - a tool artifact
+    with concurrent TMA / tcgen05 kernels on two streams: memcheck itself is clean and the delayed run here is exact.)"""
     from distill_bev_b200 import bev_encoder
     torch.manual_seed(7)
     net = _OurEncoder().to(cuda).train()
@@ -400,6 +404,7 @@ def test_side_stream_overlap_gives_identical_gradients(cuda):
             net.load_state_dict(state)
             net.zero_grad(set_to_none=True)
             ct.set_side_stream(side)
+            ct._side["test_delay_cycles"] = delay_cycles if side else 0
             if side:
                 bev_encoder.prepack(net)
             xin = x.clone().requires_grad_(True)
@@ -409,5 +414,42 @@ def test_side_stream_overlap_gives_identical_gradients(cuda):
             res.append([p.grad.clone() for p in net.parameters()] + [xin.grad.clone()])
     finally:
         ct.set_side_stream(False)
+        ct._side["test_delay_cycles"] = 0
     for a, b in zip(*res):
         assert torch.equal(a, b)
+
+
+def test_captured_training_step_with_side_stream_matches_eager(cuda):
+    """The encoder's forward + backward with prepack() and side-stream weight gradients, captured in a CUDA graph (every
+    weight gradient held back by ~1 ms inside the graph): replays give the gradients of the eager single-stream run,
+    bit for bit - the cross-stream dependencies (pack -> conv, dy -> wgrad, wgrad -> join) are graph edges."""
+    from distill_bev_b200 import bev_encoder
+    torch.manual_seed(11)
+    net = _OurEncoder().to(cuda).train()
+    x = torch.relu(torch.randn(2, 128, 32, 32, device=cuda)).contiguous(memory_format=torch.channels_last)
+    g = torch.randn(2, 256, 32, 32, device=cuda).contiguous(memory_format=torch.channels_last)
+    xin = x.clone().requires_grad_(True)
+    net(xin).backward(g)
+    want = [p.grad.clone() for p in net.parameters()] + [xin.grad.clone()]
+    xs = x.clone().requires_grad_(True)
+
+    def step():
+        net.zero_grad(set_to_none=True)
+        xs.grad = None
+        bev_encoder.prepack(net)
+        net(xs).backward(g)
+        ct.join_side_stream(cuda)
+        return [p.grad for p in net.parameters()] + [xs.grad]
+
+    try:
+        ct.set_side_stream(True)
+        ct._side["test_delay_cycles"] = 2000000
+        cap = dbev.CapturedStep(step, warmup=2, device=cuda)
+        for _ in range(2):
+            got = cap.replay()
+            torch.cuda.synchronize()
+            for a, b in zip(got, want):
+                assert torch.equal(a, b)
+    finally:
+        ct.set_side_stream(False)
+        ct._side["test_delay_cycles"] = 0
