@@ -88,6 +88,9 @@ SIGNATURES = {
                                        _ptr, _c_size, _ptr, _ptr]),
     "dbev_fgd_loss_backward": (_c_int, [_cfgp, _ptr, _ptr, _ptr, _ptr, _ptr, _c_size, _ptr, _ptr,
                                         _ptr, _ptr, _ptr, _ptr]),
+    "dbev_fgd_adapt_supported": (_c_int, [_cfgp, _c_int]),
+    "dbev_fgd_adapt_loss_forward": (_c_int, [_cfgp, _ptr, _c_int] + [_ptr] * 11 + [_c_size, _ptr, _ptr]),
+    "dbev_fgd_adapt_loss_backward": (_c_int, [_cfgp, _ptr, _c_int] + [_ptr] * 6 + [_c_size] + [_ptr] * 6),
     "dbev_pillar_encode_workspace_bytes": (_c_size, [_c_ll]),
     "dbev_pillar_encode": (_c_int, [_ptr, _ptr, _ptr, _c_int, _c_int, _c_int, _fptr, _fptr, _c_float,
                                     _c_float, _ptr, _c_int, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
@@ -133,6 +136,7 @@ SIGNATURES = {
     "dbev_conv_wgrad_tc": (_c_int, [_ptr] + [_c_int] * 5 + [_ptr] + [_c_int] * 8 + [_ptr, _c_int, _ptr, _c_size, _ptr]),
     "dbev_pack_conv_weights": (_c_int, [_ptr] + [_c_int] * 5 + [_ptr, _ptr]),
     "dbev_pack_conv_weights_train": (_c_int, [_ptr] + [_c_int] * 5 + [_ptr, _ptr, _ptr]),
+    "dbev_pack_conv_weights_batch": (_c_int, [_ptr, _c_int, _c_int, _ptr]),
     "dbev_channel_stats_workspace_bytes": (_c_size, [_c_ll, _c_int]),
     "dbev_bn_batch_stats": (_c_int, [_ptr, _c_int, _c_ll, _c_int, _ptr, _ptr, _c_float, _c_float, _ptr, _ptr, _ptr, _ptr,
                                      _c_size, _ptr]),

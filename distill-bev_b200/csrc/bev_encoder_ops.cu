@@ -25,6 +25,8 @@ namespace dbev {
 namespace {
 
 constexpr int kStatThreads = 256;
+constexpr int kPackJobWords = 8;
+constexpr int kFinalWarps = 32;   // channel_stats_final_kernel: 32 warps x 10 loads in flight cover 320 partial rows in one round
 
 // ------------------------------------------------------------------------------------------ column statistics
 // partial[blk][2][C]: block blk sums rows [blk * rows_per_block, ...); MODE 0: (sum y, sum y^2);
@@ -102,37 +104,34 @@ __global__ void __launch_bounds__(kStatThreads) channel_stats_kernel(StatArgs a)
 }
 
 // Combines the per-block partial sums in block order with fp64 accumulation (deterministic) and finalises:
-// a block owns 16 channels; lanes 0-15 / 16-31 of every warp carry the first / second statistic, the eight warps
-// each sum an eighth of the blocks with eight loads in flight (the chain of dependent loads is what this kernel costs)
+// a block owns 16 channels; lanes 0-15 / 16-31 of every warp carry the first / second statistic, the kFinalWarps warps
+// each sum their share of the partial rows with all loads in flight at once (one round of load latency, not a chain)
 template <int MODE>
-__global__ void __launch_bounds__(256) channel_stats_final_kernel(StatArgs a, int n_blocks) {
-  __shared__ double part[8][32];
+__global__ void __launch_bounds__(kFinalWarps * 32) channel_stats_final_kernel(StatArgs a, int n_blocks) {
+  __shared__ double part[kFinalWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stat = lane >> 4;
   const int c = blockIdx.x * 16 + (lane & 15);
   double t = 0.0;
   if (c < a.C) {
-    const int b0 = (int)((long long)n_blocks * warp / 8), b1 = (int)((long long)n_blocks * (warp + 1) / 8);
+    const int b0 = (int)((long long)n_blocks * warp / kFinalWarps), b1 = (int)((long long)n_blocks * (warp + 1) / kFinalWarps);
     const float* p = a.partial + stat * a.C + c;
     const long long st = 2LL * a.C;
     int b = b0;
-    double u[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (; b + 7 < b1; b += 8) {
-      float v[8];
+    for (; b < b1; b += 10) {                 // all of a warp's rows in flight at once (predicated), summed in row order
+      float v[10];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = __ldcg(p + (long long)(b + k) * st);
+      for (int k = 0; k < 10; ++k) v[k] = b + k < b1 ? __ldcg(p + (long long)(b + k) * st) : 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) u[k] += (double)v[k];
+      for (int k = 0; k < 10; ++k) t += (double)v[k];
     }
-    for (; b < b1; ++b) u[0] += (double)__ldcg(p + (long long)b * st);
-    t = ((u[0] + u[1]) + (u[2] + u[3])) + ((u[4] + u[5]) + (u[6] + u[7]));
   }
   part[warp][lane] = t;
   __syncthreads();
   if (warp != 0) return;
   double tot = 0.0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) tot += part[k][lane];
+  for (int k = 0; k < kFinalWarps; ++k) tot += part[k][lane];
   // lane l (< 16) needs the second statistic of its channel from lane l + 16
   const double other = __shfl_down_sync(0xffffffffu, tot, 16);
   if (lane >= 16 || c >= a.C) return;
@@ -362,13 +361,11 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, int CO, in
 // Both matrices of a layer in one pass (what the training step uses): a block owns a 32 (C_out) x 32 (C_in) tile of
 // the filter, staged in shared memory so that the global reads (taps fastest) and both sets of global writes
 // (C_in fastest / C_out fastest) are 128-byte runs. dgrad_mode 1: stride-1 matrix, 2: the four parity matrices.
-__global__ void __launch_bounds__(256) pack_conv_weights_tile_kernel(const float* __restrict__ w, int CO, int CI, int KH, int KW,
-                                                                     int dgrad_mode, float* __restrict__ out_f,
-                                                                     float* __restrict__ out_d) {
+__device__ __forceinline__ void pack_conv_weights_tile(const float* __restrict__ w, int CO, int CI, int KH, int KW,
+                                                       int dgrad_mode, float* __restrict__ out_f,
+                                                       float* __restrict__ out_d, int co0, int ci0, float* tile) {
   const int taps = KH * KW;
-  const int pitch = 32 * taps + 1;
-  extern __shared__ float tile[];                     // [32 co][pitch]
-  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int pitch = 32 * taps + 1;                    // tile = [32 co][pitch]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // flat, coalesced copy of the 32 rows (each 32 * taps contiguous floats); loads issued in batches of 12 so that
   // the (cold) global latency is paid three times, not 36 times
@@ -421,6 +418,27 @@ __global__ void __launch_bounds__(256) pack_conv_weights_tile_kernel(const float
   }
 }
 
+__global__ void __launch_bounds__(256) pack_conv_weights_tile_kernel(const float* __restrict__ w, int CO, int CI, int KH, int KW,
+                                                                     int dgrad_mode, float* __restrict__ out_f,
+                                                                     float* __restrict__ out_d) {
+  extern __shared__ float tile[];
+  pack_conv_weights_tile(w, CO, CI, KH, KW, dgrad_mode, out_f, out_d, blockIdx.y * 32, blockIdx.x * 32, tile);
+}
+
+// every layer of a network in ONE launch: jobs = n_jobs records of kPackJobWords int64 {w, out_fwd, out_dgrad, C_out, C_in,
+// KH * 256 + KW, dgrad_mode, first tile}; block b works on tile b - first_tile of the job that owns it
+__global__ void __launch_bounds__(256) pack_conv_weights_batch_kernel(const long long* __restrict__ jobs, int n_jobs) {
+  extern __shared__ float tile[];
+  int j = 0;
+  while (j + 1 < n_jobs && (long long)blockIdx.x >= __ldg(jobs + (j + 1) * kPackJobWords + 7)) ++j;
+  const long long* r = jobs + j * kPackJobWords;
+  const int CO = (int)__ldg(r + 3), CI = (int)__ldg(r + 4), khkw = (int)__ldg(r + 5);
+  const int t = (int)(blockIdx.x - __ldg(r + 7)), tiles_ci = (CI + 31) / 32;
+  pack_conv_weights_tile(reinterpret_cast<const float*>(__ldg(r + 0)), CO, CI, khkw >> 8, khkw & 255, (int)__ldg(r + 6),
+                         reinterpret_cast<float*>(__ldg(r + 1)), reinterpret_cast<float*>(__ldg(r + 2)), (t / tiles_ci) * 32,
+                         (t % tiles_ci) * 32, tile);
+}
+
 int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = (long long)kNumSMs * 16;
@@ -466,7 +484,7 @@ int bn_batch_stats(const float* y, int y_ld, long long rows, int C, const float*
   const int quads = C / 4, threads = quads * (kStatThreads / quads);
   channel_stats_kernel<0><<<blocks, threads, 0, stream>>>(a);
   DBEV_CHECK_LAUNCH("channel_stats_kernel<0>");
-  channel_stats_final_kernel<0><<<ceil_div(C, 16), 256, 0, stream>>>(a, blocks);
+  channel_stats_final_kernel<0><<<ceil_div(C, 16), kFinalWarps * 32, 0, stream>>>(a, blocks);
   DBEV_CHECK_LAUNCH("channel_stats_final_kernel<0>");
   return DBEV_OK;
 }
@@ -484,7 +502,7 @@ int channel_sums(const float* y, int y_ld, long long rows, int C, float* out, in
   const int quads = C / 4, threads = quads * (kStatThreads / quads);
   channel_stats_kernel<0><<<blocks, threads, 0, stream>>>(a);
   DBEV_CHECK_LAUNCH("channel_stats_kernel<0>");
-  channel_stats_final_kernel<0><<<ceil_div(C, 16), 256, 0, stream>>>(a, blocks);
+  channel_stats_final_kernel<0><<<ceil_div(C, 16), kFinalWarps * 32, 0, stream>>>(a, blocks);
   DBEV_CHECK_LAUNCH("channel_stats_final_kernel<0>");
   return DBEV_OK;
 }
@@ -513,7 +531,7 @@ int bn_backward(const float* dz, int dz_ld, const float* z, int z_ld, const floa
   const int quads = C / 4, threads = quads * (kStatThreads / quads);
   channel_stats_kernel<1><<<blocks, threads, 0, stream>>>(a);
   DBEV_CHECK_LAUNCH("channel_stats_kernel<1>");
-  channel_stats_final_kernel<1><<<ceil_div(C, 16), 256, 0, stream>>>(a, blocks);
+  channel_stats_final_kernel<1><<<ceil_div(C, 16), kFinalWarps * 32, 0, stream>>>(a, blocks);
   DBEV_CHECK_LAUNCH("channel_stats_final_kernel<1>");
   bn_bwd_apply_kernel<<<grid_for(rows * quads, 256), 256, 0, stream>>>(dz, dz_ld, z, z_ld, y, y_ld, fwd4c, bwd4c, rows, C, dy, dy_ld,
                                                                        g_out, g_ld, g_accumulate);
@@ -569,6 +587,14 @@ int pack_conv_weights_train(const float* w, int c_out, int c_in, int kh, int kw,
   pack_conv_weights_tile_kernel<<<dim3((unsigned)ceil_div(c_in, 32), (unsigned)ceil_div(c_out, 32)), 256, smem, stream>>>(
       w, c_out, c_in, kh, kw, dgrad_mode, out_fwd, out_dgrad);
   DBEV_CHECK_LAUNCH("pack_conv_weights_tile_kernel");
+  return DBEV_OK;
+}
+
+int pack_conv_weights_batch(const long long* jobs_dev, int n_jobs, int total_tiles, cudaStream_t stream) {
+  DBEV_CHECK_ARG(jobs_dev && n_jobs > 0 && total_tiles > 0, "pack_conv_weights_batch: empty job table");
+  const size_t smem = (size_t)32 * (32 * 9 + 1) * sizeof(float);
+  pack_conv_weights_batch_kernel<<<(unsigned)total_tiles, 256, smem, stream>>>(jobs_dev, n_jobs);
+  DBEV_CHECK_LAUNCH("pack_conv_weights_batch_kernel");
   return DBEV_OK;
 }
 

@@ -36,4 +36,9 @@ int pack_conv_weights(const float* w, int c_out, int c_in, int kh, int kw, int m
 int pack_conv_weights_train(const float* w, int c_out, int c_in, int kh, int kw, int dgrad_mode, float* out_fwd, float* out_dgrad,
                             cudaStream_t stream);
 
+// Every layer in one launch. jobs_dev: n_jobs records of 8 int64 in device memory
+//   {w, out_fwd (0 = skip), out_dgrad (0 = skip), C_out, C_in, KH * 256 + KW, dgrad_mode, first tile}
+// with tiles = ceil(C_out / 32) * ceil(C_in / 32) per job numbered consecutively; total_tiles = their sum.
+int pack_conv_weights_batch(const long long* jobs_dev, int n_jobs, int total_tiles, cudaStream_t stream);
+
 }  // namespace dbev

@@ -257,6 +257,29 @@ int dbev_fgd_loss_backward(const dbev_fgd_config* cfg, const float* student, con
                            (cudaStream_t)stream);
 }
 
+int dbev_fgd_adapt_supported(const dbev_fgd_config* cfg, int c_in) {
+  return cfg != nullptr && fgd_adapt_fused_supported(*cfg, c_in) ? 1 : 0;
+}
+
+int dbev_fgd_adapt_loss_forward(const dbev_fgd_config* cfg, const float* x_cl, int c_in, const float* adapt_w,
+                                const float* adapt_b, const float* teacher, const float* fg, const float* fg_scale,
+                                const int* fg_count, const float* fp, const int* fp_count, const float* conv_w,
+                                const float* conv_b, void* state, size_t state_bytes, float* losses, void* stream) {
+  DBEV_CHECK_ARG(cfg != nullptr, "fgd: null config");
+  return fgd_adapt_loss_forward(*cfg, x_cl, c_in, adapt_w, adapt_b, teacher, fg, fg_scale, fg_count, fp, fp_count, conv_w,
+                                conv_b, state, state_bytes, losses, (cudaStream_t)stream);
+}
+
+int dbev_fgd_adapt_loss_backward(const dbev_fgd_config* cfg, const float* x_cl, int c_in, const float* adapt_w,
+                                 const float* adapt_b, const float* teacher, const float* conv_w, const float* conv_b,
+                                 void* state, size_t state_bytes, const float* grad_losses, float* grad_adapted_cl,
+                                 float* grad_conv_w, float* grad_conv_b, float* grad_channel_sum, void* stream) {
+  DBEV_CHECK_ARG(cfg != nullptr, "fgd: null config");
+  return fgd_adapt_loss_backward(*cfg, x_cl, c_in, adapt_w, adapt_b, teacher, conv_w, conv_b, state, state_bytes,
+                                 grad_losses, grad_adapted_cl, grad_conv_w, grad_conv_b, grad_channel_sum,
+                                 (cudaStream_t)stream);
+}
+
 size_t dbev_pillar_encode_workspace_bytes(long long n) { return pillar_encode_ws_bytes(n); }
 
 int dbev_pillar_encode(const float* points, const int* batch_offsets, const int* coors_in,
@@ -469,6 +492,10 @@ int dbev_pack_conv_weights(const float* w, int c_out, int c_in, int kh, int kw, 
 int dbev_pack_conv_weights_train(const float* w, int c_out, int c_in, int kh, int kw, int dgrad_mode, float* out_fwd,
                                  float* out_dgrad, void* stream) {
   return pack_conv_weights_train(w, c_out, c_in, kh, kw, dgrad_mode, out_fwd, out_dgrad, (cudaStream_t)stream);
+}
+
+int dbev_pack_conv_weights_batch(const long long* jobs_dev, int n_jobs, int total_tiles, void* stream) {
+  return pack_conv_weights_batch(jobs_dev, n_jobs, total_tiles, (cudaStream_t)stream);
 }
 
 size_t dbev_channel_stats_workspace_bytes(long long rows, int C) { return channel_stats_workspace_bytes(rows, C); }

@@ -22,6 +22,8 @@
 // atomics): bit-reproducible. Masks are rasterised on the device.
 #include "distill_loss.cuh"
 
+#include "adapt_loss_tc.cuh"
+
 #include <math.h>
 
 namespace dbev {
@@ -950,6 +952,83 @@ int fgd_loss_backward(const FgdConfig& c, const float* student, const float* tea
     fgd_channel_total_kernel<<<ceil_div((long long)d.C * 32, 256), 256, 0, stream>>>(d, chan_p,
                                                                                      grad_channel_sum);
   DBEV_CHECK_LAUNCH("fgd_loss_backward");
+  return DBEV_OK;
+}
+
+bool fgd_adapt_fused_supported(const FgdConfig& c, int c_in) { return adapt_fgd_fused_supports(c_in, c.C, c.H * c.W); }
+
+// channel_wise_adaptations[index] ('1x1conv', :1004) + fgd_loss_forward in one pass: the adapted student lives only in
+// tensor memory (adapt_loss_tc.cu); everything else is the kernel sequence of fgd_loss_forward.
+int fgd_adapt_loss_forward(const FgdConfig& c, const float* x_cl, int c_in, const float* adapt_w, const float* adapt_b,
+                           const float* teacher, const float* fg, const float* fg_scale, const int* fg_count,
+                           const float* fp, const int* fp_count, const float* conv_w, const float* conv_b, void* state,
+                           size_t state_bytes, float* losses, cudaStream_t stream) {
+  FgdDims d;
+  int rc = make_dims(c, &d);
+  if (rc != DBEV_OK) return rc;
+  DBEV_CHECK_ARG(state_bytes >= fgd_state_floats(d) * sizeof(float), "fgd: state buffer too small");
+  DBEV_CHECK_ARG(!c.use_fp || (fp && fp_count), "fgd: use_fp needs fp mask and count");
+  DBEV_CHECK_ARG(!c.spatial_mask || (conv_w && conv_b), "fgd: spatial_mask needs the 3x3 conv");
+  DBEV_CHECK_ARG(c.spatial_att == 0 || c.spatial_att == 1, "fgd: spatial_att must be 0 or 1");
+  DBEV_CHECK_ARG(fgd_adapt_fused_supported(c, c_in), "fgd_adapt_loss: unsupported adaptation shape %d -> %d", c_in, c.C);
+  const FgdCfg k = make_cfg(c);
+  FgdState st = carve_state((float*)state, d);
+  dim3 grid(d.ntiles, d.B);
+  fgd_teacher_stats_kernel<<<grid, kBlock, 0, stream>>>(teacher, d, st.ta, st.tm, st.cta_p, st.ctm_p);
+  fgd_channel_means_kernel<<<ceil_div((long long)d.B * d.C * 32, 256), 256, 0, stream>>>(d, st.cta_p, st.ctm_p,
+                                                                         st.catt, st.ctm);
+  fgd_channel_softmax_kernel<<<d.B, 256, 0, stream>>>(d, k.channel_t, st.catt);
+  DBEV_CHECK_LAUNCH("fgd_adapt_loss_forward (teacher statistics)");
+  AdaptFgdArgs a = {};
+  a.bias = adapt_b, a.teacher = teacher, a.catt = st.catt, a.chan_p = st.csm_p;
+  a.sa = st.sa, a.sm = st.sm, a.d1 = st.d1, a.d2 = st.d2;
+  rc = adapt_fgd_fused(0, x_cl, adapt_w, d.B, c_in, d.C, d.HW, a, stream);
+  if (rc != DBEV_OK) return rc;
+  fgd_spatial_softmax_kernel<<<dim3(d.B, 2), 1024, 0, stream>>>(d, k.spatial_t, st.ta, st.sa);
+  fgd_channel_means_kernel<<<ceil_div((long long)d.B * d.C * 32, 256), 256, 0, stream>>>(d, st.csm_p, nullptr,
+                                                                         st.csm, nullptr);
+  fgd_combine_kernel<<<grid, kTile, 0, stream>>>(d, k, fg, fg_scale, fg_count, fp, fp_count, st.ta,
+                                                 st.sa, st.tm, st.sm, st.d1, st.d2, conv_w, conv_b,
+                                                 st.fgw, st.bgw, st.fpw, st.loss_p);
+  fgd_final_kernel<<<1, 256, 0, stream>>>(d, k, st.loss_p, st.ctm, st.csm, losses);
+  DBEV_CHECK_LAUNCH("fgd_adapt_loss_forward");
+  return DBEV_OK;
+}
+
+// Backward of the above: d loss / d (adapted student) as channels-last rows grad_adapted_cl[B, HW, C] (the tile of the
+// adapted student is recomputed on the tensor cores), its per-channel sums (the adaptation conv's bias gradient) and
+// the spatial conv's gradients. The adaptation conv's input / weight gradients are two GEMMs over grad_adapted_cl
+// (conv2d_tc / conv_wgrad_tc, called by the host side).
+int fgd_adapt_loss_backward(const FgdConfig& c, const float* x_cl, int c_in, const float* adapt_w, const float* adapt_b,
+                            const float* teacher, const float* conv_w, const float* conv_b, void* state,
+                            size_t state_bytes, const float* grad_losses, float* grad_adapted_cl, float* grad_conv_w,
+                            float* grad_conv_b, float* grad_channel_sum, cudaStream_t stream) {
+  FgdDims d;
+  int rc = make_dims(c, &d);
+  if (rc != DBEV_OK) return rc;
+  DBEV_CHECK_ARG(state_bytes >= fgd_state_floats(d) * sizeof(float), "fgd: state buffer too small");
+  DBEV_CHECK_ARG(fgd_adapt_fused_supported(c, c_in), "fgd_adapt_loss: unsupported adaptation shape %d -> %d", c_in, c.C);
+  const FgdCfg k = make_cfg(c);
+  FgdState st = carve_state((float*)state, d);
+  dim3 grid(d.ntiles, d.B);
+  if (k.spatial_mask)
+    fgd_bwd_spatial_prep_kernel<<<grid, kTile, 0, stream>>>(d, k, st.tm, st.sm, conv_w, conv_b,
+                                                            grad_losses, st.d1, st.conv_p);
+  fgd_bwd_small_kernel<<<kNumSMs, 256, 0, stream>>>(d, k, st.d1, conv_w, st.ctm, st.csm, grad_losses,
+                                                    st.conv_p, st.gsp, st.gc, grad_conv_w,
+                                                    grad_conv_b);
+  DBEV_CHECK_LAUNCH("fgd_adapt_loss_backward (small maps)");
+  float* chan_p = grad_channel_sum ? st.csm_p : nullptr;
+  AdaptFgdArgs a = {};
+  a.bias = adapt_b, a.teacher = teacher, a.catt = st.catt, a.chan_p = chan_p;
+  a.fgw = st.fgw, a.bgw = st.bgw, a.fpw = st.fpw, a.gsp = st.gsp, a.gc = st.gc, a.grad_losses = grad_losses;
+  a.w_fg = k.w_fg, a.w_bg = k.w_bg, a.w_fp = k.w_fp, a.use_fp = k.use_fp ? 1 : 0, a.channel_mask = k.channel_mask ? 1 : 0;
+  a.ds_cl = grad_adapted_cl;
+  rc = adapt_fgd_fused(1, x_cl, adapt_w, d.B, c_in, d.C, d.HW, a, stream);
+  if (rc != DBEV_OK) return rc;
+  if (grad_channel_sum)
+    fgd_channel_total_kernel<<<ceil_div((long long)d.C * 32, 256), 256, 0, stream>>>(d, chan_p, grad_channel_sum);
+  DBEV_CHECK_LAUNCH("fgd_adapt_loss_backward");
   return DBEV_OK;
 }
 

@@ -38,4 +38,18 @@ int fgd_loss_backward(const FgdConfig& c, const float* student, const float* tea
                       float* grad_conv_b, float* grad_channel_sum,
                       cudaStream_t stream);
 
+// '1x1conv' adaptation fused with the loss (adapt_loss_tc.cu): x_cl [B, HW, C_in] channels-last student feature,
+// adapt_w [C, C_in], adapt_b [C] or null; the adapted map is never materialised.
+bool fgd_adapt_fused_supported(const FgdConfig& c, int c_in);
+
+int fgd_adapt_loss_forward(const FgdConfig& c, const float* x_cl, int c_in, const float* adapt_w, const float* adapt_b,
+                           const float* teacher, const float* fg, const float* fg_scale, const int* fg_count,
+                           const float* fp, const int* fp_count, const float* conv_w, const float* conv_b, void* state,
+                           size_t state_bytes, float* losses, cudaStream_t stream);
+
+int fgd_adapt_loss_backward(const FgdConfig& c, const float* x_cl, int c_in, const float* adapt_w, const float* adapt_b,
+                            const float* teacher, const float* conv_w, const float* conv_b, void* state,
+                            size_t state_bytes, const float* grad_losses, float* grad_adapted_cl, float* grad_conv_w,
+                            float* grad_conv_b, float* grad_channel_sum, cudaStream_t stream);
+
 }  // namespace dbev

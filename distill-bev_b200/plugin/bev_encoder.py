@@ -132,21 +132,62 @@ def _stats_ws(owner, y):
     return cache[1]
 
 
+def _pack_plan(module, convs, dev):
+    """Persistent packed-weight buffers of every conv of ``module`` + the device job table of the one-launch pack.
+    Built on first use (a host -> device copy: outside CUDA graph capture), rebuilt when a weight tensor was replaced."""
+    key = tuple((m.weight.data_ptr(), tuple(m.weight.shape), m.stride[0]) for m in convs)
+    plan = getattr(module, "_dbev_pack_plan", None)
+    if plan is not None and plan["key"] == key:
+        return plan
+    if torch.cuda.is_current_stream_capturing():
+        return None
+    total = sum(m.weight.numel() for m in convs)
+    buf = torch.empty((2, total), dtype=torch.float32, device=dev)
+    rows, views, off, tile = [], [], 0, 0
+    for m in convs:
+        co, ci, kh, kw = m.weight.shape
+        n = m.weight.numel()
+        w_fwd, w_bwd = buf[0, off:off + n], buf[1, off:off + n]
+        rows.append([m.weight.data_ptr(), w_fwd.data_ptr(), w_bwd.data_ptr(), co, ci, kh * 256 + kw,
+                     1 if m.stride[0] == 1 else 2, tile])
+        views.append((w_fwd, w_bwd))
+        off += n
+        tile += ((co + 31) // 32) * ((ci + 31) // 32)
+    plan = {"key": key, "buf": buf, "views": views, "tiles": tile,
+            "jobs": torch.tensor(rows, dtype=torch.int64).to(dev)}
+    module._dbev_pack_plan = plan
+    return plan
+
+
 def prepack(module):
     """Pack the weights of every conv of ``module`` that conv_bn_act will run, now, on the side stream (or the current
-    stream when overlap is off): one pass per layer, off the critical path of the step that follows. Call it once per
-    step after the optimizer has updated the weights; a conv whose weight changed since falls back to packing in its
-    forward."""
+    stream when overlap is off), off the critical path of the step that follows: ONE launch over all layers into
+    persistent buffers (per-layer launches when the job table cannot be built, i.e. first use inside a graph capture).
+    Call it once per step after the optimizer has updated the weights; a conv whose weight changed since falls back to
+    packing in its forward."""
     convs = [m for m in module.modules() if isinstance(m, nn.Conv2d) and m.weight.is_cuda and m.groups == 1
              and m.kernel_size[0] == m.kernel_size[1] and m.kernel_size[0] in (1, 3)]
     if not convs:
         return
     dev = convs[0].weight.device
+    batched = all(m.weight.is_contiguous() and m.weight.dtype == torch.float32 and m.weight.device == dev
+                  and m.stride[0] == m.stride[1] and (m.stride[0] == 1 or (m.stride[0] == 2 and m.kernel_size[0] == 3))
+                  for m in convs)
+    plan = _pack_plan(module, convs, dev) if batched else None
     side = ct.side_stream(dev)
     cur = torch.cuda.current_stream(dev)
     if side is not None:
-        side.wait_stream(cur)
+        side.wait_stream(cur)          # also orders the overwrite of the persistent buffers after their last readers
     with torch.cuda.stream(side if side is not None else cur):
+        if plan is not None:
+            ct.pack_weights_batch(plan["jobs"], plan["tiles"])
+            ready = None
+            if side is not None:
+                ready = torch.cuda.Event()
+                ready.record(side)
+            for m, (w_fwd, w_bwd) in zip(convs, plan["views"]):
+                m._dbev_prepacked = ((m.weight.data_ptr(), m.weight._version), (w_fwd, w_bwd, ready))
+            return
         for m in convs:
             w_fwd, w_bwd = ct.pack_weights_train(m.weight, m.stride[0])
             ready = None

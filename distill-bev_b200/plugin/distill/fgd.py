@@ -277,13 +277,21 @@ class _FGDLoss(torch.autograd.Function):
 
 
 class _AdaptFGDLoss(torch.autograd.Function):
-    """channel_wise_adaptations[index] (1x1 conv, :1004) + the loss as ONE autograd node: the
-    adapted student never leaves this node and the conv's bias gradient falls out of the loss
-    backward kernel (per-channel sums of d loss / d adapted student)."""
+    """channel_wise_adaptations[index] (1x1 conv, :1004) + the loss as ONE autograd node. Fused path (C_in % 128 == 0,
+    C_out in 128 / 256 / 384 / 512): the adapted student exists only as tiles in tensor memory - the loss sums are
+    taken in the GEMM epilogue (dbev_fgd_adapt_loss_forward), the backward recomputes the tiles and emits
+    d loss / d adapted as channels-last rows for the tcgen05 input- / weight-gradient GEMMs, and the conv's bias
+    gradient falls out as per-channel sums. Other shapes: adaptation GEMM -> NCHW map -> loss kernels."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count,
                 teacher_ready=None):
+        lib = _lib.load()
+        ctx.fused = (x.shape[1] % 128 == 0 and weight.shape[0] % 128 == 0
+                     and bool(lib.dbev_fgd_adapt_supported(ctypes.byref(cfg), int(x.shape[1]))))
+        if ctx.fused:
+            return _AdaptFGDLoss._forward_fused(ctx, lib, x, weight, bias, teacher, conv_w, conv_b, cfg, fg, fg_scale,
+                                                fg_count, fp, fp_count, teacher_ready)
         from .adaptation import conv1x1_forward
         adapted, x = conv1x1_forward(x, weight, bias)
         if teacher_ready is not None:   # the adaptation conv above does not read the teacher
@@ -296,7 +304,80 @@ class _AdaptFGDLoss(torch.autograd.Function):
         return losses
 
     @staticmethod
+    def _forward_fused(ctx, lib, x, weight, bias, teacher, conv_w, conv_b, cfg, fg, fg_scale, fg_count, fp, fp_count,
+                       teacher_ready):
+        from ..ops import conv_train as ct
+        _lib.require_cuda(x, "student_feat", torch.float32)
+        _lib.require_cuda(teacher, "teacher_feat", torch.float32)
+        B, Cin, H, W = x.shape
+        C = weight.shape[0]
+        if tuple(teacher.shape) != (B, C, H, W):
+            raise RuntimeError("student %s adapted to %d channels and teacher %s must have the same shape"
+                               % (tuple(x.shape), C, tuple(teacher.shape)))
+        if cfg.spatial_mask and conv_w is None:
+            raise RuntimeError("distill_params['spatial_mask'] is set: the spatial loss needs spatial_adaptation "
+                               "(spatial_wise_adaptations[index], bevdet_distill.py:348-351, :1272-1278)")
+        dev = x.device
+        x_cl = ct.as_nhwc(x.detach())
+        if not x_cl.is_contiguous():                 # a channel slice: the GEMM's TMA map wants dense rows
+            x_cl = x_cl.contiguous()
+        teacher = teacher.detach().contiguous()
+        w2 = weight.detach().reshape(C, Cin).contiguous()
+        b1 = bias.detach().contiguous() if bias is not None else None
+        has_conv = conv_w is not None
+        if not has_conv:
+            conv_w, conv_b = torch.zeros(9, device=dev), torch.zeros(1, device=dev)
+        cw = conv_w.detach().reshape(-1).contiguous().float()
+        cb = conv_b.detach().reshape(-1).contiguous().float()
+        nbytes = lib.dbev_fgd_state_bytes(ctypes.byref(cfg))
+        state = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        losses = torch.empty(5, dtype=torch.float32, device=dev)
+        if teacher_ready is not None:
+            torch.cuda.current_stream(dev).wait_event(teacher_ready)
+        with torch.cuda.device(dev):
+            rc = lib.dbev_fgd_adapt_loss_forward(
+                ctypes.byref(cfg), _lib.ptr(x_cl), Cin, _lib.ptr(w2), _lib.ptr(b1), _lib.ptr(teacher),
+                _lib.ptr(fg.contiguous()), _lib.ptr(fg_scale.contiguous()), _lib.ptr(fg_count), _lib.ptr(fp),
+                _lib.ptr(fp_count), _lib.ptr(cw), _lib.ptr(cb), _lib.ptr(state), nbytes, _lib.ptr(losses),
+                _lib.stream_ptr(dev))
+        _lib.check(rc, "dbev_fgd_adapt_loss_forward")
+        ctx.cfg, ctx.state, ctx.has_bias, ctx.has_conv = cfg, state, bias is not None, has_conv
+        ctx.conv_shape = (conv_w.shape, conv_b.shape)
+        ctx.save_for_backward(x_cl, weight, w2, b1 if b1 is not None else cb, teacher, cw, cb)
+        return losses
+
+    @staticmethod
+    def _backward_fused(ctx, grad_losses):
+        from ..ops import conv_train as ct
+        lib = _lib.load()
+        x_cl, weight, w2, b1, teacher, cw, cb = ctx.saved_tensors
+        dev = x_cl.device
+        B, H, W, Cin = x_cl.shape
+        C = w2.shape[0]
+        want_bias = ctx.has_bias and ctx.needs_input_grad[2]
+        gl = grad_losses.contiguous().float()
+        g_cl = torch.empty((B, H, W, C), dtype=torch.float32, device=dev)
+        gw = torch.empty(9, dtype=torch.float32, device=dev)
+        gb = torch.empty(1, dtype=torch.float32, device=dev)
+        gsum = torch.empty(C, dtype=torch.float32, device=dev) if want_bias else None
+        with torch.cuda.device(dev):
+            rc = lib.dbev_fgd_adapt_loss_backward(
+                ctypes.byref(ctx.cfg), _lib.ptr(x_cl), Cin, _lib.ptr(w2), _lib.ptr(b1 if ctx.has_bias else None),
+                _lib.ptr(teacher), _lib.ptr(cw), _lib.ptr(cb), _lib.ptr(ctx.state), ctx.state.numel() * 4, _lib.ptr(gl),
+                _lib.ptr(g_cl), _lib.ptr(gw), _lib.ptr(gb), _lib.ptr(gsum), _lib.stream_ptr(dev))
+        _lib.check(rc, "dbev_fgd_adapt_loss_backward")
+        gx = gwt = None
+        if ctx.needs_input_grad[0]:
+            gx = ct.as_nchw(ct.conv_input_grad(g_cl, ct.pack_weights(weight, 1), Cin, 1, 1, 1, 0, (H, W)))
+        if ctx.needs_input_grad[1]:
+            gwt = ct.conv_weight_grad(x_cl, g_cl, 1, 1, 1, 0)
+        gw, gb = (gw.view(ctx.conv_shape[0]), gb.view(ctx.conv_shape[1])) if ctx.has_conv else (None, None)
+        return (gx, gwt, gsum, None, gw, gb, None, None, None, None, None, None, None)
+
+    @staticmethod
     def backward(ctx, grad_losses):
+        if ctx.fused:
+            return _AdaptFGDLoss._backward_fused(ctx, grad_losses)
         x, weight, adapted, teacher, cw, cb = ctx.saved_tensors
         want_bias = ctx.has_bias and ctx.needs_input_grad[2]
         gs, gw, gb, gsum = _loss_backward(ctx.cfg, ctx.state, adapted, teacher, cw, cb, grad_losses,

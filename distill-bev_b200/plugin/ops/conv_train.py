@@ -131,6 +131,21 @@ def pack_weights_train(weight, stride):
     return out[0], out[1]
 
 
+PACK_JOB_WORDS = 8
+
+
+def pack_weights_batch(jobs, total_tiles):
+    """All layers in one launch. ``jobs``: int64 device tensor [n_jobs, 8] of {w, out_fwd, out_dgrad, C_out, C_in,
+    KH * 256 + KW, dgrad_mode, first tile} (include/distill_bev_b200.h: dbev_pack_conv_weights_batch)."""
+    lib = _lib.load()
+    _lib.require_cuda(jobs, "jobs", torch.int64)
+    if jobs.dim() != 2 or jobs.shape[1] != PACK_JOB_WORDS or not jobs.is_contiguous():
+        raise ValueError("pack_weights_batch: jobs must be a contiguous [n_jobs, %d] int64 tensor" % PACK_JOB_WORDS)
+    with torch.cuda.device(jobs.device):
+        rc = lib.dbev_pack_conv_weights_batch(_lib.ptr(jobs), jobs.shape[0], int(total_tiles), _lib.stream_ptr(jobs.device))
+    _lib.check(rc, "dbev_pack_conv_weights_batch")
+
+
 def _conv_launch(x, wmat, n_cols, kh, kw, stride, pad, out, shift=None, relu=False, out_mul=1, out_add=(0, 0),
                  force=(0, 0), accumulate=False):
     """One family of launches: x NHWC (C_in = x.shape[3]) * wmat [n_cols, kh*kw*C_in] -> out NHWC view [..., n_cols]."""

@@ -457,6 +457,11 @@ int dbev_pack_conv_weights(const float* w, int c_out, int c_in, int kh, int kw, 
  * the weights (shared-memory tiles: every global access is a 128-byte run); either output may be NULL. */
 int dbev_pack_conv_weights_train(const float* w, int c_out, int c_in, int kh, int kw, int dgrad_mode, float* out_fwd,
                                  float* out_dgrad, void* stream);
+/* The same for every layer of a network in ONE launch (the per-step re-packing after the optimizer update).
+ * jobs_dev: n_jobs records of 8 int64 in DEVICE memory {w, out_fwd (0 = skip), out_dgrad (0 = skip), c_out, c_in,
+ * kh * 256 + kw, dgrad_mode, first_tile}; a job has ceil(c_out/32) * ceil(c_in/32) tiles, numbered consecutively over
+ * the jobs; total_tiles = their sum. Filters up to 3x3. */
+int dbev_pack_conv_weights_batch(const long long* jobs_dev, int n_jobs, int total_tiles, void* stream);
 
 /* Workspace of the per-channel reductions below (per-block partial sums, combined in block order). */
 size_t dbev_channel_stats_workspace_bytes(long long rows, int C);
@@ -603,6 +608,26 @@ int dbev_fgd_loss_backward(const dbev_fgd_config* cfg, const float* student, con
                            size_t state_bytes, const float* grad_losses, float* grad_student,
                            float* grad_conv_w, float* grad_conv_b, float* grad_channel_sum,
                            void* stream);
+
+/* The '1x1conv' channel_wise_adaptations layer (nn.Conv2d(C_in, C, 1), bevdet_distill.py:216-351, applied at :1004)
+ * fused with the loss: adapted = x W^T + bias is computed tile by tile on the tensor cores (TF32) and consumed in the
+ * GEMM epilogue - the adapted map [B,C,H,W] is never written or re-read. x_cl[B, H*W, C_in] is the student feature in
+ * channels-last memory (torch.channels_last), adapt_w[C, C_in], adapt_b[C] or NULL, teacher[B,C,H,W] NCHW; the other
+ * arguments, losses[5] and the state are those of dbev_fgd_loss_forward. dbev_fgd_adapt_supported: C_in % 32 == 0 and
+ * C % 32 == 0 up to 256 or C % 64 == 0 up to 512 (else the entry points return DBEV_ERR_INVALID_ARGUMENT). */
+int dbev_fgd_adapt_supported(const dbev_fgd_config* cfg, int c_in);
+int dbev_fgd_adapt_loss_forward(const dbev_fgd_config* cfg, const float* x_cl, int c_in, const float* adapt_w,
+                                const float* adapt_b, const float* teacher, const float* fg, const float* fg_scale,
+                                const int* fg_count, const float* fp, const int* fp_count, const float* conv_w,
+                                const float* conv_b, void* state, size_t state_bytes, float* losses, void* stream);
+/* Backward: grad_adapted_cl[B, H*W, C] (channels-last rows) = d sum_k grad_losses[k] losses[k] / d adapted, recomputing
+ * the adapted tiles; grad_channel_sum[C] (optional) = its sum over (b, h, w) = the gradient of adapt_b; grad_conv_w[9],
+ * grad_conv_b[1] as in dbev_fgd_loss_backward. The gradients of x and adapt_w are the two GEMMs
+ * dbev_conv2d_tc_forward_ex (transposed filter) and dbev_conv_wgrad_tc over grad_adapted_cl. */
+int dbev_fgd_adapt_loss_backward(const dbev_fgd_config* cfg, const float* x_cl, int c_in, const float* adapt_w,
+                                 const float* adapt_b, const float* teacher, const float* conv_w, const float* conv_b,
+                                 void* state, size_t state_bytes, const float* grad_losses, float* grad_adapted_cl,
+                                 float* grad_conv_w, float* grad_conv_b, float* grad_channel_sum, void* stream);
 
 /* ------------------------------------------------------------------------ *
  * Sparse 3D convolution of the sparse LiDAR teachers (LidarFormer / MVPFormer middle

@@ -453,3 +453,29 @@ def test_captured_training_step_with_side_stream_matches_eager(cuda):
     finally:
         ct.set_side_stream(False)
         ct._side["test_delay_cycles"] = 0
+
+
+def test_batched_weight_packing_matches_per_layer(cuda):
+    """prepack(): one launch over all layers (dbev_pack_conv_weights_batch) writes the same forward / input-gradient
+    matrices as the per-layer pass, for 3x3 stride 1 / stride 2, 1x1 and channel counts that are not multiples of 32;
+    the persistent buffers are re-used (same storage) and refreshed after a weight update."""
+    from distill_bev_b200 import bev_encoder
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Conv2d(160, 128, 3, 1, 1), torch.nn.Conv2d(128, 256, 3, 2, 1),
+                              torch.nn.Conv2d(72, 40, 3, 1, 1), torch.nn.Conv2d(256, 256, 1), torch.nn.Conv2d(40, 24, 3, 2, 1)).to(cuda)
+    bev_encoder.prepack(net)
+    ptrs = []
+    for m in net:
+        w_fwd, w_bwd, _ = m._dbev_prepacked[1]
+        a, b = ct.pack_weights_train(m.weight, m.stride[0])
+        assert torch.equal(w_fwd, a) and torch.equal(w_bwd, b)
+        ptrs.append(w_fwd.data_ptr())
+    with torch.no_grad():
+        for m in net:
+            m.weight.mul_(-0.5)
+    bev_encoder.prepack(net)
+    for m, ptr in zip(net, ptrs):
+        w_fwd, w_bwd, _ = m._dbev_prepacked[1]
+        assert m._dbev_prepacked[0] == (m.weight.data_ptr(), m.weight._version) and w_fwd.data_ptr() == ptr
+        a, b = ct.pack_weights_train(m.weight, m.stride[0])
+        assert torch.equal(w_fwd, a) and torch.equal(w_bwd, b)

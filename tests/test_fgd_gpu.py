@@ -189,13 +189,23 @@ def test_fused_channel_adaptation_matches_composition(cuda, B, Cs, Ct, H):
     adapted.retain_grad()
     l2 = fgd.fgd_distill_loss(teacher, adapted, boxes, p, tc, **kw)
     sum(l2.values()).backward()
-    for k in l1:
-        assert torch.equal(l1[k], l2[k]), k                     # same kernels, same order
-    assert torch.equal(g1[0], s2.grad) and torch.equal(g1[1], adapt.weight.grad)
-    assert torch.equal(g1[3], spatial.weight.grad)
+    if Cs % 128 == 0 and Ct % 128 == 0:
+        # loss sums taken in the adaptation GEMM's epilogue (csrc/adapt_loss_tc.cu): the adapted map is never
+        # materialised; same TF32 products, another summation order than the stand-alone loss kernels
+        def close(a, b, tol):
+            return float((a.double() - b.double()).abs().max()) <= tol * float(b.double().abs().max()) + 1e-12
+        for k in l1:
+            assert close(l1[k], l2[k], 1e-5), (k, float(l1[k]), float(l2[k]))
+        assert close(g1[0], s2.grad, 1e-4) and close(g1[1], adapt.weight.grad, 1e-4)
+        assert close(g1[3], spatial.weight.grad, 1e-4)
+    else:
+        for k in l1:
+            assert torch.equal(l1[k], l2[k]), k                     # same kernels, same order
+        assert torch.equal(g1[0], s2.grad) and torch.equal(g1[1], adapt.weight.grad)
+        assert torch.equal(g1[3], spatial.weight.grad)
     ref_bias = adapted.grad.double().sum(dim=(0, 2, 3))
     err = (g1[2].double() - ref_bias).abs().max().item()
-    assert err <= 1e-5 * ref_bias.abs().max().item() + 1e-12, err
+    assert err <= 2e-5 * ref_bias.abs().max().item() + 1e-12, err
     # rerun: bit-reproducible (fixed-order tile sums)
     adapt.zero_grad()
     s3 = _t(student, cuda).requires_grad_(True)
@@ -346,3 +356,59 @@ def test_backward_without_spatial_adaptation(cuda):
     assert conv.weight.grad is not None and torch.isfinite(s2.grad).all()
     with pytest.raises(RuntimeError):
         F.fgd_distill_loss(teacher, s, boxes, dict(params, spatial_mask=True), cfg)
+
+
+@pytest.mark.parametrize("B,Cs,Ct,H,W,bias,channel_mask", [(2, 128, 256, 32, 32, True, True), (1, 256, 512, 22, 22, False, True),
+                                                          (3, 128, 128, 18, 18, True, False), (2, 256, 384, 64, 64, True, True)])
+def test_adaptation_fused_into_loss_matches_torch(cuda, B, Cs, Ct, H, W, bias, channel_mask):
+    """dbev_fgd_adapt_loss_forward / backward (1x1 adaptation GEMM with the loss in its epilogue; ragged last tile,
+    one / two column parts, with / without bias):
+    * against the unfused path (adaptation GEMM -> NCHW map -> stand-alone loss kernels, same TF32 products): every
+      loss and gradient within 1e-4 - the fusion changes the summation order, nothing else;
+    * against an fp32 torch conv feeding the loss kernels: losses within 1e-3 (north_star tolerance), d x / d W /
+      d bias within 3e-3 of each tensor's max entry (TF32 operands). The spatial conv's weight gradient is a sum of
+      small differences of attention maps: cuDNN's TF32 conv moves it by 2e-2 on these inputs, so it is only checked
+      against the unfused path."""
+    from distill_bev_b200.plugin.distill.adaptation import conv1x1
+    rng = np.random.RandomState(B * 1000 + Cs + Ct + H)
+    teacher = _t(np.maximum(rng.randn(B, Ct, H, W), 0).astype(np.float32), cuda)
+    student = _t(np.maximum(rng.randn(B, Cs, H, W), 0).astype(np.float32), cuda).contiguous(memory_format=torch.channels_last)
+    boxes = [torch.from_numpy(b) for b, _ in synthetic.make_gt_boxes(B, seed=9)]
+    tc = dict(grid_size=[W * 8, H * 8, 40], point_cloud_range=[-51.2, -51.2, -5.0, 51.2, 51.2, 3.0],
+              voxel_size=[102.4 / (W * 8), 102.4 / (H * 8), 0.2])
+    p = dict(_recipe_params(), channel_mask=channel_mask, fp_as_foreground=["none"], fp_weight=0.0)
+    torch.manual_seed(2)
+    spatial = torch.nn.Conv2d(1, 1, 3, padding=1).to(cuda)
+    conv = torch.nn.Conv2d(Cs, Ct, 1, bias=bias).to(cuda)
+
+    def run(mode):
+        conv.zero_grad(), spatial.zero_grad()
+        s = student.clone().requires_grad_(True)
+        if mode == "fused":
+            losses = fgd.fgd_distill_loss(teacher, s, boxes, p, tc, channel_adaptation=conv, spatial_adaptation=spatial)
+        elif mode == "unfused":
+            losses = fgd.fgd_distill_loss(teacher, conv1x1(s, conv.weight, conv.bias), boxes, p, tc, spatial_adaptation=spatial)
+        else:
+            old = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = False
+            try:
+                losses = fgd.fgd_distill_loss(teacher, conv(s), boxes, p, tc, spatial_adaptation=spatial)
+            finally:
+                torch.backends.cudnn.allow_tf32 = old
+        sum(losses.values()).backward()
+        grads = [s.grad.clone(), conv.weight.grad.clone(), spatial.weight.grad.clone(), spatial.bias.grad.clone()]
+        return {k: float(v) for k, v in losses.items()}, grads + ([conv.bias.grad.clone()] if bias else [])
+
+    def rel(a, b):
+        return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-20)
+
+    l_f, g_f = run("fused")
+    l_u, g_u = run("unfused")
+    l_t, g_t = run("fp32")
+    for k in l_t:
+        assert abs(l_f[k] - l_u[k]) <= 1e-5 * abs(l_u[k]) + 1e-9, (k, l_f[k], l_u[k])
+        assert abs(l_f[k] - l_t[k]) <= 1e-3 * abs(l_t[k]) + 1e-9, (k, l_f[k], l_t[k])
+    for a, b in zip(g_f, g_u):
+        assert rel(a, b) <= 1e-4, rel(a, b)
+    for i in (0, 1) + ((4,) if bias else ()):
+        assert rel(g_f[i], g_t[i]) <= 3e-3, (i, rel(g_f[i], g_t[i]))

@@ -1,114 +1,94 @@
-"""Where does the bench step's time go? CPU issue time vs GPU time, GPU busy (sum of kernel
-durations from CUPTI) vs step span, and the top kernels by in-step (warm) duration."""
+"""Timeline of ONE replay of the bench step's CUDA graph from CUPTI kernel records (torch.profiler): per stream the busy
+time and the idle gaps, for every kernel its start offset, duration and how many other kernels ran beside it. Shows
+what the critical path of the step is made of (the ncu launch list gives serialised, cold-cache durations only).
+Writes gpurun_out/step_timeline.txt."""
 import collections
 import json
 import os
+import re
 import sys
-import time
+import tempfile
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-import torch  # noqa: E402
+import torch
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-def phases(hp):
-    """CPU issue time (queue empty at phase start) and GPU time of every phase of the step."""
-    import distill_bev_b200 as dbev
-    res = collections.OrderedDict()
-
-    def timed(name, fn, reps=10):
-        cpu = gpu = 0.0
-        val = None
-        for _ in range(reps):
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(True), torch.cuda.Event(True)
-            t0 = time.perf_counter()
-            a.record()
-            val = fn()
-            b.record()
-            t1 = time.perf_counter()
-            torch.cuda.synchronize()
-            cpu += (t1 - t0) * 1e3
-            gpu += a.elapsed_time(b)
-        res[name] = {"cpu_issue_ms": round(cpu / reps, 4), "gpu_ms": round(gpu / reps, 4)}
-        return val
-
-    nf = bench.BATCH * bench.FRAMES
-    geom = timed("A.geometry", lambda: hp.vt.get_geometry(*hp.d_calib))
-    plan = timed("A.plan", lambda: hp.vt.make_plan(geom, nf))
-    state = {}
-
-    def fwd():
-        state["bev"] = dbev.lift_splat(hp.depth, hp.feat, plan)
-
-    def bwd():
-        state["bev"].backward(hp.bev_grad, retain_graph=True)
-        hp.depth.grad = hp.feat.grad = None
-    timed("A.lift_fwd", fwd)
-    timed("A.lift_bwd", bwd)
-
-    def pillars():
-        with torch.no_grad():
-            return dbev.pillar_canvas(hp.d_points, hp.enc, hp.scat)
-    timed("B.pillar_canvas", pillars)
-
-    def loss():
-        losses = dbev.fgd.fgd_distill_loss(
-            hp.teacher, hp.student, hp.boxes, bench.DISTILL_PARAMS, bench.TRAIN_CFG,
-            channel_adaptation=hp.adapt, spatial_adaptation=hp.spatial, heatmaps=hp.d_gt_hm, teacher_heatmaps=hp.teacher_logit, epoch=1)
-        state["total"] = losses["kd_fg_feat_loss"] + losses["kd_bg_feat_loss"] + losses["kd_spatial_loss"] \
-            + losses["kd_fp_bg_feat_loss"]
-
-    def lbwd():
-        state["total"].backward(retain_graph=True)
-        hp.student.grad = None
-        hp.adapt.zero_grad(set_to_none=True)
-        hp.spatial.zero_grad(set_to_none=True)
-    timed("C.adapt+loss_fwd", loss)
-    timed("C.loss_bwd", lbwd)
-    return res
+def short(name):
+    name = name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+    name = re.sub(r"\(.*", "", name).replace("void ", "")
+    return name[:64]
 
 
 def main():
     dev = torch.device("cuda:0")
-    hp = bench.HotPath(dev, 0)
+    hp = bench.HotPath(dev, seed=1000)
+    hp.enable_graph()
     for _ in range(5):
         hp.step(False)
     torch.cuda.synchronize()
-    n = 20
-    t0 = time.perf_counter()
-    a, b = torch.cuda.Event(True), torch.cuda.Event(True)
-    a.record()
-    for _ in range(n):
-        hp.step(False)
-    t1 = time.perf_counter()
-    b.record()
-    torch.cuda.synchronize()
-    t2 = time.perf_counter()
-    out = {"cpu_issue_ms_per_step": (t1 - t0) / n * 1e3, "gpu_ms_per_step": a.elapsed_time(b) / n,
-           "wall_ms_per_step": (t2 - t0) / n * 1e3}
-    out["phases"] = phases(hp)
-    from torch.profiler import ProfilerActivity, profile
+    from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for _ in range(3):
             hp.step(False)
-        torch.cuda.synchronize()
-    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-    busy = sum(e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total for e in ev) / 3
-    out["gpu_busy_us_per_step"] = busy
-    agg = collections.defaultdict(lambda: [0, 0.0])
-    for e in ev:
-        d = e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
-        k = e.name.replace("(anonymous namespace)::", "").replace("void ", "")[:70]
-        agg[k][0] += 1
-        agg[k][1] += d
-    out["top"] = [(k, c / 3, round(t / 3, 1)) for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]]
-    print(json.dumps({k: v for k, v in out.items() if k not in ("top", "phases")}))
-    for k, v in out["phases"].items():
-        print("%-18s cpu issue %8.4f ms   gpu %8.4f ms" % (k, v["cpu_issue_ms"], v["gpu_ms"]))
-    for k, c, t in out["top"]:
-        print("%8.1f us  x%-4.1f %s" % (t, c, k))
+            torch.cuda.synchronize()
+    path = os.path.join(tempfile.gettempdir(), "dbev_step_trace.json")
+    prof.export_chrome_trace(path)
+    ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+    ev.sort(key=lambda e: e["ts"])
+    # split into replays at the largest gaps between consecutive kernels
+    gaps = sorted(((ev[i + 1]["ts"] - (ev[i]["ts"] + ev[i]["dur"]), i) for i in range(len(ev) - 1)), reverse=True)[:2]
+    cuts = sorted(i for _, i in gaps)
+    step = ev[cuts[0] + 1:cuts[1] + 1]           # the middle replay
+    t0 = min(e["ts"] for e in step)
+    t1 = max(e["ts"] + e["dur"] for e in step)
+    out = []
+    out.append("replay: %.1f us wall, %d kernels" % (t1 - t0, len(step)))
+    by_stream = collections.OrderedDict()
+    for e in step:
+        by_stream.setdefault(e["args"].get("stream"), []).append(e)
+    main_stream = max(by_stream, key=lambda s: len(by_stream[s]))
+    for s, es in by_stream.items():
+        busy = sum(e["dur"] for e in es)
+        first, last = es[0]["ts"] - t0, es[-1]["ts"] + es[-1]["dur"] - t0
+        out.append("stream %s%s: %3d kernels, busy %.1f us, active window %.1f .. %.1f us" %
+                   (s, " (main)" if s == main_stream else "", len(es), busy, first, last))
+    # main-stream idle gaps
+    es = by_stream[main_stream]
+    idle = [(es[i + 1]["ts"] - (es[i]["ts"] + es[i]["dur"]), short(es[i]["name"]), short(es[i + 1]["name"])) for i in range(len(es) - 1)]
+    out.append("main stream: sum of kernel durations %.1f us, sum of idle gaps %.1f us (%d gaps > 3 us)" %
+               (sum(e["dur"] for e in es), sum(g for g, _, _ in idle), sum(1 for g, _, _ in idle if g > 3)))
+    for g, a, b in sorted(idle, reverse=True)[:25]:
+        out.append("   gap %7.1f us  after %-50s before %s" % (g, a[:50], b))
+    # time with k streams active
+    edges = []
+    for e in step:
+        edges.append((e["ts"], 1)), edges.append((e["ts"] + e["dur"], -1))
+    edges.sort()
+    act, last_t, hist = 0, t0, collections.Counter()
+    for t, d in edges:
+        hist[act] += t - last_t
+        act, last_t = act + d, t
+    out.append("time by number of kernels in flight: " + ", ".join("%d: %.0f us" % (k, v) for k, v in sorted(hist.items())))
+    # per-kernel-name totals inside the replay (durations under contention)
+    agg = collections.OrderedDict()
+    for e in step:
+        a = agg.setdefault((short(e["name"]), e["args"].get("stream") == main_stream), [0, 0.0])
+        a[0] += 1
+        a[1] += e["dur"]
+    out.append("kernel totals in the replay (under contention):")
+    for (k, is_main), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+        out.append("   %-66s %s %3d %8.1f us" % (k, "main" if is_main else "side", n, t))
+    if "-v" in sys.argv:
+        out.append("sequence (start us, dur us, stream, kernel):")
+        for e in step:
+            out.append("   %8.1f %7.1f %3s %s" % (e["ts"] - t0, e["dur"], e["args"].get("stream"), short(e["name"])))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "step_timeline.txt"), "w") as f:
+        f.write("\n".join(out) + "\n")
+    print("\n".join(out[:90]))
 
 
 if __name__ == "__main__":
