@@ -141,10 +141,10 @@ SIGNATURES = {
     "dbev_bn_batch_stats": (_c_int, [_ptr, _c_int, _c_ll, _c_int, _ptr, _ptr, _c_float, _c_float, _ptr, _ptr, _ptr, _ptr,
                                      _c_size, _ptr]),
     "dbev_channel_sums": (_c_int, [_ptr, _c_int, _c_ll, _c_int, _ptr, _c_int, _ptr, _c_size, _ptr]),
-    "dbev_bn_act_forward": (_c_int, [_ptr, _c_int, _ptr, _ptr, _c_int, _c_ll, _c_int, _c_int, _ptr, _c_int, _ptr]),
+    "dbev_bn_act_forward": (_c_int, [_ptr, _c_int, _ptr, _ptr, _c_int, _c_ll, _c_int, _c_int, _ptr, _c_int, _ptr, _ptr]),
     "dbev_bn_backward": (_c_int, [_ptr, _c_int, _ptr, _c_int, _ptr, _c_int, _ptr, _c_ll, _c_int, _ptr, _ptr, _c_int, _ptr,
-                                  _c_int, _c_int, _ptr, _c_size, _ptr]),
-    "dbev_relu_mask_backward": (_c_int, [_ptr, _c_int, _ptr, _c_int, _c_ll, _c_int, _ptr, _c_int, _c_int, _ptr]),
+                                  _c_int, _c_int, _ptr, _ptr, _c_size, _ptr]),
+    "dbev_relu_mask_backward": (_c_int, [_ptr, _c_int, _ptr, _c_int, _c_ll, _c_int, _ptr, _c_int, _c_int, _ptr, _ptr]),
     "dbev_upsample_bilinear_forward": (_c_int, [_ptr] + [_c_int] * 7 + [_ptr, _c_int, _ptr]),
     "dbev_upsample_bilinear_backward": (_c_int, [_ptr] + [_c_int] * 7 + [_ptr, _c_int, _c_int, _ptr]),
     "dbev_sca_gather_rows": (_c_int, [_ptr, _ptr, _ptr] + [_c_int] * 5 + [_c_ll, _c_ll, _c_ll, _ptr, _ptr]),

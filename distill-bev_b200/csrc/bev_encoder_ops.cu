@@ -26,7 +26,7 @@ namespace {
 
 constexpr int kStatThreads = 256;
 constexpr int kPackJobWords = 8;
-constexpr int kFinalWarps = 32;   // channel_stats_final_kernel: 32 warps x 10 loads in flight cover 320 partial rows in one round
+constexpr int kFinalWarps = 16;   // channel_stats_final_kernel: 16 warps x 10 loads in flight: two rounds for 296 partial rows; 4 KB of shared memory
 
 // ------------------------------------------------------------------------------------------ column statistics
 // partial[blk][2][C]: block blk sums rows [blk * rows_per_block, ...); MODE 0: (sum y, sum y^2);
@@ -35,6 +35,7 @@ struct StatArgs {
   const float* y; int y_ld;
   const float* dz; int dz_ld;       // MODE 1
   const float* z; int z_ld;         // MODE 1, may be null (no ReLU after the BatchNorm)
+  const unsigned char* mask;        // MODE 1, alternative to z: the forward's ReLU mask, one byte per channel quad
   const float* mean_invstd;         // MODE 1: [2][C]
   long long rows; int C; int rows_per_block;
   float* partial;
@@ -55,7 +56,10 @@ __device__ __forceinline__ void stat_accum(const StatArgs& a, long long r, int q
     s2.x += v.x * v.x, s2.y += v.y * v.y, s2.z += v.z * v.z, s2.w += v.w * v.w;
   } else {
     float4 g = ld_stream_f4(a.dz + r * a.dz_ld + 4 * q);
-    if (a.z) {
+    if (a.mask) {
+      const unsigned m = __ldg(a.mask + r * (a.C >> 2) + q);
+      g.x = (m & 1u) ? g.x : 0.f, g.y = (m & 2u) ? g.y : 0.f, g.z = (m & 4u) ? g.z : 0.f, g.w = (m & 8u) ? g.w : 0.f;
+    } else if (a.z) {
       const float4 zz = ld_stream_f4(a.z + r * a.z_ld + 4 * q);
       g.x = zz.x > 0.f ? g.x : 0.f, g.y = zz.y > 0.f ? g.y : 0.f, g.z = zz.z > 0.f ? g.z : 0.f, g.w = zz.w > 0.f ? g.w : 0.f;
     }
@@ -70,7 +74,8 @@ __global__ void __launch_bounds__(kStatThreads) channel_stats_kernel(StatArgs a)
   const int quads = a.C >> 2;
   const int rgroups = blockDim.x / quads;
   const int q = threadIdx.x % quads, rg = threadIdx.x / quads;
-  __shared__ float4 red[2][kStatThreads];
+  __shared__ float4 red[kStatThreads];      // 4 KB, used for both statistics in turn (small enough to be co-resident
+                                            // with a persistent conv CTA of another stream, conv2d_tc.cu smem_reserve())
   float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, t1 = s1, t2 = s1;
   const long long r0 = (long long)blockIdx.x * a.rows_per_block;
   long long r1 = r0 + a.rows_per_block;
@@ -89,12 +94,19 @@ __global__ void __launch_bounds__(kStatThreads) channel_stats_kernel(StatArgs a)
   if (r < r1) stat_accum<MODE>(a, r, q, mu, is, s1, s2);
   s1.x += t1.x, s1.y += t1.y, s1.z += t1.z, s1.w += t1.w;
   s2.x += t2.x, s2.y += t2.y, s2.z += t2.z, s2.w += t2.w;
-  red[0][threadIdx.x] = s1, red[1][threadIdx.x] = s2;
+  red[threadIdx.x] = s1;
+  __syncthreads();
+  if (rg == 0)
+    for (int g = 1; g < rgroups; ++g) {
+      const float4 u1 = red[g * quads + q];
+      s1.x += u1.x, s1.y += u1.y, s1.z += u1.z, s1.w += u1.w;
+    }
+  __syncthreads();
+  red[threadIdx.x] = s2;
   __syncthreads();
   if (rg == 0) {
     for (int g = 1; g < rgroups; ++g) {
-      const float4 u1 = red[0][g * quads + q], u2 = red[1][g * quads + q];
-      s1.x += u1.x, s1.y += u1.y, s1.z += u1.z, s1.w += u1.w;
+      const float4 u2 = red[g * quads + q];
       s2.x += u2.x, s2.y += u2.y, s2.z += u2.z, s2.w += u2.w;
     }
     float* p = a.partial + (long long)blockIdx.x * 2 * a.C;
@@ -167,7 +179,8 @@ __global__ void __launch_bounds__(kFinalWarps * 32) channel_stats_final_kernel(S
 
 // ------------------------------------------------------------------------------------------ elementwise passes
 __global__ void bn_act_kernel(const float* __restrict__ y, int y_ld, const float* __restrict__ ab, const float* __restrict__ res,
-                              int res_ld, long long rows, int C, int relu, float* __restrict__ out, int out_ld) {
+                              int res_ld, long long rows, int C, int relu, float* __restrict__ out, int out_ld,
+                              unsigned char* __restrict__ mask) {
   const int quads = C >> 2;
   const long long total = rows * quads;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -183,7 +196,11 @@ __global__ void bn_act_kernel(const float* __restrict__ y, int y_ld, const float
       const float4 t = ld_stream_f4(res + r * res_ld + 4 * q);
       v.x += t.x, v.y += t.y, v.z += t.z, v.w += t.w;
     }
-    if (relu) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+    if (relu) {
+      // the backward's ReLU mask as one byte per quad: 1/16 of re-reading the output (out > 0 <=> pre-activation > 0)
+      if (mask) mask[i] = (unsigned char)((v.x > 0.f ? 1 : 0) | (v.y > 0.f ? 2 : 0) | (v.z > 0.f ? 4 : 0) | (v.w > 0.f ? 8 : 0));
+      v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+    }
     *reinterpret_cast<float4*>(out + r * out_ld + 4 * q) = v;
   }
 }
@@ -192,14 +209,18 @@ __global__ void bn_act_kernel(const float* __restrict__ y, int y_ld, const float
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dz, int dz_ld, const float* __restrict__ z, int z_ld,
                                     const float* __restrict__ y, int y_ld, const float* __restrict__ fwd /* a,b,mean,invstd */,
                                     const float* __restrict__ bwd /* dgamma,dbeta,m1,m2 */, long long rows, int C,
-                                    float* __restrict__ dy, int dy_ld, float* __restrict__ g_out, int g_ld, int g_accumulate) {
+                                    float* __restrict__ dy, int dy_ld, float* __restrict__ g_out, int g_ld, int g_accumulate,
+                                    const unsigned char* __restrict__ mask) {
   const int quads = C >> 2;
   const long long total = rows * quads;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / quads;
     const int q = (int)(i - r * quads);
     float4 g = ld_stream_f4(dz + r * dz_ld + 4 * q);
-    if (z) {
+    if (mask) {
+      const unsigned m = __ldg(mask + i);
+      g.x = (m & 1u) ? g.x : 0.f, g.y = (m & 2u) ? g.y : 0.f, g.z = (m & 4u) ? g.z : 0.f, g.w = (m & 8u) ? g.w : 0.f;
+    } else if (z) {
       const float4 zz = ld_stream_f4(z + r * z_ld + 4 * q);
       g.x = zz.x > 0.f ? g.x : 0.f, g.y = zz.y > 0.f ? g.y : 0.f, g.z = zz.z > 0.f ? g.z : 0.f, g.w = zz.w > 0.f ? g.w : 0.f;
     }
@@ -241,32 +262,37 @@ __device__ __forceinline__ void bilin_src(int dst, float scale, int in_size, int
   l0 = 1.f - l1;
 }
 
-// grid.y = (image, output row); a thread = (output column, channel quad), quads fastest: row weights are block-uniform
+// grid.y = (image, group of kUpRows output rows); a thread = (output column, channel quad), quads fastest: row weights
+// are block-uniform. A block walks its rows one after the other: consecutive output rows read the same two input rows,
+// which then come from L1 (a block's column range of an input row is a few KB) instead of L2.
 __global__ void upsample_bilinear_fwd_kernel(const float* __restrict__ in, int in_ld, int n_img, int h, int w, int C, int H, int W,
-                                             float sy, float sx, float* __restrict__ out, int out_ld) {
+                                             float sy, float sx, float* __restrict__ out, int out_ld, int kUpRows) {
   const int quads = C >> 2;
-  const int n = blockIdx.y / H, oy = blockIdx.y - n * H;
-  int y0, y1;
-  float ly0, ly1;
-  bilin_src(oy, sy, h, y0, y1, ly0, ly1);
-  const float* r0 = in + ((long long)n * h + y0) * w * in_ld;
-  const float* r1 = in + ((long long)n * h + y1) * w * in_ld;
-  float* orow = out + ((long long)n * H + oy) * W * out_ld;
+  const int groups = (H + kUpRows - 1) / kUpRows;
+  const int n = blockIdx.y / groups, oy_begin = (blockIdx.y - n * groups) * kUpRows;
+  const int oy_end = oy_begin + kUpRows < H ? oy_begin + kUpRows : H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W * quads; i += gridDim.x * blockDim.x) {
     const int ox = i / quads, q = i - ox * quads;
     int x0, x1;
     float lx0, lx1;
     bilin_src(ox, sx, w, x0, x1, lx0, lx1);
-    const float4 v00 = __ldg(reinterpret_cast<const float4*>(r0 + (long long)x0 * in_ld + 4 * q));
-    const float4 v01 = __ldg(reinterpret_cast<const float4*>(r0 + (long long)x1 * in_ld + 4 * q));
-    const float4 v10 = __ldg(reinterpret_cast<const float4*>(r1 + (long long)x0 * in_ld + 4 * q));
-    const float4 v11 = __ldg(reinterpret_cast<const float4*>(r1 + (long long)x1 * in_ld + 4 * q));
-    float4 o;
-    o.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
-    o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
-    o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
-    o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
-    st_stream_f4(orow + (long long)ox * out_ld + 4 * q, o);
+    for (int oy = oy_begin; oy < oy_end; ++oy) {
+      int y0, y1;
+      float ly0, ly1;
+      bilin_src(oy, sy, h, y0, y1, ly0, ly1);
+      const float* r0 = in + ((long long)n * h + y0) * w * in_ld;
+      const float* r1 = in + ((long long)n * h + y1) * w * in_ld;
+      const float4 v00 = __ldg(reinterpret_cast<const float4*>(r0 + (long long)x0 * in_ld + 4 * q));
+      const float4 v01 = __ldg(reinterpret_cast<const float4*>(r0 + (long long)x1 * in_ld + 4 * q));
+      const float4 v10 = __ldg(reinterpret_cast<const float4*>(r1 + (long long)x0 * in_ld + 4 * q));
+      const float4 v11 = __ldg(reinterpret_cast<const float4*>(r1 + (long long)x1 * in_ld + 4 * q));
+      float4 o;
+      o.x = ly0 * (lx0 * v00.x + lx1 * v01.x) + ly1 * (lx0 * v10.x + lx1 * v11.x);
+      o.y = ly0 * (lx0 * v00.y + lx1 * v01.y) + ly1 * (lx0 * v10.y + lx1 * v11.y);
+      o.z = ly0 * (lx0 * v00.z + lx1 * v01.z) + ly1 * (lx0 * v10.z + lx1 * v11.z);
+      o.w = ly0 * (lx0 * v00.w + lx1 * v01.w) + ly1 * (lx0 * v10.w + lx1 * v11.w);
+      st_stream_f4(out + (((long long)n * H + oy) * W + ox) * out_ld + 4 * q, o);
+    }
   }
 }
 
@@ -288,35 +314,42 @@ __device__ __forceinline__ int bilin_taps(int i, float s, float rs, int in_size,
   return n;
 }
 
-// gather form of the transpose: input pixel (iy, ix) sums the output gradients that read it. grid.y = (image, input row):
-// the row taps are block-uniform; a thread = (input column, channel quad)
+// gather form of the transpose: input pixel (iy, ix) sums the output gradients that read it. grid.y = (image, group of
+// kUpRows input rows); a thread = (input column, channel quad) and walks the group's rows: neighbouring input rows read
+// overlapping output rows, which then hit L1 instead of L2 (the kernel was L2-bound: every output element is read by up
+// to four input pixels)
 __global__ void upsample_bilinear_bwd_kernel(const float* __restrict__ dout, int dout_ld, int n_img, int h, int w, int C, int H,
-                                             int W, float sy, float sx, float* __restrict__ din, int din_ld, int accumulate) {
+                                             int W, float sy, float sx, float* __restrict__ din, int din_ld, int accumulate,
+                                             int kUpRows) {
   const int quads = C >> 2;
-  const int n = blockIdx.y / h, iy = blockIdx.y - n * h;
+  const int groups = (h + kUpRows - 1) / kUpRows;
+  const int n = blockIdx.y / groups, iy_begin = (blockIdx.y - n * groups) * kUpRows;
+  const int iy_end = iy_begin + kUpRows < h ? iy_begin + kUpRows : h;
   const float ry = sy > 0.f ? 1.f / sy : 0.f, rx = sx > 0.f ? 1.f / sx : 0.f;
   int oys[kMaxTaps], oxs[kMaxTaps];
   float wys[kMaxTaps], wxs[kMaxTaps];
-  const int ny = bilin_taps(iy, sy, ry, h, H, oys, wys);
   const float* b = dout + (long long)n * H * W * dout_ld;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * quads; i += gridDim.x * blockDim.x) {
     const int ix = i / quads, q = i - ix * quads;
     const int nx = bilin_taps(ix, sx, rx, w, W, oxs, wxs);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int a = 0; a < ny; ++a) {
-      const float* row = b + (long long)oys[a] * W * dout_ld + 4 * q;
-      for (int c = 0; c < nx; ++c) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(row + (long long)oxs[c] * dout_ld));
-        const float wgt = wys[a] * wxs[c];
-        acc.x += wgt * g.x, acc.y += wgt * g.y, acc.z += wgt * g.z, acc.w += wgt * g.w;
+    for (int iy = iy_begin; iy < iy_end; ++iy) {
+      const int ny = bilin_taps(iy, sy, ry, h, H, oys, wys);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int a = 0; a < ny; ++a) {
+        const float* row = b + (long long)oys[a] * W * dout_ld + 4 * q;
+        for (int c = 0; c < nx; ++c) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(row + (long long)oxs[c] * dout_ld));
+          const float wgt = wys[a] * wxs[c];
+          acc.x += wgt * g.x, acc.y += wgt * g.y, acc.z += wgt * g.z, acc.w += wgt * g.w;
+        }
       }
+      float4* o = reinterpret_cast<float4*>(din + (((long long)n * h + iy) * w + ix) * din_ld + 4 * q);
+      if (accumulate) {
+        const float4 prev = *o;
+        acc.x += prev.x, acc.y += prev.y, acc.z += prev.z, acc.w += prev.w;
+      }
+      *o = acc;
     }
-    float4* o = reinterpret_cast<float4*>(din + (((long long)n * h + iy) * w + ix) * din_ld + 4 * q);
-    if (accumulate) {
-      const float4 prev = *o;
-      acc.x += prev.x, acc.y += prev.y, acc.z += prev.z, acc.w += prev.w;
-    }
-    *o = acc;
   }
 }
 
@@ -439,6 +472,13 @@ __global__ void __launch_bounds__(256) pack_conv_weights_batch_kernel(const long
                          (t % tiles_ci) * 32, tile);
 }
 
+// rows a block of the upsampling kernels walks: 8 when that still leaves >= 1024 blocks, else fewer (small maps)
+int upsample_rows_per_block(long long blocks_x, int n_img, int rows) {
+  int r = 8;
+  while (r > 1 && blocks_x * n_img * ceil_div(rows, r) < 1024) r >>= 1;
+  return r;
+}
+
 int grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = (long long)kNumSMs * 16;
@@ -508,23 +548,24 @@ int channel_sums(const float* y, int y_ld, long long rows, int C, float* out, in
 }
 
 int bn_act_forward(const float* y, int y_ld, const float* ab, const float* residual, int res_ld, long long rows, int C, int relu,
-                   float* out, int out_ld, cudaStream_t stream) {
+                   float* out, int out_ld, unsigned char* relu_mask, cudaStream_t stream) {
   DBEV_CHECK_ARG(rows > 0 && C % 4 == 0 && y_ld % 4 == 0 && out_ld % 4 == 0 && (!residual || res_ld % 4 == 0),
                  "bn_act_forward: channel counts / strides must be multiples of 4");
-  bn_act_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, stream>>>(y, y_ld, ab, residual, res_ld, rows, C, relu, out, out_ld);
+  bn_act_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, stream>>>(y, y_ld, ab, residual, res_ld, rows, C, relu, out, out_ld,
+                                                                   relu ? relu_mask : nullptr);
   DBEV_CHECK_LAUNCH("bn_act_kernel");
   return DBEV_OK;
 }
 
 int bn_backward(const float* dz, int dz_ld, const float* z, int z_ld, const float* y, int y_ld, const float* fwd4c, long long rows,
-                int C, float* bwd4c, float* dy, int dy_ld, float* g_out, int g_ld, int g_accumulate, void* workspace,
-                size_t workspace_bytes, cudaStream_t stream) {
+                int C, float* bwd4c, float* dy, int dy_ld, float* g_out, int g_ld, int g_accumulate, const unsigned char* relu_mask,
+                void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (int rc = check_stat_shape(rows, C, "bn_backward")) return rc;
   DBEV_CHECK_ARG(workspace && workspace_bytes >= channel_stats_workspace_bytes(rows, C), "bn_backward: workspace too small");
   StatArgs a = {};
   int rpb;
   const int blocks = stat_blocks(rows, &rpb);
-  a.y = y, a.y_ld = y_ld, a.dz = dz, a.dz_ld = dz_ld, a.z = z, a.z_ld = z_ld, a.mean_invstd = fwd4c + 2 * C;
+  a.y = y, a.y_ld = y_ld, a.dz = dz, a.dz_ld = dz_ld, a.z = z, a.z_ld = z_ld, a.mask = relu_mask, a.mean_invstd = fwd4c + 2 * C;
   a.rows = rows, a.C = C, a.rows_per_block = rpb;
   a.partial = (float*)workspace;
   a.out = bwd4c;
@@ -534,16 +575,17 @@ int bn_backward(const float* dz, int dz_ld, const float* z, int z_ld, const floa
   channel_stats_final_kernel<1><<<ceil_div(C, 16), kFinalWarps * 32, 0, stream>>>(a, blocks);
   DBEV_CHECK_LAUNCH("channel_stats_final_kernel<1>");
   bn_bwd_apply_kernel<<<grid_for(rows * quads, 256), 256, 0, stream>>>(dz, dz_ld, z, z_ld, y, y_ld, fwd4c, bwd4c, rows, C, dy, dy_ld,
-                                                                       g_out, g_ld, g_accumulate);
+                                                                       g_out, g_ld, g_accumulate, relu_mask);
   DBEV_CHECK_LAUNCH("bn_bwd_apply_kernel");
   return DBEV_OK;
 }
 
 int relu_mask_backward(const float* dz, int dz_ld, const float* z, int z_ld, long long rows, int C, float* g_out, int g_ld,
-                       int accumulate, cudaStream_t stream) {
+                       int accumulate, const unsigned char* relu_mask, cudaStream_t stream) {
   DBEV_CHECK_ARG(rows > 0 && C % 4 == 0, "relu_mask_backward: C must be a multiple of 4");
+  DBEV_CHECK_ARG(z || relu_mask, "relu_mask_backward: needs the forward output z or its ReLU mask");
   bn_bwd_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, stream>>>(dz, dz_ld, z, z_ld, nullptr, 0, nullptr, nullptr, rows, C,
-                                                                         nullptr, 0, g_out, g_ld, accumulate);
+                                                                         nullptr, 0, g_out, g_ld, accumulate, relu_mask);
   DBEV_CHECK_LAUNCH("bn_bwd_apply_kernel");
   return DBEV_OK;
 }
@@ -552,9 +594,10 @@ int upsample_bilinear_forward(const float* in, int in_ld, int n_img, int h, int 
                               cudaStream_t stream) {
   DBEV_CHECK_ARG(n_img > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C % 4 == 0, "upsample_bilinear: bad shape");
   const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  DBEV_CHECK_ARG((long long)n_img * H <= 65535, "upsample_bilinear: too many output rows for one launch");
-  upsample_bilinear_fwd_kernel<<<dim3((unsigned)ceil_div((long long)W * (C / 4), 256), (unsigned)(n_img * H)), 256, 0, stream>>>(
-      in, in_ld, n_img, h, w, C, H, W, sy, sx, out, out_ld);
+  const int kUpRows = upsample_rows_per_block(ceil_div((long long)W * (C / 4), 256), n_img, H);
+  DBEV_CHECK_ARG((long long)n_img * ceil_div(H, kUpRows) <= 65535, "upsample_bilinear: too many output rows for one launch");
+  upsample_bilinear_fwd_kernel<<<dim3((unsigned)ceil_div((long long)W * (C / 4), 256), (unsigned)(n_img * ceil_div(H, kUpRows))), 256, 0, stream>>>(
+      in, in_ld, n_img, h, w, C, H, W, sy, sx, out, out_ld, kUpRows);
   DBEV_CHECK_LAUNCH("upsample_bilinear_fwd_kernel");
   return DBEV_OK;
 }
@@ -563,10 +606,11 @@ int upsample_bilinear_backward(const float* dout, int dout_ld, int n_img, int h,
                                int accumulate, cudaStream_t stream) {
   DBEV_CHECK_ARG(n_img > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C % 4 == 0, "upsample_bilinear: bad shape");
   const float sy = H > 1 ? (float)(h - 1) / (float)(H - 1) : 0.f, sx = W > 1 ? (float)(w - 1) / (float)(W - 1) : 0.f;
-  DBEV_CHECK_ARG((long long)n_img * h <= 65535, "upsample_bilinear: too many input rows for one launch");
+  const int kUpRows = upsample_rows_per_block(ceil_div((long long)w * (C / 4), 128), n_img, h);
+  DBEV_CHECK_ARG((long long)n_img * ceil_div(h, kUpRows) <= 65535, "upsample_bilinear: too many input rows for one launch");
   DBEV_CHECK_ARG(H >= h && W >= w && H <= 4 * h + 4 && W <= 4 * w + 4, "upsample_bilinear_backward: scale factors 1..4 only");
-  upsample_bilinear_bwd_kernel<<<dim3((unsigned)ceil_div((long long)w * (C / 4), 128), (unsigned)(n_img * h)), 128, 0, stream>>>(
-      dout, dout_ld, n_img, h, w, C, H, W, sy, sx, din, din_ld, accumulate);
+  upsample_bilinear_bwd_kernel<<<dim3((unsigned)ceil_div((long long)w * (C / 4), 128), (unsigned)(n_img * ceil_div(h, kUpRows))), 128, 0, stream>>>(
+      dout, dout_ld, n_img, h, w, C, H, W, sy, sx, din, din_ld, accumulate, kUpRows);
   DBEV_CHECK_LAUNCH("upsample_bilinear_bwd_kernel");
   return DBEV_OK;
 }

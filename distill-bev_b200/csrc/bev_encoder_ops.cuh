@@ -16,14 +16,14 @@ int channel_sums(const float* y, int y_ld, long long rows, int C, float* out, in
                  size_t workspace_bytes, cudaStream_t stream);
 
 int bn_act_forward(const float* y, int y_ld, const float* ab, const float* residual, int res_ld, long long rows, int C, int relu,
-                   float* out, int out_ld, cudaStream_t stream);
+                   float* out, int out_ld, unsigned char* relu_mask, cudaStream_t stream);
 
 int bn_backward(const float* dz, int dz_ld, const float* z, int z_ld, const float* y, int y_ld, const float* fwd4c, long long rows,
-                int C, float* bwd4c, float* dy, int dy_ld, float* g_out, int g_ld, int g_accumulate, void* workspace,
-                size_t workspace_bytes, cudaStream_t stream);
+                int C, float* bwd4c, float* dy, int dy_ld, float* g_out, int g_ld, int g_accumulate, const unsigned char* relu_mask,
+                void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 int relu_mask_backward(const float* dz, int dz_ld, const float* z, int z_ld, long long rows, int C, float* g_out, int g_ld,
-                       int accumulate, cudaStream_t stream);
+                       int accumulate, const unsigned char* relu_mask, cudaStream_t stream);
 
 int upsample_bilinear_forward(const float* in, int in_ld, int n_img, int h, int w, int C, int H, int W, float* out, int out_ld,
                               cudaStream_t stream);

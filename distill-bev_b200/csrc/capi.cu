@@ -513,21 +513,21 @@ int dbev_channel_sums(const float* y, int y_ld, long long rows, int C, float* ou
 }
 
 int dbev_bn_act_forward(const float* y, int y_ld, const float* ab, const float* residual, int res_ld,
-                        long long rows, int C, int relu, float* out, int out_ld, void* stream) {
-  return bn_act_forward(y, y_ld, ab, residual, res_ld, rows, C, relu, out, out_ld, (cudaStream_t)stream);
+                        long long rows, int C, int relu, float* out, int out_ld, unsigned char* relu_mask, void* stream) {
+  return bn_act_forward(y, y_ld, ab, residual, res_ld, rows, C, relu, out, out_ld, relu_mask, (cudaStream_t)stream);
 }
 
 int dbev_bn_backward(const float* dz, int dz_ld, const float* z, int z_ld, const float* y, int y_ld,
                      const float* fwd4c, long long rows, int C, float* bwd4c, float* dy, int dy_ld,
-                     float* g_out, int g_ld, int g_accumulate, void* workspace, size_t workspace_bytes,
-                     void* stream) {
-  return bn_backward(dz, dz_ld, z, z_ld, y, y_ld, fwd4c, rows, C, bwd4c, dy, dy_ld, g_out, g_ld, g_accumulate,
+                     float* g_out, int g_ld, int g_accumulate, const unsigned char* relu_mask, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  return bn_backward(dz, dz_ld, z, z_ld, y, y_ld, fwd4c, rows, C, bwd4c, dy, dy_ld, g_out, g_ld, g_accumulate, relu_mask,
                      workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int dbev_relu_mask_backward(const float* dz, int dz_ld, const float* z, int z_ld, long long rows, int C,
-                            float* g_out, int g_ld, int accumulate, void* stream) {
-  return relu_mask_backward(dz, dz_ld, z, z_ld, rows, C, g_out, g_ld, accumulate, (cudaStream_t)stream);
+                            float* g_out, int g_ld, int accumulate, const unsigned char* relu_mask, void* stream) {
+  return relu_mask_backward(dz, dz_ld, z, z_ld, rows, C, g_out, g_ld, accumulate, relu_mask, (cudaStream_t)stream);
 }
 
 int dbev_upsample_bilinear_forward(const float* in, int in_ld, int n, int h, int w, int C, int H, int W,

@@ -550,6 +550,22 @@ cudaError_t launch_conv(void (*kernel)(KArgs...), int grid, size_t smem, cudaStr
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Experiment switch: shared memory the conv kernels leave free on every SM (DBEV_SMEM_RESERVE bytes, default 0) so that
+// blocks of the memory-bound kernels of OTHER streams (BatchNorm statistics / apply, <= 5 KB each) can be co-resident
+// with a persistent conv CTA instead of waiting for the whole conv kernel to retire. Measured on the bench step:
+// 0 -> 7.70 ms, 10 KB -> 7.72 ms, 24 KB -> 7.88 ms (the conv rings get shallower, the overlap gains nothing because the
+// tensor kernels already cover 76 % of the step and the rest is dependency-bound): DESIGN.md 7.1.
+int smem_reserve() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DBEV_SMEM_RESERVE");
+    v = e ? atoi(e) : 0;
+    if (v < 0) v = 0;
+    if (v > 65536) v = 65536;
+  }
+  return v;
+}
+
 // A/B switch: DBEV_CONV_HALO = 0 (per-tap kernel for every layer), 1 (default: halo kernel, pitch 10),
 // 2 (pitch 16), 4 (no split of the last round). Measured: both pitches are bit-identical to the per-tap kernel (descriptor base-offset 0);
 // setting the descriptor's base-offset field to (start >> 7) & 7 gives wrong results.
@@ -619,7 +635,7 @@ int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in,
     hs.hx = halo_mode == 2 ? 16 : kHaloTx + 2;
     const int w_tile = c_out * kKc * 4;
     const int stage_out = 4 * 2 * 4096;       // 4 epilogue warps x 2 staging buffers x (32 px x 128 B)
-    const int smem_max = 227 * 1024 - 2048;
+    const int smem_max = 227 * 1024 - 2048 - smem_reserve();
     // (keeping all 9 * C_in/32 weight tiles of a 64 -> 64 layer resident in shared memory was tried: only
     // single-half tiles fit beside them, whose halo prefetch distance is too short - 0.132 vs 0.110 ms)
     hs.item_halves = h > 16 ? 2 : 1;      // 16-row images (the student's 512-channel stage): one M=128 half per item
@@ -813,7 +829,8 @@ int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in,
     if (small_grid) DBEV_CONV_LAUNCH(128, 5, 1);
     else if (s.tma_store) DBEV_CONV_LAUNCH(128, 2, 2);
     else DBEV_CONV_LAUNCH(128, 3, 2);
-  } else DBEV_CONV_LAUNCH(256, 4, 1);
+  } else if (smem_reserve() > 0 && s.tma_store) DBEV_CONV_LAUNCH(256, 3, 1);
+  else DBEV_CONV_LAUNCH(256, 4, 1);
 #undef DBEV_CONV_LAUNCH
   DBEV_CHECK_LAUNCH("conv2d_tc_kernel");
   return DBEV_OK;

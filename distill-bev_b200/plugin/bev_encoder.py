@@ -61,30 +61,30 @@ class _ConvBNActFn(torch.autograd.Function):
                 b = beta if beta is not None else torch.zeros_like(invstd)
                 a = g * invstd
                 fwd = torch.stack([a, b - bn.running_mean * a, bn.running_mean, invstd]).contiguous()
-            z = ct.bn_act(y, fwd, rh, relu)
+            z, mask = ct.bn_act(y, fwd, rh, relu, want_mask=True)
         elif rh is not None or relu:
-            z = ct.bn_act(y, None, rh, relu)
+            z, mask = ct.bn_act(y, None, rh, relu, want_mask=True)
         else:
-            z = y
+            z, mask = y, None
         ctx.conf = (stride, pad, relu, bn is not None, bn is not None and (bn.training or bn.running_mean is None), bn,
                     tuple(xh.shape[1:3]), residual is not None, bias is not None, owner)
-        ctx.save_for_backward(xh, weight, y, z if relu else None, fwd, gamma, w_bwd)
+        ctx.save_for_backward(xh, weight, y, mask, fwd, gamma, w_bwd)    # mask: the ReLU decision, 1 byte per 4 channels
         return ct.as_nchw(z)
 
     @staticmethod
     def backward(ctx, dz):
-        xh, weight, y, z, fwd, gamma, w_bwd = ctx.saved_tensors
+        xh, weight, y, mask, fwd, gamma, w_bwd = ctx.saved_tensors
         stride, pad, relu, has_bn, batch_stats, bn, in_hw, has_res, has_bias, owner = ctx.conf
         co, ci, kh, kw = weight.shape
         dzh = ct.as_nhwc(dz)
         need = ctx.needs_input_grad
         d_gamma = d_beta = d_bias = d_res = None
         if has_bn and batch_stats:
-            dy, bwd, g = ct.bn_backward(dzh, z, y, fwd, want_g=has_res and need[5], ws=_stats_ws(bn, y))
+            dy, bwd, g = ct.bn_backward(dzh, None, y, fwd, want_g=has_res and need[5], ws=_stats_ws(bn, y), mask=mask)
             d_gamma, d_beta = (bwd[0] if need[3] else None), (bwd[1] if need[4] else None)
             d_res = g
         else:
-            g = ct.relu_backward(dzh, z) if relu else dzh
+            g = ct.relu_backward(dzh, mask=mask) if relu else dzh
             d_res = g if has_res else None
             if has_bn:     # eval-mode BN: a fixed per-channel affine
                 dy = ct.bn_act(g, torch.stack([fwd[0], torch.zeros_like(fwd[0])]).contiguous(), None, False)

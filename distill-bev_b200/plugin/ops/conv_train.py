@@ -256,43 +256,53 @@ def channel_sums(y, out=None, accumulate=False, ws=None):
     return out
 
 
-def bn_act(y, ab=None, residual=None, relu=True, out=None):
-    """out = relu?(a * y + b (+ residual)), NHWC; `out` may be a channel slice of a wider tensor."""
+def bn_act(y, ab=None, residual=None, relu=True, out=None, want_mask=False):
+    """out = relu?(a * y + b (+ residual)), NHWC; `out` may be a channel slice of a wider tensor. want_mask (with relu):
+    also returns the ReLU mask [rows, C/4] uint8 (bit k of a byte = channel 4*quad + k was positive) that bn_backward /
+    relu_backward take instead of the output - the backward then reads 1 byte instead of 16 per channel quad."""
     lib = _lib.load()
     c, rows, ld = y.shape[3], _rows(y), nhwc_ld(y, "y")
     if out is None:
         out = torch.empty(y.shape, dtype=torch.float32, device=y.device)
     r_ld = nhwc_ld(residual, "residual") if residual is not None else 0
+    mask = torch.empty((rows, c // 4), dtype=torch.uint8, device=y.device) if (want_mask and relu) else None
     with torch.cuda.device(y.device):
         rc = lib.dbev_bn_act_forward(_lib.ptr(y), ld, _lib.ptr(ab), _lib.ptr(residual), r_ld, rows, c, 1 if relu else 0,
-                                     _lib.ptr(out), nhwc_ld(out, "out"), _lib.stream_ptr(y.device))
+                                     _lib.ptr(out), nhwc_ld(out, "out"), _lib.ptr(mask), _lib.stream_ptr(y.device))
     _lib.check(rc, "dbev_bn_act_forward")
-    return out
+    return (out, mask) if want_mask else out
 
 
-def bn_backward(dz, z, y, fwd, want_g=False, ws=None):
-    """Backward of z = relu?(BN(y) (+ identity)). z=None: no ReLU. Returns (dy, bwd[4, C] = dgamma, dbeta, .., g or None)."""
+def bn_backward(dz, z, y, fwd, want_g=False, ws=None, mask=None):
+    """Backward of z = relu?(BN(y) (+ identity)). z=None and mask=None: no ReLU; mask = bn_act(..., want_mask=True)[1]
+    replaces z. Returns (dy, bwd[4, C] = dgamma, dbeta, .., g or None)."""
     lib = _lib.load()
     c, rows = y.shape[3], _rows(y)
     ws = ws if ws is not None else stats_workspace(rows, c, y.device)
     bwd = torch.empty((4, c), dtype=torch.float32, device=y.device)
     dy = torch.empty(y.shape, dtype=torch.float32, device=y.device)
     g = torch.empty(y.shape, dtype=torch.float32, device=y.device) if want_g else None
+    if mask is not None:
+        z = None
     with torch.cuda.device(y.device):
         rc = lib.dbev_bn_backward(_lib.ptr(dz), nhwc_ld(dz, "dz"), _lib.ptr(z), nhwc_ld(z, "z") if z is not None else 0,
                                   _lib.ptr(y), nhwc_ld(y, "y"), _lib.ptr(fwd), rows, c, _lib.ptr(bwd), _lib.ptr(dy), c,
-                                  _lib.ptr(g), c, 0, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y.device))
+                                  _lib.ptr(g), c, 0, _lib.ptr(mask), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(y.device))
     _lib.check(rc, "dbev_bn_backward")
     return dy, bwd, g
 
 
-def relu_backward(dz, z):
+def relu_backward(dz, z=None, mask=None):
+    """g = dz * (z > 0), from the forward output z or its ReLU mask."""
     lib = _lib.load()
-    c, rows = z.shape[3], _rows(z)
-    g = torch.empty(z.shape, dtype=torch.float32, device=z.device)
-    with torch.cuda.device(z.device):
-        rc = lib.dbev_relu_mask_backward(_lib.ptr(dz), nhwc_ld(dz, "dz"), _lib.ptr(z), nhwc_ld(z, "z"), rows, c, _lib.ptr(g), c, 0,
-                                         _lib.stream_ptr(z.device))
+    n, h, w, c = dz.shape
+    rows = n * h * w
+    g = torch.empty((n, h, w, c), dtype=torch.float32, device=dz.device)
+    if mask is not None:
+        z = None
+    with torch.cuda.device(dz.device):
+        rc = lib.dbev_relu_mask_backward(_lib.ptr(dz), nhwc_ld(dz, "dz"), _lib.ptr(z), nhwc_ld(z, "z") if z is not None else 0,
+                                         rows, c, _lib.ptr(g), c, 0, _lib.ptr(mask), _lib.stream_ptr(dz.device))
     _lib.check(rc, "dbev_relu_mask_backward")
     return g
 

@@ -476,17 +476,19 @@ int dbev_channel_sums(const float* y, int y_ld, long long rows, int C, float* ou
                       void* workspace, size_t workspace_bytes, void* stream);
 /* out = relu?(a*y + b (+ residual)); ab[2][C] nullable (identity affine). */
 int dbev_bn_act_forward(const float* y, int y_ld, const float* ab, const float* residual, int res_ld,
-                        long long rows, int C, int relu, float* out, int out_ld, void* stream);
-/* Backward of z = relu?(BN(y) (+ identity)): g = dz * (z > 0) (z nullable: no ReLU);
+                        long long rows, int C, int relu, float* out, int out_ld, unsigned char* relu_mask, void* stream);
+/* relu_mask (nullable, [rows][C/4] bytes, written when relu != 0): bit k of byte (row, quad) = pre-activation of
+ * channel 4*quad + k > 0. The backward entry points below take it instead of z - 1/16 of the bytes of re-reading z.
+ * Backward of z = relu?(BN(y) (+ identity)): g = dz * (z > 0) (z and relu_mask both NULL: no ReLU);
  * bwd4c[4][C] = (dgamma, dbeta, mean g, mean g*yhat); dy = a*(g - mean g - yhat*mean(g*yhat));
  * g_out (nullable) receives g (the identity-branch gradient), added when g_accumulate. */
 int dbev_bn_backward(const float* dz, int dz_ld, const float* z, int z_ld, const float* y, int y_ld,
                      const float* fwd4c, long long rows, int C, float* bwd4c, float* dy, int dy_ld,
-                     float* g_out, int g_ld, int g_accumulate, void* workspace, size_t workspace_bytes,
-                     void* stream);
-/* g_out (+)= dz * (z > 0) without a BatchNorm. */
+                     float* g_out, int g_ld, int g_accumulate, const unsigned char* relu_mask, void* workspace,
+                     size_t workspace_bytes, void* stream);
+/* g_out (+)= dz * (z > 0) without a BatchNorm (z or relu_mask). */
 int dbev_relu_mask_backward(const float* dz, int dz_ld, const float* z, int z_ld, long long rows, int C,
-                            float* g_out, int g_ld, int accumulate, void* stream);
+                            float* g_out, int g_ld, int accumulate, const unsigned char* relu_mask, void* stream);
 /* nn.Upsample(mode='bilinear', align_corners=True) on NHWC, ATen's index arithmetic; the backward is a
  * gather (no atomics, deterministic). */
 int dbev_upsample_bilinear_forward(const float* in, int in_ld, int n, int h, int w, int C, int H, int W,

@@ -132,6 +132,15 @@ def test_batchnorm_train_forward_backward(cuda, c, relu, res):
     torch.testing.assert_close(bwd[1], bn.bias.grad, rtol=1e-4, atol=1e-4 * float(bn.bias.grad.abs().max()))
     if res:
         torch.testing.assert_close(g.permute(0, 3, 1, 2), r.grad, rtol=0, atol=0)
+    if relu:
+        # the ReLU mask (1 byte per channel quad, written by the forward) instead of re-reading z: identical results
+        zm, mask = ct.bn_act(yh, fwd, _nhwc(r.detach()) if res else None, True, want_mask=True)
+        assert torch.equal(zm, zh) and mask.shape == (n * h * w, c // 4) and mask.dtype == torch.uint8
+        bits = (zh.reshape(-1, c // 4, 4) > 0).to(torch.uint8)
+        assert torch.equal(mask, bits[..., 0] | (bits[..., 1] << 1) | (bits[..., 2] << 2) | (bits[..., 3] << 3))
+        dy2, bwd2, g2 = ct.bn_backward(_nhwc(dz), None, yh, fwd, want_g=res, mask=mask)
+        assert torch.equal(dy2, dy) and torch.equal(bwd2, bwd) and (not res or torch.equal(g2, g))
+        assert torch.equal(ct.relu_backward(_nhwc(dz), mask=mask), ct.relu_backward(_nhwc(dz), zh))
     sums = ct.channel_sums(yh)
     torch.testing.assert_close(sums, y.detach().sum((0, 2, 3)), rtol=1e-5, atol=1e-3)
 
