@@ -276,6 +276,7 @@ class HotPath(object):
         self.d_labels = self.h_labels.to(device)
         self.captured, self.split = None, False
         self.side = [torch.cuda.Stream(device)]
+        self.opt_stream = torch.cuda.Stream(device)
         self.h2d_bytes = (sum(t.numel() * 4 for t in self.h_calib) + sum(t.numel() * 4 for t in self.h_points)
                           + self.h_labels.numel() * 4 + self.h_box_offs.numel() * 4
                           + sum(b.numel() * 4 for b in self.boxes))
@@ -325,6 +326,11 @@ class HotPath(object):
         else:
             # sort-free splat with the frame index numbered last: the result IS the channel concat of the two frames
             bev = dbev.lift_splat(self.depth, self.feat, self.vt.make_cells(geom, BATCH * FRAMES, frames=FRAMES))
+        # the encoder's last parameter gradient exists once d loss / d bev does (before the splat's backward starts):
+        # the optimizer step waits for this event only and overlaps the rest of the backward chain (the splat's
+        # backward here; the image-view network's backward in a full detector)
+        self._enc_grads_done = torch.cuda.Event()
+        bev.register_hook(lambda g: self._enc_grads_done.record(torch.cuda.current_stream(self.dev)))
         # S: student BEV encoder (training mode)
         s_feat = self.encode(bev)
         # C: head-position distillation loss (1x1 channel adaptation inside, as in the reference)
@@ -347,9 +353,22 @@ class HotPath(object):
             p.grad = None
         return loss_vec, canvas
 
-    def _update(self):
-        self.dbev.conv_train.join_side_stream(self.dev)       # weight gradients computed beside the backward chain
-        self.optim.step()
+    def _update(self, overlap_event=None):
+        """AdamW over the trained parameters. With ``overlap_event`` (recorded when the last parameter gradient of the
+        main stream exists) the step runs on its own stream beside the tail of the backward chain."""
+        torch = self.torch
+        if overlap_event is None or not self.overlap_side:
+            self.dbev.conv_train.join_side_stream(self.dev)   # weight gradients computed beside the backward chain
+            self.optim.step()
+        else:
+            main = torch.cuda.current_stream(self.dev)
+            self.opt_stream.wait_event(overlap_event)
+            self.dbev.conv_train.join_side_stream(self.dev, self.opt_stream)
+            with torch.cuda.stream(self.opt_stream):
+                if self.reducer is not None:
+                    self.reducer.finish()                     # the optimizer stream waits for the all-reduce stream
+                self.optim.step()
+            main.wait_stream(self.opt_stream)
         if self.reducer is None:
             self.optim.zero_grad(set_to_none=True)
 
@@ -357,9 +376,10 @@ class HotPath(object):
         """One whole training step issued in one go (used eagerly and as the single captured graph when the gradient
         all-reduce is absent or captured with it)."""
         out = self._forward_backward(calib, points, labels, boxes)
-        if self.reducer is not None:
+        ev = self._enc_grads_done if self.overlap_side else None
+        if ev is None and self.reducer is not None:
             self.reducer.finish()
-        self._update()
+        self._update(ev)
         return out
 
     def _device_inputs(self):
