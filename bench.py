@@ -886,7 +886,10 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (TF32 tensor-core multiply, fp32 accumulate: the reference's "
                                                          "cuDNN arithmetic under torch defaults)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "frames": FRAMES, "parallelism": "dp%d" % world},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "frames": FRAMES, "parallelism": "dp%d" % world,
+                   "l2": "inputs larger than L2 (activations > 3 GB per step)",
+                   "collective": "%s, %d bytes per step (%s)" % (coll["collective"], coll.get("bytes_per_step", 0),
+                                                                 coll.get("comm_dtype", "-"))},
         "step_detail": {"l2": "activations larger than L2 (encoder activations > 3 GB, teacher conv activations > 2 GB per step)",
                         "collective": coll, "allreduce_mode": hp.allreduce if world > 1 else "n/a",
                         "trainable_parameters": int(hp.n_params), "optimizer": "torch.optim.AdamW(fused=True, capturable=True)",

@@ -412,3 +412,29 @@ def test_adaptation_fused_into_loss_matches_torch(cuda, B, Cs, Ct, H, W, bias, c
         assert rel(a, b) <= 1e-4, rel(a, b)
     for i in (0, 1) + ((4,) if bias else ()):
         assert rel(g_f[i], g_t[i]) <= 3e-3, (i, rel(g_f[i], g_t[i]))
+
+
+def test_fused_adaptation_entry_points_reject_bad_arguments(cuda):
+    """dbev_fgd_adapt_supported / dbev_fgd_adapt_loss_forward: shapes the tensor-core kernel does not cover return
+    DBEV_ERR_INVALID_ARGUMENT with a message (no launch); the Python side routes such shapes to the unfused path."""
+    import ctypes
+    from distill_bev_b200 import _lib
+    lib = _lib.load()
+    cfg, _ = fgd.make_config(2, 384, 16, 16, _recipe_params())
+    assert lib.dbev_fgd_adapt_supported(ctypes.byref(cfg), 256) == 1
+    assert lib.dbev_fgd_adapt_supported(ctypes.byref(cfg), 48) == 0            # C_in must be a multiple of 32
+    bad, _ = fgd.make_config(2, 288, 16, 16, _recipe_params())                 # 288 > 256 and not a multiple of 64
+    assert lib.dbev_fgd_adapt_supported(ctypes.byref(bad), 256) == 0
+    state = torch.empty(lib.dbev_fgd_state_bytes(ctypes.byref(bad)) // 4, device=cuda)
+    x = torch.zeros(2, 16, 16, 256, device=cuda)
+    w = torch.zeros(288, 256, device=cuda)
+    t = torch.zeros(2, 288, 16, 16, device=cuda)
+    m = torch.zeros(2, 16, 16, device=cuda)
+    cnt = torch.ones(2, dtype=torch.int32, device=cuda)
+    cw, cb, losses = torch.zeros(9, device=cuda), torch.zeros(1, device=cuda), torch.zeros(5, device=cuda)
+    rc = lib.dbev_fgd_adapt_loss_forward(ctypes.byref(bad), _lib.ptr(x), 256, _lib.ptr(w), None, _lib.ptr(t), _lib.ptr(m),
+                                         _lib.ptr(m), _lib.ptr(cnt), _lib.ptr(m), _lib.ptr(cnt), _lib.ptr(cw), _lib.ptr(cb),
+                                         _lib.ptr(state), state.numel() * 4, _lib.ptr(losses), _lib.stream_ptr(cuda))
+    assert rc != 0
+    with pytest.raises(RuntimeError, match="unsupported adaptation shape"):
+        _lib.check(rc, "dbev_fgd_adapt_loss_forward")
