@@ -596,7 +596,11 @@ def student_conv_roofline(hp):
         peak, how = 1100.0, "fallback: nominal dense TF32 1.1 PFLOP/s (B200_PROFILING.md)"
     ach = flops / (ms * 1e-3) / 1e12
     return {"kernel": "dbev::conv3x3_halo_kernel<256>", "bound": "tensor", "achieved": round(ach, 1), "peak": round(peak, 1),
-            "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None, "peak_source": how,
+            "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture in
+            # profiles/r02_conv_train.json (287.4 + 93.4 MB; the rest of the 134 MB output is still in L2 when the
+            # kernel ends; algorithmic: x 268 MB + W 4.7 MB + y 134 MB)
+            "traffic": 380.8e6, "peak_source": how,
             "algorithmic_flops_per_launch": flops, "launch_ms": round(ms, 5),
             "shape": "FPN_LSS conv 512 -> 256, 3x3, [8,128,128] NHWC fp32 (TF32 multiply, fp32 accumulate)",
             "ncu": "profiles/r02_conv_train.json (sm__pipe_tensor_cycles_active, per kernel)"}
