@@ -566,6 +566,16 @@ int smem_reserve() {
   return v;
 }
 
+// A/B switch: DBEV_CONV_LATTICE_TMA=0 keeps the direct stores for strided-lattice NHWC outputs.
+bool tma_lattice_store() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DBEV_CONV_LATTICE_TMA");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
 // A/B switch: DBEV_CONV_HALO = 0 (per-tap kernel for every layer), 1 (default: halo kernel, pitch 10),
 // 2 (pitch 16), 4 (no split of the last round). Measured: both pitches are bit-identical to the per-tap kernel (descriptor base-offset 0);
 // setting the descriptor's base-offset field to (start >> 7) & 7 gives wrong results.
@@ -757,18 +767,24 @@ int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in,
   DBEV_CHECK_ARG(s.tx * stride <= 256 && s.ty * stride <= 256, "conv2d_tc: tile too large for a TMA box");
 
   s.group_cols = out_groups > 1 ? c_out / out_groups : 0;
-  s.tma_store = (out_groups == 1 && !out_nchw && out_mul == 1 && out_add_y == 0 && out_add_x == 0 && out_h == s.ho && out_w == s.wo) ? 1 : 0;
+  // NHWC outputs leave through a shared-memory staging tile + TMA store, also on a strided lattice (the four parity
+  // classes of a stride-2 input gradient): the lattice of class (a, b) is itself a 4-D tensor (C, W_out, H_out, N) with
+  // pixel strides out_mul * ld and base pixel (a, b) - the direct 16-byte stores at pixel stride it replaces touch 32
+  // partial sectors per instruction and made those launches epilogue-bound.
+  s.tma_store = (out_groups == 1 && !out_nchw && tma_lattice_store()) || (out_groups == 1 && !out_nchw && out_mul == 1 && out_add_y == 0 &&
+                out_add_x == 0 && out_h == s.ho && out_w == s.wo) ? 1 : 0;
   CUtensorMap tmap_x, tmap_w, tmap_o;
   tmap_o = CUtensorMap();
   if (s.tma_store) {
     // a warp's 32 pixels of the tile: min(TX, 32) px x 32 / min(TX, 32) rows
     const int bx = s.tx < 32 ? s.tx : 32;
-    cuuint64_t dims[4] = {(cuuint64_t)out_ld, (cuuint64_t)out_w, (cuuint64_t)out_h, (cuuint64_t)n_img};
-    cuuint64_t strides[3] = {(cuuint64_t)out_ld * 4, (cuuint64_t)out_w * out_ld * 4,
+    float* obase = out + ((long long)out_add_y * out_w + out_add_x) * out_ld;
+    cuuint64_t dims[4] = {(cuuint64_t)out_ld, (cuuint64_t)s.wo, (cuuint64_t)s.ho, (cuuint64_t)n_img};
+    cuuint64_t strides[3] = {(cuuint64_t)out_mul * out_ld * 4, (cuuint64_t)out_mul * out_w * out_ld * 4,
                              (cuuint64_t)out_h * out_w * out_ld * 4};
     cuuint32_t box[4] = {(cuuint32_t)kKc, (cuuint32_t)bx, (cuuint32_t)(32 / bx), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&tmap_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)out, dims, strides, box, estr,
+    CUresult r = encode(&tmap_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)obase, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
