@@ -134,6 +134,7 @@ SIGNATURES = {
                                   + [_c_int] * 12 + [_ptr]),
     "dbev_conv_wgrad_tc_workspace_bytes": (_c_size, [_c_int] * 8),
     "dbev_conv_wgrad_tc": (_c_int, [_ptr] + [_c_int] * 5 + [_ptr] + [_c_int] * 8 + [_ptr, _c_int, _ptr, _c_size, _ptr]),
+    "dbev_conv2d_tc_dgrad_s2": (_c_int, [_ptr] + [_c_int] * 5 + [_ptr] + [_c_int] * 3 + [_ptr] + [_c_int] * 3 + [_ptr]),
     "dbev_pack_conv_weights": (_c_int, [_ptr] + [_c_int] * 5 + [_ptr, _ptr]),
     "dbev_pack_conv_weights_train": (_c_int, [_ptr] + [_c_int] * 5 + [_ptr, _ptr, _ptr]),
     "dbev_pack_conv_weights_batch": (_c_int, [_ptr, _c_int, _c_int, _ptr]),

@@ -485,6 +485,13 @@ int dbev_conv_wgrad_tc(const float* x_nhwc, int n, int h, int w, int c_in, int x
                        accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int dbev_conv2d_tc_dgrad_s2(const float* dy_nhwc, int n, int ho, int wo, int c_out, int dy_ld, const float* w_mode2,
+                            int c_in_total, int col_width, int n_col_blocks, float* dx, int dx_ld, int dx_c_off, int accumulate,
+                            void* stream) {
+  return conv2d_tc_dgrad_s2(dy_nhwc, n, ho, wo, c_out, dy_ld, w_mode2, c_in_total, col_width, n_col_blocks, dx, dx_ld, dx_c_off,
+                            accumulate, (cudaStream_t)stream);
+}
+
 int dbev_pack_conv_weights(const float* w, int c_out, int c_in, int kh, int kw, int mode, float* out, void* stream) {
   return pack_conv_weights(w, c_out, c_in, kh, kw, mode, out, (cudaStream_t)stream);
 }

@@ -25,6 +25,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <utility>
 
 namespace dbev {
@@ -48,13 +49,23 @@ struct ConvShape {
   int ncb;        // column blocks: C_out total = ncb * COUT; a work item = (pixel tile, column block), block fastest
   int accumulate; // 1: out += result (TMA reduce-add store / read-modify-write) - gradient accumulation of the
                   // training path (residual branches of BasicBlock, res_block.py:70-99)
+  // n_cls > 1: several convolutions of the SAME input with different filters / output lattices in one launch (the
+  // four parity classes of a stride-2 input gradient): a work item = (class, pixel tile, column block); class c has
+  // a ckh[c] x ckw[c] filter (its own weight matrix) and writes lattice offset (coy[c], cox[c]). n_cls == 1: the
+  // scalars above.
+  int n_cls, ckh[4], ckw[4], coy[4], cox[4];
+};
+
+// weight / output tensor maps of classes 1..3 (class 0 uses tmap_w / tmap_o)
+struct ClassMaps {
+  CUtensorMap w[3], o[3];
 };
 
 template <int COUT, int STAGES, int MINB>
 __global__ void __launch_bounds__(kConvThreads, MINB)
 conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_o, const float* __restrict__ scale, const float* __restrict__ shift,
-                 float* __restrict__ out, ConvShape s) {
+                 float* __restrict__ out, ConvShape s, const __grid_constant__ ClassMaps cmaps) {
   // programmatic dependent launch: let the next kernel of the stream start its prologue on SMs this grid has left
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -94,19 +105,22 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   // everything above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's tail; its results
   // (this kernel's input) are complete and visible after this point, and nothing is written before it
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int taps = s.kh * s.kw;
   const int per_img = s.tiles_x * s.tiles_y;
+  const int per_cls = s.n_tiles * s.ncb, n_items = per_cls * s.n_cls;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int item = blockIdx.x; item < s.n_tiles * s.ncb; item += gridDim.x) {
-        const int tile = item / s.ncb, cb = item - tile * s.ncb;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int cls = item / per_cls, rem = item - cls * per_cls;
+        const int tile = rem / s.ncb, cb = rem - tile * s.ncb;
         const int n = tile / per_img, r = tile % per_img;
         const int y0 = (r / s.tiles_x) * s.ty, x0 = (r % s.tiles_x) * s.tx;
+        const int kw_c = s.ckw[cls], taps = s.ckh[cls] * kw_c;
+        const CUtensorMap* tw = cls == 0 ? &tmap_w : &cmaps.w[cls - 1];
         for (int tap = 0; tap < taps; ++tap) {
-          const int ky = tap / s.kw, kx = tap % s.kw;
+          const int ky = tap / kw_c, kx = tap % kw_c;
           const int ix = x0 * s.stride + kx - s.pad, iy = y0 * s.stride + ky - s.pad;
           for (int cc = 0; cc < s.cin_chunks; ++cc) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -117,7 +131,7 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_addr(st)),
                 "l"(&tmap_x), "r"(smem_addr(&full_bar[stage])), "r"(cc * kKc), "r"(ix), "r"(iy), "r"(n)
                 : "memory");
-            tma_load_2d(st + kATile, &tmap_w, tap * s.c_in + cc * kKc, cb * COUT, &full_bar[stage]);
+            tma_load_2d(st + kATile, tw, tap * s.c_in + cc * kKc, cb * COUT, &full_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -129,9 +143,10 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const bool leader = elect_one();
     const uint32_t idesc = umma_idesc_tf32(kPix, COUT);
     const uint64_t desc0 = umma_desc(0, 16, 1024);
-    const int steps = taps * s.cin_chunks;
     uint32_t stage = 0, phase = 0, it = 0;
-    for (int item = blockIdx.x; item < s.n_tiles * s.ncb; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int cls_m = item / per_cls;
+      const int steps = s.ckh[cls_m] * s.ckw[cls_m] * s.cin_chunks;
       const uint32_t buf = it & 1u, use = it >> 1;
       mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -167,14 +182,16 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const uint32_t stg_row = smem_addr(stg) + (uint32_t)lane * 128u;
     const uint32_t sw_xor = (uint32_t)(lane & 7);
     uint32_t it = 0, sbuf = 0;
-    for (int item = blockIdx.x; item < s.n_tiles * s.ncb; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t buf = it & 1u, use = it >> 1;
-      const int tile = item / s.ncb, cb = item - tile * s.ncb;
+      const int cls = item / per_cls, rem = item - cls * per_cls;
+      const int tile = rem / s.ncb, cb = rem - tile * s.ncb;
+      const CUtensorMap* to = cls == 0 ? &tmap_o : &cmaps.o[cls - 1];
       const int n = tile / per_img, r = tile % per_img;
       const int ty0 = (r / s.tiles_x) * s.ty, tx0 = (r % s.tiles_x) * s.tx;
       const int oy = ty0 + py, ox = tx0 + px;
       const bool valid = oy < s.ho && ox < s.wo;
-      const int fy = oy * s.omul + s.oadd_y, fx = ox * s.omul + s.oadd_x;
+      const int fy = oy * s.omul + s.coy[cls], fx = ox * s.omul + s.cox[cls];
       const long long plane = (long long)s.h_full * s.w_full;
       float* orow = out + (((long long)n * s.h_full + fy) * s.w_full + fx) * s.ld + s.c_off;
       float* ocol = out + ((long long)n * s.ld + s.c_off) * plane + (long long)fy * s.w_full + fx;
@@ -231,12 +248,12 @@ conv2d_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (ty0 + by0 < s.ho && tx0 + bx0 < s.wo) {
               if (s.accumulate)
                 asm volatile(
-                    "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmap_o),
+                    "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(to),
                     "r"(smem_addr(stg) + sbuf * 4096u), "r"(s.c_off + ch0), "r"(tx0 + bx0), "r"(ty0 + by0), "r"(n)
                     : "memory");
               else
                 asm volatile(
-                    "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmap_o),
+                    "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(to),
                     "r"(smem_addr(stg) + sbuf * 4096u), "r"(s.c_off + ch0), "r"(tx0 + bx0), "r"(ty0 + by0), "r"(n)
                     : "memory");
             }
@@ -607,11 +624,24 @@ int conv2d_tc_forward(const float* x_nhwc, int n_img, int h, int w, int c_in, co
 // n_col_blocks * c_out output channels (w_packed / scale / shift / the output slice cover all of them) and a work
 // item is (pixel tile, block of c_out columns) - layers with few pixel tiles (16 x 16 .. 64 x 64 BEV maps) fill
 // the SMs with column blocks instead of running one under-filled launch per block.
-int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in, int x_ld, const float* w_packed,
-                         int c_out, int n_col_blocks, int kh, int kw, int stride, int pad, const float* scale,
-                         const float* shift, int relu, float* out, int out_h, int out_w, int out_ld,
-                         int out_c_off, int out_mul, int out_add_y, int out_add_x, int out_nchw,
-                         int out_groups, int force_ho, int force_wo, int accumulate, cudaStream_t stream) {
+namespace {
+
+// Classes of a multi-class launch (ConvShape::n_cls): filter size, weight matrix and lattice offset per class.
+struct ConvClasses {
+  int n;
+  int kh[4], kw[4], add_y[4], add_x[4];
+  const float* w[4];
+};
+
+int conv2d_tc_impl(const float* x_nhwc, int n_img, int h, int w, int c_in, int x_ld, const float* w_packed,
+                   int c_out, int n_col_blocks, int kh, int kw, int stride, int pad, const float* scale,
+                   const float* shift, int relu, float* out, int out_h, int out_w, int out_ld,
+                   int out_c_off, int out_mul, int out_add_y, int out_add_x, int out_nchw,
+                   int out_groups, int force_ho, int force_wo, int accumulate, const ConvClasses* classes, cudaStream_t stream) {
+  const int n_cls = classes ? classes->n : 1;
+  DBEV_CHECK_ARG(n_cls >= 1 && n_cls <= 4, "conv2d_tc: 1..4 classes");
+  DBEV_CHECK_ARG(n_cls == 1 || (out_groups == 1 && !out_nchw && force_ho > 0 && force_wo > 0 && stride == 1),
+                 "conv2d_tc: multi-class launches are stride-1 convolutions with a forced output size and NHWC lattice outputs");
   DBEV_CHECK_ARG(x_ld >= c_in && x_ld % 4 == 0, "conv2d_tc: bad input channel stride");
   DBEV_CHECK_ARG(n_col_blocks >= 1 && (n_col_blocks == 1 || out_groups == 1), "conv2d_tc: column blocks need out_groups == 1");
   const int ncb = n_col_blocks;
@@ -637,7 +667,7 @@ int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in,
   DBEV_CUDA(cudaGetDevice(&dev));
   DBEV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int halo_mode = conv_halo_mode();
-  if (halo_mode > 0 && out_groups == 1 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && h >= 16 && w >= kHaloTx && out_mul == 1 &&
+  if (n_cls == 1 && halo_mode > 0 && out_groups == 1 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && h >= 16 && w >= kHaloTx && out_mul == 1 &&
       out_add_y == 0 && out_add_x == 0 && !out_nchw && out_h == h && out_w == w && force_ho == 0 && force_wo == 0) {
     HaloShape hs;
     hs.n_img = n_img, hs.c_in = c_in, hs.ho = h, hs.wo = w;
@@ -751,8 +781,15 @@ int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in,
   s.wo = force_wo > 0 ? force_wo : (w + 2 * pad - kw) / stride + 1;
   s.accumulate = accumulate ? 1 : 0;
   DBEV_CHECK_ARG(s.ho >= 1 && s.wo >= 1, "conv2d_tc: empty output");
-  DBEV_CHECK_ARG((s.ho - 1) * out_mul + out_add_y < out_h && (s.wo - 1) * out_mul + out_add_x + out_groups - 1 < out_w,
-                 "conv2d_tc: output lattice exceeds the output tensor");
+  s.n_cls = n_cls;
+  for (int c = 0; c < 4; ++c) {
+    const bool used = c < n_cls;
+    s.ckh[c] = classes && used ? classes->kh[c] : kh, s.ckw[c] = classes && used ? classes->kw[c] : kw;
+    s.coy[c] = classes && used ? classes->add_y[c] : out_add_y, s.cox[c] = classes && used ? classes->add_x[c] : out_add_x;
+    DBEV_CHECK_ARG(s.ckh[c] >= 1 && s.ckh[c] <= 3 && s.ckw[c] >= 1 && s.ckw[c] <= 3, "conv2d_tc: class filters are 1..3 wide");
+    DBEV_CHECK_ARG((s.ho - 1) * out_mul + s.coy[c] < out_h && (s.wo - 1) * out_mul + s.cox[c] + out_groups - 1 < out_w,
+                   "conv2d_tc: output lattice exceeds the output tensor");
+  }
   // tile = TX x TY output pixels with TX * TY = 128, TX a power of two <= W_out
   int tx = 128;
   while (tx > s.wo) tx >>= 1;
@@ -775,16 +812,19 @@ int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in,
                 out_add_x == 0 && out_h == s.ho && out_w == s.wo) ? 1 : 0;
   CUtensorMap tmap_x, tmap_w, tmap_o;
   tmap_o = CUtensorMap();
-  if (s.tma_store) {
+  ClassMaps cmaps;
+  memset(&cmaps, 0, sizeof(cmaps));
+  DBEV_CHECK_ARG(n_cls == 1 || s.tma_store, "conv2d_tc: multi-class launches need the TMA-store epilogue");
+  for (int c = 0; c < n_cls && s.tma_store; ++c) {
     // a warp's 32 pixels of the tile: min(TX, 32) px x 32 / min(TX, 32) rows
     const int bx = s.tx < 32 ? s.tx : 32;
-    float* obase = out + ((long long)out_add_y * out_w + out_add_x) * out_ld;
+    float* obase = out + ((long long)s.coy[c] * out_w + s.cox[c]) * out_ld;
     cuuint64_t dims[4] = {(cuuint64_t)out_ld, (cuuint64_t)s.wo, (cuuint64_t)s.ho, (cuuint64_t)n_img};
     cuuint64_t strides[3] = {(cuuint64_t)out_mul * out_ld * 4, (cuuint64_t)out_mul * out_w * out_ld * 4,
                              (cuuint64_t)out_h * out_w * out_ld * 4};
     cuuint32_t box[4] = {(cuuint32_t)kKc, (cuuint32_t)bx, (cuuint32_t)(32 / bx), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = encode(&tmap_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)obase, dims, strides, box, estr,
+    CUresult r = encode(c == 0 ? &tmap_o : &cmaps.o[c - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)obase, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -807,13 +847,15 @@ int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in,
       return DBEV_ERR_CUDA;
     }
   }
-  {
-    const int k_total = kh * kw * c_in;
+  for (int c = 0; c < n_cls; ++c) {
+    const int k_total = s.ckh[c] * s.ckw[c] * c_in;
+    const float* wc = classes ? classes->w[c] : w_packed;
+    DBEV_CHECK_ARG(((uintptr_t)wc & 15) == 0, "conv2d_tc: weight matrices must be 16-byte aligned");
     cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)c_out * ncb};
     cuuint64_t strides[1] = {(cuuint64_t)k_total * 4};
     cuuint32_t box[2] = {(cuuint32_t)kKc, (cuuint32_t)c_out};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmap_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)w_packed, dims, strides, box, estr,
+    CUresult r = encode(c == 0 ? &tmap_w : &cmaps.w[c - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wc, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -824,10 +866,10 @@ int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in,
 #define DBEV_CONV_LAUNCH(CO, STG, MB)                                                            \
   do {                                                                                           \
     const size_t smem = (size_t)STG * (kATile + CO * kKc * 4) + (s.tma_store ? 4 * 8192 : 0) + 1024; \
-    const int grid = s.n_tiles * ncb < sms * MB ? s.n_tiles * ncb : sms * MB;                    \
+    const int grid = s.n_tiles * ncb * n_cls < sms * MB ? s.n_tiles * ncb * n_cls : sms * MB;    \
     DBEV_CUDA(cudaFuncSetAttribute(conv2d_tc_kernel<CO, STG, MB>,                                \
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    DBEV_CUDA(launch_conv(conv2d_tc_kernel<CO, STG, MB>, grid, smem, stream, tmap_x, tmap_w, tmap_o, scale, shift, out, s)); \
+    DBEV_CUDA(launch_conv(conv2d_tc_kernel<CO, STG, MB>, grid, smem, stream, tmap_x, tmap_w, tmap_o, scale, shift, out, s, cmaps)); \
   } while (0)
   // two CTAs per SM where shared memory and TMEM allow it: one CTA's epilogue / TMA latency hides
   // behind the other's MMAs (1.68 -> 1.56 ms for the whole SECOND + SECONDFPN stack); three CTAs of
@@ -836,7 +878,7 @@ int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in,
   // direct-store outputs (FPN branches) need no staging and keep the deeper rings
   // grids that do not fill the SMs twice (small BEV maps of the student encoder): one CTA per SM with a ring deep
   // enough to cover the TMA latency (a 64-column stage lasts ~190 clk, a 128-column stage ~260 clk)
-  const bool small_grid = (long long)s.n_tiles * ncb <= (long long)sms;
+  const bool small_grid = (long long)s.n_tiles * ncb * n_cls <= (long long)sms;
   if (c_out == 64) {
     if (small_grid) DBEV_CONV_LAUNCH(64, 7, 1);
     else if (s.tma_store) DBEV_CONV_LAUNCH(64, 3, 2);
@@ -850,6 +892,43 @@ int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in,
 #undef DBEV_CONV_LAUNCH
   DBEV_CHECK_LAUNCH("conv2d_tc_kernel");
   return DBEV_OK;
+}
+
+}  // namespace
+
+int conv2d_tc_forward_ex(const float* x_nhwc, int n_img, int h, int w, int c_in, int x_ld, const float* w_packed,
+                         int c_out, int n_col_blocks, int kh, int kw, int stride, int pad, const float* scale,
+                         const float* shift, int relu, float* out, int out_h, int out_w, int out_ld,
+                         int out_c_off, int out_mul, int out_add_y, int out_add_x, int out_nchw,
+                         int out_groups, int force_ho, int force_wo, int accumulate, cudaStream_t stream) {
+  return conv2d_tc_impl(x_nhwc, n_img, h, w, c_in, x_ld, w_packed, c_out, n_col_blocks, kh, kw, stride, pad, scale, shift, relu, out,
+                        out_h, out_w, out_ld, out_c_off, out_mul, out_add_y, out_add_x, out_nchw, out_groups, force_ho, force_wo,
+                        accumulate, nullptr, stream);
+}
+
+// Input gradient of a 3x3 / stride 2 / pad 1 convolution in ONE launch: dx[n, 2*ho, 2*wo, :] (+)= conv_transpose(dy, W).
+// The four parity classes (a, b) of the input pixels are stride-1 convolutions of dy with (1+a) x (1+b) taps written on
+// the 2x lattice at offset (a, b) (pack_conv_weights mode 2 holds their matrices at float offsets {0, 1, 3, 5} * C_in *
+// C_out); a work item is (class, pixel tile, column block), the 4-tap class first. Four separate launches left most SMs
+// idle on the 16^2 .. 64^2 maps (each has a quarter of the pixels and 1-4 taps of K).
+int conv2d_tc_dgrad_s2(const float* dy_nhwc, int n_img, int ho, int wo, int c_out_fwd, int dy_ld, const float* w_mode2,
+                       int c_in_fwd_total, int col_width, int n_col_blocks, float* dx, int dx_ld, int dx_c_off, int accumulate,
+                       cudaStream_t stream) {
+  DBEV_CHECK_ARG(col_width * n_col_blocks <= c_in_fwd_total, "conv2d_tc_dgrad_s2: column blocks exceed the input channels");
+  const long long per = (long long)c_in_fwd_total * c_out_fwd;
+  ConvClasses cls;
+  cls.n = 4;
+  const int order[4] = {3, 1, 2, 0};                 // heaviest class first
+  const int off[4] = {0, 1, 3, 5};
+  for (int i = 0; i < 4; ++i) {
+    const int c = order[i], a = c >> 1, b = c & 1;
+    cls.kh[i] = 1 + a, cls.kw[i] = 1 + b, cls.add_y[i] = a, cls.add_x[i] = b;
+    // rows of the class matrix = dx channels; this launch covers rows [dx_c_off, dx_c_off + col_width * n_col_blocks)
+    cls.w[i] = w_mode2 + off[c] * per + (long long)dx_c_off * (1 + a) * (1 + b) * c_out_fwd;
+  }
+  return conv2d_tc_impl(dy_nhwc, n_img, ho, wo, c_out_fwd, dy_ld, cls.w[0], col_width, n_col_blocks, cls.kh[0], cls.kw[0], 1, 0, nullptr,
+                        nullptr, 0, dx, 2 * ho, 2 * wo, dx_ld, dx_c_off, 2, cls.add_y[0], cls.add_x[0], 0, 1, ho, wo, accumulate,
+                        &cls, stream);
 }
 
 }  // namespace dbev

@@ -11,6 +11,8 @@ An "NHWC tensor" below is a torch tensor of shape [N, H, W, C] whose last stride
 (H*W*ld, W*ld, ld) for some ld >= C: a contiguous tensor or a channel slice of one (so torch.cat never needs a
 separate pass). No CPU path: CPU tensors raise.
 """
+import os
+
 import torch
 
 from ... import _lib
@@ -191,6 +193,21 @@ def conv_input_grad(dy, w_bwd, c_in, kh, kw, stride, pad, in_hw, out=None, accum
         return _conv_launch(dy, w_bwd.view(c_in, kh * kw * c_out), c_in, kh, kw, 1, kh - 1 - pad, out, accumulate=accumulate)
     if not (stride == 2 and kh == 3 and kw == 3 and pad == 1 and h == 2 * ho and w == 2 * wo):
         raise RuntimeError("conv_input_grad: stride 2 needs a 3x3 / pad 1 filter and an even input size")
+    if os.environ.get("DBEV_DGRAD_S2_MERGED", "1") != "0":
+        # the four parity classes as work items of ONE launch per column split (csrc/conv2d_tc.cu: conv2d_tc_dgrad_s2)
+        lib = _lib.load()
+        dy_ld, o_ld = nhwc_ld(dy, "dy"), nhwc_ld(out, "out")
+        c0 = 0
+        with torch.cuda.device(dy.device):
+            tiles = 4 * ((n * ho * wo + 127) // 128)        # (class, 128-pixel tile) pairs
+            fit = [wdt for wdt in _TILE_N if c_in % wdt == 0 and tiles * (c_in // wdt) >= 100]
+            parts = [(fit[0], c_in // fit[0])] if fit else _splits(c_in, n * ho * wo)
+            for width, blocks in parts:
+                rc = lib.dbev_conv2d_tc_dgrad_s2(_lib.ptr(dy), n, ho, wo, c_out, dy_ld, _lib.ptr(w_bwd), c_in, width, blocks,
+                                                 _lib.ptr(out), o_ld, c0, 1 if accumulate else 0, _lib.stream_ptr(dy.device))
+                _lib.check(rc, "dbev_conv2d_tc_dgrad_s2")
+                c0 += width * blocks
+        return out
     per = c_in * c_out
     for cls, off in enumerate((0, 1, 3, 5)):
         a, b = cls >> 1, cls & 1

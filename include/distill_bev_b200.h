@@ -448,6 +448,15 @@ int dbev_conv_wgrad_tc(const float* x_nhwc, int n, int h, int w, int c_in, int x
                        int ho, int wo, int c_out, int dy_ld, int kh, int kw, int stride, int pad, float* dw,
                        int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Input gradient of a 3x3 / stride 2 / pad 1 convolution (ResNetForBEVDet's stride-2 conv1 / downsample,
+ * backbones/resnet.py:26-34) in ONE launch: dx[n, 2*ho, 2*wo, dx_ld] channels [dx_c_off, dx_c_off + col_width *
+ * n_col_blocks) (+)= conv_transpose(dy, W). dy NHWC [n, ho, wo, c_out] (channel stride dy_ld); w_mode2 =
+ * dbev_pack_conv_weights(mode 2) of the whole layer with c_in_total input channels; col_width in {64, 128, 256}.
+ * The four parity classes of the input pixels are work items of the same launch (dbev_conv2d_tc_forward_ex with
+ * force_ho / out_mul = 2 runs them as four launches). */
+int dbev_conv2d_tc_dgrad_s2(const float* dy_nhwc, int n, int ho, int wo, int c_out, int dy_ld, const float* w_mode2,
+                            int c_in_total, int col_width, int n_col_blocks, float* dx, int dx_ld, int dx_c_off, int accumulate,
+                            void* stream);
 /* torch weight [c_out][c_in][kh][kw] -> K-major matrices for the conv kernels' TMA loads. mode 0: forward
  * [c_out][(ky*kw+kx)*c_in + ci]; mode 1: stride-1 input gradient [c_in][flipped tap * c_out + co];
  * mode 2 (3x3): the four parity-class matrices of a stride-2 input gradient at float offsets
