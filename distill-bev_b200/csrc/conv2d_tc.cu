@@ -306,6 +306,10 @@ struct HaloShape {
   int a_stages;      // halo ring depth (2; 3 for the 64-column tiles whose chunks last only ~1700 clk)
   int c_off, relu, accumulate;
   int ncb;           // column blocks (see ConvShape)
+  int ksplit, cpk;   // split-K: a work item = (tile item, column block, K part), K part fastest; each part walks cpk =
+                     // cin_chunks / ksplit input-channel chunks and adds its result to the (zeroed) output with a TMA
+                     // reduce-add - two parts commute, so the sum is bit-reproducible. Small maps only: 16 x 16 maps have
+                     // 16 pixel tiles, and 128-column tiles (full-rate MMAs) would otherwise leave half of the SMs idle.
 };
 
 __device__ __forceinline__ void halo_item(const HaloShape& s, int i, int& n, int& y0, int& x0, int& halves) {
@@ -384,25 +388,27 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       // the halo of chunk i+1 is requested while the weights of chunk i stream: at tap `ahead` the MMA
       // warp (w_stages taps behind) has left chunk i-1, so its halo stage is free without waiting
       int t_n = blockIdx.x, c_n = 0;
+      const int n_work = s.n_items * s.ncb * s.ksplit;
       auto issue_halo = [&]() {
-        if (t_n >= s.n_items * s.ncb) return;
+        if (t_n >= n_work) return;
         int n, y0, x0, halves;
-        halo_item(s, t_n / s.ncb, n, y0, x0, halves);
+        halo_item(s, (t_n / s.ksplit) / s.ncb, n, y0, x0, halves);
+        const int chunk = (t_n % s.ksplit) * s.cpk + c_n;
         { const long long t = prof ? clock64() : 0; mbar_wait(&a_empty[sa], pa ^ 1u); if (prof) pw_a += clock64() - t; }
         mbar_expect_tx(&a_full[sa], a_bytes);
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
             " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_addr(base + (size_t)sa * s.a_stage)),
-            "l"(&tmap_x), "r"(smem_addr(&a_full[sa])), "r"(c_n * kKc), "r"(x0 - 1), "r"(y0 - 1), "r"(n)
+            "l"(&tmap_x), "r"(smem_addr(&a_full[sa])), "r"(chunk * kKc), "r"(x0 - 1), "r"(y0 - 1), "r"(n)
             : "memory");
         if (++sa == (uint32_t)s.a_stages) { sa = 0; pa ^= 1u; }
-        if (++c_n == s.cin_chunks) { c_n = 0; t_n += gridDim.x; }
+        if (++c_n == s.cpk) { c_n = 0; t_n += gridDim.x; }
       };
       const int ahead = s.w_stages < 8 ? s.w_stages : 8;
       for (int i = 0; i < s.a_stages - 1; ++i) issue_halo();
-      for (int item = blockIdx.x; item < s.n_items * s.ncb; item += gridDim.x) {
-        const int cb = item % s.ncb;
-        for (int cc = 0; cc < s.cin_chunks; ++cc) {
+      for (int item = blockIdx.x; item < n_work; item += gridDim.x) {
+        const int cb = (item / s.ksplit) % s.ncb, c0 = (item % s.ksplit) * s.cpk;
+        for (int cc = c0; cc < c0 + s.cpk; ++cc) {
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             if (tap == ahead) issue_halo();
@@ -427,13 +433,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     uint32_t sa = 0, pa = 0, sw = 0, pw = 0, it = 0;
     long long mw_t = 0, mw_a = 0, mw_w = 0;
     const long long mt0 = prof ? clock64() : 0;
-    for (int item = blockIdx.x; item < s.n_items * s.ncb; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < s.n_items * s.ncb * s.ksplit; item += gridDim.x, ++it) {
       const uint32_t buf = kNBuf == 2 ? (it & 1u) : 0u, use = kNBuf == 2 ? (it >> 1) : it;
-      const int halves = item / s.ncb < s.n_full ? s.item_halves : 1;
+      const int halves = (item / s.ksplit) / s.ncb < s.n_full ? s.item_halves : 1;
       { const long long t = prof ? clock64() : 0; mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u); if (prof) mw_t += clock64() - t; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + buf * 2 * COUT;
-      for (int cc = 0; cc < s.cin_chunks; ++cc) {
+      for (int cc = 0; cc < s.cpk; ++cc) {
         { const long long t = prof ? clock64() : 0; mbar_wait(&a_full[sa], pa); if (prof) mw_a += clock64() - t; }
         const uint32_t a_units = smem_addr(base + (size_t)sa * s.a_stage) >> 4;
 #pragma unroll 1
@@ -481,11 +487,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     uint32_t it = 0, sbuf = 0;
     long long ew_f = 0;
     const long long et0 = prof ? clock64() : 0;
-    for (int item = blockIdx.x; item < s.n_items * s.ncb; item += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < s.n_items * s.ncb * s.ksplit; item += gridDim.x, ++it) {
       const uint32_t buf = kNBuf == 2 ? (it & 1u) : 0u, use = kNBuf == 2 ? (it >> 1) : it;
       int n, ty0, tx0, halves;
-      const int cb = item % s.ncb;
-      halo_item(s, item / s.ncb, n, ty0, tx0, halves);
+      const int cb = (item / s.ksplit) % s.ncb;
+      const bool first_part = item % s.ksplit == 0;      // the bias is added by one K part only
+      halo_item(s, (item / s.ksplit) / s.ncb, n, ty0, tx0, halves);
       { const long long t = prof ? clock64() : 0; mbar_wait(&tmem_full_bar[buf], use & 1u); if (prof) ew_f += clock64() - t; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -508,7 +515,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
               const float4 sc = __ldg(reinterpret_cast<const float4*>(scale + cb * COUT + cc * 32 + j));
               o.x *= sc.x, o.y *= sc.y, o.z *= sc.z, o.w *= sc.w;
             }
-            if (shift) {
+            if (shift && first_part) {
               const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + cb * COUT + cc * 32 + j));
               o.x += sh.x, o.y += sh.y, o.z += sh.z, o.w += sh.w;
             }
@@ -581,6 +588,16 @@ int smem_reserve() {
     if (v > 65536) v = 65536;
   }
   return v;
+}
+
+// A/B switch: DBEV_HALO_KSPLIT=0 disables split-K in the halo kernel.
+bool halo_ksplit() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DBEV_HALO_KSPLIT");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
 }
 
 // A/B switch: DBEV_CONV_LATTICE_TMA=0 keeps the direct stores for strided-lattice NHWC outputs.
@@ -679,11 +696,23 @@ int conv2d_tc_impl(const float* x_nhwc, int n_img, int h, int w, int c_in, int x
     // (keeping all 9 * C_in/32 weight tiles of a 64 -> 64 layer resident in shared memory was tried: only
     // single-half tiles fit beside them, whose halo prefetch distance is too short - 0.132 vs 0.110 ms)
     hs.item_halves = h > 16 ? 2 : 1;      // 16-row images (the student's 512-channel stage): one M=128 half per item
+    // small maps: if 256-pixel items would leave more than half of the SMs idle, use 128-pixel items (twice as many):
+    // the caller can then take wider column tiles for the same item count (N = 128 MMAs run at the full tensor rate,
+    // N = 64 at ~45 % - 71 vs 32 clk per MMA, the shared-memory operand floor)
+    if (hs.item_halves == 2 && 2LL * ceil_div(w, kHaloTx) * ceil_div(h, 32) * n_img * ncb <= (long long)sms + sms / 8)
+      hs.item_halves = 1;
     hs.tile_rows = 16 * hs.item_halves;
     hs.tiles_x = ceil_div(w, kHaloTx), hs.tiles_y = ceil_div(h, hs.tile_rows);
     const int n_tiles = hs.tiles_x * hs.tiles_y * n_img;
     hs.n_full = n_tiles, hs.n_items = n_tiles;
     hs.ncb = ncb;
+    // split-K in two when even the 128-pixel items leave half of the SMs idle and K is long enough to share
+    // (HaloShape::ksplit; the 512-channel stage of the student encoder on 16 x 16 maps)
+    hs.ksplit = 1;
+    if (halo_ksplit() && !relu && !scale && hs.item_halves == 1 && hs.cin_chunks % 2 == 0 && hs.cin_chunks >= 8 &&
+        2LL * n_tiles * ncb <= (long long)sms + sms / 8)
+      hs.ksplit = 2;
+    hs.cpk = hs.cin_chunks / hs.ksplit;
     if (halo_mode != 4 && hs.item_halves == 2 && ncb == 1) {
       const int rem = n_tiles % sms;
       if (rem > 0 && 2 * rem <= sms) hs.n_full = n_tiles - rem, hs.n_items = hs.n_full + 2 * rem;
@@ -697,7 +726,7 @@ int conv2d_tc_impl(const float* x_nhwc, int n_img, int h, int w, int c_in, int x
     if (w_stages > w_cap) w_stages = w_cap;
     DBEV_CHECK_ARG(w_stages >= 2, "conv2d_tc: halo tile does not fit shared memory");
     hs.w_stages = w_stages;
-    hs.c_off = out_c_off, hs.relu = relu, hs.accumulate = accumulate ? 1 : 0;
+    hs.c_off = out_c_off, hs.relu = relu, hs.accumulate = (accumulate || hs.ksplit > 1) ? 1 : 0;
     CUtensorMap tmap_x, tmap_w, tmap_o;
     {
       // NHWC output [n, H, W, ld] as (C, W, H, N); a store box = 32 channels x 8 px x 4 rows, clipped at the borders
@@ -741,7 +770,9 @@ int conv2d_tc_impl(const float* x_nhwc, int n_img, int h, int w, int c_in, int x
       }
     }
     const size_t smem = (size_t)hs.a_stages * hs.a_stage + (size_t)w_stages * w_tile + stage_out + 1024;
-    const int grid = hs.n_items * ncb < sms ? hs.n_items * ncb : sms;
+    const int grid = hs.n_items * ncb * hs.ksplit < sms ? hs.n_items * ncb * hs.ksplit : sms;
+    if (hs.ksplit > 1 && !accumulate)    // the K parts reduce-add into a zeroed output
+      DBEV_CUDA(cudaMemset2DAsync(out + out_c_off, (size_t)out_ld * 4, 0, (size_t)c_out * ncb * 4, (size_t)n_img * h * w, stream));
     // DBEV_CONV_PROF=1: per-role wait cycles (debug only: synchronises and prints after every launch)
     static long long* prof_buf = nullptr;
     long long* prof = nullptr;

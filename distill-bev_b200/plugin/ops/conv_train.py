@@ -86,7 +86,7 @@ def out_size(h, k, stride, pad):
     return (h + 2 * pad - k) // stride + 1
 
 
-def _splits(c, n_pixels):
+def _splits(c, n_pixels, k_split=False):
     """C output columns as launches of (tile width, column blocks). Layers with enough 256-pixel tiles to fill the
     SMs take the widest tiles (most reuse of the pixel operand); small BEV maps take the widest width that still
     gives ~100 (tile, block) work items, down to 64 columns."""
@@ -94,7 +94,16 @@ def _splits(c, n_pixels):
     if tiles >= 120:
         widths = _TILE_N
     else:
+        # small maps run 128-pixel work items (the kernels halve their tiles when that fills more SMs): the widest
+        # column tile that still gives ~100 items wins (128-column MMAs run at twice the rate of 64-column ones)
+        if os.environ.get("DBEV_SPLIT_HALF_TILES", "1") != "0":
+            tiles = max(1, n_pixels // 128)
         fit = [wdt for wdt in _TILE_N if c % wdt == 0 and tiles * (c // wdt) >= 100]
+        if k_split and (not fit or fit[0] == 64) and os.environ.get("DBEV_HALO_KSPLIT", "1") != "0":
+            # 3x3 / stride 1 layers with a long K: the halo kernel splits K in two when its grid would be half empty
+            # (csrc/conv2d_tc.cu HaloShape::ksplit), so 128-column tiles still give ~100 work items
+            fit2 = [wdt for wdt in _TILE_N if wdt > 64 and c % wdt == 0 and 2 * tiles * (c // wdt) >= 100]
+            fit = fit2[:1] or fit
         widths = (fit[0],) if fit else ((64,) if c % 64 == 0 else _TILE_N)
     parts, left = [], c
     for wdt in widths:
@@ -159,7 +168,9 @@ def _conv_launch(x, wmat, n_cols, kh, kw, stride, pad, out, shift=None, relu=Fal
     with torch.cuda.device(x.device):
         st = _lib.stream_ptr(x.device)
         n_pix = n * (force[0] or out_size(h, kh, stride, pad)) * (force[1] or out_size(w, kw, stride, pad))
-        for width, blocks in _splits(n_cols, n_pix):
+        k_split = (kh == 3 and kw == 3 and stride == 1 and pad == 1 and c_in >= 256 and c_in % 64 == 0 and not relu
+                   and out_mul == 1 and force == (0, 0) and h <= 16)
+        for width, blocks in _splits(n_cols, n_pix, k_split):
             part = width * blocks
             o = out[..., c0:c0 + part]
             sh = shift[c0:c0 + part] if shift is not None else None

@@ -89,7 +89,7 @@ def test_input_grad_matches_torch(cuda, n, h, w, cin, cout, k, stride):
     torch.testing.assert_close(acc, base + got, rtol=1e-5, atol=1e-5 * float(got.abs().max()))
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout,k,stride,bias", [(2, 16, 16, 640, 512, 3, 1, False), (1, 128, 128, 128, 128, 3, 2, True),
+@pytest.mark.parametrize("n,h,w,cin,cout,k,stride,bias", [(2, 16, 16, 640, 512, 3, 1, False), (8, 16, 16, 512, 512, 3, 1, True), (1, 128, 128, 128, 128, 3, 2, True),
                                                            (2, 32, 32, 256, 256, 1, 1, True), (2, 16, 16, 512, 512, 3, 1, False)])
 def test_forward_conv_matches_torch(cuda, n, h, w, cin, cout, k, stride, bias):
     torch.manual_seed(cin)
@@ -284,7 +284,8 @@ def test_encoder_forward_backward_matches_torch_modules(cuda, batch, hw):
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout,k,stride", [(2, 16, 16, 128, 128, 3, 1), (1, 32, 24, 256, 128, 3, 2), (2, 24, 16, 128, 256, 1, 1),
-                                                     (1, 64, 64, 512, 256, 3, 1), (4, 16, 16, 512, 512, 3, 1), (2, 32, 32, 256, 512, 3, 2)])
+                                                     (1, 64, 64, 512, 256, 3, 1), (4, 16, 16, 512, 512, 3, 1), (2, 32, 32, 256, 512, 3, 2),
+                                                     (8, 16, 16, 512, 512, 3, 1), (8, 32, 32, 256, 256, 3, 1)])
 def test_conv_kernels_are_exact_on_integer_data(cuda, n, h, w, cin, cout, k, stride):
     """Small integers are exact in TF32 and every partial sum stays below 2^24, so forward, input gradient and
     weight gradient must equal torch's fp32 results BIT FOR BIT: this pins the tap / halo / parity-class / split-K
