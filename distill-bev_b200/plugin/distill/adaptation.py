@@ -123,12 +123,25 @@ def _relu_only(act_layer):
 
 
 def _conv_group(x, conv, bn, relu):
-    from ..bev_encoder import conv_bn_act
+    from ..bev_encoder import conv_bn_act, _ConvBNActFn
     k, s = conv.kernel_size[0], conv.stride[0]
-    if not ((k == 1 and s == 1 and conv.padding[0] == 0) or (k == 3 and s in (1, 2) and conv.padding[0] == 1)):
-        raise NotImplementedError("adaptation conv %dx%d / stride %d: the tcgen05 training kernels cover 1x1 / stride 1 and "
-                                  "3x3 / pad 1 / stride 1-2 (downsample_2layer's 4x4 / stride 4 is not implemented)" % (k, k, s))
-    return conv_bn_act(x, conv, bn, relu=relu)
+    pad = conv.padding[0]
+    if (k == 1 and s == 1 and pad == 0) or (k == 3 and s in (1, 2) and pad == 1):
+        return conv_bn_act(x, conv, bn, relu=relu)
+    if (k == s and k > 1 and pad == 0 and conv.kernel_size[1] == k and conv.stride[1] == k and conv.groups == 1
+            and conv.dilation == (1, 1) and x.shape[2] % k == 0 and x.shape[3] % k == 0):
+        # 'downsample_2layer' (bevdet_distill.py:252-257): a k x k / stride k / pad 0 conv reads disjoint patches, i.e. it is
+        # a 1x1 conv over the space-to-depth rearrangement of x with the filter flattened (ky, kx, ci) -> K. Both
+        # rearrangements are plain tensor views / one copy that autograd differentiates; the GEMM, its input / weight
+        # gradients and the BatchNorm run on the same tcgen05 training kernels as every other adaptation conv.
+        n, c, h, w = x.shape
+        x2 = x.reshape(n, c, h // k, k, w // k, k).permute(0, 3, 5, 1, 2, 4).reshape(n, k * k * c, h // k, w // k)
+        w2 = conv.weight.permute(0, 2, 3, 1).reshape(conv.out_channels, k * k * c, 1, 1)
+        gamma = bn.weight if bn is not None else None
+        beta = bn.bias if bn is not None else None
+        return _ConvBNActFn.apply(x2, w2, conv.bias, gamma, beta, None, bn, conv, 1, 0, relu)
+    raise NotImplementedError("adaptation conv %dx%d / stride %d / pad %d: the tcgen05 training kernels cover 1x1 / stride 1, "
+                              "3x3 / pad 1 / stride 1-2 and k x k / stride k / pad 0 (patch) convolutions" % (k, k, s, pad))
 
 
 class Mlp(nn.Module):

@@ -392,7 +392,38 @@ def test_mlp_and_3x3_adaptations(cuda):
     c3 = A.Conv3x3Adaptation(256, 128).to(cuda)
     assert _relerr(c3(x), F.conv2d(x, c3.weight, c3.bias, 1, 1).detach()) <= 3e-3
     with pytest.raises(NotImplementedError):
-        A.TwoLayer(256, out_features=128, kernel_size=4, stride=4).to(cuda)(x)
+        A.TwoLayer(256, out_features=128, kernel_size=5, stride=3).to(cuda)(x)
+
+
+def test_downsample_2layer_adaptation_matches_torch_modules(cuda):
+    """'downsample_2layer' (bevdet_distill.py:252-257): TwoLayer with a 4x4 / stride-4 conv1 = a 1x1 conv over the
+    space-to-depth view; forward and every gradient against the same torch modules (fp32), bars calibrated on cuDNN TF32."""
+    from distill_bev_b200.plugin.distill import adaptation as A
+    torch.manual_seed(9)
+    ours = A.TwoLayer(256, out_features=128, kernel_size=4, stride=4).to(cuda).train()
+    assert ours.stride == (4, 4)
+
+    class Ref(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1, self.norm1 = nn.Conv2d(256, 256, 4, 4), nn.BatchNorm2d(256)
+            self.conv2, self.norm2 = nn.Conv2d(256, 128, 1), nn.BatchNorm2d(128)
+
+        def forward(self, t):
+            return torch.relu(self.norm2(self.conv2(torch.relu(self.norm1(self.conv1(t))))))
+
+    ref = Ref().to(cuda).train()
+    ref.load_state_dict({k: v for k, v in ours.state_dict().items()}, strict=True)
+    tf = copy.deepcopy(ref)
+    x = torch.relu(torch.randn(2, 256, 64, 64, device=cuda))
+    with torch.no_grad():
+        g = torch.randn_like(copy.deepcopy(ref)(x))
+    y32, g32 = _grads(ref, x, g, False)
+    ytf, gtf = _grads(tf, x, g, True)
+    yo, go = _grads(ours, x, g, False)
+    assert _relerr(yo, y32) <= max(5e-3, 2 * _relerr(ytf, y32))
+    for k in g32:
+        assert _relerr(go[k], g32[k]) <= 2.0 * _relerr(gtf[k], g32[k]) + 2e-3, (k, _relerr(go[k], g32[k]), _relerr(gtf[k], g32[k]))
 
 
 @pytest.mark.parametrize("delay_cycles", [0, 2000000])
