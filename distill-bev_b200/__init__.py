@@ -24,7 +24,7 @@ from .plugin.ops.ms_deform_attn import (MultiScaleDeformableAttnFunction,  # noq
 from .plugin.sparse_teacher import DynamicVoxelEncoder, HardSimpleVFE, SparseEncoder  # noqa: F401
 from .plugin.dense_teacher import SECOND, SECONDFPN  # noqa: F401
 from .plugin.student_convs import Conv2dTC, conv2d_tc, conv2d_tc_supported, convert_convs  # noqa: F401
-from .plugin.bev_encoder import BasicBlock, FPN_LSS, ResNetForBEVDet, conv_bn_act, upsample_cat  # noqa: F401
+from .plugin.bev_encoder import BasicBlock, Bottleneck, FPN_LSS, ResNetForBEVDet, conv_bn_act, upsample_cat  # noqa: F401
 from .plugin.ops import conv_train  # noqa: F401
 from .plugin import bev_encoder  # noqa: F401
 from .plugin.bevformer_attention import MSDeformableAttention3D, SpatialCrossAttention  # noqa: F401

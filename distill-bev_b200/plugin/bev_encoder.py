@@ -290,23 +290,78 @@ class BasicBlock(nn.Module):
         return conv_bn_act(out, self.conv2, self.bn2, residual=identity, relu=True)
 
 
+class Bottleneck(nn.Module):
+    """bricks/res_block.py:102-311 (mmdet's Bottleneck with act_cfg; sub-module names conv1 / bn1 / conv2 / bn2 / conv3 /
+    bn3 / downsample): 1x1 -> 3x3 (the strided one, style 'pytorch') -> 1x1 (x4 channels) + identity, ReLU. Every
+    conv + BatchNorm (+ residual) + ReLU group is one autograd node on the tcgen05 training kernels; `planes` must be a
+    multiple of 128 (the weight-gradient kernel's tile), e.g. num_channels = [512, 1024, 2048]."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None, style="pytorch", with_cp=False,
+                 conv_cfg=None, norm_cfg=dict(type="BN"), dcn=None, plugins=None, init_cfg=None,
+                 act_cfg=dict(type="ReLU", inplace=True)):
+        super(Bottleneck, self).__init__()
+        assert style in ("pytorch", "caffe")
+        assert dcn is None and plugins is None, "Not implemented yet."
+        if dilation != 1 or conv_cfg is not None:
+            raise NotImplementedError("Bottleneck: dilation 1 and plain Conv2d only")
+        if style == "caffe" and stride != 1:
+            raise NotImplementedError("Bottleneck style 'caffe' with stride > 1 (a strided 1x1 conv) is not implemented")
+        _check_act(act_cfg)
+        self.inplanes, self.planes, self.stride, self.dilation, self.style, self.with_cp = inplanes, planes, stride, dilation, style, with_cp
+        self.conv1_stride, self.conv2_stride = (1, stride) if style == "pytorch" else (stride, 1)
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, stride=self.conv1_stride, bias=False)
+        self.bn1 = _bn(norm_cfg, planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=self.conv2_stride, padding=1, bias=False)
+        self.bn2 = _bn(norm_cfg, planes)
+        self.conv3 = nn.Conv2d(planes, planes * self.expansion, 1, bias=False)
+        self.bn3 = _bn(norm_cfg, planes * self.expansion)
+        self.downsample = downsample
+
+    @property
+    def norm1(self):
+        return self.bn1
+
+    @property
+    def norm2(self):
+        return self.bn2
+
+    @property
+    def norm3(self):
+        return self.bn3
+
+    def forward(self, x):
+        out = conv_bn_act(x, self.conv1, self.bn1, relu=True)
+        out = conv_bn_act(out, self.conv2, self.bn2, relu=True)
+        identity = x
+        if self.downsample is not None:
+            if not isinstance(self.downsample, nn.Conv2d):
+                raise NotImplementedError("Bottleneck: downsample must be the nn.Conv2d ResNetForBEVDet builds")
+            identity = conv_bn_act(x, self.downsample, None, relu=False)
+        return conv_bn_act(out, self.conv3, self.bn3, residual=identity, relu=True)
+
+
 class ResNetForBEVDet(nn.Module):
-    """backbones/resnet.py:12-62 (block_type 'Basic', the shipped configs)."""
+    """backbones/resnet.py:12-62 (block_type 'Basic' - the shipped configs - or 'BottleNeck')."""
 
     def __init__(self, numC_input, num_layer=[2, 2, 2], num_channels=None, stride=[2, 2, 2], backbone_output_ids=None,
                  norm_cfg=dict(type="BN"), act_cfg=dict(type="ReLU", inplace=True), with_cp=False, block_type="Basic"):
         super(ResNetForBEVDet, self).__init__()
         assert len(num_layer) == len(stride)
-        if block_type != "Basic":
-            raise NotImplementedError("ResNetForBEVDet: block_type 'Basic' only (the shipped configs)")
+        assert block_type in ("Basic", "BottleNeck")
         num_channels = [numC_input * 2 ** (i + 1) for i in range(len(num_layer))] if num_channels is None else num_channels
         self.backbone_output_ids = range(len(num_layer)) if backbone_output_ids is None else backbone_output_ids
         layers, curr = [], numC_input
         for i in range(len(num_layer)):
-            layer = [BasicBlock(curr, num_channels[i], stride=stride[i],
-                                downsample=nn.Conv2d(curr, num_channels[i], 3, stride[i], 1), norm_cfg=norm_cfg, act_cfg=act_cfg)]
-            curr = num_channels[i]
-            layer.extend([BasicBlock(curr, curr, norm_cfg=norm_cfg, act_cfg=act_cfg) for _ in range(num_layer[i] - 1)])
+            down = nn.Conv2d(curr, num_channels[i], 3, stride[i], 1)
+            if block_type == "BottleNeck":            # resnet.py:26-35
+                layer = [Bottleneck(curr, num_channels[i] // 4, stride=stride[i], downsample=down, norm_cfg=norm_cfg, act_cfg=act_cfg)]
+                curr = num_channels[i]
+                layer.extend([Bottleneck(curr, curr // 4, norm_cfg=norm_cfg, act_cfg=act_cfg) for _ in range(num_layer[i] - 1)])
+            else:                                     # resnet.py:36-44
+                layer = [BasicBlock(curr, num_channels[i], stride=stride[i], downsample=down, norm_cfg=norm_cfg, act_cfg=act_cfg)]
+                curr = num_channels[i]
+                layer.extend([BasicBlock(curr, curr, norm_cfg=norm_cfg, act_cfg=act_cfg) for _ in range(num_layer[i] - 1)])
             layers.append(nn.Sequential(*layer))
         self.layers = nn.Sequential(*layers)
         self.with_cp = with_cp

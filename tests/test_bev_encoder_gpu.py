@@ -520,3 +520,61 @@ def test_batched_weight_packing_matches_per_layer(cuda):
         assert m._dbev_prepacked[0] == (m.weight.data_ptr(), m.weight._version) and w_fwd.data_ptr() == ptr
         a, b = ct.pack_weights_train(m.weight, m.stride[0])
         assert torch.equal(w_fwd, a) and torch.equal(w_bwd, b)
+
+
+def test_bottleneck_backbone_matches_torch_modules(cuda):
+    """ResNetForBEVDet(block_type='BottleNeck') (resnet.py:26-35, bricks/res_block.py:102-311): one stage of two Bottleneck
+    blocks (128 -> 512 channels, stride 2) against the same torch modules, forward and every gradient; the reference's
+    state_dict key layout (conv1 / bn1 / conv2 / bn2 / conv3 / bn3 / downsample)."""
+    torch.manual_seed(13)
+    ours = dbev.ResNetForBEVDet(128, num_layer=[2], num_channels=[512], stride=[2], block_type="BottleNeck").to(cuda).train()
+    keys = set(ours.state_dict().keys())
+    for k in ("layers.0.0.conv1.weight", "layers.0.0.bn3.running_var", "layers.0.0.downsample.bias", "layers.0.1.conv3.weight"):
+        assert k in keys, k
+
+    class RefBlock(nn.Module):
+        def __init__(self, cin, planes, stride, down):
+            super().__init__()
+            self.conv1, self.bn1 = nn.Conv2d(cin, planes, 1, bias=False), nn.BatchNorm2d(planes)
+            self.conv2, self.bn2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False), nn.BatchNorm2d(planes)
+            self.conv3, self.bn3 = nn.Conv2d(planes, planes * 4, 1, bias=False), nn.BatchNorm2d(planes * 4)
+            self.downsample = nn.Conv2d(cin, planes * 4, 3, stride, 1) if down else None
+
+        def forward(self, t):
+            out = torch.relu(self.bn1(self.conv1(t)))
+            out = torch.relu(self.bn2(self.conv2(out)))
+            out = self.bn3(self.conv3(out))
+            return torch.relu(out + (t if self.downsample is None else self.downsample(t)))
+
+    class Ref(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.layers = nn.Sequential(nn.Sequential(RefBlock(128, 128, 2, True), RefBlock(512, 128, 1, False)))
+
+        def forward(self, t):
+            return self.layers(t)
+
+    ref = Ref().to(cuda).train()
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    tf = copy.deepcopy(ref)
+    x = torch.relu(torch.randn(2, 128, 32, 32, device=cuda))
+    with torch.no_grad():
+        g = torch.randn_like(copy.deepcopy(ref)(x))
+    y32, g32 = _grads(ref, x, g, False)
+    ytf, gtf = _grads(tf, x, g, True)
+
+    class Wrap(nn.Module):
+        def __init__(self, net):
+            super().__init__()
+            self.layers = net.layers
+
+        def forward(self, t):
+            return self.layers(t)
+
+    yo, go = _grads(Wrap(ours), x, g, False)
+    assert _relerr(yo, y32) <= max(5e-3, 2 * _relerr(ytf, y32))
+    for k in g32:
+        assert _relerr(go[k], g32[k]) <= 2.0 * _relerr(gtf[k], g32[k]) + 2e-3, (k, _relerr(go[k], g32[k]), _relerr(gtf[k], g32[k]))
+    with pytest.raises(NotImplementedError):
+        bev_enc = __import__("distill_bev_b200").bev_encoder
+        bev_enc.Bottleneck(128, 128, stride=2, style="caffe")
