@@ -155,3 +155,58 @@ def test_upsample_3layer_and_mlp_match_the_reference_classes(cuda):
     ym = mlp(torch.from_numpy(ref["mlp_x"]).to(cuda))
     wm = torch.from_numpy(ref["mlp_y"]).to(cuda)
     assert float((ym - wm).abs().max()) <= 3e-3 * float(wm.abs().max())
+
+
+GOLDEN_BN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bev_encoder_bottleneck.npz")
+
+
+def _build_bottleneck():
+    torch.manual_seed(3)
+    return dbev.ResNetForBEVDet(numC_input=128, num_layer=[2], num_channels=[512], stride=[2], block_type="BottleNeck")
+
+
+def test_bottleneck_state_dict_layout_and_seeded_init_match_the_reference_class():
+    """block_type='BottleNeck' against the fixture of the UNMODIFIED reference Bottleneck (res_block.py:102-311,
+    tools/make_golden_bev_encoder.py --bottleneck): same keys, shapes and seeded tensors."""
+    ref = np.load(GOLDEN_BN)
+    net = _build_bottleneck()
+    sd = net.state_dict()
+    assert list(sd.keys()) == [str(k) for k in ref["keys"]]
+    assert [",".join(map(str, v.shape)) for v in sd.values()] == [str(s) for s in ref["shapes"]]
+    for k, v in sd.items():
+        got = _checksum(v.float()) if v.dtype != torch.long else np.array([float(v)])
+        np.testing.assert_allclose(got, ref["sum/" + k], rtol=1e-6, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.gpu
+def test_bottleneck_forward_backward_match_the_reference_class(cuda):
+    ref = np.load(GOLDEN_BN)
+    net = _build_bottleneck().to(cuda).train()
+    gen = torch.Generator().manual_seed(6)
+    x = torch.relu(torch.randn(2, 128, 16, 16, generator=gen))
+    g = torch.randn(2, 512, 8, 8, generator=gen) / (2 * 512 * 8 * 8) ** 0.5
+    np.testing.assert_allclose(_checksum(x), ref["x_sum"], rtol=1e-6)
+    np.testing.assert_allclose(_checksum(g), ref["g_sum"], rtol=1e-6, atol=1e-9)
+    xin = x.to(cuda).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = net(xin)[0]
+    loss = (y * g.to(cuda)).sum()
+    loss.backward()
+    want_y = torch.from_numpy(ref["y"]).to(cuda)
+    assert float((y - want_y).abs().max()) <= 5e-3 * float(want_y.abs().max())       # TF32 products, six conv + BN layers
+    assert abs(float(loss) - float(ref["loss"])) <= 1e-3 * float((want_y * g.to(cuda)).abs().sum())
+    want_gx = torch.from_numpy(ref["x_grad"]).to(cuda)
+    cos = float((xin.grad * want_gx).sum() / (xin.grad.norm() * want_gx.norm()))
+    # TF32 rounding flips ReLU masks; with only 128 pixels per channel the batch statistics amplify that (the bar against
+    # cuDNN TF32 is in test_bev_encoder_gpu.py::test_bottleneck_backbone_matches_torch_modules)
+    assert cos >= 0.995 and float((xin.grad - want_gx).abs().max()) <= 1.5e-1 * float(want_gx.abs().max())
+    for k, p in net.named_parameters():
+        want = float(ref["gradmax/" + k])
+        assert p.grad is not None and 0.5 * want <= float(p.grad.abs().max()) <= 2.0 * want + 1e-12, (k, want)
+    last_beta = dict(net.named_parameters())["layers.0.1.bn3.bias"].grad.cpu().numpy()
+    want = ref["grad/layers.0.1.bn3.bias"]
+    # a beta gradient is the sum of g over the pixels whose output passed the ReLU: 128 pixels per channel here, so one
+    # TF32-flipped mask bit moves it by ~1e-1 of the largest entry
+    assert np.abs(last_beta - want).max() <= 1.5e-1 * np.abs(want).max() + 1e-7
+    for k, v in net.state_dict().items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            np.testing.assert_allclose(v.cpu().numpy(), ref["after/" + k], rtol=2e-3, atol=2e-4, err_msg=k)

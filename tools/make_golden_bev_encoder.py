@@ -142,8 +142,43 @@ def adaptation_golden():
     print("wrote", p, "%.2f MB" % (os.path.getsize(p) / 1e6))
 
 
+def bottleneck_golden():
+    """ResNetForBEVDet(block_type='BottleNeck') (resnet.py:26-35) with the UNMODIFIED Bottleneck class
+    (bricks/res_block.py:102-311): one stage of two blocks, 128 -> 512 channels, stride 2, training mode, fp32 CPU.
+    Writes tests/golden/bev_encoder_bottleneck.npz (checksums of the seeded state_dict, output, gradients)."""
+    ResNetForBEVDet, _ = load_classes()
+    torch.manual_seed(3)
+    net = ResNetForBEVDet(numC_input=128, num_layer=[2], num_channels=[512], stride=[2], block_type="BottleNeck").train()
+    out = {}
+    keys, shapes = [], []
+    for k, v in net.state_dict().items():
+        keys.append(k)
+        shapes.append(",".join(map(str, v.shape)))
+        out["sum/" + k] = checksum(v.float()) if v.dtype != torch.long else np.array([float(v)])
+    gen = torch.Generator().manual_seed(6)
+    x = torch.relu(torch.randn(2, 128, 16, 16, generator=gen)).requires_grad_(True)
+    y = net(x)[0]
+    g = torch.randn(y.shape, generator=gen) / y.numel() ** 0.5
+    loss = (y * g).sum()
+    loss.backward()
+    out.update(x_sum=checksum(x), g_sum=checksum(g), y=y.detach().numpy(), loss=np.array(float(loss.detach())),
+               x_grad=x.grad.numpy(), keys=np.array(keys), shapes=np.array(shapes))
+    for k, p in net.named_parameters():
+        if p.numel() <= 4096:
+            out["grad/" + k] = p.grad.numpy()
+        out["gradmax/" + k] = np.array(float(p.grad.abs().max()))
+    for k, v in net.state_dict().items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            out["after/" + k] = v.numpy().copy()
+    path = os.path.join(ROOT, "tests", "golden", "bev_encoder_bottleneck.npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s (%d state_dict entries, %.2f MB)" % (path, len(keys), os.path.getsize(path) / 1e6))
+
+
 if __name__ == "__main__":
     if "--adaptation" in sys.argv:
         adaptation_golden()
+    elif "--bottleneck" in sys.argv:
+        bottleneck_golden()
     else:
         main()
