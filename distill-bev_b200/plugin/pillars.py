@@ -105,6 +105,14 @@ class PFNLayer(nn.Module):
         self.mode = mode
 
 
+def _rewrite_virtual_flag(features):
+    """MVP virtual points (pillar_encoder.py:108-113 / :294-299): the second-to-last point feature is the virtual
+    label, -1 for a virtual point; the encoder sees 1 for virtual and 0 for real points. In place, like the reference."""
+    flag = features[..., -2]
+    flag.copy_((flag == -1).to(features.dtype))
+    return features
+
+
 class PillarFeatureNet(nn.Module):
     """pillar_encoder.py:14-162: the hard-voxel pillar encoder of the shipped CenterPoint teacher
     (configs/_base_/models/centerpoint_02pillar_second_secfpn_nus.py:6-13). Same constructor arguments and
@@ -117,10 +125,9 @@ class PillarFeatureNet(nn.Module):
                  norm_cfg=dict(type='BN1d', eps=1e-3, momentum=0.01), mode='max', legacy=True, virtual=False):
         super(PillarFeatureNet, self).__init__()
         assert len(feat_channels) > 0
-        if len(feat_channels) != 1 or with_distance or not with_cluster_center or not with_voxel_center or virtual \
-                or mode != 'max':
+        if len(feat_channels) != 1 or with_distance or not with_cluster_center or not with_voxel_center or mode != 'max':
             raise NotImplementedError("PillarFeatureNet: only the shipped teacher configuration is implemented: one PFN "
-                                      "layer, cluster + voxel centre decorations, max pooling, no virtual points")
+                                      "layer, cluster + voxel centre decorations, max pooling")
         self.legacy = legacy
         self.in_channels = in_channels + 5
         self._with_distance, self._with_cluster_center, self._with_voxel_center = False, True, True
@@ -140,6 +147,8 @@ class PillarFeatureNet(nn.Module):
                                       "distillation teacher is always eval()")
         lib = _lib.load()
         _lib.require_cuda(features, "features", torch.float32)
+        if self.virtual:
+            _rewrite_virtual_flag(features)
         features = features.contiguous()
         m, t, f = features.shape
         layer = self.pfn_layers[0]
@@ -169,10 +178,10 @@ class DynamicPillarFeatureNet(nn.Module):
                  norm_cfg=dict(type='BN1d', eps=1e-3, momentum=0.01), mode='max', virtual=False,
                  act_cfg=dict(type='ReLU', inplace=True), use_checkpoint=False):
         super(DynamicPillarFeatureNet, self).__init__()
-        if len(feat_channels) != 1 or with_distance or not with_cluster_center or not with_voxel_center \
-                or virtual or mode != 'max':
+        if len(feat_channels) != 1 or with_distance or not with_cluster_center or not with_voxel_center or mode != 'max':
             raise NotImplementedError("only the shipped teacher configuration is implemented: one PFN "
                                       "layer, cluster + voxel centre decorations, max pooling")
+        self.virtual = virtual
         self.in_channels = in_channels + 5
         self.voxel_size = voxel_size
         self.point_cloud_range = point_cloud_range
@@ -188,6 +197,8 @@ class DynamicPillarFeatureNet(nn.Module):
 
     def forward(self, features, coors):
         batch_size = int(coors[-1, 0] + 1)
+        if self.virtual:
+            _rewrite_virtual_flag(features)
         lin, bn = self.pfn_layers[0][0], self.pfn_layers[0][1]
         if not self.training:
             scale, shift = fold_bn(bn)

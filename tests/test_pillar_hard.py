@@ -85,3 +85,40 @@ def test_kernel_full_size_teacher_front_end(cuda):
     canvas = dbev.PointPillarsScatter(64, [512, 512])(out, coors, 2)
     ref = pillar_oracle.pillar_scatter(want, coors.cpu().numpy(), 2, 512, 512)
     np.testing.assert_allclose(canvas.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_virtual_points_match_reference_class(cuda):
+    """virtual=True (MVP teachers, pillar_encoder.py:108-113): the virtual label column (-1 = virtual) is rewritten to
+    1 / 0 in place before the decorations, like the reference; output against the UNMODIFIED class on the same voxels."""
+    import distill_bev_b200 as dbev
+    gd = np.load(GOLDEN)
+    vmask = np.unpackbits(gd["virtual_mask"], axis=1)[:, :gd["voxels"].shape[1]].astype(bool)
+    feats = torch.from_numpy(gd["voxels"]).clone()
+    feats[..., -2][torch.from_numpy(vmask)] = -1.0
+    net = dbev.PillarFeatureNet(in_channels=5, feat_channels=[64], voxel_size=tuple(gd["voxel_size"]),
+                                point_cloud_range=tuple(gd["range"]), legacy=False, virtual=True)
+    net.load_state_dict({str(k): torch.from_numpy(gd["sd/" + str(k)]) for k in gd["keys"]}, strict=True)
+    net = net.to(cuda).eval()
+    f = feats.to(cuda)
+    out = net(f, torch.from_numpy(gd["num_points"]).to(cuda), torch.from_numpy(gd["coors"]).to(cuda))
+    torch.testing.assert_close(out, torch.from_numpy(gd["out_virtual"]).to(cuda), rtol=1e-5, atol=1e-5)
+    assert torch.equal(f[..., -2].cpu(), torch.from_numpy(vmask).float())          # rewritten in place, as the reference does
+    # the dynamic-voxel encoder applies the same rewrite (pillar_encoder.py:294-299)
+    dyn = dbev.DynamicPillarFeatureNet(in_channels=5, feat_channels=(64,), voxel_size=(0.2, 0.2, 8),
+                                       point_cloud_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0), virtual=True).to(cuda).eval()
+    plain = dbev.DynamicPillarFeatureNet(in_channels=5, feat_channels=(64,), voxel_size=(0.2, 0.2, 8),
+                                         point_cloud_range=(-51.2, -51.2, -5.0, 51.2, 51.2, 3.0)).to(cuda).eval()
+    plain.load_state_dict(dyn.state_dict())
+    from distill_bev_b200 import synthetic
+    pts = torch.from_numpy(synthetic.make_lidar(1, 4000, seed=5)[0]).to(cuda)
+    lab = torch.rand(pts.shape[0], device=cuda) < 0.3
+    raw = pts.clone()
+    raw[:, -2] = torch.where(lab, torch.full_like(raw[:, -2], -1.0), raw[:, -2].abs() + 0.5)
+    pre = raw.clone()
+    pre[:, -2] = lab.float()
+    vox = dbev.Voxelization([0.2, 0.2, 8], [-51.2, -51.2, -5.0, 51.2, 51.2, 3.0], -1, -1)
+    co = torch.nn.functional.pad(vox(pts), (1, 0), value=0)
+    a, ca = dyn(raw, co)
+    b, cb = plain(pre, co)
+    assert torch.equal(a, b) and torch.equal(ca, cb)

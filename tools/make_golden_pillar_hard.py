@@ -57,6 +57,19 @@ def main():
             out["keys"] = np.array(list(net.state_dict().keys()))
             for k2, v2 in net.state_dict().items():
                 out["sd/" + k2] = v2.numpy()
+    # MVP virtual points (virtual=True, pillar_encoder.py:108-113): the second-to-last feature is the virtual label,
+    # -1 for a virtual point; the same voxels with ~40 % of the points marked virtual, same weights as the runs above
+    vmask = torch.rand(voxels.shape[:2], generator=torch.Generator().manual_seed(11)) < 0.4
+    feats_v = voxels.clone()
+    feats_v[..., -2][vmask] = -1.0
+    torch.manual_seed(3)
+    net = pe.PillarFeatureNet(in_channels=5, feat_channels=[64], with_distance=False, voxel_size=tuple(vs),
+                              point_cloud_range=tuple(rng), norm_cfg=dict(type="BN1d", eps=1e-3, momentum=0.01),
+                              legacy=False, virtual=True).eval()
+    net.load_state_dict({k2: torch.from_numpy(out["sd/" + k2]) for k2 in out["keys"]})
+    with torch.no_grad():
+        out["out_virtual"] = net(feats_v, num_points, coors).numpy()
+    out["virtual_mask"] = np.packbits(vmask.numpy(), axis=1)
     path = os.path.join(ROOT, "tests", "golden", "pillar_hard.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, voxels.shape, "%.2f MB" % (os.path.getsize(path) / 1e6))
