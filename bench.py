@@ -353,12 +353,15 @@ class HotPath(object):
             p.grad = None
         return loss_vec, canvas
 
-    def _update(self, overlap_event=None):
+    def _update(self, overlap_event=None, join=True):
         """AdamW over the trained parameters. With ``overlap_event`` (recorded when the last parameter gradient of the
-        main stream exists) the step runs on its own stream beside the tail of the backward chain."""
+        main stream exists) the step runs on its own stream beside the tail of the backward chain. ``join=False``: the
+        caller has already joined the weight-gradient stream (the optimizer graph of the split mode is captured on its own:
+        a wait on the uncaptured side stream would invalidate that capture)."""
         torch = self.torch
         if overlap_event is None or not self.overlap_side:
-            self.dbev.conv_train.join_side_stream(self.dev)   # weight gradients computed beside the backward chain
+            if join:
+                self.dbev.conv_train.join_side_stream(self.dev)   # weight gradients computed beside the backward chain
             self.optim.step()
         else:
             main = torch.cuda.current_stream(self.dev)
@@ -418,7 +421,9 @@ class HotPath(object):
             for _ in range(2):            # optimizer state must exist before its capture
                 self.reducer.finish()
                 self._update()
-            self.update_graph = dbev.CapturedStep(lambda: (self._update(), self.trainable[0])[1], warmup=1, device=self.dev)
+            # _forward_backward() ends with the join of the weight-gradient stream, so the optimizer graph needs none
+            self.update_graph = dbev.CapturedStep(lambda: (self._update(join=False), self.trainable[0])[1], warmup=1,
+                                                  device=self.dev)
         else:
             self.graphs = [dbev.CapturedStep(
                 (lambda d=d: self._compute(d["calib"], d["points"], d["labels"], d["packed"])), warmup=3,
@@ -897,6 +902,8 @@ def run_ours(args):
                 hp.captured = None
                 graph_note = "eager (graph capture failed: %s)" % str(exc).splitlines()[0][:120]
                 sys.stderr.write("bench.py: CUDA graph capture failed (allreduce=%s): %s\n" % (mode, exc))
+                import traceback
+                traceback.print_exc(file=sys.stderr)
                 torch.cuda.synchronize()
 
     def barrier():
@@ -978,8 +985,11 @@ def run_ours(args):
             except Exception as exc:  # extra evidence only: never lose the headline line over it
                 line[key] = {"error": str(exc)[:200]}
     else:
-        line["roofline"] = student_conv_roofline(hp)
-        line["roofline_bev_pool"] = bev_pool_roofline(device)
+        for key, probe in (("roofline", lambda: student_conv_roofline(hp)), ("roofline_bev_pool", lambda: bev_pool_roofline(device))):
+            try:
+                line[key] = probe()
+            except Exception as exc:  # never lose the headline line over a probe
+                line[key] = {"error": str(exc)[:200]}
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
